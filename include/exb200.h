@@ -1,0 +1,223 @@
+/*
+ * exb200.h - C ABI of the B200-native sampler for exchanger's partially-collapsed
+ * Gibbs sweep.
+ *
+ * This header is the drop-in boundary.  It replaces the Rcpp entry
+ *     Rcpp::S4 sample(Rcpp::S4 init_state, int n_samples, int thin_interval,
+ *                     int burnin_interval)            (reference src/sample.cpp:118-219)
+ * which R reaches through .Call('_exchanger_sample', ...) (R/RcppExports.R:12-14,
+ * src/RcppExports.cpp:35-48).  The reference unmarshals an `ExchangERModel` S4
+ * object into its C++ `State` (src/sample.cpp:71-105), runs `State::update()`
+ * (src/state.h:60-75) in a loop and marshals the history and the final state
+ * back (src/sample.cpp:14-63,171-218).  Here the glue flattens the same S4 slots
+ * into the POD structs below; no R, Rcpp or torch type crosses this boundary.
+ *
+ * Conventions
+ *   - every id is int32 and 0-based (the glue applies the same "-1" shift as
+ *     src/sample.cpp:89-93); a missing record value is any negative number
+ *     (R's NA_INTEGER = INT32_MIN is accepted as is);
+ *   - matrices are column-major exactly as R stores them;
+ *   - the caller owns every buffer; the library copies what it needs during the
+ *     call and keeps no pointer afterwards;
+ *   - every function returns EXB200_OK or a negative status; the message is
+ *     available from exb200_last_error() (no exception crosses the ABI; the
+ *     reference reports the same conditions through Rcpp::stop / std::runtime_error
+ *     translated by BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:38-47);
+ *   - there is no CPU fallback: without a CUDA device exb200_create fails with
+ *     EXB200_ERR_NO_DEVICE.
+ */
+#ifndef EXB200_H
+#define EXB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXB200_ABI_VERSION 1
+
+enum {
+  EXB200_OK = 0,
+  EXB200_ERR_INVALID = -1,     /* malformed model (sizes, ids out of range, bad pmf) */
+  EXB200_ERR_UNSUPPORTED = -2, /* a model feature this build does not implement     */
+  EXB200_ERR_NO_DEVICE = -3,   /* no CUDA device / CUDA runtime failure at start    */
+  EXB200_ERR_CUDA = -4,        /* CUDA error during a call                           */
+  EXB200_ERR_WEIGHTS = -5,     /* a conditional had no valid outcome (the reference's
+                                  CHECK_WEIGHTS / AliasSampler errors,
+                                  src/links.cpp:415-419, src/alias_sampler.h:76-97)  */
+  EXB200_ERR_ABORTED = -6,     /* abort callback asked to stop (partial history kept) */
+  EXB200_ERR_OOM = -7
+};
+
+/* Cluster prior families: reference src/clust_params.cpp:259-281 (read_clust_params). */
+enum {
+  EXB200_CLUST_PITMAN_YOR = 0, /* PitmanYorRP; EwensRP is d = 0 (R/PitmanYorRP.R:107-109) */
+  EXB200_CLUST_GEN_COUPON = 1, /* GeneralizedCouponRP with finite kappa                   */
+  EXB200_CLUST_COUPON = 2      /* GeneralizedCouponRP with kappa = Inf                    */
+};
+
+/* Entity-value distribution prior: reference src/entities.cpp:181-211. */
+enum {
+  EXB200_ENTDIST_FIXED = 0,    /* NULL (empirical probs) or a fixed numeric pmf */
+  EXB200_ENTDIST_DIRICHLET = 1 /* DirichletRV with scalar alpha                 */
+};
+
+/*
+ * One attribute: the `Attribute` spec (R/Attribute.R:112-119) together with its
+ * `AttributeIndex` (R/AttributeIndex.R:68-88).  Replaces what
+ * readAttributeIndex (src/attribute_index.cpp:118-149), Entities::Entities
+ * (src/entities.cpp:163-212), DistortProbs::init_prior
+ * (src/distortion_probs.cpp:4-21) and DistortDistConcs::init_prior
+ * (src/distort_dist_concs.cpp:3-19) read from the S4 object.
+ */
+typedef struct exb200_attr {
+  int32_t domain_size;          /* length(index@domain)                                 */
+  int32_t is_constant;          /* 1: length(index@close_values) == 0 (categorical)     */
+  int32_t exclude_entity_value; /* spec@exclude_entity_value                            */
+  int32_t entity_dist_kind;     /* EXB200_ENTDIST_*                                     */
+  const double* probs;          /* [D] index@probs (smoothed empirical pmf)             */
+  const double* entity_dist;    /* [D] fixed pmf of the entity value, NULL = probs;
+                                   for DIRICHLET: the concentration vector              */
+  /* index@close_values in R's orientation: row v (an ENTITY value) lists the record
+     values w with p(w | v) > 0; the library inverts it like
+     src/attribute_index.cpp:125-140.  All NULL / 0 for a constant attribute.           */
+  const int64_t* close_row_ptr; /* [D + 1]                                              */
+  const int32_t* close_val_ids; /* [nnz] 0-based record values w                        */
+  const double* close_probs;    /* [nnz] p(w | v)                                       */
+  const double* max_exp_factor; /* [D] index@max_exp_factor (NULL if constant)          */
+  double distort_prob_shape1;   /* BetaRV prior on theta[.,a]; <= 0: theta stays fixed  */
+  double distort_prob_shape2;
+  double distort_dist_conc;     /* distort_dist_concs[a]; +Inf for DirichletProcess(Inf) */
+  double conc_prior_shape;      /* GammaRV prior on the DP concentration; <= 0: none    */
+  double conc_prior_rate;
+} exb200_attr;
+
+/* Cluster prior and current parameter values (clust_prior / clust_params slots). */
+typedef struct exb200_clust {
+  int32_t kind; /* EXB200_CLUST_* */
+  double alpha, d; /* Pitman-Yor values                                 */
+  double m, kappa; /* coupon values (m is integer valued)               */
+  double alpha_prior_shape, alpha_prior_rate; /* GammaRV, <= 0: fixed  */
+  double d_prior_shape1, d_prior_shape2;      /* BetaRV,  <= 0: fixed  */
+  double kappa_prior_shape, kappa_prior_rate; /* GammaRV, <= 0: fixed  */
+  double m_prior_size, m_prior_prob;          /* ShiftedNegBinomRV, size <= 0: fixed */
+} exb200_clust;
+
+/* The `ExchangERModel` slots (R/ExchangERModel.R:166-182) as flat arrays. */
+typedef struct exb200_model {
+  int32_t n_records;              /* N */
+  int32_t n_attrs;                /* A */
+  int32_t n_files;                /* F */
+  int32_t n_entities;             /* K = length(ent_ids) */
+  int32_t iteration;              /* @iteration */
+  const int32_t* rec_attrs;       /* [A x N] @rec_attrs - 1, NA kept negative           */
+  const int32_t* rec_distortions; /* [A x N] @rec_distortions                           */
+  const int32_t* file_ids;        /* [N] @file_ids - 1                                  */
+  const int32_t* links;           /* [N] @links (labels taken from ent_ids)             */
+  const int32_t* ent_ids;         /* [K] @ent_ids                                       */
+  const int32_t* ent_attrs;       /* [A x K] @ent_attrs - 1                             */
+  const double* distort_probs;    /* [F x A] @distort_probs                             */
+  const exb200_attr* attrs;       /* [A] */
+  exb200_clust clust;
+  uint64_t seed;                  /* Philox key; the glue derives it from R's RNG so
+                                     set.seed() still fixes the chain                   */
+} exb200_model;
+
+/*
+ * Caller-allocated history, filled with the save schedule of
+ * src/sample.cpp:171-197.  Row s of every array is sample s (sample-major; the R
+ * glue transposes into R's column-major n_samples x p matrices).  Any pointer may
+ * be NULL to skip that series.
+ */
+typedef struct exb200_history {
+  int32_t* links;             /* [n_samples][N]  hist_links                           */
+  double* distort_probs;      /* [n_samples][F*A] column f + a*F (sample.cpp:144-149) */
+  int32_t* distort_counts;    /* [n_samples][F*A] same column order                   */
+  double* distort_dist_concs; /* [n_samples][A]                                       */
+  int32_t* n_linked_ents;     /* [n_samples]                                          */
+  double* clust_params;       /* [n_samples][2]: (alpha, d) or (kappa, m); the glue
+                                 keeps the random ones (clust_params.cpp:161-216)      */
+  int32_t n_saved;            /* out: rows actually written                           */
+} exb200_history;
+
+/* Caller-allocated final state (what buildFinalS4State writes, sample.cpp:14-63). */
+typedef struct exb200_state {
+  int32_t iteration;
+  int32_t n_entities;          /* out: K */
+  int32_t* links;              /* [N]                                 */
+  int32_t* ent_ids;            /* [N] capacity, first K filled        */
+  int32_t* ent_attrs;          /* [A x N] capacity, first K columns   */
+  int32_t* rec_distortions;    /* [A x N]                             */
+  double* distort_probs;       /* [F x A]                             */
+  int32_t* distort_counts;     /* [F x A] Records::distorted_counts_  */
+  double* distort_dist_concs;  /* [A]                                 */
+  exb200_clust clust;          /* current values, priors echoed       */
+} exb200_state;
+
+/* Per-sweep counters of the last completed sweep (for measurement and tests). */
+typedef struct exb200_stats {
+  int64_t n_candidates;   /* sum over records of compatible candidate items        */
+  int64_t n_bucket_items; /* items visited while generating candidates             */
+  int32_t n_rounds;       /* dependency rounds of the links update                 */
+  int32_t n_wide;         /* records that took the serial wide path                */
+  int32_t n_entities;     /* K after the sweep                                     */
+  int32_t n_links_changed;/* records whose cluster changed                         */
+  int32_t n_tables;       /* blocking tables built                                 */
+  int32_t reserved;
+  float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
+      ms_distort, ms_total; /* CUDA-event times of the phases                     */
+} exb200_stats;
+
+typedef struct exb200_handle exb200_handle;
+
+/* returns EXB200_ABI_VERSION */
+int exb200_abi_version(void);
+
+/* number of visible CUDA devices (0 without a driver/GPU) */
+int exb200_device_count(void);
+
+/* Build the device state from a host model on CUDA device `device`.
+   Replaces readS4State + the State constructor (sample.cpp:71-105, state.h:42-54). */
+int exb200_create(const exb200_model* model, int device, exb200_handle** out);
+
+/* Run the sampling loop of sample() (sample.cpp:171-202): sweeps until n_samples
+   are saved.  abort_cb (may be NULL) replaces Progress::check_abort (sample.cpp:200);
+   progress_cb (may be NULL) replaces p.increment() (sample.cpp:201). */
+int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin_interval,
+               int32_t burnin_interval, exb200_history* out,
+               int (*abort_cb)(void*), void (*progress_cb)(void*, int32_t), void* ctx);
+
+/* n_sweeps applications of State::update() with nothing copied back
+   (device-resident timing; state.h:60-75). */
+int exb200_sweeps(exb200_handle* h, int32_t n_sweeps);
+
+/* Copy the current state to the caller (buildFinalS4State, sample.cpp:14-63). */
+int exb200_get_state(exb200_handle* h, exb200_state* out);
+
+int exb200_get_stats(exb200_handle* h, exb200_stats* out);
+
+/*
+ * Test hook: the conditional of one record's link in the CURRENT state, without
+ * changing it: what Links::update_link computes at src/links.cpp:361-399.
+ * cand_ids/log_weights receive up to `cap` existing candidates in ascending entity
+ * id (log prior_weight_existing + logLikelihoodWeightExisting); *log_weight_new is
+ * log prior_weight_new + logLikelihoodWeightNew.  Returns the candidate count.
+ */
+int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t* cand_ids,
+                            double* log_weights, double* log_weight_new);
+
+/* Tuning / test knobs (name, value); unknown names return EXB200_ERR_INVALID.
+   "bucket_cap", "cand_cap": thresholds above which a record takes the serial wide
+   path; "check": recompute sizes/K from the links after every sweep and compare. */
+int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
+
+void exb200_destroy(exb200_handle* h);
+
+/* Message of the last failing call on this handle (or of exb200_create when h is NULL). */
+const char* exb200_last_error(const exb200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXB200_H */
