@@ -1,0 +1,117 @@
+// Device-resident layout of the sampler state and of the per-sweep scratch.
+//
+// Records (static) ..... rec_x   int32 [N][RS]   x[0..A-1], file id at [RS-1]; RS = 8 for A <= 7 so
+//                                                that one record is one 32-byte sector
+// Indicators ........... rec_z   uint32 [N]      bit a = z[a, r]            (Records::attr_distortions_)
+// Links ................ lambda  int32 [N]       entity slot of record r     (Links::forward_index_)
+// Entities ............. ent_y   int32 [2N][ES]  attribute values; slots [0,N) hold the entities that
+//                                                exist at the start of a sweep (slot = smallest member
+//                                                record), slot N + r is the entity record r would found
+//                                                during the sweep (Entities::forward_index_)
+//                        ent_size int32 [2N]     cluster sizes              (Links::inverse_index_ sizes)
+//                        ent_head int32 [2N], rec_next int32 [N]  member lists in ascending record id
+// The reference keeps the same information in unordered_map / unordered_set containers
+// (src/links.h:23-26, src/entities.h:50-51, src/records.h:20-24).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/exb200.h"
+
+namespace exb {
+
+constexpr int NMAX_FAST = 8;        // categorical fast scheme: up to this many observed members
+constexpr int REJECT_CAP = 100000;  // safety bound of the rejection loops
+constexpr int CAND_SMEM = 256;      // compatible candidates a warp can stage for one record
+constexpr int LPE_MAX = 32;         // host-computed log prior_weight_existing(n), n < LPE_MAX
+constexpr int MAX_ATTRS = 32;
+
+// Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
+// (src/attribute_index.h:12-146) plus the alias tables that replace IndexNonUniformDiscreteDist
+// (src/discrete_dist.h:197-294).  All logarithms of static quantities are computed on the host.
+struct DevAttr {
+  int D, is_const, exclude, pad;
+  const double *psi, *phi, *om;            // empirical pmf, entity-value pmf, 1 - psi
+  const double *logpsi, *log1mpsi, *logphi;
+  const double *logE;                      // log E_{v~phi} p(x | v)  (attribute_index.cpp:55-62,94-101)
+  const double *mef;                       // max_exp_factor (all 1 for a constant attribute)
+  const int *row, *col;                    // inverted neighbourhood CSR: row w -> entity values v, ascending
+  const double *p, *logp;                  // p(w | v) and its log
+  const double *g;                         // [(NMAX_FAST+1)][D]  phi(v) / (1-psi(v))^n
+  const double *aprob; const int *aalias;  // alias tables of g_n, same shape
+  const double *pprob; const int *palias;  // alias table of psi
+  double G[NMAX_FAST + 1];                 // sum_v g_n(v)
+  double *lt_diff, *lt_same;               // per sweep, [F][D]: log(theta mef(v)); log(1 - theta mef(v))
+                                           // or log(1 - eff + eff p(v|v)) when the value is not excluded
+};
+
+// One blocking table: items (entity slots) bucketed by the values of attributes (a, b); a == b is a
+// single-attribute table.  CSR over buckets built per sweep by count / scan / fill.
+struct DevTable {
+  int a, b;
+  int Db;            // domain size of b (key = y_a * Db + y_b)
+  int exact;         // 1: bucket = key; 0: bucket = mix(key) & (B - 1)
+  uint32_t B;        // number of buckets
+  int *ptr;          // [B]  after fill: END offset of bucket (start = ptr[b-1], 0 for b = 0)
+  int *ids;          // [n_items]
+};
+
+struct ClustDev {
+  int kind;
+  double alpha, d, m, kappa;
+  double logpe[LPE_MAX];
+};
+
+struct DevState {
+  int N, A, F, RS, ES;
+  uint32_t iter;
+  uint64_t seed;
+  // model state
+  const int *rec_x;
+  uint32_t *rec_z;
+  int *lambda;
+  int *ent_y;
+  int *ent_size, *ent_head;     // current arrays [2N]
+  int *ent_size_nx, *ent_head_nx; // next arrays (written by the rename kernel)
+  int *rec_next;
+  const double *theta;          // [F*A] index f*A + a
+  const DevAttr *attrs;
+  // links-update scratch
+  double *Lnew;                 // [N] logLikelihoodWeightNew
+  uint16_t *rec_tab;            // [N] blocking table chosen for the record (0xFFFF: none)
+  uint32_t *rec_bkt;            // [N] bucket inside that table
+  const DevTable *tables;       // [A*A]
+  int *tab_usage;               // [A*A]
+  uint32_t *cand_off;           // [N]
+  int *cand_cnt;                // [N] (-1: wide record)
+  int *cand_id; double *cand_ll;// candidate pool
+  unsigned long long *pool_cursor; unsigned long long pool_cap;
+  unsigned long long *owner;    // [2N] reservation words
+  unsigned long long *fence;    // reservation word of the wide records
+  uint8_t *fin;                 // [N] 1 once the record's link is final
+  int8_t *dlo, *dhi;            // [N] bounds of the record's change of K
+  int *plo, *phi_;              // [N] exclusive prefix sums of dlo / dhi
+  int *act_in, *act_out;        // active record lists
+  int *counters;                // see CounterSlot
+  long long *counters64;        // [0] candidates, [1] bucket items visited
+  int *dev_err;                 // [0] status, [1] id
+  double *lwbuf;                // [2N] scratch of the wide path / test hook
+  int *ndist, *corr;            // [F*A] distorted counts, corrected non-distorted counts
+  int bucket_cap, cand_cap;
+  int K0;                       // number of entities at the start of the links update
+  int use_kbounds;              // 0 when prior_weight_new does not depend on K
+  ClustDev cl;
+};
+
+enum CounterSlot {
+  C_NACT_OUT = 0,   // size of act_out
+  C_MIN_ACTIVE = 1, // smallest unfinalised record of the round
+  C_WIDE_READY = 2, // wide record whose turn has come (-1: none)
+  C_CHANGED = 3,    // records whose cluster changed
+  C_DK_TOTAL = 4,   // sum of dK over finalised records
+  C_NWIDE = 5,      // wide records of the sweep
+  C_K = 6,          // entities counted by the rename kernel
+  C_COMMITTED = 7,  // records finalised in the round
+  C_NSLOTS = 16
+};
+
+} // namespace exb

@@ -1,0 +1,796 @@
+// Host side of the C ABI (include/exb200.h): device state construction, the sweep driver that
+// fixes the partially-collapsed order of State::update (src/state.h:60-75), the scalar
+// hyper-parameter updates, history streaming and state read-back.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "hostmath.hpp"
+#include "kernels.cuh"
+
+using namespace exb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostAttr {
+  int D = 0, is_const = 1, exclude = 1;
+  double s1 = 0, s2 = 0; // Beta prior on theta
+  std::vector<double> psi, phi, mef;
+  std::vector<void*> dev; // device allocations owned by this attribute
+};
+
+struct TableHost {
+  DevTable d{};
+  bool allocated = false;
+  size_t cap_items = 0;
+};
+
+} // namespace
+
+struct exb200_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int N = 0, A = 0, F = 0, RS = 8, ES = 8;
+  int iteration = 0;
+  int K = 0;
+  uint64_t seed = 0;
+  exb200_clust cl{};
+  HostStream hs;
+  std::vector<HostAttr> attrs;
+  std::vector<double> theta;   // [F*A] f*A + a
+  std::vector<int> ndist, corr;
+  DevState S{};                // device pointers (by-value kernel argument)
+  std::vector<void*> allocs;
+  DevAttr* d_attrs = nullptr;
+  std::vector<DevAttr> h_attrs;
+  std::vector<TableHost> tables; // [A*A]
+  DevTable* d_tables = nullptr;
+  int* d_active = nullptr;
+  int* d_bsum = nullptr; size_t bsum_cap = 0;
+  unsigned long long* d_cl_counts = nullptr;
+  double* d_theta = nullptr;
+  uint32_t round_ctr = 1;
+  int opt_check = 0;
+  int bucket_cap = 1 << 15, cand_cap = CAND_SMEM;
+  exb200_stats stats{};
+  cudaEvent_t ev[10]{};
+  std::string err;
+  bool poisoned = false;
+};
+
+namespace {
+
+int fail(exb200_handle* h, int code, const std::string& msg) {
+  if (h) { h->err = msg; }
+  else g_create_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      h->poisoned = true;                                                                          \
+      return fail(h, EXB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    }                                                                                              \
+  } while (0)
+
+template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return EXB200_OK;
+}
+template <class T> int upload(exb200_handle* h, T** p, const T* src, size_t n) {
+  int rc = dalloc(h, p, n);
+  if (rc) return rc;
+  if (n) CK(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return EXB200_OK;
+}
+inline int nblk(long long n, int tpb = TPB) { return (int)std::max<long long>(1, (n + tpb - 1) / tpb); }
+
+// exclusive prefix sum on the handle's stream
+template <class T_IN> int scan_exclusive(exb200_handle* h, const T_IN* in, int* out, int n) {
+  const int nb = nblk(n, SCAN_TILE);
+  if ((size_t)nb > h->bsum_cap) {
+    int rc = dalloc(h, &h->d_bsum, (size_t)nb * 2);
+    if (rc) return rc;
+    h->bsum_cap = (size_t)nb * 2;
+  }
+  k_scan_reduce<T_IN><<<nb, TPB, 0, h->stream>>>(in, n, h->d_bsum);
+  k_scan_top<<<1, 1024, 0, h->stream>>>(h->d_bsum, nb);
+  k_scan_apply<T_IN><<<nb, TPB, 0, h->stream>>>(in, out, n, h->d_bsum);
+  return EXB200_OK;
+}
+
+double prior_existing_host(const exb200_clust& c, int n) {
+  if (c.kind == EXB200_CLUST_PITMAN_YOR) return std::fabs((double)n - c.d);
+  if (c.kind == EXB200_CLUST_GEN_COUPON) return (double)n + c.kappa;
+  return 1.0;
+}
+
+void refresh_clust_dev(exb200_handle* h) {
+  ClustDev& c = h->S.cl;
+  c.kind = h->cl.kind; c.alpha = h->cl.alpha; c.d = h->cl.d; c.m = h->cl.m; c.kappa = h->cl.kappa;
+  for (int n = 0; n < LPE_MAX; n++) c.logpe[n] = std::log(prior_existing_host(h->cl, n));
+  h->S.use_kbounds = !(h->cl.kind == EXB200_CLUST_PITMAN_YOR && h->cl.d == 0.0);
+}
+
+int check_device_error(exb200_handle* h) {
+  int e[2] = {0, 0};
+  CK(cudaMemcpyAsync(e, h->S.dev_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (e[0]) {
+    h->poisoned = true;
+    return fail(h, e[0], "no valid outcome for record/entity " + std::to_string(e[1]) +
+                             " (all weights zero or a rejection sampler did not terminate)");
+  }
+  return EXB200_OK;
+}
+
+// ---- per-attribute tables (ConstantAttributeIndex / NonConstantAttributeIndex + alias tables)
+int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
+  HostAttr& ha = h->attrs[a];
+  DevAttr& da = h->h_attrs[a];
+  const int D = in.domain_size;
+  if (D < 1) return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": empty domain");
+  if (!std::isinf(in.distort_dist_conc) || in.conc_prior_shape > 0)
+    return fail(h, EXB200_ERR_UNSUPPORTED, "attribute " + std::to_string(a) +
+                ": finite distort_dist_prior concentration (DistortDistConcs::update) is not built yet");
+  if (in.entity_dist_kind != EXB200_ENTDIST_FIXED)
+    return fail(h, EXB200_ERR_UNSUPPORTED, "attribute " + std::to_string(a) +
+                ": DirichletRV entity_dist_prior (Entities::update_distributions) is not built yet");
+  ha.D = D; ha.is_const = in.is_constant != 0; ha.exclude = in.exclude_entity_value != 0;
+  ha.s1 = in.distort_prob_shape1; ha.s2 = in.distort_prob_shape2;
+  ha.psi.assign(in.probs, in.probs + D);
+  ha.phi.assign(in.entity_dist ? in.entity_dist : in.probs, (in.entity_dist ? in.entity_dist : in.probs) + D);
+  ha.mef.assign(D, 1.0);
+  if (!ha.is_const) ha.mef.assign(in.max_exp_factor, in.max_exp_factor + D);
+  std::vector<double> om(D), logpsi(D), log1mpsi(D), logphi(D), logE(D);
+  double Z = 0.0;
+  for (int v = 0; v < D; v++) {
+    if (!(ha.psi[v] > 0.0 && ha.psi[v] < 1.0) || !(ha.phi[v] >= 0.0))
+      return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid pmf");
+    om[v] = 1.0 - ha.psi[v];
+    logpsi[v] = std::log(ha.psi[v]);
+    log1mpsi[v] = std::log(om[v]);
+    logphi[v] = std::log(ha.phi[v]);
+    Z += ha.phi[v] / om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
+  }
+  // inverted neighbourhood CSR (attribute_index.cpp:125-140)
+  std::vector<int> row(D + 1, 0), col;
+  std::vector<double> p, logp;
+  if (!ha.is_const) {
+    const int64_t nnz = in.close_row_ptr[D];
+    if (nnz >= (int64_t)std::numeric_limits<int>::max())
+      return fail(h, EXB200_ERR_INVALID, "neighbourhood index too large");
+    for (int64_t j = 0; j < nnz; j++) {
+      const int w = in.close_val_ids[j];
+      if (w < 0 || w >= D) return fail(h, EXB200_ERR_INVALID, "close_val_ids out of range");
+      row[w + 1]++;
+    }
+    for (int w = 0; w < D; w++) row[w + 1] += row[w];
+    col.resize(nnz); p.resize(nnz); logp.resize(nnz);
+    std::vector<int> cur(row.begin(), row.end() - 1);
+    for (int v = 0; v < D; v++)
+      for (int64_t j = in.close_row_ptr[v]; j < in.close_row_ptr[v + 1]; j++) {
+        const int q = cur[in.close_val_ids[j]]++;
+        col[q] = v; p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
+      }
+  }
+  for (int w = 0; w < D; w++) {
+    double e;
+    if (ha.is_const) // get_exp_distortion_prob, attribute_index.cpp:55-62
+      e = ha.exclude ? Z * ha.psi[w] - ha.phi[w] * ha.psi[w] / om[w] : ha.psi[w];
+    else {           // attribute_index.cpp:94-101
+      e = 0.0;
+      for (int j = row[w]; j < row[w + 1]; j++) e += ha.phi[col[j]] * p[j];
+    }
+    logE[w] = std::log(e);
+  }
+  const int nt = ha.is_const ? NMAX_FAST + 1 : 1;
+  std::vector<double> g((size_t)nt * D), aprob((size_t)nt * D), pprob(D);
+  std::vector<int> aalias((size_t)nt * D), palias(D);
+  for (int n = 0; n < nt; n++) {
+    double G = 0.0;
+    for (int v = 0; v < D; v++) {
+      g[(size_t)n * D + v] = n == 0 ? ha.phi[v] : g[(size_t)(n - 1) * D + v] / om[v];
+      G += g[(size_t)n * D + v];
+    }
+    da.G[n] = G;
+    if (!alias_build(&g[(size_t)n * D], D, &aprob[(size_t)n * D], &aalias[(size_t)n * D]))
+      return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid entity distribution");
+  }
+  if (!alias_build(ha.psi.data(), D, pprob.data(), palias.data()))
+    return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid probs");
+  da.D = D; da.is_const = ha.is_const; da.exclude = ha.exclude; da.pad = 0;
+  int rc = 0;
+  double* dp; int* ip;
+#define UPD(field, vec) rc = upload(h, &dp, (vec).data(), (vec).size()); if (rc) return rc; da.field = dp;
+#define UPI(field, vec) rc = upload(h, &ip, (vec).data(), (vec).size()); if (rc) return rc; da.field = ip;
+  UPD(psi, ha.psi) UPD(phi, ha.phi) UPD(om, om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi)
+  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp)
+  UPD(g, g) UPD(aprob, aprob) UPI(aalias, aalias) UPD(pprob, pprob) UPI(palias, palias)
+#undef UPD
+#undef UPI
+  rc = dalloc(h, &da.lt_diff, (size_t)h->F * D); if (rc) return rc;
+  rc = dalloc(h, &da.lt_same, (size_t)h->F * D); if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream)); // the host vectors go out of scope
+  return EXB200_OK;
+}
+
+int upload_theta(exb200_handle* h) {
+  CK(cudaMemcpyAsync(h->d_theta, h->theta.data(), sizeof(double) * h->F * h->A, cudaMemcpyHostToDevice, h->stream));
+  for (int a = 0; a < h->A; a++)
+    k_theta_tables<<<nblk((long long)h->F * h->attrs[a].D), TPB, 0, h->stream>>>(h->S, a);
+  return EXB200_OK;
+}
+
+// ---- 1. cluster-prior hyper-parameters: ClustParams::update (clust_params.cpp:37-72, 74-121)
+int update_clust(exb200_handle* h) {
+  exb200_clust& c = h->cl;
+  const int N = h->N, K = h->K;
+  const bool py = c.kind == EXB200_CLUST_PITMAN_YOR, gc = c.kind == EXB200_CLUST_GEN_COUPON;
+  const bool has_a = py && c.alpha_prior_shape > 0, has_d = py && c.d_prior_shape1 > 0;
+  const bool has_k = gc && c.kappa_prior_shape > 0, has_m = gc && c.m_prior_size > 0;
+  if (!(has_a || has_d || has_k || has_m)) return EXB200_OK;
+  unsigned long long cnt[2] = {0, 0};
+  if (py || has_k) {
+    CK(cudaMemsetAsync(h->d_cl_counts, 0, sizeof cnt, h->stream));
+    k_clust_counts<<<nblk(std::max(N, K)), TPB, 0, h->stream>>>(h->S, K, py ? 1 : 0, (has_d || has_k) ? 1 : 0,
+                                                                 h->d_cl_counts);
+    CK(cudaMemcpyAsync(cnt, h->d_cl_counts, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (py) {
+    const double succ = (double)cnt[0], failn = (double)(K - 1) - succ, vfail = (double)cnt[1];
+    if (has_a) { // :92-101
+      const double w = h->hs.beta(c.alpha + 1.0, (double)N - 1.0);
+      const double shape = c.alpha_prior_shape + succ, rate = c.alpha_prior_rate - std::log(w);
+      c.alpha = h->hs.gamma(shape, 1.0 / rate);
+    }
+    if (has_d) c.d = h->hs.beta(c.d_prior_shape1 + failn, c.d_prior_shape2 + vfail); // :117-120
+  } else {
+    const double w = h->hs.beta(c.m * c.kappa + 1.0, (double)N - 1.0); // :45
+    if (has_k) { // :61-63
+      const double shape = c.kappa_prior_shape + (double)K - 1.0 + (double)cnt[1];
+      const double rate = c.kappa_prior_rate - c.m * std::log(w);
+      c.kappa = h->hs.gamma(shape, 1.0 / rate);
+    }
+    if (has_m) { // :66-71 (m_ is an int in the reference)
+      const double sz = c.m_prior_size + (double)K - 1.0;
+      const double pb = 1.0 - (1.0 - c.m_prior_prob) * std::pow(w, c.kappa);
+      c.m = (double)(int)(h->hs.negbinom(sz, pb) + (double)K);
+    }
+  }
+  return EXB200_OK;
+}
+
+int ensure_table(exb200_handle* h, int tab) {
+  TableHost& t = h->tables[tab];
+  if (t.allocated) return EXB200_OK;
+  int rc = dalloc(h, &t.d.ptr, (size_t)t.d.B + 1); if (rc) return rc;
+  rc = dalloc(h, &t.d.ids, (size_t)2 * h->N); if (rc) return rc;
+  t.allocated = true;
+  CK(cudaMemcpyAsync(h->d_tables + tab, &t.d, sizeof(DevTable), cudaMemcpyHostToDevice, h->stream));
+  return EXB200_OK;
+}
+
+// ---- 2. links: Links::update (links.cpp:477-489)
+int update_links(exb200_handle* h) {
+  DevState& S = h->S;
+  const int N = h->N, AA = h->A * h->A;
+  cudaStream_t st = h->stream;
+  S.K0 = h->K;
+  CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * AA, st));
+  CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
+  CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
+  CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
+  CK(cudaEventRecord(h->ev[1], st));
+  k_prep<<<nblk(N), TPB, 0, st>>>(S);
+  std::vector<int> usage(AA);
+  CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * AA, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev[2], st));
+  CK(cudaStreamSynchronize(st));
+  // blocking tables used by at least one record
+  std::vector<int> active;
+  for (int t = 0; t < AA; t++)
+    if (usage[t] > 0) {
+      int rc = ensure_table(h, t); if (rc) return rc;
+      active.push_back(t);
+      CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
+    }
+  h->stats.n_tables = (int)active.size();
+  if (!active.empty()) {
+    CK(cudaMemcpyAsync(h->d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, st));
+    k_index_count<<<nblk(2LL * N), TPB, 0, st>>>(S, h->d_active, (int)active.size());
+    for (int t : active) {
+      int rc = scan_exclusive<int>(h, h->tables[t].d.ptr, h->tables[t].d.ptr, (int)h->tables[t].d.B);
+      if (rc) return rc;
+    }
+    k_index_fill<<<nblk(2LL * N), TPB, 0, st>>>(S, h->d_active, (int)active.size());
+  }
+  CK(cudaEventRecord(h->ev[3], st));
+  k_cand<<<nblk((long long)N, TPB / 32), TPB, 0, st>>>(S);
+  CK(cudaEventRecord(h->ev[4], st));
+
+  // dependency rounds
+  int n_act = N;
+  const int* act = nullptr; // round 1: every record
+  int rounds = 0;
+  int hc[C_NSLOTS];
+  while (n_act > 0) {
+    rounds++;
+    const uint32_t round = h->round_ctr++;
+    if (h->round_ctr == 0xFFFFFFF0u) { // reservation words would wrap: start over
+      CK(cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, st));
+      CK(cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), st));
+      h->round_ctr = 1;
+    }
+    const int init[3] = {0, 0x7FFFFFFF, -1}; // C_NACT_OUT, C_MIN_ACTIVE, C_WIDE_READY
+    CK(cudaMemcpyAsync(S.counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    k_reserve<<<nblk(n_act), TPB, 0, st>>>(S, act, n_act, round);
+    if (S.use_kbounds) {
+      int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
+      rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
+    }
+    k_commit<<<nblk(n_act), TPB, 0, st>>>(S, act, n_act, round);
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int* next_act = S.act_out;
+    int n_next = hc[C_NACT_OUT];
+    std::swap(S.act_in, S.act_out);
+    if (hc[C_WIDE_READY] >= 0) {
+      // serial path for a record without a stored candidate list
+      const int w = hc[C_WIDE_READY];
+      k_eval_all<<<nblk(2LL * N), TPB, 0, st>>>(S, w, 2 * N);
+      k_wide_commit<<<1, 1024, 0, st>>>(S, w);
+      const int zero = 0;
+      CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+      k_compact_active<<<nblk(n_next), TPB, 0, st>>>(S, next_act, n_next);
+      CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      next_act = S.act_out;
+      n_next = hc[C_NACT_OUT];
+      std::swap(S.act_in, S.act_out);
+    } else if (n_next >= n_act && act != nullptr) {
+      return fail(h, EXB200_ERR_CUDA, "links update made no progress (internal error)");
+    }
+    act = next_act;
+    n_act = n_next;
+    if (rounds > 4 * N + 16) return fail(h, EXB200_ERR_CUDA, "links update did not terminate");
+  }
+  CK(cudaEventRecord(h->ev[5], st));
+  h->stats.n_rounds = rounds;
+  // rename entities to their smallest member; slots [0,N) of the next arrays become current
+  const int zero = 0;
+  CK(cudaMemcpyAsync(S.counters + C_K, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
+  k_canon<<<nblk(N), TPB, 0, st>>>(S);
+  std::swap(S.ent_size, S.ent_size_nx);
+  std::swap(S.ent_head, S.ent_head_nx);
+  CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+  long long c64[2];
+  CK(cudaMemcpyAsync(c64, S.counters64, sizeof c64, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev[6], st));
+  CK(cudaStreamSynchronize(st));
+  if (hc[C_K] != h->K + hc[C_DK_TOTAL])
+    return fail(h, EXB200_ERR_CUDA, "entity count mismatch after the links update: " + std::to_string(hc[C_K]) +
+                                        " vs " + std::to_string(h->K + hc[C_DK_TOTAL]));
+  h->K = hc[C_K];
+  h->stats.n_entities = h->K;
+  h->stats.n_wide = hc[C_NWIDE];
+  h->stats.n_links_changed = hc[C_CHANGED];
+  h->stats.n_candidates = c64[0];
+  h->stats.n_bucket_items = c64[1];
+  return EXB200_OK;
+}
+
+// debugging aid ("check" option): recompute sizes / member lists from the links on the host
+int check_state(exb200_handle* h) {
+  const int N = h->N;
+  std::vector<int> lam(N), size(2 * (size_t)N), head(2 * (size_t)N), next(N);
+  CK(cudaMemcpy(lam.data(), h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(size.data(), h->S.ent_size, sizeof(int) * 2 * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(head.data(), h->S.ent_head, sizeof(int) * 2 * N, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(next.data(), h->S.rec_next, sizeof(int) * N, cudaMemcpyDeviceToHost));
+  std::vector<int> cnt(N, 0);
+  int K = 0;
+  for (int r = 0; r < N; r++) {
+    if (lam[r] < 0 || lam[r] >= N) return fail(h, EXB200_ERR_CUDA, "check: link out of range");
+    cnt[lam[r]]++;
+  }
+  for (int e = 0; e < N; e++) {
+    if (cnt[e] != size[e]) return fail(h, EXB200_ERR_CUDA, "check: size mismatch at entity " + std::to_string(e));
+    if (!cnt[e]) continue;
+    K++;
+    int n = 0, prev = -1;
+    for (int r = head[e]; r >= 0; r = next[r]) {
+      if (lam[r] != e || r <= prev) return fail(h, EXB200_ERR_CUDA, "check: member list broken at entity " + std::to_string(e));
+      prev = r;
+      if (++n > cnt[e]) break;
+    }
+    if (n != cnt[e] || head[e] != e)
+      return fail(h, EXB200_ERR_CUDA, "check: member list / label mismatch at entity " + std::to_string(e));
+  }
+  if (K != h->K) return fail(h, EXB200_ERR_CUDA, "check: K mismatch");
+  return EXB200_OK;
+}
+
+// ---- one application of State::update (state.h:60-75)
+int sweep(exb200_handle* h) {
+  DevState& S = h->S;
+  cudaStream_t st = h->stream;
+  const int N = h->N, FA = h->F * h->A;
+  S.iter = (uint32_t)h->iteration;
+  h->hs.begin_sweep((uint32_t)h->iteration);
+  CK(cudaEventRecord(h->ev[0], st));
+  int rc = update_clust(h); if (rc) return rc;          // clust_params_->update(links_)
+  refresh_clust_dev(h);
+  rc = update_links(h); if (rc) return rc;              // links_.update(...)
+  k_entities<<<nblk(N), TPB, 0, st>>>(S);               // ents_.update_attributes(...)
+  // ents_.update_distributions(), cache_.update(): phi is fixed (no Dirichlet prior) -> nothing to do
+  // distort_dist_concs_.update(): concentration is infinite -> nothing to do
+  CK(cudaEventRecord(h->ev[7], st));
+  CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
+  CK(cudaMemsetAsync(S.corr, 0, sizeof(int) * FA, st));
+  const int use_smem = 2 * FA * (int)sizeof(int) <= 32768;
+  k_distort<<<nblk(N), TPB, use_smem ? 2 * FA * sizeof(int) : 0, st>>>(S, use_smem); // recs_.update_distortion
+  CK(cudaMemcpyAsync(h->ndist.data(), S.ndist, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h->corr.data(), S.corr, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(h->ev[8], st));
+  rc = check_device_error(h); if (rc) return rc;        // also synchronises
+  // distort_probs_.update (distortion_probs.cpp:30-47): file-major, attribute-minor order
+  for (int f = 0; f < h->F; f++)
+    for (int a = 0; a < h->A; a++)
+      if (h->attrs[a].s1 > 0)
+        h->theta[f * h->A + a] = h->hs.beta((double)h->ndist[f * h->A + a] + h->attrs[a].s1,
+                                            (double)h->corr[f * h->A + a] + h->attrs[a].s2);
+  rc = upload_theta(h); if (rc) return rc;
+  h->iteration++;
+  CK(cudaEventRecord(h->ev[9], st));
+  CK(cudaStreamSynchronize(st));
+  auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
+  h->stats.ms_clust = ms(0, 1); h->stats.ms_prep = ms(1, 2); h->stats.ms_index = ms(2, 3);
+  h->stats.ms_cand = ms(3, 4); h->stats.ms_rounds = ms(4, 5); h->stats.ms_canon = ms(5, 6);
+  h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
+  if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
+  return EXB200_OK;
+}
+
+} // namespace
+
+// =============================================================================================
+extern "C" {
+
+int exb200_abi_version(void) { return EXB200_ABI_VERSION; }
+
+int exb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* exb200_last_error(const exb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void exb200_destroy(exb200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
+  if (!m || !out) return fail(nullptr, EXB200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int N = m->n_records, A = m->n_attrs, F = m->n_files;
+  if (N < 2 || A < 1 || A > MAX_ATTRS || F < 1 || m->n_entities < 1)
+    return fail(nullptr, EXB200_ERR_INVALID, "need n_records >= 2, 1 <= n_attrs <= 32, n_files >= 1");
+  if ((long long)N * 2 >= (1LL << 31)) return fail(nullptr, EXB200_ERR_INVALID, "n_records too large");
+  int ndev = exb200_device_count();
+  if (ndev <= 0) return fail(nullptr, EXB200_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  if (device < 0 || device >= ndev) return fail(nullptr, EXB200_ERR_NO_DEVICE, "invalid device index");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EXB200_ERR_NO_DEVICE, "cudaSetDevice failed");
+
+  exb200_handle* h = new exb200_handle();
+  auto bail = [&](int rc) { g_create_error = h->err; exb200_destroy(h); return rc; };
+  h->device = device; h->N = N; h->A = A; h->F = F;
+  h->RS = ((A + 1 + 7) / 8) * 8; h->ES = ((A + 7) / 8) * 8;
+  h->iteration = m->iteration; h->seed = m->seed; h->cl = m->clust; h->hs.seed = m->seed;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(h, EXB200_ERR_NO_DEVICE, "cudaStreamCreate failed"));
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  const exb200_clust& c = m->clust;
+  if (c.kind < 0 || c.kind > 2) return bail(fail(h, EXB200_ERR_INVALID, "Unrecognized clust_prior"));
+  if (c.kind != EXB200_CLUST_PITMAN_YOR && c.m < (double)N)
+    return bail(fail(h, EXB200_ERR_INVALID, "Coupon collecting parameter m < n_records is currently not supported."));
+
+  // ---- host-side canonical form: entity label = smallest member record
+  std::vector<int> rec_x((size_t)N * h->RS, -1), lambda(N), size(2 * (size_t)N, 0), head(2 * (size_t)N, -1),
+      next(N, -1), ent_y(2 * (size_t)N * h->ES, 0);
+  std::vector<uint32_t> rec_z(N, 0);
+  for (int r = 0; r < N; r++) {
+    for (int a = 0; a < A; a++) {
+      const int v = m->rec_attrs[a + (size_t)A * r];
+      if (v >= m->attrs[a].domain_size) return bail(fail(h, EXB200_ERR_INVALID, "rec_attrs out of range"));
+      rec_x[(size_t)r * h->RS + a] = v < 0 ? -1 : v;
+      if (m->rec_distortions[a + (size_t)A * r]) rec_z[r] |= 1u << a;
+    }
+    const int f = m->file_ids[r];
+    if (f < 0 || f >= F) return bail(fail(h, EXB200_ERR_INVALID, "file_ids out of range"));
+    rec_x[(size_t)r * h->RS + h->RS - 1] = f;
+  }
+  {
+    std::unordered_map<int, int> slot_of; // label -> column of ent_attrs
+    slot_of.reserve((size_t)m->n_entities * 2);
+    for (int e = 0; e < m->n_entities; e++) slot_of[m->ent_ids[e]] = e;
+    std::unordered_map<int, int> rep; // label -> smallest member
+    rep.reserve((size_t)m->n_entities * 2);
+    for (int r = N - 1; r >= 0; r--) {
+      if (!slot_of.count(m->links[r])) return bail(fail(h, EXB200_ERR_INVALID, "links refers to an unknown entity"));
+      rep[m->links[r]] = r;
+    }
+    std::vector<int> tail(N, -1);
+    for (int r = 0; r < N; r++) {
+      const int cidx = rep[m->links[r]];
+      lambda[r] = cidx;
+      if (size[cidx]++ == 0) {
+        head[cidx] = r;
+        const int col = slot_of[m->links[r]];
+        for (int a = 0; a < A; a++) {
+          const int v = m->ent_attrs[a + (size_t)A * col];
+          if (v < 0 || v >= m->attrs[a].domain_size) return bail(fail(h, EXB200_ERR_INVALID, "ent_attrs out of range"));
+          ent_y[(size_t)cidx * h->ES + a] = v;
+        }
+      } else next[tail[cidx]] = r;
+      tail[cidx] = r;
+    }
+    h->K = (int)rep.size();
+  }
+  h->theta.resize((size_t)F * A);
+  for (int f = 0; f < F; f++)
+    for (int a = 0; a < A; a++) h->theta[f * A + a] = m->distort_probs[f + (size_t)F * a];
+  h->ndist.assign((size_t)F * A, 0); h->corr.assign((size_t)F * A, 0);
+  for (int r = 0; r < N; r++)
+    for (int a = 0; a < A; a++) h->ndist[rec_x[(size_t)r * h->RS + h->RS - 1] * A + a] += (rec_z[r] >> a) & 1u;
+
+  // ---- device state
+  DevState& S = h->S;
+  S.N = N; S.A = A; S.F = F; S.RS = h->RS; S.ES = h->ES; S.seed = h->seed;
+  int rc = 0;
+  int* ip; uint32_t* up;
+#define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
+  TRY(upload(h, &ip, rec_x.data(), rec_x.size())); S.rec_x = ip;
+  TRY(upload(h, &up, rec_z.data(), rec_z.size())); S.rec_z = up;
+  TRY(upload(h, &S.lambda, lambda.data(), lambda.size()));
+  TRY(upload(h, &S.ent_y, ent_y.data(), ent_y.size()));
+  TRY(upload(h, &S.ent_size, size.data(), size.size()));
+  TRY(upload(h, &S.ent_head, head.data(), head.size()));
+  TRY(upload(h, &S.ent_size_nx, size.data(), size.size()));
+  TRY(upload(h, &S.ent_head_nx, head.data(), head.size()));
+  TRY(upload(h, &S.rec_next, next.data(), next.size()));
+  TRY(dalloc(h, &h->d_theta, (size_t)F * A)); S.theta = h->d_theta;
+  h->attrs.resize(A); h->h_attrs.resize(A);
+  for (int a = 0; a < A; a++) TRY(build_attr(h, m->attrs[a], a));
+  TRY(upload(h, &h->d_attrs, h->h_attrs.data(), (size_t)A)); S.attrs = h->d_attrs;
+  TRY(dalloc(h, &S.Lnew, (size_t)N));
+  TRY(dalloc(h, &S.rec_tab, (size_t)N));
+  TRY(dalloc(h, &S.rec_bkt, (size_t)N));
+  TRY(dalloc(h, &S.tab_usage, (size_t)A * A));
+  TRY(dalloc(h, &S.cand_off, (size_t)N));
+  TRY(dalloc(h, &S.cand_cnt, (size_t)N));
+  S.pool_cap = std::min<unsigned long long>(8ull * N + (1ull << 20), 0xFFFFFFF0ull);
+  TRY(dalloc(h, &S.cand_id, (size_t)S.pool_cap));
+  TRY(dalloc(h, &S.cand_ll, (size_t)S.pool_cap));
+  TRY(dalloc(h, &S.pool_cursor, 1));
+  TRY(dalloc(h, &S.owner, (size_t)2 * N));
+  TRY(dalloc(h, &S.fence, 1));
+  TRY(dalloc(h, &S.fin, (size_t)N));
+  TRY(dalloc(h, &S.dlo, (size_t)N));
+  TRY(dalloc(h, &S.dhi, (size_t)N));
+  TRY(dalloc(h, &S.plo, (size_t)N));
+  TRY(dalloc(h, &S.phi_, (size_t)N));
+  TRY(dalloc(h, &S.act_in, (size_t)N));
+  TRY(dalloc(h, &S.act_out, (size_t)N));
+  TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
+  TRY(dalloc(h, &S.counters64, 2));
+  TRY(dalloc(h, &S.dev_err, 2));
+  TRY(dalloc(h, &S.lwbuf, (size_t)2 * N));
+  TRY(dalloc(h, &S.ndist, (size_t)F * A));
+  TRY(dalloc(h, &S.corr, (size_t)F * A));
+  TRY(dalloc(h, &h->d_active, (size_t)A * A));
+  TRY(dalloc(h, &h->d_cl_counts, 2));
+  cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
+  cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
+  cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);
+  cudaMemcpyAsync(S.ndist, h->ndist.data(), sizeof(int) * F * A, cudaMemcpyHostToDevice, h->stream);
+  // blocking-table descriptors (storage is allocated when a table is first used)
+  h->tables.resize((size_t)A * A);
+  uint32_t Bhash = 1024;
+  while (Bhash < (uint32_t)(2 * N)) Bhash <<= 1;
+  for (int a = 0; a < A; a++)
+    for (int b = a; b < A; b++) {
+      DevTable& d = h->tables[a * A + b].d;
+      d.a = a; d.b = b; d.Db = m->attrs[b].domain_size;
+      const unsigned long long keys = a == b ? (unsigned long long)m->attrs[a].domain_size
+                                             : (unsigned long long)m->attrs[a].domain_size * m->attrs[b].domain_size;
+      d.exact = keys <= (unsigned long long)Bhash;
+      d.B = d.exact ? (uint32_t)keys : Bhash;
+      d.ptr = nullptr; d.ids = nullptr;
+    }
+  {
+    std::vector<DevTable> td((size_t)A * A);
+    for (int t = 0; t < A * A; t++) td[t] = h->tables[t].d;
+    TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
+  }
+#undef TRY
+  S.bucket_cap = h->bucket_cap; S.cand_cap = h->cand_cap;
+  refresh_clust_dev(h);
+  rc = upload_theta(h);
+  if (rc) return bail(rc);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+    return bail(fail(h, EXB200_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError())));
+  *out = h;
+  return EXB200_OK;
+}
+
+int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return EXB200_ERR_INVALID;
+  const std::string n(name);
+  if (n == "check") h->opt_check = value != 0;
+  else if (n == "bucket_cap") h->bucket_cap = (int)std::max<int64_t>(0, value);
+  else if (n == "cand_cap") h->cand_cap = (int)std::min<int64_t>(CAND_SMEM, std::max<int64_t>(0, value));
+  else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
+  h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap;
+  return EXB200_OK;
+}
+
+int exb200_sweeps(exb200_handle* h, int32_t n_sweeps) {
+  if (!h) return EXB200_ERR_INVALID;
+  if (h->poisoned) return fail(h, EXB200_ERR_CUDA, "handle unusable after an earlier error: " + h->err);
+  cudaSetDevice(h->device);
+  for (int i = 0; i < n_sweeps; i++) {
+    int rc = sweep(h);
+    if (rc) return rc;
+  }
+  return EXB200_OK;
+}
+
+int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin, exb200_history* out,
+               int (*abort_cb)(void*), void (*progress_cb)(void*, int32_t), void* ctx) {
+  if (!h || !out) return EXB200_ERR_INVALID;
+  if (n_samples < 0 || thin < 1 || burnin < 0) return fail(h, EXB200_ERR_INVALID, "need n_samples >= 0, thin_interval >= 1, burnin_interval >= 0");
+  if (h->poisoned) return fail(h, EXB200_ERR_CUDA, "handle unusable after an earlier error: " + h->err);
+  cudaSetDevice(h->device);
+  const int N = h->N, FA = h->F * h->A;
+  out->n_saved = 0;
+  int sample = 0;
+  const int initial = h->iteration;
+  while (sample < n_samples) { // src/sample.cpp:171-202
+    int rc = sweep(h);
+    if (rc) return rc;
+    const int completed = h->iteration - initial;
+    if (completed >= burnin && (completed - burnin) % thin == 0) {
+      if (out->links) CK(cudaMemcpyAsync(out->links + (size_t)sample * N, h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+      if (out->n_linked_ents) out->n_linked_ents[sample] = h->K;
+      for (int f = 0; f < h->F; f++)
+        for (int a = 0; a < h->A; a++) {
+          if (out->distort_probs) out->distort_probs[(size_t)sample * FA + f + a * h->F] = h->theta[f * h->A + a];
+          if (out->distort_counts) out->distort_counts[(size_t)sample * FA + f + a * h->F] = h->ndist[f * h->A + a];
+        }
+      if (out->distort_dist_concs)
+        for (int a = 0; a < h->A; a++) out->distort_dist_concs[(size_t)sample * h->A + a] = std::numeric_limits<double>::infinity();
+      if (out->clust_params) {
+        const bool py = h->cl.kind == EXB200_CLUST_PITMAN_YOR;
+        out->clust_params[2 * (size_t)sample] = py ? h->cl.alpha : h->cl.kappa;
+        out->clust_params[2 * (size_t)sample + 1] = py ? h->cl.d : h->cl.m;
+      }
+      CK(cudaStreamSynchronize(h->stream));
+      sample++;
+      out->n_saved = sample;
+    }
+    if (abort_cb && abort_cb(ctx)) return fail(h, EXB200_ERR_ABORTED, "aborted by the caller");
+    if (progress_cb) progress_cb(ctx, completed);
+  }
+  return EXB200_OK;
+}
+
+int exb200_get_state(exb200_handle* h, exb200_state* out) {
+  if (!h || !out) return EXB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const int N = h->N, A = h->A, F = h->F;
+  std::vector<int> lam(N), size(N), y((size_t)N * h->ES);
+  std::vector<uint32_t> z(N);
+  CK(cudaMemcpyAsync(lam.data(), h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(size.data(), h->S.ent_size, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(y.data(), h->S.ent_y, sizeof(int) * (size_t)N * h->ES, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(z.data(), h->S.rec_z, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  out->iteration = h->iteration;
+  int k = 0;
+  for (int e = 0; e < N; e++)
+    if (size[e] > 0) {
+      if (out->ent_ids) out->ent_ids[k] = e;
+      if (out->ent_attrs) for (int a = 0; a < A; a++) out->ent_attrs[a + (size_t)A * k] = y[(size_t)e * h->ES + a];
+      k++;
+    }
+  out->n_entities = k;
+  if (out->links) std::memcpy(out->links, lam.data(), sizeof(int) * N);
+  if (out->rec_distortions)
+    for (int r = 0; r < N; r++)
+      for (int a = 0; a < A; a++) out->rec_distortions[a + (size_t)A * r] = (z[r] >> a) & 1u;
+  for (int f = 0; f < F; f++)
+    for (int a = 0; a < A; a++) {
+      if (out->distort_probs) out->distort_probs[f + (size_t)F * a] = h->theta[f * A + a];
+      if (out->distort_counts) out->distort_counts[f + (size_t)F * a] = h->ndist[f * A + a];
+    }
+  if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = std::numeric_limits<double>::infinity();
+  out->clust = h->cl;
+  return EXB200_OK;
+}
+
+int exb200_get_stats(exb200_handle* h, exb200_stats* out) {
+  if (!h || !out) return EXB200_ERR_INVALID;
+  *out = h->stats;
+  return EXB200_OK;
+}
+
+int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t* cand_ids, double* log_weights,
+                            double* log_weight_new) {
+  if (!h || rid < 0 || rid >= h->N) return EXB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const int N = h->N;
+  refresh_clust_dev(h);
+  h->S.iter = (uint32_t)h->iteration;
+  k_eval_all<<<nblk(N), TPB, 0, h->stream>>>(h->S, rid, N); // between sweeps only slots [0,N) are live
+  std::vector<double> lw(N);
+  std::vector<int> x(h->RS);
+  uint32_t zm = 0;
+  int own = 0, own_size = 0;
+  CK(cudaMemcpyAsync(lw.data(), h->S.lwbuf, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(x.data(), h->S.rec_x + (size_t)rid * h->RS, sizeof(int) * h->RS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&zm, h->S.rec_z + rid, sizeof zm, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&own, h->S.lambda + rid, sizeof own, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(&own_size, h->S.ent_size + own, sizeof own_size, cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (int e = 0; e < N; e++)
+    if (lw[e] == lw[e]) {
+      if (n < cap) { cand_ids[n] = e; log_weights[n] = lw[e]; }
+      n++;
+    }
+  // logLikelihoodWeightNew from the host copies of the tables (links.cpp:316-347)
+  double L = 0.0;
+  for (int a = 0; a < h->A; a++) {
+    if (x[a] < 0) continue;
+    const HostAttr& t = h->attrs[a];
+    double v;
+    if ((zm >> a) & 1u) {
+      std::vector<double> logE(t.D);
+      CK(cudaMemcpy(logE.data(), h->h_attrs[a].logE, sizeof(double) * t.D, cudaMemcpyDeviceToHost));
+      v = logE[x[a]];
+    } else v = std::log(t.phi[x[a]]);
+    L += v;
+  }
+  const int k = h->K - (own_size == 1 ? 1 : 0);
+  double pn;
+  if (h->cl.kind == EXB200_CLUST_PITMAN_YOR) pn = h->cl.alpha + h->cl.d * (double)k;
+  else if (h->cl.kind == EXB200_CLUST_GEN_COUPON) pn = h->cl.kappa * std::fabs(h->cl.m - (double)k);
+  else pn = std::fabs(h->cl.m - (double)k);
+  *log_weight_new = std::log(pn) + L;
+  return n;
+}
+
+} // extern "C"

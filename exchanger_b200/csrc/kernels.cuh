@@ -1,0 +1,928 @@
+// sm_100a kernels of the Gibbs sweep.  Each kernel names the reference function it replaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "device_state.cuh"
+#include "rng.cuh"
+
+namespace exb {
+
+#define FULL 0xFFFFFFFFu
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void dev_fail(const DevState& S, int code, int id) {
+  if (atomicCAS(&S.dev_err[0], 0, code) == 0) S.dev_err[1] = id;
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t bucket_of(const DevTable& t, int va, int vb) {
+  const uint64_t key = t.a == t.b ? (uint64_t)va : (uint64_t)va * (uint64_t)t.Db + (uint64_t)vb;
+  return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
+}
+
+// log p(w | v) = log get_distortion_prob(v, w)   (src/attribute_index.cpp:36-47, 77-92)
+__device__ __forceinline__ double log_distortion_prob(const DevAttr& t, int v, int w) {
+  if (t.is_const) {
+    if (t.exclude) return v == w ? -CUDART_INF : t.logpsi[w] - t.log1mpsi[v];
+    return t.logpsi[w];
+  }
+  if (v == w) return t.exclude ? -CUDART_INF : 0.0;
+  int lo = t.row[w], hi = t.row[w + 1];
+  const int end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t.col[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return (lo < end && t.col[lo] == v) ? t.logp[lo] : -CUDART_INF;
+}
+
+__device__ __forceinline__ double prior_existing(const ClustDev& c, int n) { // clust_params.cpp:4-27
+  if (c.kind == EXB200_CLUST_PITMAN_YOR) return fabs((double)n - c.d);
+  if (c.kind == EXB200_CLUST_GEN_COUPON) return (double)n + c.kappa;
+  return 1.0;
+}
+__device__ __forceinline__ double log_prior_existing(const ClustDev& c, int n) {
+  return n < LPE_MAX ? c.logpe[n] : log(prior_existing(c, n));
+}
+__device__ __forceinline__ double prior_new(const ClustDev& c, int k) { // clust_params.cpp:9-31
+  if (c.kind == EXB200_CLUST_PITMAN_YOR) return c.alpha + c.d * (double)k;
+  if (c.kind == EXB200_CLUST_GEN_COUPON) return c.kappa * fabs(c.m - (double)k);
+  return fabs(c.m - (double)k);
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// theta-dependent log tables (per sweep).  lt_diff[f][v] = log(theta[f,a] mef(v)) and
+// lt_same[f][v] = log(1 - theta mef(v))  or  log(1 - eff + eff p(v|v)): the two per-record
+// factors of logWeightEntityValue (src/entities.cpp:264-274).
+// ------------------------------------------------------------------------------------------
+__global__ void k_theta_tables(DevState S, int a) {
+  const DevAttr& t = S.attrs[a];
+  const int n = S.F * t.D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / t.D, v = i - f * t.D;
+    const double eff = S.theta[f * S.A + a] * t.mef[v];
+    t.lt_diff[i] = log(eff);
+    t.lt_same[i] = t.exclude ? log(1.0 - eff) : log(1.0 - eff + eff * (t.is_const ? t.psi[v] : 1.0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1a  per-record preparation of the links update.
+//   * attributes of the entity the record would found (src/links.cpp:424-468) -> slot N + r
+//   * logLikelihoodWeightNew (src/links.cpp:316-347)
+//   * choice of the blocking table: the two observed non-distorted attributes whose record
+//     values are rarest (replaces the set-size ordering of getPossibleLinks, links.cpp:187-189)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_prep(DevState S) {
+  __shared__ int s_usage[MAX_ATTRS * MAX_ATTRS];
+  const int AA = S.A * S.A;
+  for (int i = threadIdx.x; i < AA; i += blockDim.x) s_usage[i] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < S.N) {
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    int* yn = S.ent_y + (size_t)(S.N + r) * S.ES;
+    double L = 0.0;
+    int b1 = -1, b2 = -1;        // most selective observed non-distorted attributes
+    double s1 = 2.0, s2 = 2.0;
+    for (int a = 0; a < S.A; a++) {
+      const DevAttr& t = S.attrs[a];
+      const int xv = x[a];
+      const bool zz = (zm >> a) & 1u;
+      int yv;
+      if (xv < 0) { // unobserved: prior draw (links.cpp:434-437)
+        const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
+        yv = alias_draw(t.aprob, t.aalias, t.D, u.a);
+      } else {
+        L += zz ? t.logE[xv] : t.logphi[xv];
+        if (!zz) { // links.cpp:440-442
+          yv = xv;
+          const double sel = t.psi[xv];
+          if (sel < s1) { s2 = s1; b2 = b1; s1 = sel; b1 = a; }
+          else if (sel < s2) { s2 = sel; b2 = a; }
+        } else if (t.is_const) {
+          if (t.exclude) { // law of rejectionSampleConstant (links.cpp:290-314): phi/(1-psi), v != x
+            yv = xv;
+            for (int k = 0; k < REJECT_CAP; k++) {
+              const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, k);
+              yv = alias_draw(t.aprob + t.D, t.aalias + t.D, t.D, u.a);
+              if (yv != xv) break;
+            }
+            if (yv == xv) dev_fail(S, EXB200_ERR_WEIGHTS, r);
+          } else { // links.cpp:449-452
+            const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
+            yv = alias_draw(t.pprob, t.palias, t.D, u.a);
+          }
+        } else { // links.cpp:454-461: phi(v) p(x | v) over the neighbourhood of x
+          const int lo = t.row[xv], hi = t.row[xv + 1];
+          double tot = 0.0;
+          for (int j = lo; j < hi; j++) tot += t.phi[t.col[j]] * t.p[j];
+          yv = xv;
+          if (tot > 0.0) {
+            const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
+            const double tt = u.a * tot;
+            double c = 0.0;
+            int pick = -1, lastpos = xv;
+            for (int j = lo; j < hi; j++) {
+              const double w = t.phi[t.col[j]] * t.p[j];
+              if (w > 0.0) lastpos = t.col[j];
+              c += w;
+              if (tt < c) { pick = t.col[j]; break; }
+            }
+            yv = pick >= 0 ? pick : lastpos;
+          }
+        }
+      }
+      yn[a] = yv;
+    }
+    S.Lnew[r] = L;
+    S.ent_size[S.N + r] = 0;
+    S.ent_head[S.N + r] = -1;
+    S.fin[r] = 0;
+    // blocking table
+    int tab = 0xFFFF;
+    uint32_t bkt = 0;
+    if (b1 >= 0) {
+      const int ta = b2 < 0 ? b1 : min(b1, b2), tb = b2 < 0 ? b1 : max(b1, b2);
+      tab = ta * S.A + tb;
+      bkt = bucket_of(S.tables[tab], x[ta], x[tb]);
+      atomicAdd(&s_usage[tab], 1);
+    }
+    S.rec_tab[r] = (uint16_t)tab;
+    S.rec_bkt[r] = bkt;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < AA; i += blockDim.x)
+    if (s_usage[i]) atomicAdd(&S.tab_usage[i], s_usage[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b  blocking index over the items (entity slots) of the sweep: live entities [0,N) and the
+// N potential entities [N,2N).  Replaces Entities::inverse_index_ (src/entities.h:51): instead
+// of one hash set per (attribute, value) kept up to date by every change, CSR buckets over
+// attribute pairs are rebuilt once per sweep and stay fixed during the links update.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_index_count(DevState S, const int* __restrict__ active, int n_active) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * S.N) return;
+  if (i < S.N && S.ent_size[i] <= 0) return;
+  const int* y = S.ent_y + (size_t)i * S.ES;
+  for (int k = 0; k < n_active; k++) {
+    const DevTable& t = S.tables[active[k]];
+    atomicAdd(&t.ptr[bucket_of(t, y[t.a], y[t.b])], 1);
+  }
+}
+__global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __restrict__ active, int n_active) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * S.N) return;
+  if (i < S.N && S.ent_size[i] <= 0) return;
+  const int* y = S.ent_y + (size_t)i * S.ES;
+  for (int k = 0; k < n_active; k++) {
+    const DevTable& t = S.tables[active[k]];
+    const int pos = atomicAdd(&t.ptr[bucket_of(t, y[t.a], y[t.b])], 1);
+    t.ids[pos] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive prefix sum of n integers (three passes).  T_IN is int or int8_t.
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_TILE = TPB * 8;
+
+template <class T_IN>
+__global__ void __launch_bounds__(TPB) k_scan_reduce(const T_IN* __restrict__ in, int n, int* __restrict__ bsum) {
+  __shared__ int s_w[TPB / 32];
+  const int base = blockIdx.x * SCAN_TILE;
+  int v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int i = base + k * TPB + threadIdx.x;
+    if (i < n) v += (int)in[i];
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < TPB / 32; w++) t += s_w[w];
+    bsum[blockIdx.x] = t;
+  }
+}
+// one block: exclusive scan of the block sums in place
+__global__ void __launch_bounds__(1024) k_scan_top(int* __restrict__ bsum, int nb) {
+  __shared__ int s_part[1024];
+  const int per = (nb + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(nb, lo + per);
+  int t = 0;
+  for (int i = lo; i < hi; i++) t += bsum[i];
+  s_part[threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; i++) { const int x = s_part[i]; s_part[i] = run; run += x; }
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for (int i = lo; i < hi; i++) { const int x = bsum[i]; bsum[i] = run; run += x; }
+}
+template <class T_IN>
+__global__ void __launch_bounds__(TPB) k_scan_apply(const T_IN* __restrict__ in, int* __restrict__ out, int n,
+                                                    const int* __restrict__ bsum) {
+  __shared__ int s_w[TPB / 32];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  int v[8];
+  int t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    v[k] = base + k < n ? (int)in[base + k] : 0;
+    t += v[k];
+  }
+  // exclusive scan of t over the block
+  int incl = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(FULL, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int off = bsum[blockIdx.x];
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += s_w[w];
+  int run = off + incl - t;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c  candidate generation: one WARP per record (replaces getPossibleLinks, src/links.cpp:90-212,
+// and the per-candidate likelihood logLikelihoodWeightExisting, src/links.cpp:216-288).
+// The warp streams the record's bucket, gathers each item's attribute tuple (one 32-byte sector),
+// keeps the items that agree with the record on every observed non-distorted attribute
+// (links.cpp:122-131) and stores them, sorted by id, with the log-likelihood of the distorted
+// attributes.  Attribute tuples do not change during the links update, so this list is computed
+// once per sweep; only cluster sizes are read again when the record's turn comes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool item_compatible(const DevState& S, const int* x, uint32_t zm, const int* y) {
+  bool ok = true;
+  for (int a = 0; a < S.A; a++) {
+    const int xv = x[a];
+    ok &= (xv < 0) | ((zm >> a) & 1u) | (y[a] == xv);
+  }
+  return ok;
+}
+__device__ __forceinline__ double item_loglik(const DevState& S, const int* x, uint32_t zm, const int* y) {
+  double l = 0.0;
+  for (int a = 0; a < S.A; a++) {
+    const int xv = x[a];
+    if (xv >= 0 && ((zm >> a) & 1u)) l += log_distortion_prob(S.attrs[a], y[a], xv);
+  }
+  return l;
+}
+
+__global__ void __launch_bounds__(TPB) k_cand(DevState S) {
+  __shared__ int s_id[TPB / 32][CAND_SMEM];
+  __shared__ double s_ll[TPB / 32][CAND_SMEM];
+  __shared__ long long s_stat[2];
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = blockIdx.x * (TPB / 32) + wib;
+  if (r < S.N) {
+    int* ids = s_id[wib];
+    double* lls = s_ll[wib];
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    const int tab = S.rec_tab[r];
+    const int own = S.lambda[r];
+    int cnt = 0;
+    bool wide = tab == 0xFFFF;
+    int lo = 0, hi = 0;
+    if (!wide) {
+      const DevTable& t = S.tables[tab];
+      const uint32_t b = S.rec_bkt[r];
+      lo = b ? t.ptr[b - 1] : 0;
+      hi = t.ptr[b];
+      wide = hi - lo > S.bucket_cap;
+    }
+    if (!wide) {
+      const int* bucket = S.tables[tab].ids;
+      for (int base = lo; base < hi && !wide; base += 32) {
+        const int q = base + lane;
+        int item = -1;
+        bool ok = false;
+        double ll = 0.0;
+        if (q < hi) {
+          item = bucket[q];
+          if (item != S.N + r) {
+            const int* y = S.ent_y + (size_t)item * S.ES;
+            ok = item_compatible(S, x, zm, y);
+            if (ok) ll = item_loglik(S, x, zm, y);
+          }
+        }
+        const unsigned m = __ballot_sync(FULL, ok);
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (cnt + __popc(m) > S.cand_cap) wide = true;
+        else if (ok) { ids[pos] = item; lls[pos] = ll; }
+        cnt += __popc(m);
+      }
+      if (lane == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
+    }
+    uint32_t off = 0;
+    if (!wide && cnt > 0) {
+      // sort the staged candidates by id (bitonic, one warp)
+      int n2 = 1;
+      while (n2 < cnt) n2 <<= 1;
+      for (int i = cnt + lane; i < n2; i += 32) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
+      __syncwarp();
+      for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < n2; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const bool up = (i & k) == 0;
+              const int a0 = ids[i], a1 = ids[l];
+              if ((a0 > a1) == up) {
+                ids[i] = a1; ids[l] = a0;
+                const double t0 = lls[i]; lls[i] = lls[l]; lls[l] = t0;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      unsigned long long o = 0;
+      if (lane == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+      o = __shfl_sync(FULL, o, 0);
+      if (o + (unsigned long long)cnt > S.pool_cap) wide = true;
+      else {
+        off = (uint32_t)o;
+        for (int i = lane; i < cnt; i += 32) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+      }
+    }
+    if (lane == 0) {
+      S.cand_off[r] = off;
+      S.cand_cnt[r] = wide ? -1 : cnt;
+      // bounds of this record's change of K while its outcome is unknown
+      bool other = wide;
+      if (!wide) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
+      S.dlo[r] = other ? -1 : 0;
+      S.dhi[r] = 1;
+      if (wide) atomicAdd(&S.counters[C_NWIDE], 1);
+      else atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_stat[threadIdx.x])
+    atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1d  dependency rounds.  The links update must equal the sequential scan of
+// Links::update (src/links.cpp:485-488).  Every unfinalised record reserves (atomicMin of its id)
+// all the items its conditional reads or may write: its entity, its potential entity and its
+// candidates.  A record whose reservations all carry its own id has no earlier unfinalised
+// record that could change what it reads, so its conditional is already the one the sequential
+// scan would see.  Wide records (no stored candidate list) act as a fence.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long resv_key(uint32_t round, int r) {
+  return ((unsigned long long)(0xFFFFFFFFu - round) << 32) | (unsigned long long)(uint32_t)r;
+}
+
+__global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
+  __shared__ int s_min;
+  if (threadIdx.x == 0) s_min = 0x7FFFFFFF;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int mine = 0x7FFFFFFF;
+  if (i < n_act) {
+    const int r = act ? act[i] : i;
+    mine = r;
+    const unsigned long long key = resv_key(round, r);
+    const int cnt = S.cand_cnt[r];
+    if (cnt < 0) {
+      atomicMin(S.fence, key);
+    } else {
+      atomicMin(&S.owner[S.lambda[r]], key);
+      atomicMin(&S.owner[S.N + r], key);
+      const int* ids = S.cand_id + S.cand_off[r];
+      for (int j = 0; j < cnt; j++) atomicMin(&S.owner[ids[j]], key);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(FULL, mine, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(&s_min, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_min != 0x7FFFFFFF) atomicMin(&S.counters[C_MIN_ACTIVE], s_min);
+}
+
+// move record r from entity `own` to `target`, keeping member lists sorted (the role of
+// Links::set_link, src/links.cpp:6-39, and Entities::add / remove, src/entities.cpp:18-69)
+__device__ __forceinline__ void apply_move(const DevState& S, int r, int own, int target) {
+  if (target != own) {
+    int h = S.ent_head[own];
+    if (h == r) S.ent_head[own] = S.rec_next[r];
+    else {
+      while (S.rec_next[h] != r) h = S.rec_next[h];
+      S.rec_next[h] = S.rec_next[r];
+    }
+    S.ent_size[own] -= 1;
+    h = S.ent_head[target];
+    if (h < 0 || r < h) { S.rec_next[r] = h; S.ent_head[target] = r; }
+    else {
+      int nx = S.rec_next[h];
+      while (nx >= 0 && nx < r) { h = nx; nx = S.rec_next[h]; }
+      S.rec_next[r] = nx;
+      S.rec_next[h] = r;
+    }
+    S.ent_size[target] += 1;
+    S.lambda[r] = target;
+  }
+}
+
+// decision "found a new entity" given the number of entities k seen by prior_weight_new
+__device__ __forceinline__ bool decide_new(const DevState& S, int r, int k, double m1, double srel, double u1,
+                                           bool& invalid) {
+  const double lwn = log(prior_new(S.cl, k)) + S.Lnew[r];
+  const double m2 = m1 > lwn ? m1 : lwn;
+  invalid = !(m2 > -CUDART_INF);
+  const double wa = exp(lwn - m2);
+  const double wb = m1 > -CUDART_INF ? srel * exp(m1 - m2) : 0.0;
+  return u1 * (wa + wb) < wa;
+}
+
+__global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool stay = false;
+  int r = -1;
+  if (i < n_act) {
+    r = act ? act[i] : i;
+    stay = true;
+    const int cnt = S.cand_cnt[r];
+    const unsigned long long key = resv_key(round, r);
+    const unsigned long long fence = *S.fence;
+    const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
+    if (cnt < 0) {
+      // wide record: its turn comes when every earlier record is final
+      if (S.counters[C_MIN_ACTIVE] == r) S.counters[C_WIDE_READY] = r;
+    } else if (!fenced) {
+      const int own = S.lambda[r];
+      const int* ids = S.cand_id + S.cand_off[r];
+      bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
+      for (int j = 0; j < cnt && mine; j++) mine = S.owner[ids[j]] == key;
+      if (mine) {
+        const double* lls = S.cand_ll + S.cand_off[r];
+        const bool single = S.ent_size[own] == 1;
+        // weights of the live candidates (links.cpp:372-388)
+        double m1 = -CUDART_INF;
+        for (int j = 0; j < cnt; j++) {
+          const int e = ids[j];
+          int sz = S.ent_size[e];
+          if (e == own) sz = single ? 0 : sz - 1; // links.cpp:359, :375
+          if (sz > 0) {
+            const double lw = log_prior_existing(S.cl, sz) + lls[j];
+            m1 = lw > m1 ? lw : m1;
+          }
+        }
+        double srel = 0.0;
+        if (m1 > -CUDART_INF)
+          for (int j = 0; j < cnt; j++) {
+            const int e = ids[j];
+            int sz = S.ent_size[e];
+            if (e == own) sz = single ? 0 : sz - 1;
+            if (sz > 0) srel += exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+          }
+        const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+        // number of entities seen by prior_weight_new (links.cpp:390): exact when every earlier
+        // record is final, otherwise an interval
+        bool inv_lo = false, inv_hi = false;
+        const int klo = S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0);
+        const int khi = S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0);
+        const bool new_lo = decide_new(S, r, klo, m1, srel, u.a, inv_lo);
+        const bool new_hi = klo == khi ? new_lo : decide_new(S, r, khi, m1, srel, u.a, inv_hi);
+        if (new_lo == new_hi) {
+          if (inv_lo || inv_hi) dev_fail(S, EXB200_ERR_WEIGHTS, r); // "no valid links for record"
+          int target;
+          if (new_lo) target = S.N + r;
+          else {
+            const double tt = u.b * srel;
+            double c = 0.0;
+            int pick = -1, lastpos = -1;
+            for (int j = 0; j < cnt; j++) {
+              const int e = ids[j];
+              int sz = S.ent_size[e];
+              if (e == own) sz = single ? 0 : sz - 1;
+              if (sz <= 0) continue;
+              const double w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+              if (w > 0.0) lastpos = e;
+              c += w;
+              if (tt < c) { pick = e; break; }
+            }
+            target = pick >= 0 ? pick : lastpos;
+            if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+          }
+          const int dk = (new_lo ? 1 : 0) - (single ? 1 : 0);
+          if (!(target == own || (single && new_lo))) atomicAdd(&S.counters[C_CHANGED], 1);
+          apply_move(S, r, own, target);
+          S.fin[r] = 1;
+          S.dlo[r] = (int8_t)dk;
+          S.dhi[r] = (int8_t)dk;
+          if (dk) atomicAdd(&S.counters[C_DK_TOTAL], dk);
+          stay = false;
+        } else {
+          // entity-wise ready, only K is still uncertain: tighten this record's bounds
+          S.dlo[r] = single ? -1 : 0;
+          S.dhi[r] = single ? 0 : 1;
+        }
+      }
+    }
+  }
+  // append the records that stay to the next active list
+  const unsigned m = __ballot_sync(FULL, stay);
+  if (m) {
+    int base = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(&S.counters[C_NACT_OUT], __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (stay) S.act_out[base + __popc(m & ((1u << lane) - 1u))] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wide path and test hook: the conditional of ONE record against every item, in item order.
+// lwbuf[i] = log prior_weight_existing + logLikelihoodWeightExisting, NaN if i is no candidate.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  double out = CUDART_NAN;
+  const int own = S.lambda[r];
+  int sz = S.ent_size[i];
+  if (i == own) sz = sz == 1 ? 0 : sz - 1;
+  if (sz > 0 && i != S.N + r) {
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    const int* y = S.ent_y + (size_t)i * S.ES;
+    if (item_compatible(S, x, zm, y)) out = log_prior_existing(S.cl, sz) + item_loglik(S, x, zm, y);
+  }
+  S.lwbuf[i] = out;
+}
+
+// one block: ordered reduction over lwbuf, decision and commit of the wide record r
+__global__ void __launch_bounds__(1024) k_wide_commit(DevState S, int r) {
+  __shared__ double s_part[1024];
+  __shared__ double s_m1, s_tt;
+  __shared__ int s_chunk, s_target;
+  const int n = 2 * S.N;
+  const int per = (n + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(n, lo + per);
+  double m = -CUDART_INF;
+  for (int i = lo; i < hi; i++) { const double v = S.lwbuf[i]; if (v == v && v > m) m = v; }
+  s_part[threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mm = -CUDART_INF;
+    for (int i = 0; i < 1024; i++) mm = s_part[i] > mm ? s_part[i] : mm;
+    s_m1 = mm;
+  }
+  __syncthreads();
+  const double m1 = s_m1;
+  double sum = 0.0;
+  if (m1 > -CUDART_INF)
+    for (int i = lo; i < hi; i++) { const double v = S.lwbuf[i]; if (v == v) sum += exp(v - m1); }
+  __syncthreads();
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  const int own = S.lambda[r];
+  if (threadIdx.x == 0) {
+    double srel = 0.0;
+    for (int i = 0; i < 1024; i++) srel += s_part[i];
+    const bool single = S.ent_size[own] == 1;
+    const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+    const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
+    bool invalid = false;
+    const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
+    if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
+    s_chunk = -1;
+    s_target = is_new ? S.N + r : -1;
+    if (!is_new) {
+      const double tt = u.b * srel;
+      double c = 0.0;
+      int chunk = -1, lastpos = -1;
+      for (int i = 0; i < 1024; i++) {
+        if (s_part[i] > 0.0) lastpos = i;
+        if (tt < c + s_part[i]) { chunk = i; break; }
+        c += s_part[i];
+      }
+      if (chunk < 0) { chunk = lastpos; c = 0.0; s_tt = -1.0; } // rounding: take the last positive one
+      else s_tt = tt - c;
+      s_chunk = chunk;
+    }
+  }
+  __syncthreads();
+  if (s_chunk >= 0 && (int)threadIdx.x == s_chunk) {
+    const double tt = s_tt;
+    double c = 0.0;
+    int pick = -1, lastpos = -1;
+    for (int i = lo; i < hi; i++) {
+      const double v = S.lwbuf[i];
+      if (!(v == v)) continue;
+      const double w = exp(v - m1);
+      if (w > 0.0) lastpos = i;
+      c += w;
+      if (tt >= 0.0 && tt < c) { pick = i; break; }
+    }
+    s_target = pick >= 0 ? pick : lastpos;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int target = s_target;
+    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+    const bool single = S.ent_size[own] == 1, is_new = target == S.N + r;
+    const int dk = (is_new ? 1 : 0) - (single ? 1 : 0);
+    if (!(target == own || (single && is_new))) atomicAdd(&S.counters[C_CHANGED], 1);
+    apply_move(S, r, own, target);
+    S.fin[r] = 1;
+    S.dlo[r] = (int8_t)dk;
+    S.dhi[r] = (int8_t)dk;
+    if (dk) atomicAdd(&S.counters[C_DK_TOTAL], dk);
+  }
+}
+
+// drop a finalised wide record from the active list
+__global__ void __launch_bounds__(TPB) k_compact_active(DevState S, const int* __restrict__ act, int n_act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = i < n_act ? (act ? act[i] : i) : -1;
+  const bool stay = r >= 0 && !S.fin[r];
+  const unsigned m = __ballot_sync(FULL, stay);
+  if (m) {
+    int base = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == (__ffs(m) - 1)) base = atomicAdd(&S.counters[C_NACT_OUT], __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (stay) S.act_out[base + __popc(m & ((1u << lane) - 1u))] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1e  rename every entity to its smallest member record (the head of its sorted member list).
+// Slots [0,N) of the "next" arrays become the entity table of the following phases.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_canon(DevState S) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int rep = 0;
+  if (r < S.N) {
+    const int e = S.lambda[r];
+    const int c = S.ent_head[e];
+    S.lambda[r] = c;
+    rep = c == r;
+    S.ent_size_nx[r] = rep ? S.ent_size[e] : 0;
+    S.ent_head_nx[r] = rep ? r : -1;
+  }
+  rep = warp_sum(rep);
+  if ((threadIdx.x & 31) == 0 && rep) atomicAdd(&S.counters[C_K], rep);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2  entity attribute resampling (replaces Entities::update_attributes, logWeightEntityValue,
+// drawEntityValueSequential and drawEntityValueIndex, src/entities.cpp:236-469).
+// One thread per entity slot: >= 65% of the entities are singletons whose only member is the
+// record with the same index, so member reads are coalesced; larger clusters walk their
+// sorted member list.  Persistent distributions come from device alias tables.
+// ------------------------------------------------------------------------------------------
+__device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, int a, int v, int head) {
+  double lw = t.logphi[v];
+  for (int r = head; r >= 0; r = S.rec_next[r]) {
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const int xv = x[a];
+    if (xv < 0) continue;
+    const int f = x[S.RS - 1];
+    if (xv == v) lw += t.lt_same[f * t.D + v];
+    else {
+      lw += t.lt_diff[f * t.D + v];
+      lw += log_distortion_prob(t, v, xv);
+    }
+  }
+  return lw;
+}
+
+__device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
+  const DevAttr& t = S.attrs[a];
+  int nobs = 0, first = -1;
+  for (int r = head; r >= 0; r = S.rec_next[r]) {
+    const int xv = S.rec_x[(size_t)r * S.RS + a];
+    if (xv >= 0) { if (first < 0) first = xv; nobs++; }
+  }
+  const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
+  if (nobs == 0) return alias_draw(t.aprob, t.aalias, t.D, u0.a); // entities.cpp:387-389
+
+  if (t.is_const && t.exclude && nobs <= NMAX_FAST) {
+    // whole-domain weights of drawEntityValueSequential (entities.cpp:298-348) in closed form:
+    // explicit for the members' values, C phi(v)/(1-psi(v))^nobs for every other value
+    int vals[NMAX_FAST];
+    double w[NMAX_FAST];
+    int nv = 0;
+    double Cc = 1.0;
+    for (int r = head; r >= 0; r = S.rec_next[r]) {
+      const int* x = S.rec_x + (size_t)r * S.RS;
+      const int xv = x[a];
+      if (xv < 0) continue;
+      Cc *= S.theta[x[S.RS - 1] * S.A + a] * t.psi[xv];
+      bool seen = false;
+      for (int j = 0; j < nv; j++) seen |= vals[j] == xv;
+      if (!seen) vals[nv++] = xv;
+    }
+    const double* g = t.g + (size_t)nobs * t.D;
+    double sumw = 0.0, rest = t.G[nobs];
+    for (int j = 0; j < nv; j++) {
+      const int v = vals[j];
+      double ww = t.phi[v];
+      for (int r = head; r >= 0; r = S.rec_next[r]) {
+        const int* x = S.rec_x + (size_t)r * S.RS;
+        const int xv = x[a];
+        if (xv < 0) continue;
+        const double th = S.theta[x[S.RS - 1] * S.A + a];
+        ww *= xv == v ? 1.0 - th : th * t.psi[xv] / t.om[v];
+      }
+      w[j] = ww;
+      sumw += ww;
+      rest -= g[v];
+    }
+    if (rest < 0.0) rest = 0.0;
+    const double wrest = Cc * rest, total = sumw + wrest;
+    if (!(total > 0.0) || !isfinite(total)) { dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
+    const double tt = u0.a * total;
+    double c = 0.0;
+    for (int j = 0; j < nv; j++) { c += w[j]; if (tt < c) return vals[j]; }
+    if (!(wrest > 0.0))
+      for (int j = nv - 1; j >= 0; j--) if (w[j] > 0.0) return vals[j];
+    const double* ap = t.aprob + (size_t)nobs * t.D;
+    const int* aa = t.aalias + (size_t)nobs * t.D;
+    for (int k = 1; k < REJECT_CAP; k++) {
+      const U2 u = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, k);
+      const int v = alias_draw(ap, aa, t.D, u.a);
+      bool hit = false;
+      for (int j = 0; j < nv; j++) hit |= vals[j] == v;
+      if (!hit) return v;
+    }
+    dev_fail(S, EXB200_ERR_WEIGHTS, e);
+    return first;
+  }
+
+  // general scheme: explicit support, inverse CDF in support order.  Support: the whole domain
+  // for a constant attribute (entities.cpp:315-329); the first observed member value and its
+  // neighbourhood otherwise (a subset of entities.cpp:361-383 that holds all the mass)
+  const int lo = t.is_const ? 0 : t.row[first], hi = t.is_const ? t.D : t.row[first + 1];
+  const int ns = t.is_const ? t.D : 1 + (hi - lo);
+  double m = -CUDART_INF;
+  for (int j = 0; j < ns; j++) {
+    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
+    if (!t.is_const && j > 0 && v == first) continue;
+    const double lw = log_weight_entity_value(S, t, a, v, head);
+    m = lw > m ? lw : m;
+  }
+  if (!(m > -CUDART_INF)) { dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
+  double total = 0.0;
+  for (int j = 0; j < ns; j++) {
+    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
+    if (!t.is_const && j > 0 && v == first) continue;
+    total += exp(log_weight_entity_value(S, t, a, v, head) - m);
+  }
+  const double tt = u0.a * total;
+  double c = 0.0;
+  int lastpos = first;
+  for (int j = 0; j < ns; j++) {
+    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
+    if (!t.is_const && j > 0 && v == first) continue;
+    const double w = exp(log_weight_entity_value(S, t, a, v, head) - m);
+    if (w > 0.0) lastpos = v;
+    c += w;
+    if (tt < c) return v;
+  }
+  return lastpos;
+}
+
+__global__ void __launch_bounds__(TPB) k_entities(DevState S) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.N || S.ent_size[e] <= 0) return;
+  const int head = S.ent_head[e];
+  int* y = S.ent_y + (size_t)e * S.ES;
+  for (int a = 0; a < S.A; a++) y[a] = draw_entity_value(S, e, a, head);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3  distortion indicators (replaces Records::update_distortion, src/records.cpp:70-138):
+// elementwise over records x attributes, counts reduced per (file, attribute) with warp
+// ballots into shared memory and one global atomic per block and bin.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_distort(DevState S, int use_smem) {
+  extern __shared__ int s_cnt[]; // [2][F*A] when use_smem
+  const int FA = S.F * S.A;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < 2 * FA; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+  }
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < S.N;
+  const int* x = S.rec_x + (size_t)(live ? r : 0) * S.RS;
+  const int f = live ? x[S.RS - 1] : -1;
+  const int* y = S.ent_y + (size_t)(live ? S.lambda[r] : 0) * S.ES;
+  const unsigned peers = __match_any_sync(FULL, f);
+  const bool leader = live && (threadIdx.x & 31) == (__ffs(peers) - 1);
+  uint32_t zm = 0;
+  for (int a = 0; a < S.A; a++) {
+    bool zz = false, cor = false;
+    if (live) {
+      const DevAttr& t = S.attrs[a];
+      const int xv = x[a], yv = y[a];
+      const double th = S.theta[f * S.A + a];
+      const bool need_u = xv < 0 || (xv == yv && !t.exclude) || t.mef[yv] != 1.0;
+      U2 u;
+      u.a = 0.0; u.b = 0.0;
+      if (need_u) u = uniforms(S.seed, r, S.iter, PH_DISTORT, a, 0);
+      if (xv < 0) zz = u.a < th;                       // records.cpp:95-100
+      else if (xv == yv) {
+        if (!t.exclude) {                               // records.cpp:109-112
+          const double pr1 = th * (t.is_const ? t.psi[xv] : 1.0), pr0 = 1.0 - th;
+          zz = u.a < pr1 / (pr1 + pr0);
+        }
+      } else zz = true;                                 // records.cpp:114-116
+      double pr1 = t.mef[yv];                           // records.cpp:122-133
+      bool alt;
+      if (pr1 == 1.0) alt = true;
+      else {
+        const double pr0 = 1.0 - pr1;
+        pr1 *= zz ? th : 1.0 - th;
+        alt = u.b < pr1 / (pr1 + pr0);
+      }
+      cor = alt && !zz;                                 // records.cpp:134
+      zm |= (uint32_t)zz << a;
+    }
+    const unsigned bz = __ballot_sync(FULL, zz), bc = __ballot_sync(FULL, cor);
+    if (leader) {
+      const int nz = __popc(bz & peers), nc = __popc(bc & peers);
+      if (use_smem) {
+        if (nz) atomicAdd(&s_cnt[f * S.A + a], nz);
+        if (nc) atomicAdd(&s_cnt[FA + f * S.A + a], nc);
+      } else {
+        if (nz) atomicAdd(&S.ndist[f * S.A + a], nz);
+        if (nc) atomicAdd(&S.corr[f * S.A + a], nc);
+      }
+    }
+  }
+  if (live) S.rec_z[r] = zm;
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < FA; i += blockDim.x) {
+      if (s_cnt[i]) atomicAdd(&S.ndist[i], s_cnt[i]);
+      if (s_cnt[FA + i]) atomicAdd(&S.corr[i], s_cnt[FA + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bernoulli sums of ClustParams::update (src/clust_params.cpp:52-58, 83-90, 108-114); the scalar
+// Beta / Gamma / NegBinom draws that consume them stay on the host.
+// out[0] += #{ i in [1, K-1] : u_i < alpha / (alpha + d i) }
+// out[1] += sum over clusters, j in [1, size-1]: PY: u >= (j-1)/(j-d);  coupon: u < kappa/(kappa+j)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_clust_counts(DevState S, int K, int do_u, int do_v, unsigned long long* out) {
+  int cu = 0, cv = 0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (do_u && i >= 1 && i <= K - 1) {
+    const U2 u = uniforms(S.seed, i, S.iter, PH_CLUST_U, 0, 0);
+    cu = u.a < S.cl.alpha / (S.cl.alpha + S.cl.d * (double)i);
+  }
+  if (do_v && i < S.N) {
+    const int sz = S.ent_size[i];
+    for (int j = 1; j <= sz - 1; j++) {
+      const U2 u = uniforms(S.seed, i, S.iter, PH_CLUST_V, 0, j);
+      if (S.cl.kind == EXB200_CLUST_PITMAN_YOR) cv += u.a >= ((double)j - 1.0) / ((double)j - S.cl.d);
+      else cv += u.a < S.cl.kappa / (S.cl.kappa + (double)j);
+    }
+  }
+  cu = warp_sum(cu);
+  cv = warp_sum(cv);
+  if ((threadIdx.x & 31) == 0) {
+    if (cu) atomicAdd(&out[0], (unsigned long long)cu);
+    if (cv) atomicAdd(&out[1], (unsigned long long)cv);
+  }
+}
+
+} // namespace exb
