@@ -512,11 +512,15 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         // number of entities seen by prior_weight_new (links.cpp:390): exact when every earlier
         // record is final, otherwise an interval
         bool inv_lo = false, inv_hi = false;
-        const int klo = S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0);
-        const int khi = S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0);
+        // (with r taken out there are between 0 and N-1 entities, whatever the earlier records do)
+        const int klo = max(0, S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0));
+        const int khi = min(S.N - 1, S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0));
         const bool new_lo = decide_new(S, r, klo, m1, srel, u.a, inv_lo);
         const bool new_hi = klo == khi ? new_lo : decide_new(S, r, khi, m1, srel, u.a, inv_hi);
-        if (new_lo == new_hi) {
+        // prior_weight_new is monotone in K (alpha + d K; kappa |m - K|) unless the interval
+        // straddles the kink of |m - K|; only then the end points do not decide
+        const bool kink = S.cl.kind != EXB200_CLUST_PITMAN_YOR && (double)klo < S.cl.m && S.cl.m < (double)khi;
+        if (new_lo == new_hi && !kink) {
           if (inv_lo || inv_hi) dev_fail(S, EXB200_ERR_WEIGHTS, r); // "no valid links for record"
           int target;
           if (new_lo) target = S.N + r;

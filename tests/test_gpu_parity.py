@@ -1,0 +1,179 @@
+"""GPU parity tests: the CUDA sampler, called through the C ABI, against the oracle on the same
+seeded inputs.  Integer outputs (links, entity attributes, distortion indicators and counts)
+must be identical; theta and the cluster hyper-parameters are host draws from those integers
+and must be identical too."""
+import numpy as np
+import pytest
+
+from checkers import OracleSampler
+from exchanger_b200 import BetaRV, PitmanYorRP, GammaRV
+from exchanger_b200.analysis import clusters_to_membership, pairwise_measures, smp_clusters
+from exchanger_b200.capi import Exb200Error
+from exchanger_b200.sampler import Sampler, run_inference
+from fixtures import PRIORS, load_rldata, model_with_files, readme_attr_params, readme_model
+from exchanger_b200 import exchanger
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ("links", "ent_ids", "ent_attrs", "rec_distortions", "distort_counts")
+
+
+def assert_same_state(a, b, where=""):
+    for k in INT_KEYS:
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), f"{k} differs {where}"
+    assert np.array_equal(a["distort_probs"], b["distort_probs"]), f"theta differs {where}"
+    for k in ("alpha", "d", "m", "kappa"):
+        assert a["clust"][k] == b["clust"][k], f"{k} differs {where}"
+    assert a["iteration"] == b["iteration"]
+
+
+def lockstep(model, n_sweeps, seed=11, every=1, **options):
+    gpu, oracle = Sampler(model, seed=seed), OracleSampler(model, seed=seed)
+    gpu.set_option("check", 1)
+    for k, v in options.items():
+        gpu.set_option(k, v)
+    stats = []
+    for i in range(0, n_sweeps, every):
+        gpu.sweeps(every)
+        oracle.sweeps(every)
+        assert_same_state(gpu.state(), oracle.state(), f"after sweep {i + every}")
+        stats.append(gpu.stats())
+    gpu.close()
+    return stats
+
+
+@pytest.mark.parametrize("prior", list(PRIORS))
+def test_rldata500_lockstep_every_prior(prior):
+    """C1 (RLdata500, README attributes) under every cluster-prior family."""
+    m, _ = readme_model("rldata500", clust_prior=PRIORS[prior](500))
+    stats = lockstep(m, 30)
+    assert max(s["n_rounds"] for s in stats) >= 2  # the dependency rounds were exercised
+
+
+def test_wide_path_gives_the_same_chain():
+    """Forcing most records onto the serial wide path (no stored candidate list) must not change
+    a single integer: results do not depend on the batching."""
+    m, _ = readme_model("rldata500", n=200)
+    stats = lockstep(m, 8, cand_cap=1, bucket_cap=2)
+    assert sum(s["n_wide"] for s in stats) > 50
+
+
+def test_missing_values_and_many_attributes():
+    """NA paths: the mostly-missing second name components as two extra attributes (7 in all)."""
+    cols, _ = load_rldata("rldata500", 300)
+    m = exchanger(cols, readme_attr_params(with_c2=True), PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    assert (m.rec_attrs < 0).sum() > 0
+    lockstep(m, 20)
+
+
+def test_several_files():
+    m, _ = model_with_files("rldata500", n_files=3)
+    lockstep(m, 20)
+
+
+def test_entity_value_not_excluded():
+    """exclude_entity_value = FALSE: random indicator for agreeing values (records.cpp:109-112),
+    empirical new-entity draw (links.cpp:449-452), whole-domain entity weights."""
+    m, _ = readme_model("rldata500", n=250, exclude=False)
+    lockstep(m, 15)
+
+
+def test_informative_distortion_prior_and_fixed_theta():
+    cols, _ = load_rldata("rldata500")
+    ap = readme_attr_params(prior=BetaRV(10, 1000))
+    ap["bm"].distort_prob_prior = 0.02  # fixed probability: DistortProbs::update skips it
+    m = exchanger(cols, ap, PRIORS["pitman_yor"](500))
+    lockstep(m, 25)
+
+
+def test_rldata10000_lockstep():
+    """C2-shaped: RLdata10000 with the README attributes, Ewens prior; the early sweeps have the
+    long candidate tails."""
+    m, _ = readme_model("rldata10000", clust_prior=PRIORS["ewens"](10000))
+    stats = lockstep(m, 6)
+    assert stats[-1]["n_candidates"] > 10000
+
+
+def test_rldata10000_pitman_yor_steady_state():
+    m, _ = readme_model("rldata10000")
+    lockstep(m, 24, every=8)
+
+
+def test_link_conditional_matches_oracle():
+    m, _ = readme_model("rldata500")
+    gpu, oracle = Sampler(m, seed=4), OracleSampler(m, seed=4)
+    gpu.sweeps(12)
+    oracle.sweeps(12)
+    n_cmp = 0
+    for r in range(500):
+        gi, gw, gn = gpu.link_conditional(r)
+        oi, ow, on = oracle.link_conditional(r)
+        assert np.array_equal(gi, oi)
+        assert np.allclose(gw, ow, rtol=1e-12, atol=0) or np.array_equal(gw, ow)
+        assert abs(gn - on) <= 1e-12 * abs(on)
+        n_cmp += len(gi)
+    assert n_cmp > 50
+    gpu.close()
+
+
+def test_results_do_not_depend_on_batching_thresholds():
+    """Same seed, different wide-path thresholds -> identical chains (property test that holds at
+    any size: the sweep is sequentially consistent, batching is only scheduling)."""
+    m, _ = readme_model("rldata10000", n=4000)
+    states = []
+    for opts in (dict(), dict(cand_cap=4, bucket_cap=64), dict(cand_cap=32, bucket_cap=8)):
+        with Sampler(m, seed=3) as g:
+            for k, v in opts.items():
+                g.set_option(k, v)
+            g.sweeps(6)
+            states.append(g.state())
+    for s in states[1:]:
+        assert_same_state(states[0], s)
+
+
+def test_run_inference_schedule_history_and_resume():
+    """Save schedule of sample() (src/sample.cpp:171-197) and resuming from fit.state
+    (R/run_inference.R:104-115): 3 + 3 resumed samples equal one run of 6."""
+    m, _ = readme_model("rldata500", n=300)
+    fit = run_inference(m, n_samples=6, thin_interval=2, burnin_interval=3, seed=9)
+    assert fit.history["links"].shape == (6, 300)
+    assert fit.state.iteration == 3 + 2 * 5  # first sample at the last burn-in sweep
+    assert fit.mcpar == (3, 13, 2)
+    assert fit.history["clust_params"].shape == (6, 2) and fit.history["clust_params_names"] == ["alpha", "d"]
+    # the oracle on the same schedule
+    o = OracleSampler(m, seed=9)
+    o.sweeps(3)
+    for s in range(6):
+        if s:
+            o.sweeps(2)
+        st = o.state()
+        assert np.array_equal(fit.history["links"][s], st["links"])
+        assert fit.history["n_linked_ents"][s, 0] == len(st["ent_ids"])
+        assert np.array_equal(fit.history["distort_probs"][s], st["distort_probs"].T.ravel())
+        assert np.array_equal(fit.history["distort_counts"][s], st["distort_counts"].T.ravel())
+    a = run_inference(m, n_samples=3, thin_interval=2, burnin_interval=3, seed=9)
+    b = run_inference(a, n_samples=3, thin_interval=2, seed=9)
+    assert np.array_equal(b.history["links"], fit.history["links"])
+    assert b.state.iteration == fit.state.iteration
+
+
+def test_unsupported_model_features_fail_loudly():
+    from exchanger_b200 import DirichletProcess, Attribute, CategoricalAttribute
+    cols, _ = load_rldata("rldata500", 100)
+    ap = readme_attr_params()
+    ap["bm"] = CategoricalAttribute(BetaRV(1, 1), distort_dist_prior=DirichletProcess(GammaRV(2, 1e-4)))
+    m = exchanger(cols, ap, PRIORS["pitman_yor"](100))
+    with pytest.raises(Exb200Error) as e:
+        Sampler(m)
+    assert e.value.status == -2
+
+
+@pytest.mark.slow
+def test_rldata500_posterior_f1():
+    """README run (100 samples, thin 10, burn-in 1000): smp_clusters pairwise F1 0.98 +- one pair
+    (README.md:137-138; reference over 7 seeds: 0.97-0.99), K around 450."""
+    m, ident = readme_model("rldata500")
+    fit = run_inference(m, n_samples=100, thin_interval=10, burnin_interval=1000, seed=5)
+    pm = pairwise_measures(ident, clusters_to_membership(smp_clusters(fit.history["links"]), 500))
+    assert 0.96 <= pm["f1score"] <= 1.0 and pm["tp"] >= 48
+    assert abs(fit.history["n_linked_ents"].mean() - 449.65) < 1.5
