@@ -217,6 +217,7 @@ def load_library(path: str | None = None):
     lib.exb200_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(CHistory),
                                C.c_void_p, C.c_void_p, C.c_void_p]
     lib.exb200_sweeps.argtypes = [H, C.c_int32]
+    lib.exb200_sweeps_timed.argtypes = [H, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.exb200_get_state.argtypes = [H, C.POINTER(CState)]
     lib.exb200_get_stats.argtypes = [H, C.POINTER(CStats)]
     lib.exb200_link_conditional.argtypes = [H, C.c_int32, C.c_int32, c_i32p, c_f64p, c_f64p]
@@ -225,13 +226,53 @@ def load_library(path: str | None = None):
     lib.exb200_destroy.restype = None
     lib.exb200_last_error.argtypes = [H]
     lib.exb200_last_error.restype = C.c_char_p
+    lib.exb200_neighbours_create.argtypes = [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
+                                             C.POINTER(H)]
+    lib.exb200_neighbours_nnz.argtypes = [H]
+    lib.exb200_neighbours_nnz.restype = C.c_int64
+    lib.exb200_neighbours_get.argtypes = [H, c_i64p, c_i32p, c_f64p, c_f64p]
+    lib.exb200_neighbours_destroy.argtypes = [H]
+    lib.exb200_neighbours_destroy.restype = None
     if path is None:
         _LIB = lib
     return lib
 
 
+def levenshtein_neighbours(domain, threshold: int, include_self: bool = False, device: int = 0):
+    """Thresholded-Levenshtein neighbourhoods of a domain of (ASCII) strings on the GPU: the
+    ``close_values`` / ``max_exp_factor`` slots that ``compute_close_values`` builds
+    (R/AttributeIndex.R:117-137).  Returns ``(row_ptr, val_ids, probs, max_exp_factor)``."""
+    lib = load_library()
+    n = len(domain)
+    chars = np.zeros((n, 32), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int32)
+    for i, s in enumerate(domain):
+        b = s.encode("latin-1", errors="replace")
+        if len(b) > 31:
+            raise ValueError("strings longer than 31 bytes are not supported by the GPU neighbourhood builder")
+        lens[i] = len(b)
+        chars[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    h = C.c_void_p()
+    rc = lib.exb200_neighbours_create(chars.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(c_i32p), n,
+                                      int(threshold), int(include_self), device, C.byref(h))
+    if rc != EXB200_OK:
+        raise Exb200Error(rc, lib.exb200_last_error(None).decode())
+    try:
+        nnz = lib.exb200_neighbours_nnz(h)
+        row_ptr = np.zeros(n + 1, np.int64)
+        cols = np.zeros(nnz, np.int32)
+        probs = np.zeros(nnz)
+        mef = np.zeros(n)
+        lib.exb200_neighbours_get(h, row_ptr.ctypes.data_as(c_i64p), cols.ctypes.data_as(c_i32p),
+                                  probs.ctypes.data_as(c_f64p), mef.ctypes.data_as(c_f64p))
+    finally:
+        lib.exb200_neighbours_destroy(h)
+    return row_ptr, cols, probs, mef
+
+
 EXPORTED_SYMBOLS = [
-    "exb200_abi_version", "exb200_device_count", "exb200_create", "exb200_run", "exb200_sweeps",
+    "exb200_abi_version", "exb200_device_count", "exb200_create", "exb200_run", "exb200_sweeps", "exb200_sweeps_timed",
     "exb200_get_state", "exb200_get_stats", "exb200_link_conditional", "exb200_set_option",
-    "exb200_destroy", "exb200_last_error",
+    "exb200_destroy", "exb200_last_error", "exb200_neighbours_create", "exb200_neighbours_nnz",
+    "exb200_neighbours_get", "exb200_neighbours_destroy",
 ]

@@ -36,6 +36,7 @@ struct DevAttr {
   const double *mef;                       // max_exp_factor (all 1 for a constant attribute)
   const int *row, *col;                    // inverted neighbourhood CSR: row w -> entity values v, ascending
   const double *p, *logp;                  // p(w | v) and its log
+  const double *cs;                        // per row: inclusive prefix sums of phi(v) mef(v) p(w|v)
   const double *g;                         // [(NMAX_FAST+1)][D]  phi(v) / (1-psi(v))^n
   const double *aprob; const int *aalias;  // alias tables of g_n, same shape
   const double *pprob; const int *palias;  // alias table of psi

@@ -12,6 +12,7 @@
 
 #include "hostmath.hpp"
 #include "kernels.cuh"
+#include "neighbours.cuh"
 
 using namespace exb;
 
@@ -56,6 +57,7 @@ struct exb200_handle {
   int* d_bsum = nullptr; size_t bsum_cap = 0;
   unsigned long long* d_cl_counts = nullptr;
   double* d_theta = nullptr;
+  uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
   uint32_t round_ctr = 1;
   int opt_check = 0;
   int bucket_cap = 1 << 15, cand_cap = CAND_SMEM;
@@ -63,6 +65,7 @@ struct exb200_handle {
   cudaEvent_t ev[10]{};
   std::string err;
   bool poisoned = false;
+  long long n_launches = 0; // kernels launched by this handle
 };
 
 namespace {
@@ -96,6 +99,12 @@ template <class T> int upload(exb200_handle* h, T** p, const T* src, size_t n) {
   if (n) CK(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   return EXB200_OK;
 }
+#define KLAUNCH(h, kern, grid, block, smem, ...)                      \
+  do {                                                                 \
+    kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);       \
+    (h)->n_launches++;                                                 \
+  } while (0)
+
 inline int nblk(long long n, int tpb = TPB) { return (int)std::max<long long>(1, (n + tpb - 1) / tpb); }
 
 // exclusive prefix sum on the handle's stream
@@ -106,9 +115,9 @@ template <class T_IN> int scan_exclusive(exb200_handle* h, const T_IN* in, int* 
     if (rc) return rc;
     h->bsum_cap = (size_t)nb * 2;
   }
-  k_scan_reduce<T_IN><<<nb, TPB, 0, h->stream>>>(in, n, h->d_bsum);
-  k_scan_top<<<1, 1024, 0, h->stream>>>(h->d_bsum, nb);
-  k_scan_apply<T_IN><<<nb, TPB, 0, h->stream>>>(in, out, n, h->d_bsum);
+  KLAUNCH(h, k_scan_reduce<T_IN>, nb, TPB, 0, in, n, h->d_bsum);
+  KLAUNCH(h, k_scan_top, 1, 1024, 0, h->d_bsum, nb);
+  KLAUNCH(h, k_scan_apply<T_IN>, nb, TPB, 0, in, out, n, h->d_bsum);
   return EXB200_OK;
 }
 
@@ -168,7 +177,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
   }
   // inverted neighbourhood CSR (attribute_index.cpp:125-140)
   std::vector<int> row(D + 1, 0), col;
-  std::vector<double> p, logp;
+  std::vector<double> p, logp, cs;
   if (!ha.is_const) {
     const int64_t nnz = in.close_row_ptr[D];
     if (nnz >= (int64_t)std::numeric_limits<int>::max())
@@ -186,6 +195,14 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
         const int q = cur[in.close_val_ids[j]]++;
         col[q] = v; p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
       }
+  }
+  cs.resize(p.size());
+  for (int w = 0; w < D && !ha.is_const; w++) {
+    double c = 0.0;
+    for (int j = row[w]; j < row[w + 1]; j++) {
+      c += ha.phi[col[j]] * ha.mef[col[j]] * p[j];
+      cs[j] = c;
+    }
   }
   for (int w = 0; w < D; w++) {
     double e;
@@ -218,7 +235,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
 #define UPD(field, vec) rc = upload(h, &dp, (vec).data(), (vec).size()); if (rc) return rc; da.field = dp;
 #define UPI(field, vec) rc = upload(h, &ip, (vec).data(), (vec).size()); if (rc) return rc; da.field = ip;
   UPD(psi, ha.psi) UPD(phi, ha.phi) UPD(om, om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi)
-  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp)
+  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp) UPD(cs, cs)
   UPD(g, g) UPD(aprob, aprob) UPI(aalias, aalias) UPD(pprob, pprob) UPI(palias, palias)
 #undef UPD
 #undef UPI
@@ -231,7 +248,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
 int upload_theta(exb200_handle* h) {
   CK(cudaMemcpyAsync(h->d_theta, h->theta.data(), sizeof(double) * h->F * h->A, cudaMemcpyHostToDevice, h->stream));
   for (int a = 0; a < h->A; a++)
-    k_theta_tables<<<nblk((long long)h->F * h->attrs[a].D), TPB, 0, h->stream>>>(h->S, a);
+    KLAUNCH(h, k_theta_tables, nblk((long long)h->F * h->attrs[a].D), TPB, 0, h->S, a);
   return EXB200_OK;
 }
 
@@ -246,7 +263,7 @@ int update_clust(exb200_handle* h) {
   unsigned long long cnt[2] = {0, 0};
   if (py || has_k) {
     CK(cudaMemsetAsync(h->d_cl_counts, 0, sizeof cnt, h->stream));
-    k_clust_counts<<<nblk(std::max(N, K)), TPB, 0, h->stream>>>(h->S, K, py ? 1 : 0, (has_d || has_k) ? 1 : 0,
+    KLAUNCH(h, k_clust_counts, nblk(std::max(N, K)), TPB, 0, h->S, K, py ? 1 : 0, (has_d || has_k) ? 1 : 0,
                                                                  h->d_cl_counts);
     CK(cudaMemcpyAsync(cnt, h->d_cl_counts, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -296,7 +313,7 @@ int update_links(exb200_handle* h) {
   CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
   CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
   CK(cudaEventRecord(h->ev[1], st));
-  k_prep<<<nblk(N), TPB, 0, st>>>(S);
+  KLAUNCH(h, k_prep, nblk(N), TPB, 0, S);
   std::vector<int> usage(AA);
   CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * AA, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[2], st));
@@ -312,15 +329,15 @@ int update_links(exb200_handle* h) {
   h->stats.n_tables = (int)active.size();
   if (!active.empty()) {
     CK(cudaMemcpyAsync(h->d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, st));
-    k_index_count<<<nblk(2LL * N), TPB, 0, st>>>(S, h->d_active, (int)active.size());
+    KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)active.size());
     for (int t : active) {
       int rc = scan_exclusive<int>(h, h->tables[t].d.ptr, h->tables[t].d.ptr, (int)h->tables[t].d.B);
       if (rc) return rc;
     }
-    k_index_fill<<<nblk(2LL * N), TPB, 0, st>>>(S, h->d_active, (int)active.size());
+    KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)active.size());
   }
   CK(cudaEventRecord(h->ev[3], st));
-  k_cand<<<nblk((long long)N, TPB / 32), TPB, 0, st>>>(S);
+  KLAUNCH(h, k_cand, nblk((long long)N, TPB / 32), TPB, 0, S);
   CK(cudaEventRecord(h->ev[4], st));
 
   // dependency rounds
@@ -338,12 +355,12 @@ int update_links(exb200_handle* h) {
     }
     const int init[3] = {0, 0x7FFFFFFF, -1}; // C_NACT_OUT, C_MIN_ACTIVE, C_WIDE_READY
     CK(cudaMemcpyAsync(S.counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_reserve<<<nblk(n_act), TPB, 0, st>>>(S, act, n_act, round);
+    KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
     if (S.use_kbounds) {
       int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
       rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
     }
-    k_commit<<<nblk(n_act), TPB, 0, st>>>(S, act, n_act, round);
+    KLAUNCH(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int* next_act = S.act_out;
@@ -352,11 +369,11 @@ int update_links(exb200_handle* h) {
     if (hc[C_WIDE_READY] >= 0) {
       // serial path for a record without a stored candidate list
       const int w = hc[C_WIDE_READY];
-      k_eval_all<<<nblk(2LL * N), TPB, 0, st>>>(S, w, 2 * N);
-      k_wide_commit<<<1, 1024, 0, st>>>(S, w);
+      KLAUNCH(h, k_eval_all, nblk(2LL * N), TPB, 0, S, w, 2 * N);
+      KLAUNCH(h, k_wide_commit, 1, 1024, 0, S, w);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
-      k_compact_active<<<nblk(n_next), TPB, 0, st>>>(S, next_act, n_next);
+      KLAUNCH(h, k_compact_active, nblk(n_next), TPB, 0, S, next_act, n_next);
       CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       next_act = S.act_out;
@@ -374,7 +391,7 @@ int update_links(exb200_handle* h) {
   // rename entities to their smallest member; slots [0,N) of the next arrays become current
   const int zero = 0;
   CK(cudaMemcpyAsync(S.counters + C_K, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
-  k_canon<<<nblk(N), TPB, 0, st>>>(S);
+  KLAUNCH(h, k_canon, nblk(N), TPB, 0, S);
   std::swap(S.ent_size, S.ent_size_nx);
   std::swap(S.ent_head, S.ent_head_nx);
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -436,14 +453,15 @@ int sweep(exb200_handle* h) {
   int rc = update_clust(h); if (rc) return rc;          // clust_params_->update(links_)
   refresh_clust_dev(h);
   rc = update_links(h); if (rc) return rc;              // links_.update(...)
-  k_entities<<<nblk(N), TPB, 0, st>>>(S);               // ents_.update_attributes(...)
+  KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_mask);   // ents_.update_attributes(...)
+  KLAUNCH(h, k_entities_general, nblk((N + 31) / 32, TPB / 32), TPB, 0, S, h->d_gen_mask);
   // ents_.update_distributions(), cache_.update(): phi is fixed (no Dirichlet prior) -> nothing to do
   // distort_dist_concs_.update(): concentration is infinite -> nothing to do
   CK(cudaEventRecord(h->ev[7], st));
   CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
   CK(cudaMemsetAsync(S.corr, 0, sizeof(int) * FA, st));
   const int use_smem = 2 * FA * (int)sizeof(int) <= 32768;
-  k_distort<<<nblk(N), TPB, use_smem ? 2 * FA * sizeof(int) : 0, st>>>(S, use_smem); // recs_.update_distortion
+  KLAUNCH(h, k_distort, nblk(N), TPB, use_smem ? 2 * FA * sizeof(int) : 0, S, use_smem); // recs_.update_distortion
   CK(cudaMemcpyAsync(h->ndist.data(), S.ndist, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h->corr.data(), S.corr, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[8], st));
@@ -611,6 +629,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.corr, (size_t)F * A));
   TRY(dalloc(h, &h->d_active, (size_t)A * A));
   TRY(dalloc(h, &h->d_cl_counts, 2));
+  TRY(dalloc(h, &h->d_gen_mask, (size_t)N));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
   cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);
@@ -666,6 +685,31 @@ int exb200_sweeps(exb200_handle* h, int32_t n_sweeps) {
     if (rc) return rc;
   }
   return EXB200_OK;
+}
+
+int exb200_sweeps_timed(exb200_handle* h, int32_t n_sweeps, float* device_ms, int64_t* launches) {
+  if (!h) return EXB200_ERR_INVALID;
+  if (h->poisoned) return fail(h, EXB200_ERR_CUDA, "handle unusable after an earlier error: " + h->err);
+  cudaSetDevice(h->device);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const long long l0 = h->n_launches;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventRecord(e0, h->stream));
+  int rc = EXB200_OK;
+  for (int i = 0; i < n_sweeps && !rc; i++) rc = sweep(h);
+  if (!rc) {
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (device_ms) *device_ms = ms;
+    if (launches) *launches = h->n_launches - l0;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin, exb200_history* out,
@@ -754,7 +798,7 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
   const int N = h->N;
   refresh_clust_dev(h);
   h->S.iter = (uint32_t)h->iteration;
-  k_eval_all<<<nblk(N), TPB, 0, h->stream>>>(h->S, rid, N); // between sweeps only slots [0,N) are live
+  KLAUNCH(h, k_eval_all, nblk(N), TPB, 0, h->S, rid, N); // between sweeps only slots [0,N) are live
   std::vector<double> lw(N);
   std::vector<int> x(h->RS);
   uint32_t zm = 0;
@@ -792,5 +836,93 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
   *log_weight_new = std::log(pn) + L;
   return n;
 }
+
+} // extern "C"
+
+// =============================================================================================
+// value neighbourhoods (one-off model preparation; R/AttributeIndex.R:117-137)
+struct exb200_neighbours {
+  std::vector<int64_t> row_ptr;
+  std::vector<int32_t> cols;
+  std::vector<double> probs, mef;
+};
+
+extern "C" {
+
+int exb200_neighbours_create(const uint8_t* chars, const int32_t* lens, int32_t n, int32_t threshold,
+                             int32_t include_self, int device, exb200_neighbours** out) {
+  if (!chars || !lens || !out || n < 1 || threshold < 0 || threshold > 8)
+    return fail(nullptr, EXB200_ERR_INVALID, "neighbours: bad arguments (threshold must be an integer in [0, 8])");
+  for (int i = 0; i < n; i++)
+    if (lens[i] < 0 || lens[i] >= NB_STRIDE) return fail(nullptr, EXB200_ERR_INVALID, "neighbours: strings must be shorter than 32 bytes");
+  if (exb200_device_count() <= 0) return fail(nullptr, EXB200_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EXB200_ERR_NO_DEVICE, "cudaSetDevice failed");
+  uint8_t *d_str = nullptr, *d_dist = nullptr;
+  int *d_len = nullptr, *d_cnt = nullptr, *d_col = nullptr;
+  long long* d_row = nullptr;
+  auto cleanup = [&]() { cudaFree(d_str); cudaFree(d_dist); cudaFree(d_len); cudaFree(d_cnt); cudaFree(d_col); cudaFree(d_row); };
+#define NCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(nullptr, EXB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+  NCK(cudaMalloc(&d_str, (size_t)n * NB_STRIDE));
+  NCK(cudaMalloc(&d_len, sizeof(int) * (size_t)n));
+  NCK(cudaMalloc(&d_cnt, sizeof(int) * (size_t)n));
+  NCK(cudaMalloc(&d_row, sizeof(long long) * ((size_t)n + 1)));
+  NCK(cudaMemcpy(d_str, chars, (size_t)n * NB_STRIDE, cudaMemcpyHostToDevice));
+  NCK(cudaMemcpy(d_len, lens, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  const int nb = (n + NB_TILE - 1) / NB_TILE;
+  k_neighbours<<<nb, NB_TILE>>>(d_str, d_len, n, threshold, include_self, 0, d_cnt, nullptr, nullptr, nullptr);
+  std::vector<int> cnt(n);
+  NCK(cudaMemcpy(cnt.data(), d_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+  exb200_neighbours* r = new exb200_neighbours();
+  r->row_ptr.assign((size_t)n + 1, 0);
+  for (int i = 0; i < n; i++) r->row_ptr[i + 1] = r->row_ptr[i] + cnt[i];
+  const int64_t nnz = r->row_ptr[n];
+  std::vector<uint8_t> dist((size_t)nnz);
+  r->cols.resize((size_t)nnz);
+  if (nnz > 0) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "row pointer width");
+    cudaError_t e1 = cudaMalloc(&d_col, sizeof(int) * (size_t)nnz), e2 = cudaMalloc(&d_dist, (size_t)nnz);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { delete r; cleanup(); return fail(nullptr, EXB200_ERR_OOM, "neighbours: out of device memory"); }
+    cudaMemcpy(d_row, r->row_ptr.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice);
+    k_neighbours<<<nb, NB_TILE>>>(d_str, d_len, n, threshold, include_self, 1, nullptr, d_row, d_col, d_dist);
+    cudaError_t e3 = cudaMemcpy(r->cols.data(), d_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost);
+    cudaError_t e4 = cudaMemcpy(dist.data(), d_dist, (size_t)nnz, cudaMemcpyDeviceToHost);
+    if (e3 != cudaSuccess || e4 != cudaSuccess) { delete r; cleanup(); return fail(nullptr, EXB200_ERR_CUDA, std::string("neighbours: ") + cudaGetErrorString(e3 != cudaSuccess ? e3 : e4)); }
+  }
+  cleanup();
+#undef NCK
+  // probabilities exp(-d) / sum and max_exp_factor = exp(-0.5 min_d / max_d) (AttributeIndex.R:128-135)
+  r->probs.resize((size_t)nnz);
+  r->mef.assign((size_t)n, 0.0);
+  double max_d = 0.0;
+  bool any = false;
+  for (int64_t j = 0; j < nnz; j++) { max_d = std::max(max_d, (double)dist[j]); any = true; }
+  (void)any;
+  for (int i = 0; i < n; i++) {
+    double sum = 0.0, min_d = std::numeric_limits<double>::infinity();
+    for (int64_t j = r->row_ptr[i]; j < r->row_ptr[i + 1]; j++) {
+      r->probs[j] = std::exp(-(double)dist[j]);
+      sum += r->probs[j];
+      min_d = std::min(min_d, (double)dist[j]);
+    }
+    for (int64_t j = r->row_ptr[i]; j < r->row_ptr[i + 1]; j++) r->probs[j] /= sum;
+    r->mef[i] = std::isfinite(min_d) ? std::exp(-0.5 * min_d / max_d) : 0.0;
+  }
+  *out = r;
+  return EXB200_OK;
+}
+
+int64_t exb200_neighbours_nnz(const exb200_neighbours* nb) { return nb ? (int64_t)nb->cols.size() : -1; }
+
+int exb200_neighbours_get(const exb200_neighbours* nb, int64_t* row_ptr, int32_t* val_ids, double* probs,
+                          double* max_exp_factor) {
+  if (!nb) return EXB200_ERR_INVALID;
+  if (row_ptr) std::memcpy(row_ptr, nb->row_ptr.data(), sizeof(int64_t) * nb->row_ptr.size());
+  if (val_ids) std::memcpy(val_ids, nb->cols.data(), sizeof(int32_t) * nb->cols.size());
+  if (probs) std::memcpy(probs, nb->probs.data(), sizeof(double) * nb->probs.size());
+  if (max_exp_factor) std::memcpy(max_exp_factor, nb->mef.data(), sizeof(double) * nb->mef.size());
+  return EXB200_OK;
+}
+
+void exb200_neighbours_destroy(exb200_neighbours* nb) { delete nb; }
 
 } // extern "C"

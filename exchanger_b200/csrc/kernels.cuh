@@ -334,7 +334,10 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
           if (item != S.N + r) {
             const int* y = S.ent_y + (size_t)item * S.ES;
             ok = item_compatible(S, x, zm, y);
-            if (ok) ll = item_loglik(S, x, zm, y);
+            if (ok) {
+              ll = item_loglik(S, x, zm, y);
+              ok = ll > -CUDART_INF; // zero weight whatever its size: never chosen, adds 0 to every sum
+            }
           }
         }
         const unsigned m = __ballot_sync(FULL, ok);
@@ -789,45 +792,135 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
     return first;
   }
 
-  // general scheme: explicit support, inverse CDF in support order.  Support: the whole domain
-  // for a constant attribute (entities.cpp:315-329); the first observed member value and its
-  // neighbourhood otherwise (a subset of entities.cpp:361-383 that holds all the mass)
-  const int lo = t.is_const ? 0 : t.row[first], hi = t.is_const ? t.D : t.row[first + 1];
-  const int ns = t.is_const ? t.D : 1 + (hi - lo);
-  double m = -CUDART_INF;
-  for (int j = 0; j < ns; j++) {
-    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
-    if (!t.is_const && j > 0 && v == first) continue;
-    const double lw = log_weight_entity_value(S, t, a, v, head);
-    m = lw > m ? lw : m;
+  if (!t.is_const && t.exclude && nobs == 1) {
+    // one observed member value x (singletons above all): every v != x has weight
+    // theta phi(v) mef(v) p(x|v) whose row sums are static, so drawEntityValueIndex
+    // (entities.cpp:351-431) reduces to "keep x" versus a search in the row's prefix sums
+    double th = 0.0;
+    for (int r = head; r >= 0; r = S.rec_next[r]) {
+      const int* x = S.rec_x + (size_t)r * S.RS;
+      if (x[a] >= 0) th = S.theta[x[S.RS - 1] * S.A + a];
+    }
+    const int lo = t.row[first], hi = t.row[first + 1];
+    const double wx = t.phi[first] * (1.0 - th * t.mef[first]);
+    const double rsum = hi > lo ? t.cs[hi - 1] : 0.0;
+    const double total = wx + th * rsum;
+    if (!(total > 0.0) || !isfinite(total)) { dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
+    const double tt = u0.a * total;
+    if (tt < wx || hi == lo) return first;
+    const double t2 = tt - wx;
+    int a0 = lo, b0 = hi; // first j with t2 < th * cs[j]
+    while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t2 < th * t.cs[mid]) b0 = mid; else a0 = mid + 1; }
+    if (a0 == hi) { // rounding: the first entry that reaches the row total
+      a0 = lo; b0 = hi - 1;
+      while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t.cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
+    }
+    return t.col[a0];
   }
-  if (!(m > -CUDART_INF)) { dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
-  double total = 0.0;
-  for (int j = 0; j < ns; j++) {
-    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
-    if (!t.is_const && j > 0 && v == first) continue;
-    total += exp(log_weight_entity_value(S, t, a, v, head) - m);
-  }
-  const double tt = u0.a * total;
-  double c = 0.0;
-  int lastpos = first;
-  for (int j = 0; j < ns; j++) {
-    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
-    if (!t.is_const && j > 0 && v == first) continue;
-    const double w = exp(log_weight_entity_value(S, t, a, v, head) - m);
-    if (w > 0.0) lastpos = v;
-    c += w;
-    if (tt < c) return v;
-  }
-  return lastpos;
+
+  return -1; // general scheme: left to the warp-cooperative kernel below
 }
 
-__global__ void __launch_bounds__(TPB) k_entities(DevState S) {
+// General scheme, one WARP per (entity, attribute): explicit support - the whole domain for a
+// constant attribute (entities.cpp:315-329), else the first observed member value followed by its
+// neighbourhood row (a subset of entities.cpp:361-383 that holds all the mass).  Lanes take
+// consecutive support entries; weights exp(lw - max) are summed per chunk of 32 with the warp's
+// shuffle scan and chunk totals sequentially - the oracle uses the same association order.
+__device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head) {
+  const DevAttr& t = S.attrs[a];
+  const int lane = threadIdx.x & 31;
+  int first = -1;
+  for (int r = head; r >= 0 && first < 0; r = S.rec_next[r]) {
+    const int xv = S.rec_x[(size_t)r * S.RS + a];
+    if (xv >= 0) first = xv;
+  }
+  const int lo = t.is_const ? 0 : t.row[first];
+  const int ns = t.is_const ? t.D : 1 + (t.row[first + 1] - lo);
+  const int nchunk = (ns + 31) >> 5;
+  auto weight_log = [&](int j) -> double {
+    if (j >= ns) return -CUDART_INF;
+    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
+    if (!t.is_const && j > 0 && v == first) return -CUDART_INF;
+    return log_weight_entity_value(S, t, a, v, head);
+  };
+  double m = -CUDART_INF;
+  for (int c = 0; c < nchunk; c++) {
+    const double lw = weight_log(32 * c + lane);
+    m = lw > m ? lw : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m, o); m = y > m ? y : m; }
+  if (!(m > -CUDART_INF)) { if (lane == 0) dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
+  double total = 0.0;
+  for (int c = 0; c < nchunk; c++) {
+    const double lw = weight_log(32 * c + lane);
+    double x = lw > -CUDART_INF ? exp(lw - m) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
+    total += __shfl_sync(FULL, x, 31);
+  }
+  const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
+  const double tt = u0.a * total;
+  double run = 0.0;
+  int lastpos = -1;
+  for (int c = 0; c < nchunk; c++) {
+    const int j = 32 * c + lane;
+    const double lw = weight_log(j);
+    const double w = lw > -CUDART_INF ? exp(lw - m) : 0.0;
+    double x = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
+    const double tc = __shfl_sync(FULL, x, 31);
+    const unsigned pos = __ballot_sync(FULL, w > 0.0);
+    if (pos) lastpos = 32 * c + (31 - __clz(pos));
+    if (tt < run + tc) {
+      const unsigned hit = __ballot_sync(FULL, j < ns && tt < run + x);
+      if (hit) {
+        const int jj = 32 * c + (__ffs(hit) - 1);
+        return t.is_const ? jj : (jj == 0 ? first : t.col[lo + jj - 1]);
+      }
+    }
+    run += tc;
+  }
+  if (lastpos < 0) return first;
+  return t.is_const ? lastpos : (lastpos == 0 ? first : t.col[lo + lastpos - 1]);
+}
+
+__global__ void __launch_bounds__(TPB) k_entities(DevState S, uint32_t* __restrict__ gen_mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= S.N || S.ent_size[e] <= 0) return;
-  const int head = S.ent_head[e];
-  int* y = S.ent_y + (size_t)e * S.ES;
-  for (int a = 0; a < S.A; a++) y[a] = draw_entity_value(S, e, a, head);
+  if (e >= S.N) return;
+  uint32_t need = 0;
+  if (S.ent_size[e] > 0) {
+    const int head = S.ent_head[e];
+    int* y = S.ent_y + (size_t)e * S.ES;
+    for (int a = 0; a < S.A; a++) {
+      const int v = draw_entity_value(S, e, a, head);
+      if (v >= 0) y[a] = v; else need |= 1u << a;
+    }
+  }
+  gen_mask[e] = need;
+}
+
+// one warp per 32 entity slots: the (entity, attribute) pairs flagged by k_entities
+__global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const uint32_t* __restrict__ gen_mask) {
+  const int lane = threadIdx.x & 31;
+  const int base = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32;
+  if (base >= S.N) return;
+  const uint32_t mine = base + lane < S.N ? gen_mask[base + lane] : 0u;
+  unsigned todo = __ballot_sync(FULL, mine != 0u);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int e = base + src;
+    uint32_t mask = __shfl_sync(FULL, mine, src);
+    const int head = S.ent_head[e];
+    while (mask) {
+      const int a = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int v = draw_entity_value_warp(S, e, a, head);
+      if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

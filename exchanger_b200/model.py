@@ -523,3 +523,48 @@ def model_with_state(model: ExchangERModel, state: dict) -> ExchangERModel:
         cp.m, cp.kappa = float(cl["m"]), float(cl["kappa"])
     out.clust_params = cp
     return out
+
+
+def exchanger_coded(codes: np.ndarray, domains: Sequence[Sequence[str]], attr_names: Sequence[str],
+                    attr_params: Sequence[Attribute], clust_prior, file_ids: np.ndarray | None = None,
+                    neighbours: Mapping[str, tuple] | None = None, na_fill_seed: int = 0
+                    ) -> ExchangERModel:
+    """``exchanger()`` for data that is already integer coded (at 10 M rows
+    R's ``factor`` / ``data.matrix`` path, R/ExchangERModel.R:306-311, is the slow part of model
+    construction).  ``codes`` is ``[A, N]`` with 0-based level codes and negative = NA; attributes
+    must already be ordered categorical first.  Everything else follows ``exchanger()``:
+    singleton initial links, prior-mean hyper-parameters, NA entity values drawn from the
+    empirical pmf."""
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    A, N = codes.shape
+    if N < 2:
+        raise ValueError("data must contain at least two records for ER to be feasible")
+    if any(not s.categorical for s in attr_params[:sum(s.categorical for s in attr_params)]):
+        raise ValueError("categorical attributes must come first")
+    if isinstance(clust_prior, GeneralizedCouponRP) and not _is_rv(clust_prior.m) and clust_prior.m < N:
+        raise ValueError("Coupon collecting parameter m < n_records is currently not supported.")
+    rec_attrs = np.where(codes < 0, NA_INT, codes).astype(np.int32)
+    indices = []
+    for a, (name, spec) in enumerate(zip(attr_names, attr_params)):
+        nb = None if neighbours is None else neighbours.get(name)
+        indices.append(build_attribute_index(rec_attrs[a], domains[a], None if spec.categorical else spec.dist_fn,
+                                             spec.exclude_entity_value, nb))
+    theta0 = np.array([s.distort_prob_prior.mean() if isinstance(s.distort_prob_prior, BetaRV)
+                       else float(s.distort_prob_prior) for s in attr_params])
+    if file_ids is None:
+        file_ids = np.zeros(N, np.int32)
+    n_files = int(file_ids.max()) + 1
+    ent_attrs = rec_attrs.copy()
+    rng = np.random.default_rng(na_fill_seed)
+    for a, idx in enumerate(indices):
+        if idx.n_missing > 0:
+            miss = ent_attrs[a] < 0
+            ent_attrs[a, miss] = rng.choice(len(idx.probs), size=int(miss.sum()), p=idx.probs)
+    ids = np.arange(N, dtype=np.int32)
+    return ExchangERModel(
+        iteration=0, attr_names=list(attr_names), attr_params=list(attr_params),
+        file_ids=np.asarray(file_ids, np.int32), file_levels=list(range(n_files)), rec_ids=None,
+        rec_attrs=rec_attrs, rec_distortions=np.zeros((A, N), np.int32), ent_attrs=ent_attrs,
+        ent_ids=ids.copy(), links=ids.copy(), distort_probs=np.tile(theta0, (n_files, 1)),
+        distort_dist_concs=np.array([s.distort_dist_prior.mean_alpha() for s in attr_params]),
+        clust_params=clust_params_from_prior(clust_prior, N), clust_prior=clust_prior, attr_indices=indices)

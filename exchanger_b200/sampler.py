@@ -42,6 +42,13 @@ class Sampler:
         """``n`` applications of State::update() (src/state.h:60-75), nothing copied back."""
         self._check(self.lib.exb200_sweeps(self.h, int(n)))
 
+    def sweeps_timed(self, n: int):
+        """``n`` sweeps; returns (device milliseconds from CUDA events on the library's stream,
+        kernels launched)."""
+        ms, nl = C.c_float(), C.c_int64()
+        self._check(self.lib.exb200_sweeps_timed(self.h, int(n), C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
     def run(self, n_samples: int, thin_interval: int = 1, burnin_interval: int = 0) -> dict:
         """The sampling loop of ``sample()`` (src/sample.cpp:171-202) into fresh host arrays."""
         N, FA, A = self.N, self.F * self.A, self.A

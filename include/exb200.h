@@ -192,6 +192,10 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin_interval,
    (device-resident timing; state.h:60-75). */
 int exb200_sweeps(exb200_handle* h, int32_t n_sweeps);
 
+/* exb200_sweeps bracketed by CUDA events on the library's own stream (torch.cuda.Event only sees
+   torch's streams): elapsed device milliseconds and the number of kernels launched. */
+int exb200_sweeps_timed(exb200_handle* h, int32_t n_sweeps, float* device_ms, int64_t* launches);
+
 /* Copy the current state to the caller (buildFinalS4State, sample.cpp:14-63). */
 int exb200_get_state(exb200_handle* h, exb200_state* out);
 
@@ -213,6 +217,24 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
 int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
 
 void exb200_destroy(exb200_handle* h);
+
+/*
+ * One-off model preparation on the GPU: the value neighbourhoods of a string attribute under
+ * transform_dist_fn(Levenshtein(), threshold) - what compute_close_values builds in R
+ * (R/AttributeIndex.R:117-137; the result fills exb200_attr.close_* and max_exp_factor).
+ * `chars` holds n strings of at most 31 bytes each, packed with a stride of 32 bytes;
+ * distances are unit-cost edit distances over bytes; pairs farther apart than `threshold`
+ * (an integer, <= 8) are not neighbours; a value is its own neighbour only if include_self
+ * (i.e. exclude_entity_value = FALSE).  Not part of the sweep.
+ */
+typedef struct exb200_neighbours exb200_neighbours;
+int exb200_neighbours_create(const uint8_t* chars, const int32_t* lens, int32_t n, int32_t threshold,
+                             int32_t include_self, int device, exb200_neighbours** out);
+int64_t exb200_neighbours_nnz(const exb200_neighbours* nb);
+/* row_ptr [n+1], val_ids [nnz], probs [nnz] (exp(-d) normalised per row), max_exp_factor [n] */
+int exb200_neighbours_get(const exb200_neighbours* nb, int64_t* row_ptr, int32_t* val_ids, double* probs,
+                          double* max_exp_factor);
+void exb200_neighbours_destroy(exb200_neighbours* nb);
 
 /* Message of the last failing call on this handle (or of exb200_create when h is NULL). */
 const char* exb200_last_error(const exb200_handle* h);

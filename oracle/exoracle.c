@@ -132,6 +132,7 @@ typedef struct {
   double Z;                       /* sum_v phi/(1-psi) (attribute_index.cpp:26-34) */
   int64_t *row;                   /* inverted neighbourhood: row w -> (v, p(w|v)), v ascending */
   int *col; double *p, *logp;
+  double *cs;                     /* per row: inclusive prefix sums of phi(v) mef(v) p(w|v) */
   double *mef;                    /* max_exp_factor (1 for constant, attribute_index.cpp:49) */
   double **g; double G[NMAX_FAST + 1]; alias_t Tg[NMAX_FAST + 1]; /* phi/(1-psi)^n */
   alias_t Tpsi;
@@ -263,6 +264,14 @@ static int attr_refresh(attr_t *t) {
     }
     t->logE[w] = log(e);
   }
+  if (!t->is_const)
+    for (int w = 0; w < D; w++) {
+      double c = 0.0;
+      for (int64_t j = t->row[w]; j < t->row[w + 1]; j++) {
+        c += t->phi[t->col[j]] * t->mef[t->col[j]] * t->p[j];
+        t->cs[j] = c;
+      }
+    }
   for (int n = 0; n <= NMAX_FAST; n++) {
     if (t->Tg[n].prob) alias_free(&t->Tg[n]);
     double G = 0.0;
@@ -340,6 +349,7 @@ exo *exo_create(const exb200_model *m) {
       t->row = (int64_t *)calloc(D + 1, sizeof(int64_t));
       t->col = (int *)malloc(sizeof(int) * (nnz + 1)); t->p = (double *)malloc(sizeof(double) * (nnz + 1));
       t->logp = (double *)malloc(sizeof(double) * (nnz + 1));
+      t->cs = (double *)malloc(sizeof(double) * (nnz + 1));
       for (int64_t j = 0; j < nnz; j++) t->row[in->close_val_ids[j] + 1]++;
       for (int w = 0; w < D; w++) t->row[w + 1] += t->row[w];
       int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * D);
@@ -388,7 +398,7 @@ void exo_destroy(exo *s) {
   for (int a = 0; a < s->A; a++) {
     attr_t *t = &s->at[a];
     free(t->psi); free(t->phi); free(t->logpsi); free(t->log1mpsi); free(t->om); free(t->logphi);
-    free(t->logE); free(t->mef); free(t->row); free(t->col); free(t->p); free(t->logp);
+    free(t->logE); free(t->mef); free(t->row); free(t->col); free(t->p); free(t->logp); free(t->cs);
     for (int n = 0; n <= NMAX_FAST; n++) { free(t->g[n]); if (t->Tg[n].prob) alias_free(&t->Tg[n]); }
     free(t->g); if (t->Tpsi.prob) alias_free(&t->Tpsi);
   }
@@ -633,6 +643,16 @@ static void phase_canon(exo *s) {
 }
 
 /* ------------------------------------------------------------------ 3. entity attributes */
+/* inclusive scan of 32 values in the association order of a warp's shuffle scan:
+   for o = 1, 2, 4, 8, 16: x[i] += x[i - o] (all lanes at once) */
+static void ks_scan32(double x[32]) {
+  for (int o = 1; o < 32; o <<= 1) {
+    double y[32];
+    for (int i = 0; i < 32; i++) y[i] = i >= o ? x[i] + x[i - o] : x[i];
+    memcpy(x, y, sizeof y);
+  }
+}
+
 /* logWeightEntityValue for infinite concentration (entities.cpp:236-296) */
 static double log_weight_entity_value(const exo *s, int v, int a, const int *mem, int n) {
   const attr_t *t = &s->at[a];
@@ -710,40 +730,74 @@ static int draw_entity_value(exo *s, int e, int a, const int *mem, int n) {
     return first;
   }
 
-  /* general scheme: explicit support, inverse CDF in support order */
-  int ns; int *sup; int own_sup = 0;
-  if (t->is_const) { /* whole domain, entities.cpp:315-329 */
-    ns = t->D; sup = NULL;
-  } else { /* first observed member value and its neighbourhood: every other value has
-              p(x_first | v) = 0 (entities.cpp:361-383 builds a superset) */
+  if (!t->is_const && t->exclude && nobs == 1) {
+    /* one observed member value x (singletons above all): every v != x has weight
+       theta * phi(v) mef(v) p(x|v), whose row sums are static, so drawEntityValueIndex
+       (entities.cpp:351-431) reduces to "keep x" versus a search in the row's prefix sums */
+    double th = 0.0;
+    for (int i = 0; i < n; i++)
+      if (s->x[mem[i] * A + a] >= 0) th = s->theta[s->fid[mem[i]] * A + a];
     int64_t lo = t->row[first], hi = t->row[first + 1];
-    sup = (int *)malloc(sizeof(int) * (hi - lo + 1)); own_sup = 1;
-    ns = 0; sup[ns++] = first;
-    for (int64_t j = lo; j < hi; j++) if (t->col[j] != first) sup[ns++] = t->col[j];
+    double wx = t->phi[first] * (1.0 - th * t->mef[first]);
+    double rsum = hi > lo ? t->cs[hi - 1] : 0.0;
+    double total = wx + th * rsum;
+    if (!(total > 0.0) || !isfinite(total)) { set_err(s, e, "no valid entity values for attribute"); return first; }
+    double tt = u * total;
+    if (tt < wx || hi == lo) return first;
+    double t2 = tt - wx;
+    int64_t a0 = lo, b0 = hi; /* first j with t2 < th * cs[j] */
+    while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (t2 < th * t->cs[mid]) b0 = mid; else a0 = mid + 1; }
+    if (a0 == hi) { /* rounding: the first entry that reaches the row total */
+      a0 = lo; b0 = hi - 1;
+      while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (t->cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
+    }
+    return t->col[a0];
   }
+
+  /* general scheme: explicit support.  Constant attribute: the whole domain
+     (entities.cpp:315-329).  Otherwise the first observed member value followed by its
+     neighbourhood row - every other value has p(x_first | v) = 0 (entities.cpp:361-383 builds a
+     superset); a row entry equal to x_first (possible when the value is not excluded) gets
+     weight 0 so that it is not counted twice.
+     The weights exp(lw - max) are summed in chunks of 32 consecutive support entries with the
+     Kogge-Stone order of a warp scan (ks_scan32), chunk totals sequentially: the order the CUDA
+     kernel uses, so both sides round identically. */
+  int64_t lo = t->is_const ? 0 : t->row[first];
+  int ns = t->is_const ? t->D : 1 + (int)(t->row[first + 1] - lo);
   double *lw = (double *)malloc(sizeof(double) * ns), m = -INFINITY;
+  int *sup = (int *)malloc(sizeof(int) * ns);
   for (int j = 0; j < ns; j++) {
-    lw[j] = log_weight_entity_value(s, sup ? sup[j] : j, a, mem, n);
+    int v = t->is_const ? j : (j == 0 ? first : t->col[lo + j - 1]);
+    sup[j] = v;
+    lw[j] = (!t->is_const && j > 0 && v == first) ? -INFINITY : log_weight_entity_value(s, v, a, mem, n);
     if (lw[j] > m) m = lw[j];
   }
-  int pick = -1, lastpos = -1;
+  int pick = -1;
   if (!(m > -INFINITY)) {
     set_err(s, e, "no valid entity values for attribute");
     pick = 0;
   } else {
-    double total = 0.0;
-    for (int j = 0; j < ns; j++) total += exp(lw[j] - m);
-    double tt = u * total, c = 0.0;
-    for (int j = 0; j < ns; j++) {
-      double w = exp(lw[j] - m);
-      if (w > 0.0) lastpos = j;
-      c += w;
-      if (tt < c) { pick = j; break; }
+    int nchunk = (ns + 31) / 32;
+    double total = 0.0, sc[32];
+    for (int c = 0; c < nchunk; c++) {
+      for (int i = 0; i < 32; i++) sc[i] = 32 * c + i < ns ? exp(lw[32 * c + i] - m) : 0.0;
+      ks_scan32(sc);
+      total += sc[31];
     }
-    if (pick < 0) pick = lastpos;
+    double tt = u * total, run = 0.0;
+    for (int c = 0; c < nchunk && pick < 0; c++) {
+      for (int i = 0; i < 32; i++) sc[i] = 32 * c + i < ns ? exp(lw[32 * c + i] - m) : 0.0;
+      ks_scan32(sc);
+      if (tt < run + sc[31])
+        for (int i = 0; i < 32 && 32 * c + i < ns; i++)
+          if (tt < run + sc[i]) { pick = 32 * c + i; break; }
+      run += sc[31];
+    }
+    if (pick < 0)
+      for (int j = ns - 1; j >= 0; j--) if (exp(lw[j] - m) > 0.0) { pick = j; break; }
   }
-  int v = sup ? sup[pick] : pick;
-  free(lw); if (own_sup) free(sup);
+  int v = sup[pick];
+  free(lw); free(sup);
   return v;
 }
 
