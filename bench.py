@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the Gibbs sweep (BASELINE.json metric: Gibbs sweeps/s and record-link updates/s on
+synthetic RLdata-shaped records, 1-8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA sampler
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own C++ on host cores
+
+A step is one application of State::update() (src/state.h:60-75) to the whole record set.
+Prints ONE JSON line (rank 0).  With N > 1 GPUs every rank runs an independent chain on the same
+records (BASELINE config 5; no data-path collective) and `value` is the aggregate over chains.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (records, cluster prior, description)
+    "c3": (1_000_000, "pitman_yor", "synthetic 1M RLdata-shaped records, 5 attributes, Pitman-Yor prior"),
+    "c4": (10_000_000, "gen_coupon", "synthetic 10M RLdata-shaped records, 5 attributes, GeneralizedCoupon RP"),
+}
+A = 5
+DATA_SEED = 20260101
+CPU_SAMPLE_RECORDS = 20_000
+
+
+def clust_prior(kind: str, n: int):
+    from exchanger_b200 import BetaRV, GammaRV, GeneralizedCouponRP, PitmanYorRP
+    if kind == "pitman_yor":
+        return PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1))
+    return GeneralizedCouponRP(n, GammaRV(1, 1))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One chain of the reference's own State::update() (oracle/_ref) on the bounded sample."""
+    n_rec, kind, seed, burn, warm, steps = args
+    from checkers import RefSampler
+    from exchanger_b200.model import Levenshtein, compute_close_values, transform_dist_fn
+    from exchanger_b200.synthetic import synth_model
+
+    def pyn(dom, thr):
+        return compute_close_values(dom, transform_dist_fn(Levenshtein(), thr), False)
+
+    model, _ = synth_model(n_rec, clust_prior(kind, n_rec), seed=DATA_SEED, neighbour_fn=pyn)
+    ref = RefSampler(model, seed=seed)
+    ref.update(burn + warm)
+    t0 = time.perf_counter()
+    ref.update(steps)
+    return time.perf_counter() - t0
+
+
+def reference_throughput(kind: str, n_workload: int, steps: int, warmup: int, procs: int, burn: int = 12):
+    """sweeps/s of the reference CPU sampler, expressed at the workload size: the sample's
+    link-updates/s divided by the workload's record count (optimistic for the reference, whose
+    per-record cost grows with N)."""
+    import multiprocessing as mp
+    jobs = [(CPU_SAMPLE_RECORDS, kind, 100 + i, burn, warmup, steps) for i in range(procs)]
+    if procs == 1:
+        secs = [_ref_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            secs = pool.map(_ref_worker, jobs)
+    t = max(secs)
+    updates_per_s = procs * steps * CPU_SAMPLE_RECORDS / t
+    return updates_per_s / n_workload, updates_per_s, t
+
+
+def sample_text(procs: int, steps: int, burn: int) -> str:
+    return (f"{procs} independent chain(s) of the reference's own State::update() (oracle/_ref) on a "
+            f"{CPU_SAMPLE_RECORDS}-record sample of the same synthetic generator, {burn} burn-in sweeps, "
+            f"{steps} timed sweeps each; sweeps/s = link-updates/s / workload records")
+
+
+def run_reference(opt, n_records, kind, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = max(1, min(os.cpu_count() or 1, 32))
+    burn = 12
+    v, ups, t = reference_throughput(kind, n_records, opt.steps, opt.warmup, procs, burn)
+    line = {
+        "impl": "reference", "metric": "gibbs_sweeps_per_s", "value": v, "unit": "sweeps/s",
+        "link_updates_per_s": ups, "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup,
+        "ms_per_step": 1e3 * t / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind},
+        "cpu_baseline": {"value": v, "unit": "sweeps/s", "cores": procs, "kind": "reference",
+                         "sample": sample_text(procs, opt.steps, burn)},
+        "e2e": {"value": v, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- this repo's arm
+def run_ours(opt, n_records, kind, desc):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from exchanger_b200.model import model_with_state
+    from exchanger_b200.sampler import Sampler
+    from exchanger_b200.synthetic import synth_model
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    t_build = time.perf_counter()
+    model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED)
+    t_build = time.perf_counter() - t_build
+    gpu = Sampler(model, seed=1000 + rank, device=local)
+    gpu.sweeps(opt.burnin)          # untimed: reach the steady-state regime
+    gpu.sweeps(opt.warmup)          # W warm-up steps
+    barrier()
+    clocks = ClockSampler(local)
+    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_cand", "ms_rounds", "ms_canon", "ms_entities",
+                  "ms_distort", "ms_total")
+    acc = {k: 0.0 for k in phase_keys}
+    cand = rounds = wide = launches = 0
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(opt.steps):      # EXACTLY K steps
+        ms, nl = gpu.sweeps_timed(1)
+        dev_ms += ms
+        launches += nl
+        st = gpu.stats()
+        for k in phase_keys:
+            acc[k] += st[k]
+        cand += st["n_candidates"]
+        rounds += st["n_rounds"]
+        wide += st["n_wide"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    k_ent = gpu.stats()["n_entities"]
+    secs = torch.tensor([max(wall, dev_ms / 1e3)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    t_max = float(secs.item())
+    value = world * opt.steps / t_max
+
+    # ---- end to end through the public API with host buffers (create -> run -> state -> destroy)
+    host_model = model_with_state(model, gpu.state())
+    gpu.close()
+    barrier()
+    te = time.perf_counter()
+    with Sampler(host_model, seed=2000 + rank, device=local) as g2:
+        h2d = g2.flat.nbytes()
+        hist = g2.run(opt.steps, 1, 0)     # every sweep saved: links row copied back each step
+        fin = g2.state()
+    barrier()
+    te = time.perf_counter() - te
+    d2h = sum(v.nbytes for v in hist.values() if hasattr(v, "nbytes")) + \
+        sum(v.nbytes for v in fin.values() if hasattr(v, "nbytes"))
+    es = torch.tensor([te], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(es, op=dist.ReduceOp.MAX)
+    e2e_value = world * opt.steps / float(es.item())
+
+    if rank == 0:
+        # ---- roofline of the dominant single kernel (algorithmic bytes: DESIGN.md section 5)
+        n, cbar, rho = n_records, cand / opt.steps / n_records, k_ent / n_records
+        kernels = {
+            "k_cand (links: candidate generation)": (acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
+            "k_entities (entity attributes)": (acc["ms_entities"], n * (4 + 4 * A + 4 * A * rho)),
+            "k_distort (distortion indicators)": (acc["ms_distort"], n * (9 * A + 4)),
+            "k_prep (links: new-entity attributes)": (acc["ms_prep"], n * (5 * A + 4 + 4 * A + 8)),
+        }
+        name, (ms_k, bytes_k) = max(kernels.items(), key=lambda kv: kv[1][0])
+        peak, peak_src = peaks()
+        achieved = bytes_k / (ms_k / opt.steps * 1e-3) / 1e9
+        sweep_bytes = n * ((5 * A + 8 + cbar * (4 * A + 8)) + (4 + 4 * A + 4 * A * rho) + (9 * A + 4))
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name.split(" ")[0])
+        # ---- CPU baseline: the reference's own sampler, one core, bounded sample
+        cpu = None
+        if world == 1 and not opt.no_cpu_baseline:
+            try:
+                v, ups, _ = reference_throughput(kind, n_records, 6, 1, 1, burn=12)
+                cpu = {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "reference",
+                       "link_updates_per_s": ups, "sample": sample_text(1, 6, 12)}
+            except Exception as e:  # the checker is missing: say so, do not fake a number
+                cpu = {"value": None, "unit": "sweeps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        line = {
+            "metric": "gibbs_sweeps_per_s", "value": value, "unit": "sweeps/s",
+            "link_updates_per_s": value * n_records,
+            "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": 1e3 * t_max / opt.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind,
+                       "distort_prior": "Beta(1,50)", "parallelism": f"{world} independent chain(s)",
+                       "burnin_sweeps": opt.burnin, "model_build_s": round(t_build, 1),
+                       "l2": f"inputs larger than L2: resident state {n_records * 150 / 1e6:.0f} MB streamed every sweep"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d / opt.steps),
+                    "d2h_bytes_per_step": int(d2h / opt.steps)},
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_k, "kernel_ms": ms_k / opt.steps,
+                         "sweep": {"algorithmic_bytes": sweep_bytes, "ms": acc["ms_total"] / opt.steps,
+                                   "achieved": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9,
+                                   "frac": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9 / peak}},
+            "cpu_baseline": cpu,
+            "phases_ms": {k[3:]: acc[k] / opt.steps for k in phase_keys},
+            "sweep_stats": {"candidates_per_record": cbar, "entities_per_record": rho,
+                            "rounds_per_sweep": rounds / opt.steps, "wide_records_per_sweep": wide / opt.steps},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("EXB200_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--records", type=int, default=0, help="override the record count (debugging)")
+    ap.add_argument("--burnin", type=int, default=20, help="untimed sweeps before the warm-up")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opt = ap.parse_args()
+    opt.warmup = max(opt.warmup, 3)
+    n_records, kind, desc = WORKLOADS[opt.workload]
+    if opt.records:
+        n_records = opt.records
+        desc += f" (records overridden to {n_records})"
+    if opt.impl == "reference":
+        run_reference(opt, n_records, kind, desc)
+    else:
+        run_ours(opt, n_records, kind, desc)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,7 +83,7 @@ class CStats(C.Structure):
     _fields_ = [
         ("n_candidates", C.c_int64), ("n_bucket_items", C.c_int64),
         ("n_rounds", C.c_int32), ("n_wide", C.c_int32), ("n_entities", C.c_int32),
-        ("n_links_changed", C.c_int32), ("n_tables", C.c_int32), ("reserved", C.c_int32),
+        ("n_links_changed", C.c_int32), ("n_tables", C.c_int32), ("n_long", C.c_int32),
         ("ms_clust", C.c_float), ("ms_prep", C.c_float), ("ms_index", C.c_float),
         ("ms_cand", C.c_float), ("ms_rounds", C.c_float), ("ms_canon", C.c_float),
         ("ms_entities", C.c_float), ("ms_distort", C.c_float), ("ms_total", C.c_float),

@@ -24,6 +24,9 @@ constexpr int REJECT_CAP = 100000;  // safety bound of the rejection loops
 constexpr int CAND_SMEM = 256;      // compatible candidates a warp can stage for one record
 constexpr int LPE_MAX = 32;         // host-computed log prior_weight_existing(n), n < LPE_MAX
 constexpr int MAX_ATTRS = 32;
+constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that may form blocking keys
+constexpr int N_TABLES = 1 << KEY_ATTRS;
+constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
 
 // Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
 // (src/attribute_index.h:12-146) plus the alias tables that replace IndexNonUniformDiscreteDist
@@ -45,13 +48,13 @@ struct DevAttr {
                                            // or log(1 - eff + eff p(v|v)) when the value is not excluded
 };
 
-// One blocking table: items (entity slots) bucketed by the values of attributes (a, b); a == b is a
-// single-attribute table.  CSR over buckets built per sweep by count / scan / fill.
+// One blocking table: items (entity slots) bucketed by their values on a set of key attributes
+// (bit k of `mask` = key attribute k).  CSR over buckets built per sweep by count / scan / fill.
 struct DevTable {
-  int a, b;
-  int Db;            // domain size of b (key = y_a * Db + y_b)
-  int exact;         // 1: bucket = key; 0: bucket = mix(key) & (B - 1)
+  uint32_t mask;
+  int exact;         // 1: bucket = mixed-radix key; 0: bucket = mix(key) & (B - 1)
   uint32_t B;        // number of buckets
+  int pad;
   int *ptr;          // [B]  after fill: END offset of bucket (start = ptr[b-1], 0 for b = 0)
   int *ids;          // [n_items]
 };
@@ -78,10 +81,14 @@ struct DevState {
   const DevAttr *attrs;
   // links-update scratch
   double *Lnew;                 // [N] logLikelihoodWeightNew
-  uint16_t *rec_tab;            // [N] blocking table chosen for the record (0xFFFF: none)
+  uint16_t *rec_tab;            // [N] key mask of the blocking table chosen for the record (0: none)
   uint32_t *rec_bkt;            // [N] bucket inside that table
-  const DevTable *tables;       // [A*A]
-  int *tab_usage;               // [A*A]
+  const DevTable *tables;       // [2^n_key] indexed by key mask
+  int *tab_usage;               // [2^n_key]
+  const uint16_t *tab_remap;    // [2^n_key] wanted key mask -> mask of the table that is built (0: none)
+  int n_key;                    // number of key attributes
+  int key_attr[KEY_ATTRS];      // key position -> attribute
+  int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
   uint32_t *cand_off;           // [N]
   int *cand_cnt;                // [N] (-1: wide record)
   int *cand_id; double *cand_ll;// candidate pool
@@ -91,13 +98,17 @@ struct DevState {
   uint8_t *fin;                 // [N] 1 once the record's link is final
   int8_t *dlo, *dhi;            // [N] bounds of the record's change of K
   int *plo, *phi_;              // [N] exclusive prefix sums of dlo / dhi
-  int *act_in, *act_out;        // active record lists
+  int *act_in, *act_out;        // active records with short candidate lists (thread per record)
+  int *actl_in, *actl_out;      // active records with long candidate lists (warp per record)
+  int *long_todo;               // records whose candidates did not fit a warp's staging area
+  double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path
   int *counters;                // see CounterSlot
   long long *counters64;        // [0] candidates, [1] bucket items visited
   int *dev_err;                 // [0] status, [1] id
   double *lwbuf;                // [2N] scratch of the wide path / test hook
   int *ndist, *corr;            // [F*A] distorted counts, corrected non-distorted counts
-  int bucket_cap, cand_cap;
+  int bucket_cap, cand_cap, long_cap, long_min; // thresholds: see exb200_set_option
+  double est_threshold;         // expected bucket size above which the full key is used
   int K0;                       // number of entities at the start of the links update
   int use_kbounds;              // 0 when prior_weight_new does not depend on K
   ClustDev cl;
@@ -111,7 +122,9 @@ enum CounterSlot {
   C_DK_TOTAL = 4,   // sum of dK over finalised records
   C_NWIDE = 5,      // wide records of the sweep
   C_K = 6,          // entities counted by the rename kernel
-  C_COMMITTED = 7,  // records finalised in the round
+  C_NACTL_OUT = 7,  // size of actl_out
+  C_NLONG_TODO = 8, // size of long_todo
+  C_NACTL_INIT = 9, // long records found by candidate generation
   C_NSLOTS = 16
 };
 

@@ -30,7 +30,7 @@ struct HostAttr {
 struct TableHost {
   DevTable d{};
   bool allocated = false;
-  size_t cap_items = 0;
+  unsigned long long keys = 1; // size of the key space (product of the domain sizes)
 };
 
 } // namespace
@@ -51,16 +51,20 @@ struct exb200_handle {
   std::vector<void*> allocs;
   DevAttr* d_attrs = nullptr;
   std::vector<DevAttr> h_attrs;
-  std::vector<TableHost> tables; // [A*A]
+  std::vector<TableHost> tables; // [2^n_key] indexed by key mask
   DevTable* d_tables = nullptr;
   int* d_active = nullptr;
+  uint16_t* d_remap = nullptr;
   int* d_bsum = nullptr; size_t bsum_cap = 0;
   unsigned long long* d_cl_counts = nullptr;
   double* d_theta = nullptr;
   uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
   uint32_t round_ctr = 1;
   int opt_check = 0;
-  int bucket_cap = 1 << 15, cand_cap = CAND_SMEM;
+  int bucket_cap = 1 << 18, cand_cap = CAND_SMEM, long_cap = 8192, long_min = 32;
+  double est_threshold = 16.0;
+  double table_min_share = 0.002; // a key mask wanted by a smaller share of the records gets no table of its own
+  int n_tab = 0; // 2^n_key
   exb200_stats stats{};
   cudaEvent_t ev[10]{};
   std::string err;
@@ -305,27 +309,46 @@ int ensure_table(exb200_handle* h, int tab) {
 // ---- 2. links: Links::update (links.cpp:477-489)
 int update_links(exb200_handle* h) {
   DevState& S = h->S;
-  const int N = h->N, AA = h->A * h->A;
+  const int N = h->N, NT = h->n_tab;
   cudaStream_t st = h->stream;
   S.K0 = h->K;
-  CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * AA, st));
+  CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * NT, st));
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
   CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
   CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
   CK(cudaEventRecord(h->ev[1], st));
   KLAUNCH(h, k_prep, nblk(N), TPB, 0, S);
-  std::vector<int> usage(AA);
-  CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * AA, cudaMemcpyDeviceToHost, st));
+  std::vector<int> usage(NT);
+  CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * NT, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[2], st));
   CK(cudaStreamSynchronize(st));
-  // blocking tables used by at least one record
+  // Which blocking tables to build.  A table costs one atomic per item and pass, so a key mask
+  // wanted by few records is served by the most selective table that is built anyway and whose
+  // mask is a subset of it (bigger buckets, same candidates after the compatibility filter).
   std::vector<int> active;
-  for (int t = 0; t < AA; t++)
-    if (usage[t] > 0) {
-      int rc = ensure_table(h, t); if (rc) return rc;
-      active.push_back(t);
-      CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
+  std::vector<uint16_t> remap(NT, 0);
+  {
+    const long long min_use = std::max<long long>(1, (long long)((double)N * h->table_min_share));
+    std::vector<int> wanted;
+    for (int t = 1; t < NT; t++) if (usage[t] > 0) wanted.push_back(t);
+    std::sort(wanted.begin(), wanted.end(), [&](int a, int b) { return usage[a] > usage[b]; });
+    auto keys_of = [&](int t) { return h->tables[t].keys; };
+    for (int t : wanted) {
+      int best = 0;
+      if (usage[t] < min_use)
+        for (int b : active)
+          if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
+      // fall back only if the substitute is selective enough for this table's records
+      if (best && (double)(2LL * N) / (double)keys_of(best) * (double)usage[t] > 64.0 * (double)(2LL * N)) best = 0;
+      if (best == 0) { best = t; active.push_back(t); }
+      remap[t] = (uint16_t)best;
     }
+  }
+  for (int t : active) {
+    int rc = ensure_table(h, t); if (rc) return rc;
+    CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
+  }
+  CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * NT, cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
   if (!active.empty()) {
     CK(cudaMemcpyAsync(h->d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, st));
@@ -338,14 +361,23 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaEventRecord(h->ev[3], st));
   KLAUNCH(h, k_cand, nblk((long long)N, TPB / 32), TPB, 0, S);
+  int hc[C_NSLOTS];
+  CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
+    const size_t smem = (size_t)h->long_cap * (sizeof(double) + sizeof(int));
+    KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 8), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  h->stats.n_long = hc[C_NACTL_INIT];
   CK(cudaEventRecord(h->ev[4], st));
 
   // dependency rounds
-  int n_act = N;
-  const int* act = nullptr; // round 1: every record
+  int n_act = N, n_actl = hc[C_NACTL_INIT];
+  const int* act = nullptr; // round 1: every record (the short kernels skip the long ones)
   int rounds = 0;
-  int hc[C_NSLOTS];
-  while (n_act > 0) {
+  while (n_act + n_actl > 0) {
     rounds++;
     const uint32_t round = h->round_ctr++;
     if (h->round_ctr == 0xFFFFFFF0u) { // reservation words would wrap: start over
@@ -355,22 +387,29 @@ int update_links(exb200_handle* h) {
     }
     const int init[3] = {0, 0x7FFFFFFF, -1}; // C_NACT_OUT, C_MIN_ACTIVE, C_WIDE_READY
     CK(cudaMemcpyAsync(S.counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
+    CK(cudaMemsetAsync(S.counters + C_NACTL_OUT, 0, sizeof(int), st));
+    if (n_act > 0) KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
+    if (n_actl > 0) KLAUNCH(h, k_reserve_w, nblk(n_actl, TPB / 32), TPB, 0, S, S.actl_in, n_actl, round);
     if (S.use_kbounds) {
       int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
       rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
     }
-    KLAUNCH(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
+    if (n_act > 0) KLAUNCH(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
+    if (n_actl > 0) KLAUNCH(h, k_commit_w, nblk(n_actl, TPB / 32), TPB, 0, S, S.actl_in, n_actl, round);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int* next_act = S.act_out;
     int n_next = hc[C_NACT_OUT];
+    const int n_nextl = hc[C_NACTL_OUT];
     std::swap(S.act_in, S.act_out);
+    std::swap(S.actl_in, S.actl_out);
     if (hc[C_WIDE_READY] >= 0) {
       // serial path for a record without a stored candidate list
       const int w = hc[C_WIDE_READY];
       KLAUNCH(h, k_eval_all, nblk(2LL * N), TPB, 0, S, w, 2 * N);
-      KLAUNCH(h, k_wide_commit, 1, 1024, 0, S, w);
+      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 0);
+      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 1);
+      KLAUNCH(h, k_wide_commit, 1, 32, 0, S, w);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_compact_active, nblk(n_next), TPB, 0, S, next_act, n_next);
@@ -379,11 +418,12 @@ int update_links(exb200_handle* h) {
       next_act = S.act_out;
       n_next = hc[C_NACT_OUT];
       std::swap(S.act_in, S.act_out);
-    } else if (n_next >= n_act && act != nullptr) {
+    } else if (n_next + n_nextl >= n_act + n_actl && act != nullptr) {
       return fail(h, EXB200_ERR_CUDA, "links update made no progress (internal error)");
     }
     act = next_act;
     n_act = n_next;
+    n_actl = n_nextl;
     if (rounds > 4 * N + 16) return fail(h, EXB200_ERR_CUDA, "links update did not terminate");
   }
   CK(cudaEventRecord(h->ev[5], st));
@@ -605,7 +645,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.Lnew, (size_t)N));
   TRY(dalloc(h, &S.rec_tab, (size_t)N));
   TRY(dalloc(h, &S.rec_bkt, (size_t)N));
-  TRY(dalloc(h, &S.tab_usage, (size_t)A * A));
+  TRY(dalloc(h, &S.tab_usage, (size_t)N_TABLES));
   TRY(dalloc(h, &S.cand_off, (size_t)N));
   TRY(dalloc(h, &S.cand_cnt, (size_t)N));
   S.pool_cap = std::min<unsigned long long>(8ull * N + (1ull << 20), 0xFFFFFFF0ull);
@@ -621,41 +661,62 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.phi_, (size_t)N));
   TRY(dalloc(h, &S.act_in, (size_t)N));
   TRY(dalloc(h, &S.act_out, (size_t)N));
+  TRY(dalloc(h, &S.actl_in, (size_t)N));
+  TRY(dalloc(h, &S.actl_out, (size_t)N));
+  TRY(dalloc(h, &S.long_todo, (size_t)N));
+  TRY(dalloc(h, &S.wide_part, (size_t)WIDE_BLOCKS * (TPB + 2)));
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
   TRY(dalloc(h, &S.counters64, 2));
   TRY(dalloc(h, &S.dev_err, 2));
   TRY(dalloc(h, &S.lwbuf, (size_t)2 * N));
   TRY(dalloc(h, &S.ndist, (size_t)F * A));
   TRY(dalloc(h, &S.corr, (size_t)F * A));
-  TRY(dalloc(h, &h->d_active, (size_t)A * A));
+  TRY(dalloc(h, &h->d_active, (size_t)N_TABLES));
+  TRY(dalloc(h, &h->d_remap, (size_t)N_TABLES)); S.tab_remap = h->d_remap;
   TRY(dalloc(h, &h->d_cl_counts, 2));
   TRY(dalloc(h, &h->d_gen_mask, (size_t)N));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
   cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);
   cudaMemcpyAsync(S.ndist, h->ndist.data(), sizeof(int) * F * A, cudaMemcpyHostToDevice, h->stream);
-  // blocking-table descriptors (storage is allocated when a table is first used)
-  h->tables.resize((size_t)A * A);
+  // blocking-table descriptors (storage is allocated when a table is first used).  Key attributes:
+  // up to KEY_ATTRS attributes with the largest domains; a table is identified by its key mask.
+  {
+    std::vector<int> order(A);
+    for (int a = 0; a < A; a++) order[a] = a;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return m->attrs[x].domain_size > m->attrs[y].domain_size; });
+    S.n_key = std::min(A, KEY_ATTRS);
+    for (int a = 0; a < MAX_ATTRS; a++) S.key_pos[a] = -1;
+    std::vector<int> keys(order.begin(), order.begin() + S.n_key);
+    std::sort(keys.begin(), keys.end());
+    for (int k = 0; k < S.n_key; k++) { S.key_attr[k] = keys[k]; S.key_pos[keys[k]] = (int8_t)k; }
+    h->n_tab = 1 << S.n_key;
+  }
+  h->tables.resize((size_t)h->n_tab);
   uint32_t Bhash = 1024;
   while (Bhash < (uint32_t)(2 * N)) Bhash <<= 1;
-  for (int a = 0; a < A; a++)
-    for (int b = a; b < A; b++) {
-      DevTable& d = h->tables[a * A + b].d;
-      d.a = a; d.b = b; d.Db = m->attrs[b].domain_size;
-      const unsigned long long keys = a == b ? (unsigned long long)m->attrs[a].domain_size
-                                             : (unsigned long long)m->attrs[a].domain_size * m->attrs[b].domain_size;
-      d.exact = keys <= (unsigned long long)Bhash;
-      d.B = d.exact ? (uint32_t)keys : Bhash;
-      d.ptr = nullptr; d.ids = nullptr;
-    }
+  for (int t = 1; t < h->n_tab; t++) {
+    DevTable& d = h->tables[t].d;
+    d.mask = (uint32_t)t;
+    unsigned long long keys = 1;
+    for (int k = 0; k < S.n_key; k++)
+      if (t >> k & 1) keys = std::min<unsigned long long>(keys * (unsigned long long)m->attrs[S.key_attr[k]].domain_size, 1ull << 40);
+    h->tables[t].keys = keys;
+    d.exact = keys <= (unsigned long long)Bhash;
+    d.B = d.exact ? (uint32_t)keys : Bhash;
+    d.ptr = nullptr; d.ids = nullptr;
+  }
   {
-    std::vector<DevTable> td((size_t)A * A);
-    for (int t = 0; t < A * A; t++) td[t] = h->tables[t].d;
+    std::vector<DevTable> td((size_t)h->n_tab);
+    for (int t = 0; t < h->n_tab; t++) td[t] = h->tables[t].d;
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
+  if (cudaFuncSetAttribute(k_cand_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    return bail(fail(h, EXB200_ERR_CUDA, "cannot reserve shared memory for k_cand_long"));
 #undef TRY
-  S.bucket_cap = h->bucket_cap; S.cand_cap = h->cand_cap;
+  S.bucket_cap = h->bucket_cap; S.cand_cap = h->cand_cap; S.long_cap = h->long_cap; S.long_min = h->long_min;
+  S.est_threshold = h->est_threshold;
   refresh_clust_dev(h);
   rc = upload_theta(h);
   if (rc) return bail(rc);
@@ -671,8 +732,13 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   if (n == "check") h->opt_check = value != 0;
   else if (n == "bucket_cap") h->bucket_cap = (int)std::max<int64_t>(0, value);
   else if (n == "cand_cap") h->cand_cap = (int)std::min<int64_t>(CAND_SMEM, std::max<int64_t>(0, value));
+  else if (n == "long_cap") h->long_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(0, value));
+  else if (n == "long_min") h->long_min = (int)std::max<int64_t>(0, value);
+  else if (n == "est_threshold") h->est_threshold = (double)value;
+  else if (n == "table_min_ppm") h->table_min_share = (double)value * 1e-6;
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
-  h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap;
+  h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap; h->S.long_cap = h->long_cap;
+  h->S.long_min = h->long_min; h->S.est_threshold = h->est_threshold;
   return EXB200_OK;
 }
 

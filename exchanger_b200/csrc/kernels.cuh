@@ -23,8 +23,14 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
-__device__ __forceinline__ uint32_t bucket_of(const DevTable& t, int va, int vb) {
-  const uint64_t key = t.a == t.b ? (uint64_t)va : (uint64_t)va * (uint64_t)t.Db + (uint64_t)vb;
+// bucket of an attribute tuple y under the key mask of table t (mixed-radix key over the key
+// attributes in the mask; hashed when the key space is larger than the bucket array)
+__device__ __forceinline__ uint32_t bucket_of(const DevState& S, const DevTable& t, const int* y) {
+  uint64_t key = 0;
+  for (uint32_t m = t.mask; m; m &= m - 1) {
+    const int a = S.key_attr[__ffs(m) - 1];
+    key = key * (uint64_t)S.attrs[a].D + (uint64_t)y[a];
+  }
   return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
 }
 
@@ -84,12 +90,13 @@ __global__ void k_theta_tables(DevState S, int a) {
 // K1a  per-record preparation of the links update.
 //   * attributes of the entity the record would found (src/links.cpp:424-468) -> slot N + r
 //   * logLikelihoodWeightNew (src/links.cpp:316-347)
-//   * choice of the blocking table: the two observed non-distorted attributes whose record
-//     values are rarest (replaces the set-size ordering of getPossibleLinks, links.cpp:187-189)
+//   * choice of the blocking key: the two observed non-distorted attributes whose record values
+//     are rarest, or all of them when that pair is expected to match many items (replaces the
+//     set-size ordering of getPossibleLinks, links.cpp:187-189)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
-  __shared__ int s_usage[MAX_ATTRS * MAX_ATTRS];
-  const int AA = S.A * S.A;
+  __shared__ int s_usage[N_TABLES];
+  const int AA = 1 << S.n_key;
   for (int i = threadIdx.x; i < AA; i += blockDim.x) s_usage[i] = 0;
   __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,7 +105,8 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
     const uint32_t zm = S.rec_z[r];
     int* yn = S.ent_y + (size_t)(S.N + r) * S.ES;
     double L = 0.0;
-    int b1 = -1, b2 = -1;        // most selective observed non-distorted attributes
+    int b1 = -1, b2 = -1;        // key positions of the most selective observed non-distorted attributes
+    uint32_t nd_mask = 0;
     double s1 = 2.0, s2 = 2.0;
     for (int a = 0; a < S.A; a++) {
       const DevAttr& t = S.attrs[a];
@@ -112,9 +120,12 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
         L += zz ? t.logE[xv] : t.logphi[xv];
         if (!zz) { // links.cpp:440-442
           yv = xv;
-          const double sel = t.psi[xv];
-          if (sel < s1) { s2 = s1; b2 = b1; s1 = sel; b1 = a; }
-          else if (sel < s2) { s2 = sel; b2 = a; }
+          if (S.key_pos[a] >= 0) {
+            nd_mask |= 1u << S.key_pos[a];
+            const double sel = t.psi[xv];
+            if (sel < s1) { s2 = s1; b2 = b1; s1 = sel; b1 = S.key_pos[a]; }
+            else if (sel < s2) { s2 = sel; b2 = S.key_pos[a]; }
+          }
         } else if (t.is_const) {
           if (t.exclude) { // law of rejectionSampleConstant (links.cpp:290-314): phi/(1-psi), v != x
             yv = xv;
@@ -155,16 +166,14 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
     S.ent_head[S.N + r] = -1;
     S.fin[r] = 0;
     // blocking table
-    int tab = 0xFFFF;
-    uint32_t bkt = 0;
+    uint32_t tab = 0;
     if (b1 >= 0) {
-      const int ta = b2 < 0 ? b1 : min(b1, b2), tb = b2 < 0 ? b1 : max(b1, b2);
-      tab = ta * S.A + tb;
-      bkt = bucket_of(S.tables[tab], x[ta], x[tb]);
+      const uint32_t pair = (1u << b1) | (b2 >= 0 ? 1u << b2 : 0u);
+      const double est = 2.0 * (double)S.N * s1 * (b2 >= 0 ? s2 : 1.0);
+      tab = est > S.est_threshold ? nd_mask : pair;
       atomicAdd(&s_usage[tab], 1);
     }
-    S.rec_tab[r] = (uint16_t)tab;
-    S.rec_bkt[r] = bkt;
+    S.rec_tab[r] = (uint16_t)tab; // the table actually used is tab_remap[tab] (chosen on the host)
   }
   __syncthreads();
   for (int i = threadIdx.x; i < AA; i += blockDim.x)
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(TPB) k_index_count(DevState S, const int* __re
   const int* y = S.ent_y + (size_t)i * S.ES;
   for (int k = 0; k < n_active; k++) {
     const DevTable& t = S.tables[active[k]];
-    atomicAdd(&t.ptr[bucket_of(t, y[t.a], y[t.b])], 1);
+    atomicAdd(&t.ptr[bucket_of(S, t, y)], 1);
   }
 }
 __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __restrict__ active, int n_active) {
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __res
   const int* y = S.ent_y + (size_t)i * S.ES;
   for (int k = 0; k < n_active; k++) {
     const DevTable& t = S.tables[active[k]];
-    const int pos = atomicAdd(&t.ptr[bucket_of(t, y[t.a], y[t.b])], 1);
+    const int pos = atomicAdd(&t.ptr[bucket_of(S, t, y)], 1);
     t.ids[pos] = i;
   }
 }
@@ -297,6 +306,16 @@ __device__ __forceinline__ double item_loglik(const DevState& S, const int* x, u
   return l;
 }
 
+// finish one record's candidate list: bounds of its change of K and registration as a long record
+__device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint32_t off, int cnt, bool other) {
+  S.cand_off[r] = off;
+  S.cand_cnt[r] = cnt;
+  S.dlo[r] = other ? -1 : 0; // while its outcome is unknown the record may lower K only if it can join another entity
+  S.dhi[r] = 1;
+  if (cnt < 0) atomicAdd(&S.counters[C_NWIDE], 1);
+  else if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
+}
+
 __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
   __shared__ int s_id[TPB / 32][CAND_SMEM];
   __shared__ double s_ll[TPB / 32][CAND_SMEM];
@@ -310,21 +329,22 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     double* lls = s_ll[wib];
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
-    const int tab = S.rec_tab[r];
+    const int tab = S.tab_remap[S.rec_tab[r]];
     const int own = S.lambda[r];
     int cnt = 0;
-    bool wide = tab == 0xFFFF;
+    bool wide = tab == 0, spill = false;
     int lo = 0, hi = 0;
     if (!wide) {
       const DevTable& t = S.tables[tab];
-      const uint32_t b = S.rec_bkt[r];
+      const uint32_t b = bucket_of(S, t, x);
+      if (lane == 0) S.rec_bkt[r] = b;
       lo = b ? t.ptr[b - 1] : 0;
       hi = t.ptr[b];
       wide = hi - lo > S.bucket_cap;
     }
     if (!wide) {
       const int* bucket = S.tables[tab].ids;
-      for (int base = lo; base < hi && !wide; base += 32) {
+      for (int base = lo; base < hi && !spill; base += 32) {
         const int q = base + lane;
         int item = -1;
         bool ok = false;
@@ -342,22 +362,102 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
         }
         const unsigned m = __ballot_sync(FULL, ok);
         const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (cnt + __popc(m) > S.cand_cap) wide = true;
+        if (cnt + __popc(m) > S.cand_cap) spill = true;
         else if (ok) { ids[pos] = item; lls[pos] = ll; }
         cnt += __popc(m);
       }
       if (lane == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
     }
-    uint32_t off = 0;
-    if (!wide && cnt > 0) {
-      // sort the staged candidates by id (bitonic, one warp)
+    if (spill) {
+      // more candidates than a warp can stage: a whole block takes the record (k_cand_long)
+      if (lane == 0) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r;
+    } else {
+      uint32_t off = 0;
+      if (!wide && cnt > 0) {
+        // sort the staged candidates by id (bitonic, one warp)
+        int n2 = 1;
+        while (n2 < cnt) n2 <<= 1;
+        for (int i = cnt + lane; i < n2; i += 32) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
+        __syncwarp();
+        for (int k = 2; k <= n2; k <<= 1)
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n2; i += 32) {
+              const int l = i ^ j;
+              if (l > i) {
+                const bool up = (i & k) == 0;
+                const int a0 = ids[i], a1 = ids[l];
+                if ((a0 > a1) == up) {
+                  ids[i] = a1; ids[l] = a0;
+                  const double t0 = lls[i]; lls[i] = lls[l]; lls[l] = t0;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        unsigned long long o = 0;
+        if (lane == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+        o = __shfl_sync(FULL, o, 0);
+        if (o + (unsigned long long)cnt > S.pool_cap) wide = true;
+        else {
+          off = (uint32_t)o;
+          for (int i = lane; i < cnt; i += 32) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+        }
+      }
+      if (lane == 0) {
+        bool other = wide;
+        if (!wide) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
+        finish_candidates(S, r, off, wide ? -1 : cnt, other);
+        if (!wide) atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_stat[threadIdx.x])
+    atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+}
+
+// One BLOCK per record whose candidates overflowed the warp staging area: same scan, staged in
+// dynamic shared memory (long_cap entries), sorted by a block-wide bitonic network.
+__global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int cap) {
+  extern __shared__ unsigned char s_raw[];
+  double* lls = reinterpret_cast<double*>(s_raw);
+  int* ids = reinterpret_cast<int*>(lls + cap);
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_off;
+  for (int w = blockIdx.x; w < n_todo; w += gridDim.x) {
+    const int r = S.long_todo[w];
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    const DevTable& t = S.tables[S.tab_remap[S.rec_tab[r]]];
+    const uint32_t b = S.rec_bkt[r];
+    const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+    const int own = S.lambda[r];
+    for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
+      if (s_cnt > cap) break; // already too many: the record takes the wide path (benign race: any exit is a valid exit)
+      const int q = q0 + threadIdx.x;
+      if (q >= hi) continue;
+      const int item = t.ids[q];
+      if (item == S.N + r) continue;
+      const int* y = S.ent_y + (size_t)item * S.ES;
+      if (!item_compatible(S, x, zm, y)) continue;
+      const double ll = item_loglik(S, x, zm, y);
+      if (!(ll > -CUDART_INF)) continue;
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    bool wide = cnt > cap;
+    if (!wide) {
       int n2 = 1;
       while (n2 < cnt) n2 <<= 1;
-      for (int i = cnt + lane; i < n2; i += 32) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
-      __syncwarp();
+      for (int i = cnt + threadIdx.x; i < n2; i += blockDim.x) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
+      __syncthreads();
       for (int k = 2; k <= n2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = lane; i < n2; i += 32) {
+          for (int i = threadIdx.x; i < n2; i += blockDim.x) {
             const int l = i ^ j;
             if (l > i) {
               const bool up = (i & k) == 0;
@@ -368,32 +468,24 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
               }
             }
           }
-          __syncwarp();
+          __syncthreads();
         }
-      unsigned long long o = 0;
-      if (lane == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
-      o = __shfl_sync(FULL, o, 0);
+      if (threadIdx.x == 0) s_off = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+      __syncthreads();
+      const unsigned long long o = s_off;
       if (o + (unsigned long long)cnt > S.pool_cap) wide = true;
-      else {
-        off = (uint32_t)o;
-        for (int i = lane; i < cnt; i += 32) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+      else for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+      if (threadIdx.x == 0) {
+        bool other = wide;
+        if (!wide) other = cnt > 1 || (cnt == 1 && ids[0] != own);
+        finish_candidates(S, r, wide ? 0u : (uint32_t)o, wide ? -1 : cnt, other);
+        if (!wide) atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
       }
+    } else if (threadIdx.x == 0) {
+      finish_candidates(S, r, 0u, -1, true);
     }
-    if (lane == 0) {
-      S.cand_off[r] = off;
-      S.cand_cnt[r] = wide ? -1 : cnt;
-      // bounds of this record's change of K while its outcome is unknown
-      bool other = wide;
-      if (!wide) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
-      S.dlo[r] = other ? -1 : 0;
-      S.dhi[r] = 1;
-      if (wide) atomicAdd(&S.counters[C_NWIDE], 1);
-      else atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
-    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x < 2 && s_stat[threadIdx.x])
-    atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -403,6 +495,8 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
 // candidates.  A record whose reservations all carry its own id has no earlier unfinalised
 // record that could change what it reads, so its conditional is already the one the sequential
 // scan would see.  Wide records (no stored candidate list) act as a fence.
+// Records with short lists take one thread each; records with more than long_min candidates take
+// a warp each (k_reserve_w / k_commit_w) - same arithmetic in the same order.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long resv_key(uint32_t round, int r) {
   return ((unsigned long long)(0xFFFFFFFFu - round) << 32) | (unsigned long long)(uint32_t)r;
@@ -416,16 +510,18 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
   int mine = 0x7FFFFFFF;
   if (i < n_act) {
     const int r = act ? act[i] : i;
-    mine = r;
-    const unsigned long long key = resv_key(round, r);
     const int cnt = S.cand_cnt[r];
-    if (cnt < 0) {
-      atomicMin(S.fence, key);
-    } else {
-      atomicMin(&S.owner[S.lambda[r]], key);
-      atomicMin(&S.owner[S.N + r], key);
-      const int* ids = S.cand_id + S.cand_off[r];
-      for (int j = 0; j < cnt; j++) atomicMin(&S.owner[ids[j]], key);
+    if (cnt <= S.long_min) { // long records are handled by k_reserve_w
+      mine = r;
+      const unsigned long long key = resv_key(round, r);
+      if (cnt < 0) {
+        atomicMin(S.fence, key);
+      } else {
+        atomicMin(&S.owner[S.lambda[r]], key);
+        atomicMin(&S.owner[S.N + r], key);
+        const int* ids = S.cand_id + S.cand_off[r];
+        for (int j = 0; j < cnt; j++) atomicMin(&S.owner[ids[j]], key);
+      }
     }
   }
 #pragma unroll
@@ -433,6 +529,22 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
   if ((threadIdx.x & 31) == 0) atomicMin(&s_min, mine);
   __syncthreads();
   if (threadIdx.x == 0 && s_min != 0x7FFFFFFF) atomicMin(&S.counters[C_MIN_ACTIVE], s_min);
+}
+
+__global__ void __launch_bounds__(TPB) k_reserve_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  if (i >= n_act) return;
+  const int r = act[i];
+  const unsigned long long key = resv_key(round, r);
+  const int cnt = S.cand_cnt[r];
+  const int* ids = S.cand_id + S.cand_off[r];
+  if (lane == 0) {
+    atomicMin(&S.owner[S.lambda[r]], key);
+    atomicMin(&S.owner[S.N + r], key);
+    atomicMin(&S.counters[C_MIN_ACTIVE], r);
+  }
+  for (int j = lane; j < cnt; j += 32) atomicMin(&S.owner[ids[j]], key);
 }
 
 // move record r from entity `own` to `target`, keeping member lists sorted (the role of
@@ -470,21 +582,55 @@ __device__ __forceinline__ bool decide_new(const DevState& S, int r, int k, doub
   return u1 * (wa + wb) < wa;
 }
 
+// Given the existing-candidate summary (m1, srel) decide "new" for the interval of K that the
+// unfinalised earlier records leave open.  Returns 0: existing, 1: new, 2: cannot decide yet.
+__device__ __forceinline__ int decide_with_bounds(const DevState& S, int r, bool single, double m1, double srel,
+                                                  double u1) {
+  // with r taken out there are between 0 and N-1 entities, whatever the earlier records do
+  const int klo = max(0, S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0));
+  const int khi = min(S.N - 1, S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0));
+  bool inv_lo = false, inv_hi = false;
+  const bool new_lo = decide_new(S, r, klo, m1, srel, u1, inv_lo);
+  const bool new_hi = klo == khi ? new_lo : decide_new(S, r, khi, m1, srel, u1, inv_hi);
+  // prior_weight_new is monotone in K (alpha + d K; kappa |m - K|) unless the interval straddles
+  // the kink of |m - K|; only then the end points do not decide
+  const bool kink = S.cl.kind != EXB200_CLUST_PITMAN_YOR && (double)klo < S.cl.m && S.cl.m < (double)khi;
+  if (new_lo != new_hi || kink) return 2;
+  if (inv_lo || inv_hi) dev_fail(S, EXB200_ERR_WEIGHTS, r); // "no valid links for record" (links.cpp:415-419)
+  return new_lo ? 1 : 0;
+}
+
+__device__ __forceinline__ void finalize_record(const DevState& S, int r, int own, int target, bool single) {
+  const bool is_new = target == S.N + r;
+  const int dk = (is_new ? 1 : 0) - (single ? 1 : 0);
+  if (!(target == own || (single && is_new))) atomicAdd(&S.counters[C_CHANGED], 1);
+  apply_move(S, r, own, target);
+  S.fin[r] = 1;
+  S.dlo[r] = (int8_t)dk;
+  S.dhi[r] = (int8_t)dk;
+  if (dk) atomicAdd(&S.counters[C_DK_TOTAL], dk);
+}
+
+__device__ __forceinline__ int live_size(const DevState& S, int e, int own, bool single) {
+  const int sz = S.ent_size[e];
+  return e == own ? (single ? 0 : sz - 1) : sz; // links.cpp:359, :375
+}
+
 __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool stay = false;
   int r = -1;
   if (i < n_act) {
     r = act ? act[i] : i;
-    stay = true;
     const int cnt = S.cand_cnt[r];
+    stay = cnt <= S.long_min; // long records live in the other list
     const unsigned long long key = resv_key(round, r);
     const unsigned long long fence = *S.fence;
     const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
     if (cnt < 0) {
       // wide record: its turn comes when every earlier record is final
       if (S.counters[C_MIN_ACTIVE] == r) S.counters[C_WIDE_READY] = r;
-    } else if (!fenced) {
+    } else if (stay && !fenced) {
       const int own = S.lambda[r];
       const int* ids = S.cand_id + S.cand_off[r];
       bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
@@ -495,9 +641,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         // weights of the live candidates (links.cpp:372-388)
         double m1 = -CUDART_INF;
         for (int j = 0; j < cnt; j++) {
-          const int e = ids[j];
-          int sz = S.ent_size[e];
-          if (e == own) sz = single ? 0 : sz - 1; // links.cpp:359, :375
+          const int sz = live_size(S, ids[j], own, single);
           if (sz > 0) {
             const double lw = log_prior_existing(S.cl, sz) + lls[j];
             m1 = lw > m1 ? lw : m1;
@@ -506,51 +650,30 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         double srel = 0.0;
         if (m1 > -CUDART_INF)
           for (int j = 0; j < cnt; j++) {
-            const int e = ids[j];
-            int sz = S.ent_size[e];
-            if (e == own) sz = single ? 0 : sz - 1;
+            const int sz = live_size(S, ids[j], own, single);
             if (sz > 0) srel += exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
           }
         const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-        // number of entities seen by prior_weight_new (links.cpp:390): exact when every earlier
-        // record is final, otherwise an interval
-        bool inv_lo = false, inv_hi = false;
-        // (with r taken out there are between 0 and N-1 entities, whatever the earlier records do)
-        const int klo = max(0, S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0));
-        const int khi = min(S.N - 1, S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0));
-        const bool new_lo = decide_new(S, r, klo, m1, srel, u.a, inv_lo);
-        const bool new_hi = klo == khi ? new_lo : decide_new(S, r, khi, m1, srel, u.a, inv_hi);
-        // prior_weight_new is monotone in K (alpha + d K; kappa |m - K|) unless the interval
-        // straddles the kink of |m - K|; only then the end points do not decide
-        const bool kink = S.cl.kind != EXB200_CLUST_PITMAN_YOR && (double)klo < S.cl.m && S.cl.m < (double)khi;
-        if (new_lo == new_hi && !kink) {
-          if (inv_lo || inv_hi) dev_fail(S, EXB200_ERR_WEIGHTS, r); // "no valid links for record"
+        const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
+        if (dec != 2) {
           int target;
-          if (new_lo) target = S.N + r;
+          if (dec == 1) target = S.N + r;
           else {
             const double tt = u.b * srel;
             double c = 0.0;
             int pick = -1, lastpos = -1;
             for (int j = 0; j < cnt; j++) {
-              const int e = ids[j];
-              int sz = S.ent_size[e];
-              if (e == own) sz = single ? 0 : sz - 1;
+              const int sz = live_size(S, ids[j], own, single);
               if (sz <= 0) continue;
               const double w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
-              if (w > 0.0) lastpos = e;
+              if (w > 0.0) lastpos = ids[j];
               c += w;
-              if (tt < c) { pick = e; break; }
+              if (tt < c) { pick = ids[j]; break; }
             }
             target = pick >= 0 ? pick : lastpos;
             if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
           }
-          const int dk = (new_lo ? 1 : 0) - (single ? 1 : 0);
-          if (!(target == own || (single && new_lo))) atomicAdd(&S.counters[C_CHANGED], 1);
-          apply_move(S, r, own, target);
-          S.fin[r] = 1;
-          S.dlo[r] = (int8_t)dk;
-          S.dhi[r] = (int8_t)dk;
-          if (dk) atomicAdd(&S.counters[C_DK_TOTAL], dk);
+          finalize_record(S, r, own, target, single);
           stay = false;
         } else {
           // entity-wise ready, only K is still uncertain: tighten this record's bounds
@@ -569,6 +692,90 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
     base = __shfl_sync(FULL, base, __ffs(m) - 1);
     if (stay) S.act_out[base + __popc(m & ((1u << lane) - 1u))] = r;
   }
+}
+
+// One WARP per record with a long candidate list.  Lanes gather sizes and evaluate weights in
+// parallel; the sums are accumulated in candidate order (lane by lane through shuffles), i.e. with
+// exactly the association of the sequential loop in k_commit and in the oracle.
+__global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  if (i >= n_act) return;
+  const int r = act[i];
+  const int cnt = S.cand_cnt[r];
+  const unsigned long long key = resv_key(round, r);
+  const unsigned long long fence = *S.fence;
+  const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
+  bool stay = true;
+  if (!fenced) {
+    const int own = S.lambda[r];
+    const int* ids = S.cand_id + S.cand_off[r];
+    const double* lls = S.cand_ll + S.cand_off[r];
+    bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
+    for (int j = lane; j < cnt; j += 32) mine &= S.owner[ids[j]] == key;
+    mine = __all_sync(FULL, mine);
+    if (mine) {
+      const bool single = S.ent_size[own] == 1;
+      const int nchunk = (cnt + 31) >> 5;
+      double m1 = -CUDART_INF;
+      for (int c = 0; c < nchunk; c++) {
+        const int j = 32 * c + lane;
+        if (j < cnt) {
+          const int sz = live_size(S, ids[j], own, single);
+          if (sz > 0) { const double lw = log_prior_existing(S.cl, sz) + lls[j]; m1 = lw > m1 ? lw : m1; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m1, o); m1 = y > m1 ? y : m1; }
+      double srel = 0.0;
+      if (m1 > -CUDART_INF)
+        for (int c = 0; c < nchunk; c++) {
+          const int j = 32 * c + lane;
+          double w = 0.0;
+          if (j < cnt) {
+            const int sz = live_size(S, ids[j], own, single);
+            if (sz > 0) w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+          }
+          for (int k = 0; k < 32; k++) srel += __shfl_sync(FULL, w, k); // candidate order; dead ones add 0
+        }
+      const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+      const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
+      if (dec != 2) {
+        int target;
+        if (dec == 1) target = S.N + r;
+        else {
+          const double tt = u.b * srel;
+          double cum = 0.0;
+          int pick = -1, lastpos = -1;
+          for (int c = 0; c < nchunk && pick < 0; c++) {
+            const int j = 32 * c + lane;
+            double w = 0.0;
+            int e = -1;
+            if (j < cnt) {
+              e = ids[j];
+              const int sz = live_size(S, e, own, single);
+              if (sz > 0) w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+            }
+            for (int k = 0; k < 32 && pick < 0; k++) {
+              const double wk = __shfl_sync(FULL, w, k);
+              const int ek = __shfl_sync(FULL, e, k);
+              if (wk > 0.0) lastpos = ek;
+              cum += wk;
+              if (wk > 0.0 && tt < cum) pick = ek; // a dead candidate adds 0 and can never be the first to pass tt
+            }
+          }
+          target = pick >= 0 ? pick : lastpos;
+          if (target < 0) { if (lane == 0) dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+        }
+        if (lane == 0) finalize_record(S, r, own, target, single);
+        stay = false;
+      } else if (lane == 0) {
+        S.dlo[r] = single ? -1 : 0;
+        S.dhi[r] = single ? 0 : 1;
+      }
+    }
+  }
+  if (stay && lane == 0) S.actl_out[atomicAdd(&S.counters[C_NACTL_OUT], 1)] = r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -591,88 +798,97 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
   S.lwbuf[i] = out;
 }
 
-// one block: ordered reduction over lwbuf, decision and commit of the wide record r
-__global__ void __launch_bounds__(1024) k_wide_commit(DevState S, int r) {
-  __shared__ double s_part[1024];
-  __shared__ double s_m1, s_tt;
-  __shared__ int s_chunk, s_target;
+// The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 256
+// contiguous sub-chunks (one thread each).  pass 0: maxima; pass 1: sums of exp(lw - max) per
+// thread and per block.  wide_part layout: [0, WB) block maxima, [WB, 2 WB) block sums,
+// [2 WB, 2 WB + WB*256) thread sums.
+__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int pass) {
+  __shared__ double s_v[TPB];
   const int n = 2 * S.N;
-  const int per = (n + 1023) / 1024;
-  const int lo = threadIdx.x * per, hi = min(n, lo + per);
-  double m = -CUDART_INF;
-  for (int i = lo; i < hi; i++) { const double v = S.lwbuf[i]; if (v == v && v > m) m = v; }
-  s_part[threadIdx.x] = m;
+  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+  const long long b_lo = blockIdx.x * per_b, b_hi = min((long long)n, b_lo + per_b);
+  const long long per_t = (per_b + TPB - 1) / TPB;
+  const long long lo = min(b_hi, b_lo + threadIdx.x * per_t), hi = min(b_hi, lo + per_t);
+  double m1 = -CUDART_INF;
+  if (pass == 1) for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[b] > m1 ? S.wide_part[b] : m1;
+  double acc = pass == 0 ? -CUDART_INF : 0.0;
+  for (long long i = lo; i < hi; i++) {
+    const double v = S.lwbuf[i];
+    if (!(v == v)) continue;
+    if (pass == 0) acc = v > acc ? v : acc;
+    else if (m1 > -CUDART_INF) acc += exp(v - m1);
+  }
+  s_v[threadIdx.x] = acc;
+  if (pass == 1) S.wide_part[2 * WIDE_BLOCKS + blockIdx.x * TPB + threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double mm = -CUDART_INF;
-    for (int i = 0; i < 1024; i++) mm = s_part[i] > mm ? s_part[i] : mm;
-    s_m1 = mm;
-  }
-  __syncthreads();
-  const double m1 = s_m1;
-  double sum = 0.0;
-  if (m1 > -CUDART_INF)
-    for (int i = lo; i < hi; i++) { const double v = S.lwbuf[i]; if (v == v) sum += exp(v - m1); }
-  __syncthreads();
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  const int own = S.lambda[r];
-  if (threadIdx.x == 0) {
-    double srel = 0.0;
-    for (int i = 0; i < 1024; i++) srel += s_part[i];
-    const bool single = S.ent_size[own] == 1;
-    const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-    const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
-    bool invalid = false;
-    const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
-    if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
-    s_chunk = -1;
-    s_target = is_new ? S.N + r : -1;
-    if (!is_new) {
-      const double tt = u.b * srel;
-      double c = 0.0;
-      int chunk = -1, lastpos = -1;
-      for (int i = 0; i < 1024; i++) {
-        if (s_part[i] > 0.0) lastpos = i;
-        if (tt < c + s_part[i]) { chunk = i; break; }
-        c += s_part[i];
-      }
-      if (chunk < 0) { chunk = lastpos; c = 0.0; s_tt = -1.0; } // rounding: take the last positive one
-      else s_tt = tt - c;
-      s_chunk = chunk;
-    }
-  }
-  __syncthreads();
-  if (s_chunk >= 0 && (int)threadIdx.x == s_chunk) {
-    const double tt = s_tt;
-    double c = 0.0;
-    int pick = -1, lastpos = -1;
-    for (int i = lo; i < hi; i++) {
-      const double v = S.lwbuf[i];
-      if (!(v == v)) continue;
-      const double w = exp(v - m1);
-      if (w > 0.0) lastpos = i;
-      c += w;
-      if (tt >= 0.0 && tt < c) { pick = i; break; }
-    }
-    s_target = pick >= 0 ? pick : lastpos;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int target = s_target;
-    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
-    const bool single = S.ent_size[own] == 1, is_new = target == S.N + r;
-    const int dk = (is_new ? 1 : 0) - (single ? 1 : 0);
-    if (!(target == own || (single && is_new))) atomicAdd(&S.counters[C_CHANGED], 1);
-    apply_move(S, r, own, target);
-    S.fin[r] = 1;
-    S.dlo[r] = (int8_t)dk;
-    S.dhi[r] = (int8_t)dk;
-    if (dk) atomicAdd(&S.counters[C_DK_TOTAL], dk);
+    double t = pass == 0 ? -CUDART_INF : 0.0;
+    for (int k = 0; k < TPB; k++) t = pass == 0 ? (s_v[k] > t ? s_v[k] : t) : t + s_v[k];
+    S.wide_part[pass * WIDE_BLOCKS + blockIdx.x] = t;
   }
 }
 
-// drop a finalised wide record from the active list
+// decision and commit of the wide record r (one thread walks block sums, thread sums, items)
+__global__ void k_wide_commit(DevState S, int r) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int n = 2 * S.N;
+  double m1 = -CUDART_INF, srel = 0.0;
+  for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[b] > m1 ? S.wide_part[b] : m1;
+  for (int b = 0; b < WIDE_BLOCKS; b++) srel += S.wide_part[WIDE_BLOCKS + b];
+  const int own = S.lambda[r];
+  const bool single = S.ent_size[own] == 1;
+  const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+  const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
+  bool invalid = false;
+  const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
+  if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
+  int target = S.N + r;
+  if (!is_new) {
+    const double tt = u.b * srel;
+    double c = 0.0;
+    int blk = -1, lastb = -1;
+    for (int b = 0; b < WIDE_BLOCKS; b++) {
+      const double sb = S.wide_part[WIDE_BLOCKS + b];
+      if (sb > 0.0) lastb = b;
+      if (tt < c + sb) { blk = b; break; }
+      c += sb;
+    }
+    bool tail = false;
+    if (blk < 0) { blk = lastb; tail = true; } // rounding: the last positive item
+    target = -1;
+    if (blk >= 0) {
+      const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+      const long long b_lo = blk * per_b, b_hi = min((long long)n, b_lo + per_b);
+      const long long per_t = (per_b + TPB - 1) / TPB;
+      const double* ts = S.wide_part + 2 * WIDE_BLOCKS + (size_t)blk * TPB;
+      int th = -1, lastt = -1;
+      for (int q = 0; q < TPB && !tail; q++) {
+        if (ts[q] > 0.0) lastt = q;
+        if (tt < c + ts[q]) { th = q; break; }
+        c += ts[q];
+      }
+      if (tail) { for (int q = 0; q < TPB; q++) if (ts[q] > 0.0) lastt = q; }
+      if (th < 0) { th = lastt; tail = true; }
+      if (th >= 0) {
+        const long long lo = min(b_hi, b_lo + th * per_t), hi = min(b_hi, lo + per_t);
+        int lastpos = -1;
+        for (long long i = lo; i < hi; i++) {
+          const double v = S.lwbuf[i];
+          if (!(v == v)) continue;
+          const double w = exp(v - m1);
+          if (w > 0.0) lastpos = (int)i;
+          c += w;
+          if (!tail && tt < c) { target = (int)i; break; }
+        }
+        if (target < 0) target = lastpos;
+      }
+    }
+    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+  }
+  finalize_record(S, r, own, target, single);
+}
+
+// drop finalised records from an active list
 __global__ void __launch_bounds__(TPB) k_compact_active(DevState S, const int* __restrict__ act, int n_act) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = i < n_act ? (act ? act[i] : i) : -1;
@@ -686,6 +902,7 @@ __global__ void __launch_bounds__(TPB) k_compact_active(DevState S, const int* _
     if (stay) S.act_out[base + __popc(m & ((1u << lane) - 1u))] = r;
   }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // K1e  rename every entity to its smallest member record (the head of its sorted member list).

@@ -113,7 +113,7 @@ class Sampler:
     def stats(self) -> dict:
         s = CStats()
         self._check(self.lib.exb200_get_stats(self.h, C.byref(s)))
-        return {name: getattr(s, name) for name, _ in CStats._fields_ if name != "reserved"}
+        return {name: getattr(s, name) for name, _ in CStats._fields_}
 
     def link_conditional(self, rid: int, cap: int = 65536):
         ids = np.zeros(cap, np.int32)

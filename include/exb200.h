@@ -164,7 +164,7 @@ typedef struct exb200_stats {
   int32_t n_entities;     /* K after the sweep                                     */
   int32_t n_links_changed;/* records whose cluster changed                         */
   int32_t n_tables;       /* blocking tables built                                 */
-  int32_t reserved;
+  int32_t n_long;         /* records handled by the warp-per-record path (long lists)      */
   float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
       ms_distort, ms_total; /* CUDA-event times of the phases                     */
 } exb200_stats;
@@ -211,9 +211,16 @@ int exb200_get_stats(exb200_handle* h, exb200_stats* out);
 int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t* cand_ids,
                             double* log_weights, double* log_weight_new);
 
-/* Tuning / test knobs (name, value); unknown names return EXB200_ERR_INVALID.
-   "bucket_cap", "cand_cap": thresholds above which a record takes the serial wide
-   path; "check": recompute sizes/K from the links after every sweep and compare. */
+/* Tuning / test knobs (name, value); unknown names return EXB200_ERR_INVALID.  None of them
+   changes a result, only how the work is scheduled:
+     "cand_cap"  candidates a warp stages per record (<= 256); more go to a block-wide kernel
+     "long_cap"  candidates a block stages per record (<= 16384); more: serial wide path
+     "long_min"  list length above which a record's turn is taken by a warp instead of a thread
+     "bucket_cap" bucket length above which a record takes the serial wide path
+     "est_threshold" expected bucket size above which the blocking key uses every usable attribute
+     "table_min_ppm" share of the records (parts per million) below which a key mask gets no
+                 blocking table of its own and uses a coarser one
+     "check"     recompute sizes / member lists / K from the links after every sweep and compare */
 int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
 
 void exb200_destroy(exb200_handle* h);

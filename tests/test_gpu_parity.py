@@ -54,8 +54,18 @@ def test_wide_path_gives_the_same_chain():
     """Forcing most records onto the serial wide path (no stored candidate list) must not change
     a single integer: results do not depend on the batching."""
     m, _ = readme_model("rldata500", n=200)
-    stats = lockstep(m, 8, cand_cap=1, bucket_cap=2)
+    stats = lockstep(m, 8, cand_cap=1, long_cap=0)
     assert sum(s["n_wide"] for s in stats) > 50
+
+
+def test_block_staged_and_warp_committed_lists_give_the_same_chain():
+    """cand_cap=1 sends every record with two or more candidates through the block-wide staging
+    kernel; long_min=0 lets a warp (instead of a thread) take every record's turn."""
+    m, _ = readme_model("rldata500")
+    stats = lockstep(m, 12, cand_cap=1, long_min=0)
+    assert sum(s["n_long"] for s in stats) > 500
+    m, _ = readme_model("rldata10000", n=3000, clust_prior=PRIORS["gen_coupon"](3000))
+    lockstep(m, 6, long_min=1, est_threshold=0)
 
 
 def test_missing_values_and_many_attributes():
@@ -121,7 +131,8 @@ def test_results_do_not_depend_on_batching_thresholds():
     any size: the sweep is sequentially consistent, batching is only scheduling)."""
     m, _ = readme_model("rldata10000", n=4000)
     states = []
-    for opts in (dict(), dict(cand_cap=4, bucket_cap=64), dict(cand_cap=32, bucket_cap=8)):
+    for opts in (dict(), dict(cand_cap=4, long_cap=64, long_min=2), dict(cand_cap=32, bucket_cap=8, est_threshold=1),
+                 dict(table_min_ppm=1000000), dict(table_min_ppm=0, est_threshold=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
