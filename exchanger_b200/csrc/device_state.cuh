@@ -90,7 +90,7 @@ struct DevState {
   int key_attr[KEY_ATTRS];      // key position -> attribute
   int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
   uint32_t *cand_off;           // [N]
-  int *cand_cnt;                // [N] (-1: wide record)
+  int *cand_cnt;                // [N] >= 0: stored list; -1: wide (turn taken first); -2: serial fence; -3: unclassified
   int *cand_id; double *cand_ll;// candidate pool
   unsigned long long *pool_cursor; unsigned long long pool_cap;
   unsigned long long *owner;    // [2N] reservation words
@@ -101,6 +101,8 @@ struct DevState {
   int *act_in, *act_out;        // active records with short candidate lists (thread per record)
   int *actl_in, *actl_out;      // active records with long candidate lists (warp per record)
   int *long_todo;               // records whose candidates did not fit a warp's staging area
+  int *wide_list;               // records with more than wide_threshold possible links (taken first)
+  int *unk_list;                // records without a usable blocking bucket: classified one by one
   double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path
   int *counters;                // see CounterSlot
   long long *counters64;        // [0] candidates, [1] bucket items visited
@@ -125,6 +127,9 @@ enum CounterSlot {
   C_NACTL_OUT = 7,  // size of actl_out
   C_NLONG_TODO = 8, // size of long_todo
   C_NACTL_INIT = 9, // long records found by candidate generation
+  C_NUNK = 10,      // size of unk_list
+  C_NFENCE = 11,    // records that take their turn serially inside the rounds
+  C_COUNT = 12,     // scratch of k_count_all
   C_NSLOTS = 16
 };
 

@@ -61,7 +61,7 @@ struct exb200_handle {
   uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
   uint32_t round_ctr = 1;
   int opt_check = 0;
-  int bucket_cap = 1 << 18, cand_cap = CAND_SMEM, long_cap = 8192, long_min = 32;
+  int bucket_cap = 1 << 18, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
   double est_threshold = 16.0;
   double table_min_share = 0.002; // a key mask wanted by a smaller share of the records gets no table of its own
   int n_tab = 0; // 2^n_key
@@ -370,8 +370,51 @@ int update_links(exb200_handle* h) {
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  // records without a usable bucket: count their possible links to classify them
+  std::vector<int> wide;
+  int n_fence = hc[C_NFENCE];
+  if (hc[C_NUNK] > 0) {
+    std::vector<int> unk(hc[C_NUNK]);
+    CK(cudaMemcpyAsync(unk.data(), S.unk_list, sizeof(int) * unk.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r : unk) {
+      int count = 0;
+      CK(cudaMemsetAsync(S.counters + C_COUNT, 0, sizeof(int), st));
+      KLAUNCH(h, k_count_all, nblk(2LL * N), TPB, 0, S, r);
+      CK(cudaMemcpyAsync(&count, S.counters + C_COUNT, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int code = count > h->long_cap ? -1 : -2;
+      CK(cudaMemcpyAsync(S.cand_cnt + r, &code, sizeof(int), cudaMemcpyHostToDevice, st));
+      if (code == -1) wide.push_back(r); else n_fence++;
+    }
+  }
+  if (hc[C_NWIDE] > 0) {
+    const size_t n0 = wide.size();
+    wide.resize(n0 + hc[C_NWIDE]);
+    CK(cudaMemcpyAsync(wide.data() + n0, S.wide_list, sizeof(int) * hc[C_NWIDE], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   h->stats.n_long = hc[C_NACTL_INIT];
+  h->stats.n_wide = (int)wide.size() + n_fence;
   CK(cudaEventRecord(h->ev[4], st));
+  // Scan order: records with more than wide_threshold possible links take their turn
+  // first, in ascending id, one at a time against every item; then everybody else in ascending id.
+  int dk_wide = 0;
+  if (!wide.empty()) {
+    std::sort(wide.begin(), wide.end());
+    for (int w : wide) {
+      KLAUNCH(h, k_eval_all, nblk(2LL * N), TPB, 0, S, w, 2 * N);
+      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 0);
+      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 1);
+      KLAUNCH(h, k_wide_commit, 1, 32, 0, S, w);
+    }
+    CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(S.act_out, wide.data(), sizeof(int) * wide.size(), cudaMemcpyHostToDevice, st));
+    KLAUNCH(h, k_clear_bounds, nblk((long long)wide.size()), TPB, 0, S, S.act_out, (int)wide.size());
+    CK(cudaMemsetAsync(S.counters + C_DK_TOTAL, 0, sizeof(int), st));
+    CK(cudaStreamSynchronize(st));
+    S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
+  }
 
   // dependency rounds
   int n_act = N, n_actl = hc[C_NACTL_INIT];
@@ -439,12 +482,11 @@ int update_links(exb200_handle* h) {
   CK(cudaMemcpyAsync(c64, S.counters64, sizeof c64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[6], st));
   CK(cudaStreamSynchronize(st));
-  if (hc[C_K] != h->K + hc[C_DK_TOTAL])
+  if (hc[C_K] != h->K + dk_wide + hc[C_DK_TOTAL])
     return fail(h, EXB200_ERR_CUDA, "entity count mismatch after the links update: " + std::to_string(hc[C_K]) +
-                                        " vs " + std::to_string(h->K + hc[C_DK_TOTAL]));
+                                        " vs " + std::to_string(h->K + dk_wide + hc[C_DK_TOTAL]));
   h->K = hc[C_K];
   h->stats.n_entities = h->K;
-  h->stats.n_wide = hc[C_NWIDE];
   h->stats.n_links_changed = hc[C_CHANGED];
   h->stats.n_candidates = c64[0];
   h->stats.n_bucket_items = c64[1];
@@ -664,6 +706,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.actl_in, (size_t)N));
   TRY(dalloc(h, &S.actl_out, (size_t)N));
   TRY(dalloc(h, &S.long_todo, (size_t)N));
+  TRY(dalloc(h, &S.wide_list, (size_t)N));
+  TRY(dalloc(h, &S.unk_list, (size_t)N));
   TRY(dalloc(h, &S.wide_part, (size_t)WIDE_BLOCKS * (TPB + 2)));
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
   TRY(dalloc(h, &S.counters64, 2));
@@ -732,7 +776,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   if (n == "check") h->opt_check = value != 0;
   else if (n == "bucket_cap") h->bucket_cap = (int)std::max<int64_t>(0, value);
   else if (n == "cand_cap") h->cand_cap = (int)std::min<int64_t>(CAND_SMEM, std::max<int64_t>(0, value));
-  else if (n == "long_cap") h->long_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(0, value));
+  else if (n == "wide_threshold") h->long_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(0, value));
   else if (n == "long_min") h->long_min = (int)std::max<int64_t>(0, value);
   else if (n == "est_threshold") h->est_threshold = (double)value;
   else if (n == "table_min_ppm") h->table_min_share = (double)value * 1e-6;

@@ -312,7 +312,9 @@ __device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint
   S.cand_cnt[r] = cnt;
   S.dlo[r] = other ? -1 : 0; // while its outcome is unknown the record may lower K only if it can join another entity
   S.dhi[r] = 1;
-  if (cnt < 0) atomicAdd(&S.counters[C_NWIDE], 1);
+  if (cnt == -1) S.wide_list[atomicAdd(&S.counters[C_NWIDE], 1)] = r;
+  else if (cnt == -2) atomicAdd(&S.counters[C_NFENCE], 1);
+  else if (cnt == -3) S.unk_list[atomicAdd(&S.counters[C_NUNK], 1)] = r;
   else if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
 }
 
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     const int tab = S.tab_remap[S.rec_tab[r]];
     const int own = S.lambda[r];
     int cnt = 0;
-    bool wide = tab == 0, spill = false;
+    bool wide = tab == 0, spill = false, overflow = false;
     int lo = 0, hi = 0;
     if (!wide) {
       const DevTable& t = S.tables[tab];
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
       if (lane == 0) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r;
     } else {
       uint32_t off = 0;
-      if (!wide && cnt > 0) {
+      if (!wide && cnt > 0 && cnt <= S.long_cap) {
         // sort the staged candidates by id (bitonic, one warp)
         int n2 = 1;
         while (n2 < cnt) n2 <<= 1;
@@ -397,17 +399,20 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
         unsigned long long o = 0;
         if (lane == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
         o = __shfl_sync(FULL, o, 0);
-        if (o + (unsigned long long)cnt > S.pool_cap) wide = true;
+        if (o + (unsigned long long)cnt > S.pool_cap) overflow = true;
         else {
           off = (uint32_t)o;
           for (int i = lane; i < cnt; i += 32) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
         }
       }
       if (lane == 0) {
-        bool other = wide;
-        if (!wide) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
-        finish_candidates(S, r, off, wide ? -1 : cnt, other);
-        if (!wide) atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
+        // no usable bucket: the host counts this record's possible links to classify it (-3);
+        // candidate pool exhausted: serial turn inside the rounds (-2)
+        const int code = wide ? -3 : (cnt > S.long_cap ? -1 : (overflow ? -2 : cnt));
+        bool other = code < 0;
+        if (code >= 0) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
+        finish_candidates(S, r, off, code, other);
+        if (code >= 0) atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
       }
     }
   }
@@ -473,16 +478,15 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       if (threadIdx.x == 0) s_off = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
       __syncthreads();
       const unsigned long long o = s_off;
-      if (o + (unsigned long long)cnt > S.pool_cap) wide = true;
-      else for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+      const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
+      if (!overflow) for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
       if (threadIdx.x == 0) {
-        bool other = wide;
-        if (!wide) other = cnt > 1 || (cnt == 1 && ids[0] != own);
-        finish_candidates(S, r, wide ? 0u : (uint32_t)o, wide ? -1 : cnt, other);
-        if (!wide) atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
+        const bool other = overflow || cnt > 1 || (cnt == 1 && ids[0] != own);
+        finish_candidates(S, r, overflow ? 0u : (uint32_t)o, overflow ? -2 : cnt, other);
+        if (!overflow) atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
       }
     } else if (threadIdx.x == 0) {
-      finish_candidates(S, r, 0u, -1, true);
+      finish_candidates(S, r, 0u, -1, true); // more than wide_threshold possible links: its turn comes first
     }
     __syncthreads();
   }
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
   if (i < n_act) {
     const int r = act ? act[i] : i;
     const int cnt = S.cand_cnt[r];
-    if (cnt <= S.long_min) { // long records are handled by k_reserve_w
+    if (cnt <= S.long_min && !S.fin[r]) { // long records: k_reserve_w; wide records are final already
       mine = r;
       const unsigned long long key = resv_key(round, r);
       if (cnt < 0) {
@@ -623,14 +627,15 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
   if (i < n_act) {
     r = act ? act[i] : i;
     const int cnt = S.cand_cnt[r];
-    stay = cnt <= S.long_min; // long records live in the other list
+    stay = cnt <= S.long_min && !S.fin[r]; // long records live in the other list; wide ones are final
     const unsigned long long key = resv_key(round, r);
     const unsigned long long fence = *S.fence;
     const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
-    if (cnt < 0) {
-      // wide record: its turn comes when every earlier record is final
+    if (!stay) {
+    } else if (cnt < 0) {
+      // serial record: its turn comes when every earlier record is final
       if (S.counters[C_MIN_ACTIVE] == r) S.counters[C_WIDE_READY] = r;
-    } else if (stay && !fenced) {
+    } else if (!fenced) {
       const int own = S.lambda[r];
       const int* ids = S.cand_id + S.cand_off[r];
       bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
@@ -798,6 +803,21 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
   S.lwbuf[i] = out;
 }
 
+// number of possible links of record r (compatible items of non-zero likelihood among all the
+// items of the sweep, whatever their size): classifies records that have no usable bucket
+__global__ void __launch_bounds__(TPB) k_count_all(DevState S, int r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int ok = 0;
+  if (i < 2 * S.N && i != S.N + r && !(i < S.N && S.ent_size[i] <= 0)) {
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    const int* y = S.ent_y + (size_t)i * S.ES;
+    ok = item_compatible(S, x, zm, y) && item_loglik(S, x, zm, y) > -CUDART_INF;
+  }
+  ok = warp_sum(ok);
+  if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&S.counters[C_COUNT], ok);
+}
+
 // The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 256
 // contiguous sub-chunks (one thread each).  pass 0: maxima; pass 1: sums of exp(lw - max) per
 // thread and per block.  wide_part layout: [0, WB) block maxima, [WB, 2 WB) block sums,
@@ -886,6 +906,12 @@ __global__ void k_wide_commit(DevState S, int r) {
     if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
   }
   finalize_record(S, r, own, target, single);
+}
+
+// wide records are final before the rounds start and their change of K is folded into K0
+__global__ void __launch_bounds__(TPB) k_clear_bounds(DevState S, const int* __restrict__ list, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { S.dlo[list[i]] = 0; S.dhi[list[i]] = 0; }
 }
 
 // drop finalised records from an active list

@@ -211,10 +211,13 @@ int exb200_get_stats(exb200_handle* h, exb200_stats* out);
 int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t* cand_ids,
                             double* log_weights, double* log_weight_new);
 
-/* Tuning / test knobs (name, value); unknown names return EXB200_ERR_INVALID.  None of them
-   changes a result, only how the work is scheduled:
+/* Options (name, value); unknown names return EXB200_ERR_INVALID.
+   One option is part of the sampling specification (it fixes the systematic-scan order of the
+   links update) and therefore changes the chain:
+     "wide_threshold" (default 4096, <= 16384): records with more possible links than this
+                 take their turn first, in ascending id, before all other records
+   The others change no result, only how the work is scheduled:
      "cand_cap"  candidates a warp stages per record (<= 256); more go to a block-wide kernel
-     "long_cap"  candidates a block stages per record (<= 16384); more: serial wide path
      "long_min"  list length above which a record's turn is taken by a warp instead of a thread
      "bucket_cap" bucket length above which a record takes the serial wide path
      "est_threshold" expected bucket size above which the blocking key uses every usable attribute

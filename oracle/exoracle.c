@@ -22,8 +22,11 @@
  * bit for bit (the same rules are implemented by the CUDA sampler; DESIGN.md "sampling
  * specification"):
  *   - randomness is Philox4x32-10 keyed by (seed; id, iteration, phase, attribute, slot);
- *   - records are visited in ascending id (as the reference does, links.cpp:485-488),
- *     candidate entities and entity members in ascending id;
+ *   - records are visited in ascending id (as the reference does, links.cpp:485-488), except
+ *     that records with more than `wide_threshold` possible links (compatible items of non-zero
+ *     likelihood, counted over all entity slots of the sweep, live or not) take their turn first,
+ *     in ascending id: a fixed systematic-scan order that depends only on quantities the links
+ *     update does not change.  Candidate entities and entity members in ascending id;
  *   - one-shot discrete draws use the inverse CDF in that order instead of a throw-away
  *     alias table (links.cpp:421-422, entities.cpp:346-347); persistent distributions
  *     (phi, psi, phi/(1-psi)^n) use alias tables (alias_sampler.cpp:3-49);
@@ -150,10 +153,11 @@ typedef struct exo {
   uint32_t host_ctr;
   int err_rec; char err[256];
   /* statistics of the last sweep */
-  long long n_cand; int n_changed;
+  long long n_cand; int n_changed, n_wide;
   /* scratch for the links update */
   double *Lnew; int idx_attr; int *bptr, *bitem;
   int brute;
+  int wide_threshold;             /* scan order: records with more possible links go first */
   int *corr;                      /* [F*A] corrected non-distorted counts of the last sweep */
 } exo;
 
@@ -310,6 +314,7 @@ exo *exo_create(const exb200_model *m) {
   s->ndist = (int *)calloc(F * A, sizeof(int));
   s->Lnew = (double *)malloc(sizeof(double) * N);
   s->corr = (int *)calloc(F * A, sizeof(int));
+  s->wide_threshold = 4096;
   s->bitem = (int *)malloc(sizeof(int) * 2 * N);
   s->at = (attr_t *)calloc(A, sizeof(attr_t));
   for (int i = 0; i < N * A; i++) {
@@ -577,13 +582,40 @@ static int link_candidates(const exo *s, int r, int **ids, double **lw, int *cap
   return n;
 }
 
+/* number of possible links of record r: compatible items of non-zero likelihood among all 2N
+   entity slots of the sweep (whatever their current size), its own potential entity excluded */
+static int count_possible_links(const exo *s, int r, int stop_after) {
+  const int N = s->N, A = s->A;
+  int a0 = s->idx_attr, xv0 = s->x[r * A + a0];
+  int use_bucket = !s->brute && xv0 >= 0 && !s->z[r * A + a0];
+  int lo = use_bucket ? s->bptr[xv0] : 0, hi = use_bucket ? s->bptr[xv0 + 1] : 2 * N;
+  int n = 0;
+  for (int q = lo; q < hi && n <= stop_after; q++) {
+    int e = use_bucket ? s->bitem[q] : q;
+    if (e == N + r) continue;
+    if (e < N && s->esize[e] <= 0) continue; /* slots [0,N) without an entity at the start of the sweep */
+    if (!compatible(s, r, e)) continue;
+    if (loglik_existing(s, r, e) > -INFINITY) n++;
+  }
+  return n;
+}
+
 static void phase_links(exo *s) {
   const int N = s->N;
   uint32_t it = (uint32_t)s->iteration;
   int *ids = NULL, cap = 0; double *lw = NULL;
   links_prepare(s);
   s->n_cand = 0; s->n_changed = 0;
-  for (int r = 0; r < N; r++) {
+  /* scan order: records with more than wide_threshold possible links first, then the others */
+  int *order = (int *)malloc(sizeof(int) * N), no = 0;
+  char *is_wide = (char *)calloc(N, 1);
+  for (int r = 0; r < N; r++) is_wide[r] = count_possible_links(s, r, s->wide_threshold) > s->wide_threshold;
+  for (int r = 0; r < N; r++) if (is_wide[r]) order[no++] = r;
+  s->n_wide = no;
+  for (int r = 0; r < N; r++) if (!is_wide[r]) order[no++] = r;
+  free(is_wide);
+  for (int oi = 0; oi < N; oi++) {
+    int r = order[oi];
     int own = s->lambda[r], single = s->esize[own] == 1;
     int n = link_candidates(s, r, &ids, &lw, &cap);
     s->n_cand += n;
@@ -621,7 +653,7 @@ static void phase_links(exo *s) {
     s->lambda[r] = target;
     if (!(target == own || (single && target == N + r))) s->n_changed++;
   }
-  free(ids); free(lw);
+  free(ids); free(lw); free(order);
 }
 
 /* rename every entity to its smallest member record; attributes move along so that the
@@ -885,6 +917,8 @@ int exo_sweeps(exo *s, int n) {
   return EXB200_OK;
 }
 void exo_set_brute(exo *s, int on) { s->brute = on; }
+void exo_set_wide_threshold(exo *s, int w) { s->wide_threshold = w; }
+int exo_n_wide(exo *s) { return s->n_wide; }
 
 /* same layout as exb200_get_state */
 void exo_get_state(exo *s, exb200_state *out) {

@@ -115,6 +115,8 @@ class OracleSampler:
         lib.exo_sweeps.argtypes = [C.c_void_p, C.c_int]
         lib.exo_sweep_phases.argtypes = [C.c_void_p, C.c_int]
         lib.exo_set_brute.argtypes = [C.c_void_p, C.c_int]
+        lib.exo_set_wide_threshold.argtypes = [C.c_void_p, C.c_int]
+        lib.exo_n_wide.argtypes = [C.c_void_p]
         lib.exo_get_state.argtypes = [C.c_void_p, C.POINTER(CState)]
         lib.exo_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), c_i32p, c_i32p]
         lib.exo_last_error.restype = C.c_char_p
@@ -143,6 +145,12 @@ class OracleSampler:
 
     def set_brute(self, on=True):
         self.lib.exo_set_brute(self.h, int(on))
+
+    def set_wide_threshold(self, w):
+        self.lib.exo_set_wide_threshold(self.h, int(w))
+
+    def n_wide(self):
+        return self.lib.exo_n_wide(self.h)
 
     def state(self):
         return read_state(lambda st: self.lib.exo_get_state(self.h, C.byref(st)), self.N, self.A, self.F)

@@ -27,9 +27,12 @@ def assert_same_state(a, b, where=""):
     assert a["iteration"] == b["iteration"]
 
 
-def lockstep(model, n_sweeps, seed=11, every=1, **options):
+def lockstep(model, n_sweeps, seed=11, every=1, wide_threshold=None, **options):
     gpu, oracle = Sampler(model, seed=seed), OracleSampler(model, seed=seed)
     gpu.set_option("check", 1)
+    if wide_threshold is not None:  # part of the sampling specification: set on both sides
+        gpu.set_option("wide_threshold", wide_threshold)
+        oracle.set_wide_threshold(wide_threshold)
     for k, v in options.items():
         gpu.set_option(k, v)
     stats = []
@@ -50,12 +53,22 @@ def test_rldata500_lockstep_every_prior(prior):
     assert max(s["n_rounds"] for s in stats) >= 2  # the dependency rounds were exercised
 
 
-def test_wide_path_gives_the_same_chain():
-    """Forcing most records onto the serial wide path (no stored candidate list) must not change
-    a single integer: results do not depend on the batching."""
-    m, _ = readme_model("rldata500", n=200)
-    stats = lockstep(m, 8, cand_cap=1, long_cap=0)
-    assert sum(s["n_wide"] for s in stats) > 50
+@pytest.mark.parametrize("threshold", [0, 2, 5])
+def test_wide_records_take_their_turn_first(threshold):
+    """Scan order of the specification: records with more than `wide_threshold` possible links go
+    first (serial path against every item), the rest follows in ascending id.  Small thresholds
+    push many records of RLdata500 through that path."""
+    m, _ = readme_model("rldata500", n=250)
+    stats = lockstep(m, 8, wide_threshold=threshold)
+    assert sum(s["n_wide"] for s in stats) > (50 if threshold == 0 else 0)
+
+
+def test_serial_fence_inside_the_rounds():
+    """Records that cannot get a bucket (bucket_cap=0) but have few possible links are not wide by
+    the specification: they take their turn serially, in id order, inside the rounds."""
+    m, _ = readme_model("rldata500", n=150)
+    stats = lockstep(m, 5, bucket_cap=0)
+    assert sum(s["n_wide"] for s in stats) > 100
 
 
 def test_block_staged_and_warp_committed_lists_give_the_same_chain():
@@ -131,7 +144,7 @@ def test_results_do_not_depend_on_batching_thresholds():
     any size: the sweep is sequentially consistent, batching is only scheduling)."""
     m, _ = readme_model("rldata10000", n=4000)
     states = []
-    for opts in (dict(), dict(cand_cap=4, long_cap=64, long_min=2), dict(cand_cap=32, bucket_cap=8, est_threshold=1),
+    for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=8, est_threshold=1),
                  dict(table_min_ppm=1000000), dict(table_min_ppm=0, est_threshold=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
