@@ -61,7 +61,7 @@ struct exb200_handle {
   uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
   uint32_t round_ctr = 1;
   int opt_check = 0;
-  int bucket_cap = 1 << 18, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
+  int bucket_cap = 2048, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
   double est_threshold = 16.0;
   double table_min_share = 0.002; // a key mask wanted by a smaller share of the records gets no table of its own
   int n_tab = 0; // 2^n_key

@@ -342,9 +342,9 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
       if (lane == 0) S.rec_bkt[r] = b;
       lo = b ? t.ptr[b - 1] : 0;
       hi = t.ptr[b];
-      wide = hi - lo > S.bucket_cap;
+      spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
     }
-    if (!wide) {
+    if (!wide && !spill) {
       const int* bucket = S.tables[tab].ids;
       for (int base = lo; base < hi && !spill; base += 32) {
         const int q = base + lane;

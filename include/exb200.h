@@ -219,7 +219,7 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
    The others change no result, only how the work is scheduled:
      "cand_cap"  candidates a warp stages per record (<= 256); more go to a block-wide kernel
      "long_min"  list length above which a record's turn is taken by a warp instead of a thread
-     "bucket_cap" bucket length above which a record takes the serial wide path
+     "bucket_cap" bucket length above which a block instead of a warp scans the bucket
      "est_threshold" expected bucket size above which the blocking key uses every usable attribute
      "table_min_ppm" share of the records (parts per million) below which a key mask gets no
                  blocking table of its own and uses a coarser one

@@ -1,0 +1,49 @@
+"""Multi-chain host logic on CPU: two ranks over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from exchanger_b200.chains import chain_seed, coreference_counts, coreference_probs, merged_coreference_probs
+
+
+def test_chain_seeds_are_distinct():
+    seeds = {chain_seed(7, r) for r in range(64)} | {chain_seed(8, r) for r in range(64)}
+    assert len(seeds) == 128
+
+
+def test_coreference_probs_single_chain():
+    links = np.array([[0, 0, 2, 3], [0, 1, 1, 3], [0, 0, 2, 2]])
+    pairs = np.array([[0, 1], [2, 3], [1, 2]])
+    assert coreference_counts(links, pairs).tolist() == [2, 1, 1]
+    assert np.allclose(coreference_probs(links, pairs), [2 / 3, 1 / 3, 1 / 3])
+    with pytest.raises(ValueError):
+        coreference_counts(links, np.array([[0, 9]]))
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    links = rng.integers(0, 4, size=(5 + rank, 12))  # chains of different lengths
+    pairs = np.array([[0, 1], [2, 3], [4, 11]])
+    merged = merged_coreference_probs(links, pairs)
+    out[rank] = (links, merged)
+    dist.destroy_process_group()
+
+
+def test_merged_coreference_probs_two_ranks_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    pairs = np.array([[0, 1], [2, 3], [4, 11]])
+    both = np.concatenate([out[0][0], out[1][0]], axis=0)
+    expect = coreference_probs(both, pairs)
+    assert np.allclose(out[0][1], expect) and np.allclose(out[1][1], expect)
