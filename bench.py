@@ -185,8 +185,8 @@ def run_ours(opt, n_records, kind, desc):
     gpu.sweeps(opt.warmup)          # W warm-up steps
     barrier()
     clocks = ClockSampler(local)
-    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_cand", "ms_rounds", "ms_canon", "ms_entities",
-                  "ms_distort", "ms_total")
+    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_cand", "ms_cand_long", "ms_wide", "ms_rounds", "ms_canon",
+                  "ms_entities", "ms_distort", "ms_total")
     acc = {k: 0.0 for k in phase_keys}
     cand = rounds = wide = launches = 0
     dev_ms = 0.0

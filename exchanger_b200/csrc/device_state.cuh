@@ -21,12 +21,14 @@ namespace exb {
 
 constexpr int NMAX_FAST = 8;        // categorical fast scheme: up to this many observed members
 constexpr int REJECT_CAP = 100000;  // safety bound of the rejection loops
-constexpr int CAND_SMEM = 256;      // compatible candidates a warp can stage for one record
+constexpr int CAND_SMEM = 64;       // compatible candidates an 8-lane group can stage for one record
 constexpr int LPE_MAX = 32;         // host-computed log prior_weight_existing(n), n < LPE_MAX
 constexpr int MAX_ATTRS = 32;
 constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that may form blocking keys
 constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
+constexpr int WIDE_BATCH = 8;       // serial records whose likelihoods are evaluated in one pass over the items
+constexpr int HUGE_CAP = 16386;     // scratch entries of the grid-wide bucket scan
 
 // Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
 // (src/attribute_index.h:12-146) plus the alias tables that replace IndexNonUniformDiscreteDist
@@ -81,11 +83,17 @@ struct DevState {
   const DevAttr *attrs;
   // links-update scratch
   double *Lnew;                 // [N] logLikelihoodWeightNew
-  uint16_t *rec_tab;            // [N] key mask of the blocking table chosen for the record (0: none)
+  uint16_t *rec_tab;            // [N] key mask the record would like: every usable key attribute when its best
+                                //     pair is expected to match many items, else that pair (0: none)
+  uint16_t *rec_alt;            // [N] key mask of its best pair
+  uint8_t *twin;                // [N] 1: potential entity N+r has the same attributes as entity slot r (a
+                                //     singleton of r); it is then not indexed but implied by slot r
   uint32_t *rec_bkt;            // [N] bucket inside that table
   const DevTable *tables;       // [2^n_key] indexed by key mask
-  int *tab_usage;               // [2^n_key]
-  const uint16_t *tab_remap;    // [2^n_key] wanted key mask -> mask of the table that is built (0: none)
+  int *tab_usage;               // [2][2^n_key] records wanting each full mask / each pair mask
+  float *tab_est;               // [2^n_key] sum over the records wanting a full mask of the expected size
+                                //           of their pair bucket (what falling back to the pair would cost)
+  const uint16_t *tab_remap;    // [2][2^n_key] wanted full mask / pair mask -> mask of a built table (0: none)
   int n_key;                    // number of key attributes
   int key_attr[KEY_ATTRS];      // key position -> attribute
   int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
@@ -103,11 +111,15 @@ struct DevState {
   int *long_todo;               // records whose candidates did not fit a warp's staging area
   int *wide_list;               // records with more than wide_threshold possible links (taken first)
   int *unk_list;                // records without a usable blocking bucket: classified one by one
+  int *huge_list;               // records whose bucket is scanned by the whole grid
+  int *huge_id; double *huge_ll;// [HUGE_CAP] scratch of that scan
+  int *batch_list;              // [WIDE_BATCH] records of the current k_eval_batch
+  int huge_min;                 // bucket length above which the whole grid scans it
   double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path
   int *counters;                // see CounterSlot
   long long *counters64;        // [0] candidates, [1] bucket items visited
   int *dev_err;                 // [0] status, [1] id
-  double *lwbuf;                // [2N] scratch of the wide path / test hook
+  double *lwbuf;                // [WIDE_BATCH][2N] scratch of the serial path / test hook
   int *ndist, *corr;            // [F*A] distorted counts, corrected non-distorted counts
   int bucket_cap, cand_cap, long_cap, long_min; // thresholds: see exb200_set_option
   double est_threshold;         // expected bucket size above which the full key is used
@@ -129,7 +141,8 @@ enum CounterSlot {
   C_NACTL_INIT = 9, // long records found by candidate generation
   C_NUNK = 10,      // size of unk_list
   C_NFENCE = 11,    // records that take their turn serially inside the rounds
-  C_COUNT = 12,     // scratch of k_count_all
+  C_COUNT = 12,     // scratch of k_count_all / k_huge_scan
+  C_NHUGE = 13,     // size of huge_list
   C_NSLOTS = 16
 };
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -61,12 +62,14 @@ struct exb200_handle {
   uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
   uint32_t round_ctr = 1;
   int opt_check = 0;
-  int bucket_cap = 2048, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
+  int trace = std::getenv("EXB200_TRACE") ? 1 : 0;
+  int bucket_cap = 512, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
   double est_threshold = 16.0;
-  double table_min_share = 0.002; // a key mask wanted by a smaller share of the records gets no table of its own
+  int huge_min = 65536;
+  double table_full_cost = 1.0, table_pair_cost = 0.25; // cost of building a table, in bucket visits per item
   int n_tab = 0; // 2^n_key
   exb200_stats stats{};
-  cudaEvent_t ev[10]{};
+  cudaEvent_t ev[12]{};
   std::string err;
   bool poisoned = false;
   long long n_launches = 0; // kernels launched by this handle
@@ -312,43 +315,50 @@ int update_links(exb200_handle* h) {
   const int N = h->N, NT = h->n_tab;
   cudaStream_t st = h->stream;
   S.K0 = h->K;
-  CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * NT, st));
+  CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * 2 * N_TABLES, st));
+  CK(cudaMemsetAsync(S.tab_est, 0, sizeof(float) * N_TABLES, st));
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
   CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
   CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
   CK(cudaEventRecord(h->ev[1], st));
   KLAUNCH(h, k_prep, nblk(N), TPB, 0, S);
-  std::vector<int> usage(NT);
-  CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * NT, cudaMemcpyDeviceToHost, st));
+  std::vector<int> usage(2 * (size_t)N_TABLES);
+  std::vector<float> est(N_TABLES);
+  CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * usage.size(), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(est.data(), S.tab_est, sizeof(float) * est.size(), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[2], st));
   CK(cudaStreamSynchronize(st));
-  // Which blocking tables to build.  A table costs one atomic per item and pass, so a key mask
-  // wanted by few records is served by the most selective table that is built anyway and whose
-  // mask is a subset of it (bigger buckets, same candidates after the compatibility filter).
+  // Which blocking tables to build.  A table costs atomics for every item, so
+  //  * a full key mask gets a table only if sending its records to their pair tables instead would
+  //    cost more bucket visits (est) than building it;
+  //  * a pair mask wanted by few records is served by the most selective table that is built anyway
+  //    and whose mask is a subset of it (bigger buckets, same candidates after the filter).
   std::vector<int> active;
-  std::vector<uint16_t> remap(NT, 0);
+  std::vector<uint16_t> remap(2 * (size_t)N_TABLES, 0);
   {
-    const long long min_use = std::max<long long>(1, (long long)((double)N * h->table_min_share));
+    const double items = 1.2 * (double)N;
+    std::vector<char> built(NT, 0);
+    for (int t = 1; t < NT; t++)
+      if (usage[t] > 0 && (double)est[t] >= h->table_full_cost * items) { built[t] = 1; active.push_back(t); remap[t] = (uint16_t)t; }
     std::vector<int> wanted;
-    for (int t = 1; t < NT; t++) if (usage[t] > 0) wanted.push_back(t);
-    std::sort(wanted.begin(), wanted.end(), [&](int a, int b) { return usage[a] > usage[b]; });
-    auto keys_of = [&](int t) { return h->tables[t].keys; };
+    for (int t = 1; t < NT; t++) if (usage[N_TABLES + t] > 0) wanted.push_back(t);
+    std::sort(wanted.begin(), wanted.end(), [&](int a, int b) { return usage[N_TABLES + a] > usage[N_TABLES + b]; });
+    auto keys_of = [&](int t) { return (double)h->tables[t].keys; };
     for (int t : wanted) {
       int best = 0;
-      if (usage[t] < min_use)
-        for (int b : active)
-          if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
-      // fall back only if the substitute is selective enough for this table's records
-      if (best && (double)(2LL * N) / (double)keys_of(best) * (double)usage[t] > 64.0 * (double)(2LL * N)) best = 0;
-      if (best == 0) { best = t; active.push_back(t); }
-      remap[t] = (uint16_t)best;
+      for (int b : active)
+        if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
+      // expected bucket visits through the substitute versus the cost of a table of its own
+      if (best && (double)usage[N_TABLES + t] * items / keys_of(best) > h->table_pair_cost * items) best = 0;
+      if (best == 0) { best = t; if (!built[t]) { built[t] = 1; active.push_back(t); } }
+      remap[N_TABLES + t] = (uint16_t)best;
     }
   }
   for (int t : active) {
     int rc = ensure_table(h, t); if (rc) return rc;
     CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
   }
-  CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * NT, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * remap.size(), cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
   if (!active.empty()) {
     CK(cudaMemcpyAsync(h->d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, st));
@@ -360,7 +370,8 @@ int update_links(exb200_handle* h) {
     KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)active.size());
   }
   CK(cudaEventRecord(h->ev[3], st));
-  KLAUNCH(h, k_cand, nblk((long long)N, TPB / 32), TPB, 0, S);
+  KLAUNCH(h, k_cand, nblk((long long)N, TPB / GL), TPB, 0, S);
+  CK(cudaEventRecord(h->ev[10], st));
   int hc[C_NSLOTS];
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -369,6 +380,17 @@ int update_links(exb200_handle* h) {
     KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 8), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (hc[C_NHUGE] > 0) { // buckets so long that the whole grid scans them, one record at a time
+      std::vector<int> huge(hc[C_NHUGE]);
+      CK(cudaMemcpyAsync(huge.data(), S.huge_list, sizeof(int) * huge.size(), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (int r : huge) {
+        KLAUNCH(h, k_huge_scan, 148 * 4, TPB, 0, S, r, h->long_cap);
+        KLAUNCH(h, k_huge_finish, 1, TPB, smem, S, r, h->long_cap);
+      }
+      CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
   }
   // records without a usable bucket: count their possible links to classify them
   std::vector<int> wide;
@@ -402,11 +424,17 @@ int update_links(exb200_handle* h) {
   int dk_wide = 0;
   if (!wide.empty()) {
     std::sort(wide.begin(), wide.end());
-    for (int w : wide) {
-      KLAUNCH(h, k_eval_all, nblk(2LL * N), TPB, 0, S, w, 2 * N);
-      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 0);
-      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 1);
-      KLAUNCH(h, k_wide_commit, 1, 32, 0, S, w);
+    for (size_t g = 0; g < wide.size(); g += WIDE_BATCH) {
+      // likelihoods of a batch in one pass over the items, then one record after the other
+      // against the sizes its predecessors left
+      const int nb = (int)std::min<size_t>(WIDE_BATCH, wide.size() - g);
+      CK(cudaMemcpyAsync(S.batch_list, wide.data() + g, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, nb);
+      for (int b = 0; b < nb; b++) {
+        const int w = wide[g + b];
+        KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, b);
+        KLAUNCH(h, k_wide_commit, 1, TPB, 0, S, w, b);
+      }
     }
     CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(S.act_out, wide.data(), sizeof(int) * wide.size(), cudaMemcpyHostToDevice, st));
@@ -415,6 +443,7 @@ int update_links(exb200_handle* h) {
     CK(cudaStreamSynchronize(st));
     S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
   }
+  CK(cudaEventRecord(h->ev[11], st));
 
   // dependency rounds
   int n_act = N, n_actl = hc[C_NACTL_INIT];
@@ -441,6 +470,8 @@ int update_links(exb200_handle* h) {
     if (n_actl > 0) KLAUNCH(h, k_commit_w, nblk(n_actl, TPB / 32), TPB, 0, S, S.actl_in, n_actl, round);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (h->trace) std::fprintf(stderr, "[exb200] round %d: short %d long %d -> %d %d%s\n", rounds, n_act, n_actl,
+                               hc[C_NACT_OUT], hc[C_NACTL_OUT], hc[C_WIDE_READY] >= 0 ? " (serial record)" : "");
     const int* next_act = S.act_out;
     int n_next = hc[C_NACT_OUT];
     const int n_nextl = hc[C_NACTL_OUT];
@@ -449,10 +480,10 @@ int update_links(exb200_handle* h) {
     if (hc[C_WIDE_READY] >= 0) {
       // serial path for a record without a stored candidate list
       const int w = hc[C_WIDE_READY];
-      KLAUNCH(h, k_eval_all, nblk(2LL * N), TPB, 0, S, w, 2 * N);
-      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 0);
-      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, 1);
-      KLAUNCH(h, k_wide_commit, 1, 32, 0, S, w);
+      CK(cudaMemcpyAsync(S.batch_list, &w, sizeof(int), cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, 1);
+      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, 0);
+      KLAUNCH(h, k_wide_commit, 1, TPB, 0, S, w, 0);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_compact_active, nblk(n_next), TPB, 0, S, next_act, n_next);
@@ -560,7 +591,7 @@ int sweep(exb200_handle* h) {
   CK(cudaStreamSynchronize(st));
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
   h->stats.ms_clust = ms(0, 1); h->stats.ms_prep = ms(1, 2); h->stats.ms_index = ms(2, 3);
-  h->stats.ms_cand = ms(3, 4); h->stats.ms_rounds = ms(4, 5); h->stats.ms_canon = ms(5, 6);
+  h->stats.ms_cand = ms(3, 10); h->stats.ms_cand_long = ms(10, 4); h->stats.ms_wide = ms(4, 11); h->stats.ms_rounds = ms(11, 5); h->stats.ms_canon = ms(5, 6);
   h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
   if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
   return EXB200_OK;
@@ -687,7 +718,10 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.Lnew, (size_t)N));
   TRY(dalloc(h, &S.rec_tab, (size_t)N));
   TRY(dalloc(h, &S.rec_bkt, (size_t)N));
-  TRY(dalloc(h, &S.tab_usage, (size_t)N_TABLES));
+  TRY(dalloc(h, &S.tab_usage, (size_t)2 * N_TABLES));
+  TRY(dalloc(h, &S.tab_est, (size_t)N_TABLES));
+  TRY(dalloc(h, &S.rec_alt, (size_t)N));
+  TRY(dalloc(h, &S.twin, (size_t)N));
   TRY(dalloc(h, &S.cand_off, (size_t)N));
   TRY(dalloc(h, &S.cand_cnt, (size_t)N));
   S.pool_cap = std::min<unsigned long long>(8ull * N + (1ull << 20), 0xFFFFFFF0ull);
@@ -712,11 +746,15 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
   TRY(dalloc(h, &S.counters64, 2));
   TRY(dalloc(h, &S.dev_err, 2));
-  TRY(dalloc(h, &S.lwbuf, (size_t)2 * N));
+  TRY(dalloc(h, &S.lwbuf, (size_t)WIDE_BATCH * 2 * N));
+  TRY(dalloc(h, &S.huge_list, (size_t)N));
+  TRY(dalloc(h, &S.huge_id, (size_t)HUGE_CAP));
+  TRY(dalloc(h, &S.huge_ll, (size_t)HUGE_CAP));
+  TRY(dalloc(h, &S.batch_list, (size_t)WIDE_BATCH));
   TRY(dalloc(h, &S.ndist, (size_t)F * A));
   TRY(dalloc(h, &S.corr, (size_t)F * A));
   TRY(dalloc(h, &h->d_active, (size_t)N_TABLES));
-  TRY(dalloc(h, &h->d_remap, (size_t)N_TABLES)); S.tab_remap = h->d_remap;
+  TRY(dalloc(h, &h->d_remap, (size_t)2 * N_TABLES)); S.tab_remap = h->d_remap;
   TRY(dalloc(h, &h->d_cl_counts, 2));
   TRY(dalloc(h, &h->d_gen_mask, (size_t)N));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
@@ -756,11 +794,12 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
-  if (cudaFuncSetAttribute(k_cand_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+  if (cudaFuncSetAttribute(k_huge_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_cand_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return bail(fail(h, EXB200_ERR_CUDA, "cannot reserve shared memory for k_cand_long"));
 #undef TRY
   S.bucket_cap = h->bucket_cap; S.cand_cap = h->cand_cap; S.long_cap = h->long_cap; S.long_min = h->long_min;
-  S.est_threshold = h->est_threshold;
+  S.est_threshold = h->est_threshold; S.huge_min = h->huge_min;
   refresh_clust_dev(h);
   rc = upload_theta(h);
   if (rc) return bail(rc);
@@ -779,10 +818,11 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "wide_threshold") h->long_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(0, value));
   else if (n == "long_min") h->long_min = (int)std::max<int64_t>(0, value);
   else if (n == "est_threshold") h->est_threshold = (double)value;
-  else if (n == "table_min_ppm") h->table_min_share = (double)value * 1e-6;
+  else if (n == "huge_min") h->huge_min = (int)std::max<int64_t>(0, value);
+  else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
   h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap; h->S.long_cap = h->long_cap;
-  h->S.long_min = h->long_min; h->S.est_threshold = h->est_threshold;
+  h->S.long_min = h->long_min; h->S.est_threshold = h->est_threshold; h->S.huge_min = h->huge_min;
   return EXB200_OK;
 }
 

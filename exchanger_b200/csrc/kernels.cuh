@@ -95,9 +95,10 @@ __global__ void k_theta_tables(DevState S, int a) {
 //     set-size ordering of getPossibleLinks, links.cpp:187-189)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
-  __shared__ int s_usage[N_TABLES];
+  __shared__ int s_usage[2 * N_TABLES];
+  __shared__ float s_est[N_TABLES];
   const int AA = 1 << S.n_key;
-  for (int i = threadIdx.x; i < AA; i += blockDim.x) s_usage[i] = 0;
+  for (int i = threadIdx.x; i < AA; i += blockDim.x) { s_usage[i] = 0; s_usage[AA + i] = 0; s_est[i] = 0.f; }
   __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < S.N) {
@@ -166,18 +167,30 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
     S.ent_head[S.N + r] = -1;
     S.fin[r] = 0;
     // blocking table
-    uint32_t tab = 0;
+    uint32_t tab = 0, pair = 0;
     if (b1 >= 0) {
-      const uint32_t pair = (1u << b1) | (b2 >= 0 ? 1u << b2 : 0u);
+      pair = (1u << b1) | (b2 >= 0 ? 1u << b2 : 0u);
       const double est = 2.0 * (double)S.N * s1 * (b2 >= 0 ? s2 : 1.0);
       tab = est > S.est_threshold ? nd_mask : pair;
-      atomicAdd(&s_usage[tab], 1);
+      atomicAdd(&s_usage[AA + pair], 1);
+      if (tab != pair) { atomicAdd(&s_usage[tab], 1); atomicAdd(&s_est[tab], (float)est); }
     }
-    S.rec_tab[r] = (uint16_t)tab; // the table actually used is tab_remap[tab] (chosen on the host)
+    S.rec_tab[r] = (uint16_t)tab; // the tables actually built are chosen on the host (tab_remap)
+    S.rec_alt[r] = (uint16_t)pair;
+    // twin: r alone in entity slot r and its potential entity would have the same attributes
+    bool tw = S.lambda[r] == r && S.ent_size[r] == 1;
+    if (tw) {
+      const int* ye = S.ent_y + (size_t)r * S.ES;
+      for (int a = 0; a < S.A; a++) tw &= ye[a] == yn[a];
+    }
+    S.twin[r] = tw;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < AA; i += blockDim.x)
+  for (int i = threadIdx.x; i < AA; i += blockDim.x) {
     if (s_usage[i]) atomicAdd(&S.tab_usage[i], s_usage[i]);
+    if (s_usage[AA + i]) atomicAdd(&S.tab_usage[N_TABLES + i], s_usage[AA + i]);
+    if (s_est[i] != 0.f) atomicAdd(&S.tab_est[i], s_est[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
 __global__ void __launch_bounds__(TPB) k_index_count(DevState S, const int* __restrict__ active, int n_active) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * S.N) return;
-  if (i < S.N && S.ent_size[i] <= 0) return;
+  if (i < S.N ? S.ent_size[i] <= 0 : S.twin[i - S.N]) return;
   const int* y = S.ent_y + (size_t)i * S.ES;
   for (int k = 0; k < n_active; k++) {
     const DevTable& t = S.tables[active[k]];
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(TPB) k_index_count(DevState S, const int* __re
 __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __restrict__ active, int n_active) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * S.N) return;
-  if (i < S.N && S.ent_size[i] <= 0) return;
+  if (i < S.N ? S.ent_size[i] <= 0 : S.twin[i - S.N]) return;
   const int* y = S.ent_y + (size_t)i * S.ES;
   for (int k = 0; k < n_active; k++) {
     const DevTable& t = S.tables[active[k]];
@@ -318,20 +331,26 @@ __device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint
   else if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
 }
 
+// Eight lanes per record (four records per warp): candidate lists are short (1.2-1.4 entries on
+// average), so narrow groups keep four times as many independent gather chains in flight.
+constexpr int GL = 8;
 __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
-  __shared__ int s_id[TPB / 32][CAND_SMEM];
-  __shared__ double s_ll[TPB / 32][CAND_SMEM];
+  __shared__ int s_id[TPB / GL][CAND_SMEM];
+  __shared__ double s_ll[TPB / GL][CAND_SMEM];
   __shared__ long long s_stat[2];
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int r = blockIdx.x * (TPB / 32) + wib;
+  const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gsh = lane & ~(GL - 1);
+  const unsigned gmask = 0xFFu << gsh;
+  const int gib = threadIdx.x / GL;
+  const int r = blockIdx.x * (TPB / GL) + gib;
   if (r < S.N) {
-    int* ids = s_id[wib];
-    double* lls = s_ll[wib];
+    int* ids = s_id[gib];
+    double* lls = s_ll[gib];
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
-    const int tab = S.tab_remap[S.rec_tab[r]];
+    int tab = S.tab_remap[S.rec_tab[r]];
+    if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
     const int own = S.lambda[r];
     int cnt = 0;
     bool wide = tab == 0, spill = false, overflow = false;
@@ -339,15 +358,15 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     if (!wide) {
       const DevTable& t = S.tables[tab];
       const uint32_t b = bucket_of(S, t, x);
-      if (lane == 0) S.rec_bkt[r] = b;
+      if (gl == 0) S.rec_bkt[r] = b;
       lo = b ? t.ptr[b - 1] : 0;
       hi = t.ptr[b];
       spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
     }
     if (!wide && !spill) {
       const int* bucket = S.tables[tab].ids;
-      for (int base = lo; base < hi && !spill; base += 32) {
-        const int q = base + lane;
+      for (int base = lo; base < hi && !spill; base += GL) {
+        const int q = base + gl;
         int item = -1;
         bool ok = false;
         double ll = 0.0;
@@ -362,28 +381,35 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
             }
           }
         }
-        const unsigned m = __ballot_sync(FULL, ok);
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (cnt + __popc(m) > S.cand_cap) spill = true;
-        else if (ok) { ids[pos] = item; lls[pos] = ll; }
-        cnt += __popc(m);
+        // an indexed slot whose potential entity is its twin stands for both items
+        const bool tw = ok && item < S.N && item != r && S.twin[item];
+        const unsigned m = (__ballot_sync(gmask, ok) >> gsh) & 0xFFu, m2 = (__ballot_sync(gmask, tw) >> gsh) & 0xFFu;
+        const unsigned below = (1u << gl) - 1u;
+        const int pos = cnt + __popc(m & below) + __popc(m2 & below);
+        const int add = __popc(m) + __popc(m2);
+        if (cnt + add > S.cand_cap) spill = true;
+        else if (ok) {
+          ids[pos] = item; lls[pos] = ll;
+          if (tw) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
+        }
+        cnt += add;
       }
-      if (lane == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
+      if (gl == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
     }
     if (spill) {
-      // more candidates than a warp can stage: a whole block takes the record (k_cand_long)
-      if (lane == 0) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r;
+      // long bucket or more candidates than a group can stage: a whole block takes the record
+      if (gl == 0) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r;
     } else {
       uint32_t off = 0;
       if (!wide && cnt > 0 && cnt <= S.long_cap) {
-        // sort the staged candidates by id (bitonic, one warp)
+        // sort the staged candidates by id (bitonic, eight lanes)
         int n2 = 1;
         while (n2 < cnt) n2 <<= 1;
-        for (int i = cnt + lane; i < n2; i += 32) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
-        __syncwarp();
+        for (int i = cnt + gl; i < n2; i += GL) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
+        __syncwarp(gmask);
         for (int k = 2; k <= n2; k <<= 1)
           for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < n2; i += 32) {
+            for (int i = gl; i < n2; i += GL) {
               const int l = i ^ j;
               if (l > i) {
                 const bool up = (i & k) == 0;
@@ -394,18 +420,18 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
                 }
               }
             }
-            __syncwarp();
+            __syncwarp(gmask);
           }
         unsigned long long o = 0;
-        if (lane == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
-        o = __shfl_sync(FULL, o, 0);
+        if (gl == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+        o = __shfl_sync(gmask, o, gsh);
         if (o + (unsigned long long)cnt > S.pool_cap) overflow = true;
         else {
           off = (uint32_t)o;
-          for (int i = lane; i < cnt; i += 32) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+          for (int i = gl; i < cnt; i += GL) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
         }
       }
-      if (lane == 0) {
+      if (gl == 0) {
         // no usable bucket: the host counts this record's possible links to classify it (-3);
         // candidate pool exhausted: serial turn inside the rounds (-2)
         const int code = wide ? -3 : (cnt > S.long_cap ? -1 : (overflow ? -2 : cnt));
@@ -421,8 +447,50 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
 }
 
-// One BLOCK per record whose candidates overflowed the warp staging area: same scan, staged in
-// dynamic shared memory (long_cap entries), sorted by a block-wide bitonic network.
+// Block-wide tail of candidate staging: sort `cnt` staged (id, ll) pairs by id, append them to the
+// pool and register the record (cnt > cap: more than wide_threshold possible links).
+__device__ void stage_sort_store(const DevState& S, int r, int own, int* ids, double* lls, int cnt, int cap,
+                                 unsigned long long* s_off) {
+  bool wide = cnt > cap;
+  if (!wide) {
+    int n2 = 1;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = cnt + threadIdx.x; i < n2; i += blockDim.x) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const bool up = (i & k) == 0;
+            const int a0 = ids[i], a1 = ids[l];
+            if ((a0 > a1) == up) {
+              ids[i] = a1; ids[l] = a0;
+              const double t0 = lls[i]; lls[i] = lls[l]; lls[l] = t0;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    if (threadIdx.x == 0) *s_off = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+    __syncthreads();
+    const unsigned long long o = *s_off;
+    const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
+    if (!overflow) for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+    if (threadIdx.x == 0) {
+      const bool other = overflow || cnt > 1 || (cnt == 1 && ids[0] != own);
+      finish_candidates(S, r, overflow ? 0u : (uint32_t)o, overflow ? -2 : cnt, other);
+      if (!overflow) atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
+    }
+  } else if (threadIdx.x == 0) {
+    finish_candidates(S, r, 0u, -1, true); // more than wide_threshold possible links: its turn comes first
+  }
+  __syncthreads();
+}
+
+// One BLOCK per record whose bucket is long or whose candidates overflowed a group's staging area:
+// same scan, staged in dynamic shared memory (wide_threshold entries), sorted block-wide.
+// Buckets longer than huge_min are left to the grid-wide k_huge_scan.
 __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int cap) {
   extern __shared__ unsigned char s_raw[];
   double* lls = reinterpret_cast<double*>(s_raw);
@@ -435,12 +503,19 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
     __syncthreads();
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
-    const DevTable& t = S.tables[S.tab_remap[S.rec_tab[r]]];
+    int tab = S.tab_remap[S.rec_tab[r]];
+    if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+    const DevTable& t = S.tables[tab];
     const uint32_t b = S.rec_bkt[r];
     const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
     const int own = S.lambda[r];
+    if (hi - lo > S.huge_min) {
+      if (threadIdx.x == 0) S.huge_list[atomicAdd(&S.counters[C_NHUGE], 1)] = r;
+      __syncthreads();
+      continue;
+    }
     for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
-      if (s_cnt > cap) break; // already too many: the record takes the wide path (benign race: any exit is a valid exit)
+      if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
       const int q = q0 + threadIdx.x;
       if (q >= hi) continue;
       const int item = t.ids[q];
@@ -449,47 +524,51 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       if (!item_compatible(S, x, zm, y)) continue;
       const double ll = item_loglik(S, x, zm, y);
       if (!(ll > -CUDART_INF)) continue;
-      const int pos = atomicAdd(&s_cnt, 1);
+      const bool tw = item < S.N && item != r && S.twin[item];
+      const int pos = atomicAdd(&s_cnt, tw ? 2 : 1);
       if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
+      if (tw && pos + 1 < cap) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
     }
     __syncthreads();
-    const int cnt = s_cnt;
-    bool wide = cnt > cap;
-    if (!wide) {
-      int n2 = 1;
-      while (n2 < cnt) n2 <<= 1;
-      for (int i = cnt + threadIdx.x; i < n2; i += blockDim.x) { ids[i] = 0x7FFFFFFF; lls[i] = 0.0; }
-      __syncthreads();
-      for (int k = 2; k <= n2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-            const int l = i ^ j;
-            if (l > i) {
-              const bool up = (i & k) == 0;
-              const int a0 = ids[i], a1 = ids[l];
-              if ((a0 > a1) == up) {
-                ids[i] = a1; ids[l] = a0;
-                const double t0 = lls[i]; lls[i] = lls[l]; lls[l] = t0;
-              }
-            }
-          }
-          __syncthreads();
-        }
-      if (threadIdx.x == 0) s_off = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
-      __syncthreads();
-      const unsigned long long o = s_off;
-      const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
-      if (!overflow) for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
-      if (threadIdx.x == 0) {
-        const bool other = overflow || cnt > 1 || (cnt == 1 && ids[0] != own);
-        finish_candidates(S, r, overflow ? 0u : (uint32_t)o, overflow ? -2 : cnt, other);
-        if (!overflow) atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
-      }
-    } else if (threadIdx.x == 0) {
-      finish_candidates(S, r, 0u, -1, true); // more than wide_threshold possible links: its turn comes first
-    }
-    __syncthreads();
+    stage_sort_store(S, r, own, ids, lls, s_cnt, cap, &s_off);
   }
+}
+
+// A huge bucket is scanned by the whole grid: compatible items of non-zero likelihood go to a
+// scratch list (unordered), then one block sorts and stores it (k_huge_finish).
+__global__ void __launch_bounds__(TPB) k_huge_scan(DevState S, int r, int cap) {
+  const int* x = S.rec_x + (size_t)r * S.RS;
+  const uint32_t zm = S.rec_z[r];
+  int tab = S.tab_remap[S.rec_tab[r]];
+  if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+  const DevTable& t = S.tables[tab];
+  const uint32_t b = S.rec_bkt[r];
+  const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+  for (int q = lo + blockIdx.x * blockDim.x + threadIdx.x; q < hi; q += gridDim.x * blockDim.x) {
+    if (S.counters[C_COUNT] > cap) return;
+    const int item = t.ids[q];
+    if (item == S.N + r) continue;
+    const int* y = S.ent_y + (size_t)item * S.ES;
+    if (!item_compatible(S, x, zm, y)) continue;
+    const double ll = item_loglik(S, x, zm, y);
+    if (!(ll > -CUDART_INF)) continue;
+    const bool tw = item < S.N && item != r && S.twin[item];
+    const int pos = atomicAdd(&S.counters[C_COUNT], tw ? 2 : 1);
+    if (pos < cap) { S.huge_id[pos] = item; S.huge_ll[pos] = ll; }
+    if (tw && pos + 1 < cap) { S.huge_id[pos + 1] = S.N + item; S.huge_ll[pos + 1] = ll; }
+  }
+}
+__global__ void __launch_bounds__(TPB) k_huge_finish(DevState S, int r, int cap) {
+  extern __shared__ unsigned char s_raw[];
+  double* lls = reinterpret_cast<double*>(s_raw);
+  int* ids = reinterpret_cast<int*>(lls + cap);
+  __shared__ unsigned long long s_off;
+  const int cnt = S.counters[C_COUNT];
+  if (cnt <= cap)
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { ids[i] = S.huge_id[i]; lls[i] = S.huge_ll[i]; }
+  __syncthreads();
+  stage_sort_store(S, r, S.lambda[r], ids, lls, cnt, cap, &s_off);
+  if (threadIdx.x == 0) S.counters[C_COUNT] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -784,9 +863,10 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
 }
 
 // ------------------------------------------------------------------------------------------
-// wide path and test hook: the conditional of ONE record against every item, in item order.
-// lwbuf[i] = log prior_weight_existing + logLikelihoodWeightExisting, NaN if i is no candidate.
+// serial path (records without a stored candidate list) and test hook: the conditional of ONE record
+// against every item, in item order.
 // ------------------------------------------------------------------------------------------
+// test hook: lwbuf[i] = log prior_weight_existing + logLikelihoodWeightExisting, NaN if no candidate
 __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
@@ -801,6 +881,146 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
     if (item_compatible(S, x, zm, y)) out = log_prior_existing(S.cl, sz) + item_loglik(S, x, zm, y);
   }
   S.lwbuf[i] = out;
+}
+
+// The size-independent part for up to WIDE_BATCH records at once (each item tuple is read once):
+// lwbuf[b][i] = logLikelihoodWeightExisting of record list[b] with item i, NaN if incompatible.
+__global__ void __launch_bounds__(TPB) k_eval_batch(DevState S, const int* __restrict__ list, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 2 * S.N;
+  if (i >= n) return;
+  int y[MAX_ATTRS];
+  const int* yp = S.ent_y + (size_t)i * S.ES;
+  for (int a = 0; a < S.A; a++) y[a] = yp[a];
+  for (int b = 0; b < nb; b++) {
+    const int r = list[b];
+    const int* x = S.rec_x + (size_t)r * S.RS;
+    const uint32_t zm = S.rec_z[r];
+    double out = CUDART_NAN;
+    if (i != S.N + r && item_compatible(S, x, zm, y)) out = item_loglik(S, x, zm, y);
+    S.lwbuf[(size_t)b * n + i] = out;
+  }
+}
+
+// log-weight of item i for record r from the batched likelihood and the CURRENT sizes
+__device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, int i, int own, bool single) {
+  const double v = ll[i];
+  if (!(v == v)) return CUDART_NAN;
+  const int sz = live_size(S, i, own, single);
+  return sz > 0 ? log_prior_existing(S.cl, sz) + v : CUDART_NAN;
+}
+
+// The item range is cut into WIDE_BLOCKS contiguous chunks, one block each.  A block streams its chunk
+// (coalesced) and leaves (max, sum of exp(lw - max)) in wide_part[2b], wide_part[2b+1].
+__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot) {
+  __shared__ double s_m[TPB], s_s[TPB];
+  const int n = 2 * S.N;
+  const double* ll = S.lwbuf + (size_t)slot * n;
+  const int own = S.lambda[r];
+  const bool single = S.ent_size[own] == 1;
+  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+  const long long b_lo = blockIdx.x * per_b, b_hi = min((long long)n, b_lo + per_b);
+  double m = -CUDART_INF, sum = 0.0;
+  for (long long i = b_lo + threadIdx.x; i < b_hi; i += TPB) {
+    const double v = wide_lw(S, ll, (int)i, own, single);
+    if (!(v == v) || !(v > -CUDART_INF)) continue;
+    if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
+  }
+  s_m[threadIdx.x] = m; s_s[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mm = -CUDART_INF, t = 0.0;
+    for (int k = 0; k < TPB; k++) mm = s_m[k] > mm ? s_m[k] : mm;
+    if (mm > -CUDART_INF) for (int k = 0; k < TPB; k++) if (s_m[k] > -CUDART_INF) t += s_s[k] * exp(s_m[k] - mm);
+    S.wide_part[2 * blockIdx.x] = mm;
+    S.wide_part[2 * blockIdx.x + 1] = t;
+  }
+}
+
+// decision and commit of the serial record r: one block; thread 0 walks the block sums, the 256
+// threads re-sum the chosen chunk in contiguous pieces, thread 0 walks pieces and items
+__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot) {
+  __shared__ double s_piece[TPB];
+  __shared__ double s_m1, s_tt, s_c;
+  __shared__ int s_blk, s_target, s_tail;
+  const int n = 2 * S.N;
+  const double* ll = S.lwbuf + (size_t)slot * n;
+  const int own = S.lambda[r];
+  const bool single = S.ent_size[own] == 1;
+  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+  if (threadIdx.x == 0) {
+    double m1 = -CUDART_INF, srel = 0.0;
+    for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[2 * b] > m1 ? S.wide_part[2 * b] : m1;
+    if (m1 > -CUDART_INF)
+      for (int b = 0; b < WIDE_BLOCKS; b++)
+        if (S.wide_part[2 * b] > -CUDART_INF) srel += S.wide_part[2 * b + 1] * exp(S.wide_part[2 * b] - m1);
+    const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+    const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
+    bool invalid = false;
+    const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
+    if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
+    s_m1 = m1; s_blk = -1; s_tail = 0; s_target = is_new ? S.N + r : -1; s_c = 0.0;
+    if (!is_new) {
+      const double tt = u.b * srel;
+      double c = 0.0;
+      int blk = -1, lastb = -1;
+      for (int b = 0; b < WIDE_BLOCKS; b++) {
+        const double sb = S.wide_part[2 * b] > -CUDART_INF ? S.wide_part[2 * b + 1] * exp(S.wide_part[2 * b] - m1) : 0.0;
+        if (sb > 0.0) lastb = b;
+        if (tt < c + sb) { blk = b; break; }
+        c += sb;
+      }
+      if (blk < 0) { blk = lastb; s_tail = 1; } // rounding: the last positive item
+      s_blk = blk; s_tt = tt; s_c = c;
+    }
+  }
+  __syncthreads();
+  if (s_blk >= 0) {
+    const double m1 = s_m1;
+    const long long b_lo = s_blk * per_b, b_hi = min((long long)n, b_lo + per_b);
+    const long long per_t = (per_b + TPB - 1) / TPB;
+    const long long lo = min(b_hi, b_lo + threadIdx.x * per_t), hi = min(b_hi, lo + per_t);
+    double acc = 0.0;
+    for (long long i = lo; i < hi; i++) {
+      const double v = wide_lw(S, ll, (int)i, own, single);
+      if (v == v) acc += exp(v - m1);
+    }
+    s_piece[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double tt = s_tt;
+      double c = s_c;
+      bool tail = s_tail != 0;
+      int th = -1, lastt = -1;
+      for (int q = 0; q < TPB; q++) {
+        if (s_piece[q] > 0.0) lastt = q;
+        if (!tail && tt < c + s_piece[q]) { th = q; break; }
+        if (!tail) c += s_piece[q];
+      }
+      if (th < 0) { th = lastt; tail = true; }
+      int target = -1;
+      if (th >= 0) {
+        const long long plo = min(b_hi, b_lo + th * per_t), phi = min(b_hi, plo + per_t);
+        int lastpos = -1;
+        for (long long i = plo; i < phi; i++) {
+          const double v = wide_lw(S, ll, (int)i, own, single);
+          if (!(v == v)) continue;
+          const double w = exp(v - m1);
+          if (w > 0.0) lastpos = (int)i;
+          c += w;
+          if (!tail && tt < c) { target = (int)i; break; }
+        }
+        if (target < 0) target = lastpos;
+      }
+      s_target = target;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int target = s_target;
+    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+    finalize_record(S, r, own, target, single);
+  }
 }
 
 // number of possible links of record r (compatible items of non-zero likelihood among all the
@@ -956,7 +1176,10 @@ __global__ void __launch_bounds__(TPB) k_canon(DevState S) {
 // record with the same index, so member reads are coalesced; larger clusters walk their
 // sorted member list.  Persistent distributions come from device alias tables.
 // ------------------------------------------------------------------------------------------
-__device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, int a, int v, int head) {
+// `row_first` / `row_j`: when v was taken from position row_j of the neighbourhood row of value
+// row_first, log p(row_first | v) is that row entry - no search for members with this value
+__device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, int a, int v, int head,
+                                          int row_first = -1, int row_j = -1) {
   double lw = t.logphi[v];
   for (int r = head; r >= 0; r = S.rec_next[r]) {
     const int* x = S.rec_x + (size_t)r * S.RS;
@@ -966,7 +1189,7 @@ __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, i
     if (xv == v) lw += t.lt_same[f * t.D + v];
     else {
       lw += t.lt_diff[f * t.D + v];
-      lw += log_distortion_prob(t, v, xv);
+      lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
     }
   }
   return lw;
@@ -1084,11 +1307,15 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
     if (j >= ns) return -CUDART_INF;
     const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
     if (!t.is_const && j > 0 && v == first) return -CUDART_INF;
-    return log_weight_entity_value(S, t, a, v, head);
+    return log_weight_entity_value(S, t, a, v, head, t.is_const ? -1 : first, (t.is_const || j == 0) ? -1 : lo + j - 1);
   };
+  // the log-weights of the first chunks stay in registers for the two later passes
+  constexpr int NC = 4;
+  double lwc[NC];
   double m = -CUDART_INF;
   for (int c = 0; c < nchunk; c++) {
     const double lw = weight_log(32 * c + lane);
+    if (c < NC) lwc[c] = lw;
     m = lw > m ? lw : m;
   }
 #pragma unroll
@@ -1096,7 +1323,7 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
   if (!(m > -CUDART_INF)) { if (lane == 0) dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
   double total = 0.0;
   for (int c = 0; c < nchunk; c++) {
-    const double lw = weight_log(32 * c + lane);
+    const double lw = c < NC ? lwc[c] : weight_log(32 * c + lane);
     double x = lw > -CUDART_INF ? exp(lw - m) : 0.0;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
@@ -1108,7 +1335,7 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
   int lastpos = -1;
   for (int c = 0; c < nchunk; c++) {
     const int j = 32 * c + lane;
-    const double lw = weight_log(j);
+    const double lw = c < NC ? lwc[c] : weight_log(j);
     const double w = lw > -CUDART_INF ? exp(lw - m) : 0.0;
     double x = w;
 #pragma unroll

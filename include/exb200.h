@@ -166,7 +166,7 @@ typedef struct exb200_stats {
   int32_t n_tables;       /* blocking tables built                                 */
   int32_t n_long;         /* records handled by the warp-per-record path (long lists)      */
   float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
-      ms_distort, ms_total; /* CUDA-event times of the phases                     */
+      ms_distort, ms_total, ms_cand_long, ms_wide; /* CUDA-event times of the phases */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;
@@ -220,9 +220,10 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
      "cand_cap"  candidates a warp stages per record (<= 256); more go to a block-wide kernel
      "long_min"  list length above which a record's turn is taken by a warp instead of a thread
      "bucket_cap" bucket length above which a block instead of a warp scans the bucket
+     "huge_min"  bucket length above which the whole grid scans the bucket
      "est_threshold" expected bucket size above which the blocking key uses every usable attribute
-     "table_min_ppm" share of the records (parts per million) below which a key mask gets no
-                 blocking table of its own and uses a coarser one
+     "table_cost_permille" assumed cost of building one blocking table, in bucket visits per item
+                 x 1000 (default 1000); 0 builds every table that some record wants
      "check"     recompute sizes / member lists / K from the links after every sweep and compare */
 int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
 

@@ -18,7 +18,7 @@ for i in range(nsw):
     t0 = time.time(); g.sweeps(1); dt = time.time() - t0
     s = g.stats()
     print(f"sweep {i}: wall {dt*1e3:.1f} ms dev {s['ms_total']:.1f} | clust {s['ms_clust']:.2f} prep {s['ms_prep']:.2f} index {s['ms_index']:.2f} "
-          f"cand {s['ms_cand']:.2f} rounds {s['ms_rounds']:.2f}({s['n_rounds']}) canon {s['ms_canon']:.2f} ent {s['ms_entities']:.2f} dist {s['ms_distort']:.2f} | "
+          f"cand {s['ms_cand']:.2f}+{s['ms_cand_long']:.2f} wide {s['ms_wide']:.2f} rounds {s['ms_rounds']:.2f}({s['n_rounds']}) long={s['n_long']} canon {s['ms_canon']:.2f} ent {s['ms_entities']:.2f} dist {s['ms_distort']:.2f} | "
           f"K={s['n_entities']} cand/rec={s['n_candidates']/N:.2f} bucket/rec={s['n_bucket_items']/N:.1f} wide={s['n_wide']} tables={s['n_tables']} changed={s['n_links_changed']}", flush=True)
 st = g.state()
 from exchanger_b200.analysis import pairwise_measures

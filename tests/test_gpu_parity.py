@@ -149,8 +149,8 @@ def test_results_do_not_depend_on_batching_thresholds():
     any size: the sweep is sequentially consistent, batching is only scheduling)."""
     m, _ = readme_model("rldata10000", n=4000)
     states = []
-    for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1),
-                 dict(table_min_ppm=1000000), dict(table_min_ppm=0, est_threshold=0)):
+    for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1), dict(bucket_cap=0, huge_min=0),
+                 dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
