@@ -742,7 +742,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.long_todo, (size_t)N));
   TRY(dalloc(h, &S.wide_list, (size_t)N));
   TRY(dalloc(h, &S.unk_list, (size_t)N));
-  TRY(dalloc(h, &S.wide_part, (size_t)WIDE_BLOCKS * (TPB + 2)));
+  TRY(dalloc(h, &S.wide_part, (size_t)3 * WIDE_PIECES));
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
   TRY(dalloc(h, &S.counters64, 2));
   TRY(dalloc(h, &S.dev_err, 2));
@@ -775,8 +775,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     h->n_tab = 1 << S.n_key;
   }
   h->tables.resize((size_t)h->n_tab);
-  uint32_t Bhash = 1024;
-  while (Bhash < (uint32_t)(2 * N)) Bhash <<= 1;
+  uint32_t Bhash = 1024; // about one bucket per indexed item (twins are not indexed)
+  while ((double)Bhash < 1.2 * (double)N) Bhash <<= 1;
   for (int t = 1; t < h->n_tab; t++) {
     DevTable& d = h->tables[t].d;
     d.mask = (uint32_t)t;

@@ -910,112 +910,139 @@ __device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, i
   return sz > 0 ? log_prior_existing(S.cl, sz) + v : CUDART_NAN;
 }
 
-// The item range is cut into WIDE_BLOCKS contiguous chunks, one block each.  A block streams its chunk
-// (coalesced) and leaves (max, sum of exp(lw - max)) in wide_part[2b], wide_part[2b+1].
+// The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 8
+// contiguous pieces (one warp each, lanes strided: coalesced).  Every warp leaves
+// (max, sum of exp(lw - max)) of its piece in wide_part[2p], wide_part[2p+1], p = 8 block + warp.
+constexpr int WIDE_PIECES = WIDE_BLOCKS * (TPB / 32);
+__device__ __forceinline__ void wide_piece(const DevState& S, int p, long long& lo, long long& hi) {
+  const long long n = 2LL * S.N;
+  const long long per_b = (n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+  const long long per_w = (per_b + (TPB / 32) - 1) / (TPB / 32);
+  const long long b_lo = (p / (TPB / 32)) * per_b, b_hi = min(n, b_lo + per_b);
+  lo = min(b_hi, b_lo + (p % (TPB / 32)) * per_w);
+  hi = min(b_hi, lo + per_w);
+}
 __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot) {
-  __shared__ double s_m[TPB], s_s[TPB];
   const int n = 2 * S.N;
   const double* ll = S.lwbuf + (size_t)slot * n;
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
-  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
-  const long long b_lo = blockIdx.x * per_b, b_hi = min((long long)n, b_lo + per_b);
+  const int lane = threadIdx.x & 31, p = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  long long lo, hi;
+  wide_piece(S, p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
-  for (long long i = b_lo + threadIdx.x; i < b_hi; i += TPB) {
+  for (long long i = lo + lane; i < hi; i += 32) {
     const double v = wide_lw(S, ll, (int)i, own, single);
     if (!(v == v) || !(v > -CUDART_INF)) continue;
     if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
   }
-  s_m[threadIdx.x] = m; s_s[threadIdx.x] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double mm = -CUDART_INF, t = 0.0;
-    for (int k = 0; k < TPB; k++) mm = s_m[k] > mm ? s_m[k] : mm;
-    if (mm > -CUDART_INF) for (int k = 0; k < TPB; k++) if (s_m[k] > -CUDART_INF) t += s_s[k] * exp(s_m[k] - mm);
-    S.wide_part[2 * blockIdx.x] = mm;
-    S.wide_part[2 * blockIdx.x + 1] = t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double m2 = __shfl_xor_sync(FULL, m, o), s2 = __shfl_xor_sync(FULL, sum, o);
+    const double mm = m2 > m ? m2 : m;
+    if (mm > -CUDART_INF) sum = (m > -CUDART_INF ? sum * exp(m - mm) : 0.0) + (m2 > -CUDART_INF ? s2 * exp(m2 - mm) : 0.0);
+    m = mm;
   }
+  if (lane == 0) { S.wide_part[2 * p] = m; S.wide_part[2 * p + 1] = sum; }
 }
 
-// decision and commit of the serial record r: one block; thread 0 walks the block sums, the 256
-// threads re-sum the chosen chunk in contiguous pieces, thread 0 walks pieces and items
+// decision and commit of the serial record r (one block): scale the piece sums to the global max in
+// parallel, walk block sums and piece sums in order, then one warp scans the chosen piece in order
 __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot) {
-  __shared__ double s_piece[TPB];
+  __shared__ double s_bsum[WIDE_BLOCKS];
+  __shared__ double s_red[TPB];
   __shared__ double s_m1, s_tt, s_c;
-  __shared__ int s_blk, s_target, s_tail;
+  __shared__ int s_piece, s_target, s_tail;
   const int n = 2 * S.N;
   const double* ll = S.lwbuf + (size_t)slot * n;
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
-  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
+  double* scaled = S.wide_part + 2 * WIDE_PIECES;
+  double m = -CUDART_INF;
+  for (int p = threadIdx.x; p < WIDE_PIECES; p += TPB) m = S.wide_part[2 * p] > m ? S.wide_part[2 * p] : m;
+  s_red[threadIdx.x] = m;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double m1 = -CUDART_INF, srel = 0.0;
-    for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[2 * b] > m1 ? S.wide_part[2 * b] : m1;
-    if (m1 > -CUDART_INF)
-      for (int b = 0; b < WIDE_BLOCKS; b++)
-        if (S.wide_part[2 * b] > -CUDART_INF) srel += S.wide_part[2 * b + 1] * exp(S.wide_part[2 * b] - m1);
+    double mm = -CUDART_INF;
+    for (int k = 0; k < TPB; k++) mm = s_red[k] > mm ? s_red[k] : mm;
+    s_m1 = mm;
+  }
+  __syncthreads();
+  const double m1 = s_m1;
+  for (int b = threadIdx.x; b < WIDE_BLOCKS; b += TPB) {
+    double t = 0.0;
+    for (int w = 0; w < TPB / 32; w++) {
+      const int p = b * (TPB / 32) + w;
+      const double mp = S.wide_part[2 * p];
+      const double sc = mp > -CUDART_INF ? S.wide_part[2 * p + 1] * exp(mp - m1) : 0.0;
+      scaled[p] = sc;
+      t += sc;
+    }
+    s_bsum[b] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double srel = 0.0;
+    for (int b = 0; b < WIDE_BLOCKS; b++) srel += s_bsum[b];
     const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
     const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
     bool invalid = false;
     const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
     if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
-    s_m1 = m1; s_blk = -1; s_tail = 0; s_target = is_new ? S.N + r : -1; s_c = 0.0;
+    s_piece = -1; s_tail = 0; s_target = is_new ? S.N + r : -1;
     if (!is_new) {
       const double tt = u.b * srel;
       double c = 0.0;
       int blk = -1, lastb = -1;
       for (int b = 0; b < WIDE_BLOCKS; b++) {
-        const double sb = S.wide_part[2 * b] > -CUDART_INF ? S.wide_part[2 * b + 1] * exp(S.wide_part[2 * b] - m1) : 0.0;
-        if (sb > 0.0) lastb = b;
-        if (tt < c + sb) { blk = b; break; }
-        c += sb;
+        if (s_bsum[b] > 0.0) lastb = b;
+        if (tt < c + s_bsum[b]) { blk = b; break; }
+        c += s_bsum[b];
       }
-      if (blk < 0) { blk = lastb; s_tail = 1; } // rounding: the last positive item
-      s_blk = blk; s_tt = tt; s_c = c;
+      bool tail = false;
+      if (blk < 0) { blk = lastb; tail = true; } // rounding: the last positive item
+      if (blk >= 0) {
+        int pc = -1, lastp = -1;
+        for (int w = 0; w < TPB / 32; w++) {
+          const int p = blk * (TPB / 32) + w;
+          if (scaled[p] > 0.0) lastp = p;
+          if (!tail && tt < c + scaled[p]) { pc = p; break; }
+          if (!tail) c += scaled[p];
+        }
+        if (pc < 0) { pc = lastp; tail = true; }
+        s_piece = pc;
+      }
+      s_tt = tt; s_c = c; s_tail = tail;
     }
   }
   __syncthreads();
-  if (s_blk >= 0) {
-    const double m1 = s_m1;
-    const long long b_lo = s_blk * per_b, b_hi = min((long long)n, b_lo + per_b);
-    const long long per_t = (per_b + TPB - 1) / TPB;
-    const long long lo = min(b_hi, b_lo + threadIdx.x * per_t), hi = min(b_hi, lo + per_t);
-    double acc = 0.0;
-    for (long long i = lo; i < hi; i++) {
-      const double v = wide_lw(S, ll, (int)i, own, single);
-      if (v == v) acc += exp(v - m1);
-    }
-    s_piece[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const double tt = s_tt;
-      double c = s_c;
-      bool tail = s_tail != 0;
-      int th = -1, lastt = -1;
-      for (int q = 0; q < TPB; q++) {
-        if (s_piece[q] > 0.0) lastt = q;
-        if (!tail && tt < c + s_piece[q]) { th = q; break; }
-        if (!tail) c += s_piece[q];
+  if (s_piece >= 0 && threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    long long lo, hi;
+    wide_piece(S, s_piece, lo, hi);
+    const double tt = s_tt;
+    const bool tail = s_tail != 0;
+    double c = s_c;
+    int target = -1, lastpos = -1;
+    for (long long base = lo; base < hi && target < 0; base += 32) {
+      const long long i = base + lane;
+      double w = 0.0;
+      if (i < hi) {
+        const double v = wide_lw(S, ll, (int)i, own, single);
+        if (v == v) w = exp(v - m1);
       }
-      if (th < 0) { th = lastt; tail = true; }
-      int target = -1;
-      if (th >= 0) {
-        const long long plo = min(b_hi, b_lo + th * per_t), phi = min(b_hi, plo + per_t);
-        int lastpos = -1;
-        for (long long i = plo; i < phi; i++) {
-          const double v = wide_lw(S, ll, (int)i, own, single);
-          if (!(v == v)) continue;
-          const double w = exp(v - m1);
-          if (w > 0.0) lastpos = (int)i;
-          c += w;
-          if (!tail && tt < c) { target = (int)i; break; }
-        }
-        if (target < 0) target = lastpos;
-      }
-      s_target = target;
+      double x = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
+      const unsigned pos = __ballot_sync(FULL, w > 0.0);
+      if (pos) lastpos = (int)base + (31 - __clz(pos));
+      const unsigned hit = __ballot_sync(FULL, !tail && w > 0.0 && tt < c + x);
+      if (hit) target = (int)base + (__ffs(hit) - 1);
+      c += __shfl_sync(FULL, x, 31);
     }
-    __syncthreads();
+    if (lane == 0) s_target = target >= 0 ? target : lastpos;
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int target = s_target;
     if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
