@@ -185,10 +185,10 @@ def run_ours(opt, n_records, kind, desc):
     gpu.sweeps(opt.warmup)          # W warm-up steps
     barrier()
     clocks = ClockSampler(local)
-    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_cand", "ms_cand_long", "ms_wide", "ms_rounds", "ms_canon",
-                  "ms_entities", "ms_distort", "ms_total")
+    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_index_count", "ms_index_fill", "ms_cand", "ms_cand_long",
+                  "ms_wide", "ms_rounds", "ms_canon", "ms_entities", "ms_distort", "ms_total")
     acc = {k: 0.0 for k in phase_keys}
-    cand = rounds = wide = launches = 0
+    cand = rounds = wide = launches = tables = 0
     dev_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(opt.steps):      # EXACTLY K steps
@@ -201,6 +201,7 @@ def run_ours(opt, n_records, kind, desc):
         cand += st["n_candidates"]
         rounds += st["n_rounds"]
         wide += st["n_wide"]
+        tables += st["n_tables"]
     barrier()
     wall = time.perf_counter() - t0
     clk = clocks.stop()
@@ -232,7 +233,10 @@ def run_ours(opt, n_records, kind, desc):
     if rank == 0:
         # ---- roofline of the dominant single kernel (algorithmic bytes: DESIGN.md section 5)
         n, cbar, rho = n_records, cand / opt.steps / n_records, k_ent / n_records
+        items, tbar = 1.2 * n, tables / opt.steps  # indexed entity slots (twins excluded), tables built
         kernels = {
+            "k_index_fill (links: blocking index)": (acc["ms_index_fill"], items * (4 * A + 4 * tbar)),
+            "k_index_count (links: blocking index)": (acc["ms_index_count"], items * 4 * A),
             "k_cand (links: candidate generation)": (acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
             "k_entities (entity attributes)": (acc["ms_entities"], n * (4 + 4 * A + 4 * A * rho)),
             "k_distort (distortion indicators)": (acc["ms_distort"], n * (9 * A + 4)),
@@ -276,7 +280,8 @@ def run_ours(opt, n_records, kind, desc):
             "cpu_baseline": cpu,
             "phases_ms": {k[3:]: acc[k] / opt.steps for k in phase_keys},
             "sweep_stats": {"candidates_per_record": cbar, "entities_per_record": rho,
-                            "rounds_per_sweep": rounds / opt.steps, "wide_records_per_sweep": wide / opt.steps},
+                            "rounds_per_sweep": rounds / opt.steps, "wide_records_per_sweep": wide / opt.steps,
+                            "tables_per_sweep": tbar},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

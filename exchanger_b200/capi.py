@@ -87,7 +87,8 @@ class CStats(C.Structure):
         ("ms_clust", C.c_float), ("ms_prep", C.c_float), ("ms_index", C.c_float),
         ("ms_cand", C.c_float), ("ms_rounds", C.c_float), ("ms_canon", C.c_float),
         ("ms_entities", C.c_float), ("ms_distort", C.c_float), ("ms_total", C.c_float),
-        ("ms_cand_long", C.c_float), ("ms_wide", C.c_float),
+        ("ms_cand_long", C.c_float), ("ms_wide", C.c_float), ("ms_index_count", C.c_float),
+        ("ms_index_fill", C.c_float),
     ]
 
 

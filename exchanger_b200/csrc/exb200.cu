@@ -56,6 +56,9 @@ struct exb200_handle {
   DevTable* d_tables = nullptr;
   int* d_active = nullptr;
   uint16_t* d_remap = nullptr;
+  PartBuild pb{};              // partitioned build of the large tables
+  int* d_part_tabs = nullptr;
+  int pb_tables_cap = 0;
   int* d_bsum = nullptr; size_t bsum_cap = 0;
   unsigned long long* d_cl_counts = nullptr;
   double* d_theta = nullptr;
@@ -66,12 +69,14 @@ struct exb200_handle {
   int bucket_cap = 512, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
   double est_threshold = 16.0;
   int huge_min = 65536;
+  int index_partitioned = 1;
   double table_full_cost = 1.0, table_pair_cost = 0.25; // cost of building a table, in bucket visits per item
   int n_tab = 0; // 2^n_key
   exb200_stats stats{};
-  cudaEvent_t ev[12]{};
+  cudaEvent_t ev[16]{};
   std::string err;
   bool poisoned = false;
+  bool has_index_events = false;
   long long n_launches = 0; // kernels launched by this handle
 };
 
@@ -356,19 +361,59 @@ int update_links(exb200_handle* h) {
   }
   for (int t : active) {
     int rc = ensure_table(h, t); if (rc) return rc;
-    CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
   }
   CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * remap.size(), cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
   if (!active.empty()) {
-    CK(cudaMemcpyAsync(h->d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, st));
-    KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)active.size());
+    // tables with many buckets are built by partitioning (k_part_a / k_part_b); the few small ones
+    // (their bucket arrays stay in the L2) by global atomics (k_index_count / k_index_fill)
+    std::vector<int> large, small, tiny;
     for (int t : active) {
+      const uint32_t B = h->tables[t].d.B;
+      const bool part = h->index_partitioned && B >= 16u * PART_SIZE && B <= (uint32_t)MAX_PARTS * PART_SIZE && (int)large.size() < PA_MAX_TABS;
+      if (part) large.push_back(t);
+      else if (h->index_partitioned && B <= (uint32_t)SMALL_B_MAX) { tiny.push_back(t); small.push_back(t); }
+      else small.push_back(t);
+    }
+    // `small` keeps the tiny tables for the memset / scan; they are removed from the atomic kernels' list
+    std::vector<int> atomic_tabs;
+    for (int t : small) if (std::find(tiny.begin(), tiny.end(), t) == tiny.end()) atomic_tabs.push_back(t);
+    for (int t : small) CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
+    if (!large.empty()) {
+      const long long cap = 2LL * N;
+      if ((int)large.size() > h->pb_tables_cap) {
+        const int want = std::min(PA_MAX_TABS, ((int)large.size() + 7) / 8 * 8);
+        int rc = dalloc(h, &h->pb.pairs, (size_t)want * cap); if (rc) return rc;
+        h->pb_tables_cap = want;
+      }
+      PartBuild& P = h->pb;
+      P.n_tab = (int)large.size(); P.tabs = h->d_part_tabs; P.cap = cap;
+      CK(cudaMemcpyAsync(h->d_part_tabs, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice, st));
+      CK(cudaMemsetAsync(P.part_cnt, 0, sizeof(int) * (size_t)P.n_tab * MAX_PARTS, st));
+    }
+    CK(cudaMemcpyAsync(h->d_active, atomic_tabs.data(), sizeof(int) * atomic_tabs.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->ev[12], st));
+    if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
+    for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 0);
+    if (!large.empty()) {
+      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * 2 * large.size() * MAX_PARTS, S, h->pb, 0);
+      KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
+    }
+    CK(cudaEventRecord(h->ev[13], st));
+    for (int t : small) {
       int rc = scan_exclusive<int>(h, h->tables[t].d.ptr, h->tables[t].d.ptr, (int)h->tables[t].d.B);
       if (rc) return rc;
     }
-    KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)active.size());
-  }
+    CK(cudaEventRecord(h->ev[14], st));
+    if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
+    for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 1);
+    if (!large.empty()) {
+      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * 2 * large.size() * MAX_PARTS, S, h->pb, 1);
+      k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
+      h->n_launches++;
+    }
+    h->has_index_events = true;
+  } else h->has_index_events = false;
   CK(cudaEventRecord(h->ev[3], st));
   KLAUNCH(h, k_cand, nblk((long long)N, TPB / GL), TPB, 0, S);
   CK(cudaEventRecord(h->ev[10], st));
@@ -591,6 +636,8 @@ int sweep(exb200_handle* h) {
   CK(cudaStreamSynchronize(st));
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
   h->stats.ms_clust = ms(0, 1); h->stats.ms_prep = ms(1, 2); h->stats.ms_index = ms(2, 3);
+  h->stats.ms_index_count = h->has_index_events ? ms(12, 13) : 0.f;
+  h->stats.ms_index_fill = h->has_index_events ? ms(14, 3) : 0.f;
   h->stats.ms_cand = ms(3, 10); h->stats.ms_cand_long = ms(10, 4); h->stats.ms_wide = ms(4, 11); h->stats.ms_rounds = ms(11, 5); h->stats.ms_canon = ms(5, 6);
   h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
   if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
@@ -755,6 +802,9 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.corr, (size_t)F * A));
   TRY(dalloc(h, &h->d_active, (size_t)N_TABLES));
   TRY(dalloc(h, &h->d_remap, (size_t)2 * N_TABLES)); S.tab_remap = h->d_remap;
+  TRY(dalloc(h, &h->d_part_tabs, (size_t)N_TABLES));
+  TRY(dalloc(h, &h->pb.part_cnt, (size_t)PA_MAX_TABS * MAX_PARTS));
+  TRY(dalloc(h, &h->pb.part_start, (size_t)PA_MAX_TABS * (MAX_PARTS + 1)));
   TRY(dalloc(h, &h->d_cl_counts, 2));
   TRY(dalloc(h, &h->d_gen_mask, (size_t)N));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
@@ -794,7 +844,10 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
-  if (cudaFuncSetAttribute(k_huge_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_index_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_part_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_part_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_huge_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_cand_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
     return bail(fail(h, EXB200_ERR_CUDA, "cannot reserve shared memory for k_cand_long"));
 #undef TRY
@@ -819,6 +872,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "long_min") h->long_min = (int)std::max<int64_t>(0, value);
   else if (n == "est_threshold") h->est_threshold = (double)value;
   else if (n == "huge_min") h->huge_min = (int)std::max<int64_t>(0, value);
+  else if (n == "index_partitioned") h->index_partitioned = value != 0;
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
   h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap; h->S.long_cap = h->long_cap;

@@ -221,6 +221,175 @@ __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __res
   }
 }
 
+// Tables with few buckets (date pairs and triples, single attributes): all items fall on a few
+// thousand counters, so the counts are aggregated per block in shared memory.  phase 0 adds the
+// block histogram to ptr[]; after the exclusive scan, phase 1 reserves one slice per (block, bucket)
+// with a single atomicAdd on ptr[b] (which thereby ends as the bucket's END offset) and places the ids.
+constexpr int SMALL_B_MAX = 49152;
+__global__ void __launch_bounds__(TPB) k_index_small(DevState S, int tab, int phase) {
+  extern __shared__ int s_dyn[]; // [B]
+  const DevTable& t = S.tables[tab];
+  const int B = (int)t.B;
+  const int n = 2 * S.N;
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+  for (int b = threadIdx.x; b < B; b += TPB) s_dyn[b] = 0;
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += TPB)
+    if (i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N])
+      atomicAdd(&s_dyn[bucket_of(S, t, S.ent_y + (size_t)i * S.ES)], 1);
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += TPB)
+    if (s_dyn[b]) s_dyn[b] = atomicAdd(&t.ptr[b], s_dyn[b]); // phase 0: value unused; phase 1: slice base
+  if (phase == 0) return;
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += TPB)
+    if (i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N])
+      t.ids[atomicAdd(&s_dyn[bucket_of(S, t, S.ent_y + (size_t)i * S.ES)], 1)] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b'  partitioned build of the large blocking tables.  Random global atomics (one per item,
+// table and pass) bound k_index_count / k_index_fill; for tables with many buckets the CSR is
+// built like a two-level bucket sort instead:
+//   pass A  every (item, table) pair goes to partition p = bucket >> PART_BITS.  Blocks own
+//           contiguous item ranges, histogram their range per table in shared memory and reserve
+//           one contiguous slice per (block, partition) - one global atomic per non-empty bin.
+//   pass B  one block per (table, partition): the 2^PART_BITS buckets of the partition are
+//           counted, scanned and filled entirely in shared memory; ptr / ids are written once.
+// The order of the ids inside a bucket is arbitrary (candidate lists are sorted later).
+// ------------------------------------------------------------------------------------------
+constexpr int PART_BITS = 14;
+constexpr int PART_SIZE = 1 << PART_BITS;
+constexpr int MAX_PARTS = 1024;          // partitions per table (bucket arrays up to 2^24)
+constexpr int PA_BLOCKS = 148 * 8;       // blocks of pass A
+constexpr int PA_MAX_TABS = 24;          // tables per pass-A launch (shared memory: 8 KB each)
+
+struct PartBuild {
+  int n_tab;                 // large tables of this launch
+  const int* tabs;           // their key masks
+  int* part_cnt;             // [n_tab][MAX_PARTS] pairs per partition, then running cursors
+  int* part_start;           // [n_tab][MAX_PARTS + 1] exclusive prefix of part_cnt
+  unsigned long long* pairs; // [n_tab][cap] (item << PART_BITS | low bucket bits), grouped by partition
+  long long cap;             // pairs per table
+};
+
+__device__ __forceinline__ bool item_indexed(const DevState& S, int i) {
+  return i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N];
+}
+
+// phase 0: partition histogram; phase 1: scatter of the pairs.  Every item tuple is read once per
+// phase for all tables; shared memory holds one histogram (and one slice base) per table.
+__global__ void __launch_bounds__(TPB) k_part_a(DevState S, PartBuild P, int phase) {
+  extern __shared__ int s_dyn[];
+  int* s_cnt = s_dyn;                         // [n_tab][MAX_PARTS]
+  int* s_base = s_dyn + P.n_tab * MAX_PARTS;  // [n_tab][MAX_PARTS] (phase 1)
+  const int n = 2 * S.N;
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+  const int nbins = P.n_tab * MAX_PARTS;
+  for (int q = threadIdx.x; q < nbins; q += TPB) s_cnt[q] = 0;
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += TPB)
+    if (item_indexed(S, i)) {
+      const int* y = S.ent_y + (size_t)i * S.ES;
+      for (int k = 0; k < P.n_tab; k++)
+        atomicAdd(&s_cnt[k * MAX_PARTS + (bucket_of(S, S.tables[P.tabs[k]], y) >> PART_BITS)], 1);
+    }
+  __syncthreads();
+  if (phase == 0) {
+    for (int q = threadIdx.x; q < nbins; q += TPB)
+      if (s_cnt[q]) atomicAdd(&P.part_cnt[q], s_cnt[q]);
+    return;
+  }
+  // reserve this block's slice of every partition, then place the pairs
+  for (int q = threadIdx.x; q < nbins; q += TPB) {
+    s_base[q] = s_cnt[q] ? atomicAdd(&P.part_cnt[q], s_cnt[q]) : 0;
+    s_cnt[q] = 0;
+  }
+  __syncthreads();
+  for (int i = i0 + threadIdx.x; i < i1; i += TPB)
+    if (item_indexed(S, i)) {
+      const int* y = S.ent_y + (size_t)i * S.ES;
+      for (int k = 0; k < P.n_tab; k++) {
+        const uint32_t b = bucket_of(S, S.tables[P.tabs[k]], y);
+        const int q = k * MAX_PARTS + (b >> PART_BITS);
+        const int pos = s_base[q] + atomicAdd(&s_cnt[q], 1);
+        P.pairs[(size_t)k * P.cap + pos] =
+            ((unsigned long long)(uint32_t)i << PART_BITS) | (unsigned long long)(b & (PART_SIZE - 1));
+      }
+    }
+}
+
+// exclusive prefix of the partition counts of every large table; the counts become cursors
+__global__ void __launch_bounds__(TPB) k_part_scan(PartBuild P) {
+  __shared__ int s_sum[TPB];
+  const int k = blockIdx.x;
+  int* cnt = P.part_cnt + k * MAX_PARTS;
+  int* start = P.part_start + k * (MAX_PARTS + 1);
+  constexpr int per = MAX_PARTS / TPB;
+  int t = 0;
+  for (int j = 0; j < per; j++) t += cnt[threadIdx.x * per + j];
+  s_sum[threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int q = 0; q < TPB; q++) { const int x = s_sum[q]; s_sum[q] = run; run += x; }
+    start[MAX_PARTS] = run;
+  }
+  __syncthreads();
+  int run = s_sum[threadIdx.x];
+  for (int j = 0; j < per; j++) {
+    const int p = threadIdx.x * per + j;
+    const int x = cnt[p];
+    start[p] = run;
+    cnt[p] = run; // cursor of pass A's scatter
+    run += x;
+  }
+}
+
+// pass B: one block per (table, partition); the PART_SIZE bucket counters live in shared memory
+__global__ void __launch_bounds__(TPB) k_part_b(DevState S, PartBuild P) {
+  extern __shared__ int s_cnt[]; // [PART_SIZE]
+  __shared__ int s_w[TPB];
+  const int k = blockIdx.y, p = blockIdx.x;
+  const DevTable& t = S.tables[P.tabs[k]];
+  const int np = (int)((t.B + PART_SIZE - 1) >> PART_BITS);
+  if (p >= np) return;
+  const int* start = P.part_start + k * (MAX_PARTS + 1);
+  const int lo = start[p], hi = start[p + 1];
+  const unsigned long long* pairs = P.pairs + (size_t)k * P.cap;
+  for (int b = threadIdx.x; b < PART_SIZE; b += TPB) s_cnt[b] = 0;
+  __syncthreads();
+  for (int q = lo + threadIdx.x; q < hi; q += TPB) atomicAdd(&s_cnt[(int)(pairs[q] & (PART_SIZE - 1))], 1);
+  __syncthreads();
+  // exclusive scan of the counters (each thread owns PART_SIZE / TPB consecutive ones)
+  constexpr int PER = PART_SIZE / TPB;
+  int tsum = 0;
+  for (int j = 0; j < PER; j++) tsum += s_cnt[threadIdx.x * PER + j];
+  s_w[threadIdx.x] = tsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int q = 0; q < TPB; q++) { const int x = s_w[q]; s_w[q] = run; run += x; }
+  }
+  __syncthreads();
+  int run = lo + s_w[threadIdx.x];
+  const uint32_t b0 = (uint32_t)p << PART_BITS;
+  for (int j = 0; j < PER; j++) {
+    const int b = threadIdx.x * PER + j;
+    const int c = s_cnt[b];
+    s_cnt[b] = run;           // start of the bucket: cursor of the fill below
+    run += c;
+    if (b0 + b < t.B) t.ptr[b0 + b] = run; // END offset of the bucket
+  }
+  __syncthreads();
+  for (int q = lo + threadIdx.x; q < hi; q += TPB) {
+    const unsigned long long v = pairs[q];
+    t.ids[atomicAdd(&s_cnt[(int)(v & (PART_SIZE - 1))], 1)] = (int)(v >> PART_BITS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // exclusive prefix sum of n integers (three passes).  T_IN is int or int8_t.
 // ------------------------------------------------------------------------------------------

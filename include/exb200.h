@@ -166,7 +166,7 @@ typedef struct exb200_stats {
   int32_t n_tables;       /* blocking tables built                                 */
   int32_t n_long;         /* records handled by the warp-per-record path (long lists)      */
   float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
-      ms_distort, ms_total, ms_cand_long, ms_wide; /* CUDA-event times of the phases */
+      ms_distort, ms_total, ms_cand_long, ms_wide, ms_index_count, ms_index_fill; /* CUDA-event times */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;
