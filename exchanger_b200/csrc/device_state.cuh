@@ -42,6 +42,7 @@ struct DevAttr {
   const int *row, *col;                    // inverted neighbourhood CSR: row w -> entity values v, ascending
   const double *p, *logp;                  // p(w | v) and its log
   const double *cs;                        // per row: inclusive prefix sums of phi(v) mef(v) p(w|v)
+  const double *csn;                       // per row: inclusive prefix sums of phi(v) p(w|v) (new-entity draw)
   const double *g;                         // [(NMAX_FAST+1)][D]  phi(v) / (1-psi(v))^n
   const double *aprob; const int *aalias;  // alias tables of g_n, same shape
   const double *pprob; const int *palias;  // alias table of psi
@@ -103,7 +104,8 @@ struct DevState {
   unsigned long long *pool_cursor; unsigned long long pool_cap;
   unsigned long long *owner;    // [2N] reservation words
   unsigned long long *fence;    // reservation word of the wide records
-  uint8_t *fin;                 // [N] 1 once the record's link is final
+  uint8_t *fin;                 // [N] 1 once the record's link is final; 2: ready (owns its items, weights cached)
+  double *rdy_m1, *rdy_srel;    // [N] cached max log-weight and relative sum of a ready record
   int8_t *dlo, *dhi;            // [N] bounds of the record's change of K
   int *plo, *phi_;              // [N] exclusive prefix sums of dlo / dhi
   int *act_in, *act_out;        // active records with short candidate lists (thread per record)

@@ -189,7 +189,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
   }
   // inverted neighbourhood CSR (attribute_index.cpp:125-140)
   std::vector<int> row(D + 1, 0), col;
-  std::vector<double> p, logp, cs;
+  std::vector<double> p, logp, cs, csn;
   if (!ha.is_const) {
     const int64_t nnz = in.close_row_ptr[D];
     if (nnz >= (int64_t)std::numeric_limits<int>::max())
@@ -209,11 +209,14 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
       }
   }
   cs.resize(p.size());
+  csn.resize(p.size());
   for (int w = 0; w < D && !ha.is_const; w++) {
-    double c = 0.0;
+    double c = 0.0, cn = 0.0;
     for (int j = row[w]; j < row[w + 1]; j++) {
       c += ha.phi[col[j]] * ha.mef[col[j]] * p[j];
       cs[j] = c;
+      cn += ha.phi[col[j]] * p[j];
+      csn[j] = cn;
     }
   }
   for (int w = 0; w < D; w++) {
@@ -247,7 +250,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
 #define UPD(field, vec) rc = upload(h, &dp, (vec).data(), (vec).size()); if (rc) return rc; da.field = dp;
 #define UPI(field, vec) rc = upload(h, &ip, (vec).data(), (vec).size()); if (rc) return rc; da.field = ip;
   UPD(psi, ha.psi) UPD(phi, ha.phi) UPD(om, om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi)
-  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp) UPD(cs, cs)
+  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp) UPD(cs, cs) UPD(csn, csn)
   UPD(g, g) UPD(aprob, aprob) UPI(aalias, aalias) UPD(pprob, pprob) UPI(palias, palias)
 #undef UPD
 #undef UPI
@@ -778,6 +781,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.owner, (size_t)2 * N));
   TRY(dalloc(h, &S.fence, 1));
   TRY(dalloc(h, &S.fin, (size_t)N));
+  TRY(dalloc(h, &S.rdy_m1, (size_t)N));
+  TRY(dalloc(h, &S.rdy_srel, (size_t)N));
   TRY(dalloc(h, &S.dlo, (size_t)N));
   TRY(dalloc(h, &S.dhi, (size_t)N));
   TRY(dalloc(h, &S.plo, (size_t)N));

@@ -140,23 +140,20 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
             const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
             yv = alias_draw(t.pprob, t.palias, t.D, u.a);
           }
-        } else { // links.cpp:454-461: phi(v) p(x | v) over the neighbourhood of x
+        } else { // links.cpp:454-461: phi(v) p(x | v) over the neighbourhood of x (static prefix sums)
           const int lo = t.row[xv], hi = t.row[xv + 1];
-          double tot = 0.0;
-          for (int j = lo; j < hi; j++) tot += t.phi[t.col[j]] * t.p[j];
+          const double tot = hi > lo ? t.csn[hi - 1] : 0.0;
           yv = xv;
           if (tot > 0.0) {
             const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
             const double tt = u.a * tot;
-            double c = 0.0;
-            int pick = -1, lastpos = xv;
-            for (int j = lo; j < hi; j++) {
-              const double w = t.phi[t.col[j]] * t.p[j];
-              if (w > 0.0) lastpos = t.col[j];
-              c += w;
-              if (tt < c) { pick = t.col[j]; break; }
+            int a0 = lo, b0 = hi; // first j with tt < csn[j]
+            while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (tt < t.csn[mid]) b0 = mid; else a0 = mid + 1; }
+            if (a0 == hi) { // rounding: the last entry of positive weight
+              a0 = lo; b0 = hi - 1;
+              while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t.csn[mid] >= tot) b0 = mid; else a0 = mid + 1; }
             }
-            yv = pick >= 0 ? pick : lastpos;
+            yv = t.col[a0];
           }
         }
       }
@@ -225,7 +222,7 @@ __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __res
 // thousand counters, so the counts are aggregated per block in shared memory.  phase 0 adds the
 // block histogram to ptr[]; after the exclusive scan, phase 1 reserves one slice per (block, bucket)
 // with a single atomicAdd on ptr[b] (which thereby ends as the bucket's END offset) and places the ids.
-constexpr int SMALL_B_MAX = 49152;
+constexpr int SMALL_B_MAX = 8192;
 __global__ void __launch_bounds__(TPB) k_index_small(DevState S, int tab, int phase) {
   extern __shared__ int s_dyn[]; // [B]
   const DevTable& t = S.tables[tab];
@@ -763,7 +760,7 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
   if (i < n_act) {
     const int r = act ? act[i] : i;
     const int cnt = S.cand_cnt[r];
-    if (cnt <= S.long_min && !S.fin[r]) { // long records: k_reserve_w; wide records are final already
+    if (cnt <= S.long_min && S.fin[r] != 1) { // long records: k_reserve_w; wide records are final already
       mine = r;
       const unsigned long long key = resv_key(round, r);
       if (cnt < 0) {
@@ -875,7 +872,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
   if (i < n_act) {
     r = act ? act[i] : i;
     const int cnt = S.cand_cnt[r];
-    stay = cnt <= S.long_min && !S.fin[r]; // long records live in the other list; wide ones are final
+    stay = cnt <= S.long_min && S.fin[r] != 1; // long records live in the other list; wide ones are final
     const unsigned long long key = resv_key(round, r);
     const unsigned long long fence = *S.fence;
     const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
@@ -964,24 +961,36 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
     const int own = S.lambda[r];
     const int* ids = S.cand_id + S.cand_off[r];
     const double* lls = S.cand_ll + S.cand_off[r];
-    bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
-    for (int j = lane; j < cnt; j += 32) mine &= S.owner[ids[j]] == key;
-    mine = __all_sync(FULL, mine);
+    // a record that owned all its items once owns them until its turn (earlier unfinalised records
+    // only disappear) and nothing it reads can change: its weights are computed once
+    const bool ready = S.fin[r] == 2;
+    bool mine = ready;
+    if (!ready) {
+      mine = S.owner[own] == key && S.owner[S.N + r] == key;
+      for (int j0 = 0; j0 < cnt && mine; j0 += 32) {
+        const int j = j0 + lane;
+        mine = __all_sync(FULL, j >= cnt || S.owner[ids[j]] == key);
+      }
+    }
     if (mine) {
       const bool single = S.ent_size[own] == 1;
       const int nchunk = (cnt + 31) >> 5;
       double m1 = -CUDART_INF;
-      for (int c = 0; c < nchunk; c++) {
+      if (ready) m1 = S.rdy_m1[r];
+      else for (int c = 0; c < nchunk; c++) {
         const int j = 32 * c + lane;
         if (j < cnt) {
           const int sz = live_size(S, ids[j], own, single);
           if (sz > 0) { const double lw = log_prior_existing(S.cl, sz) + lls[j]; m1 = lw > m1 ? lw : m1; }
         }
       }
+      if (!ready) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m1, o); m1 = y > m1 ? y : m1; }
+        for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m1, o); m1 = y > m1 ? y : m1; }
+      }
       double srel = 0.0;
-      if (m1 > -CUDART_INF)
+      if (ready) srel = S.rdy_srel[r];
+      else if (m1 > -CUDART_INF)
         for (int c = 0; c < nchunk; c++) {
           const int j = 32 * c + lane;
           double w = 0.0;
@@ -1025,6 +1034,7 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
       } else if (lane == 0) {
         S.dlo[r] = single ? -1 : 0;
         S.dhi[r] = single ? 0 : 1;
+        if (!ready) { S.fin[r] = 2; S.rdy_m1[r] = m1; S.rdy_srel[r] = srel; }
       }
     }
   }
@@ -1334,7 +1344,7 @@ __global__ void __launch_bounds__(TPB) k_clear_bounds(DevState S, const int* __r
 __global__ void __launch_bounds__(TPB) k_compact_active(DevState S, const int* __restrict__ act, int n_act) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = i < n_act ? (act ? act[i] : i) : -1;
-  const bool stay = r >= 0 && !S.fin[r];
+  const bool stay = r >= 0 && S.fin[r] != 1;
   const unsigned m = __ballot_sync(FULL, stay);
   if (m) {
     int base = 0;
