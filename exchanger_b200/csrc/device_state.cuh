@@ -106,6 +106,7 @@ struct DevState {
   unsigned long long *fence;    // reservation word of the wide records
   uint8_t *fin;                 // [N] 1 once the record's link is final; 2: ready (owns its items, weights cached)
   double *rdy_m1, *rdy_srel;    // [N] cached max log-weight and relative sum of a ready record
+  uint8_t *referenced;          // [2N] 1: the item is on some record's stored candidate list
   int8_t *dlo, *dhi;            // [N] bounds of the record's change of K
   int *plo, *phi_;              // [N] exclusive prefix sums of dlo / dhi
   int *act_in, *act_out;        // active records with short candidate lists (thread per record)
@@ -145,6 +146,7 @@ enum CounterSlot {
   C_NFENCE = 11,    // records that take their turn serially inside the rounds
   C_COUNT = 12,     // scratch of k_count_all / k_huge_scan
   C_NHUGE = 13,     // size of huge_list
+  C_NOLIST = 14,    // records without a stored list (wide / serial): they may join any entity
   C_NSLOTS = 16
 };
 

@@ -328,6 +328,7 @@ int update_links(exb200_handle* h) {
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
   CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
   CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(S.referenced, 0, (size_t)2 * N, st));
   CK(cudaEventRecord(h->ev[1], st));
   KLAUNCH(h, k_prep, nblk(N), TPB, 0, S);
   std::vector<int> usage(2 * (size_t)N_TABLES);
@@ -399,7 +400,7 @@ int update_links(exb200_handle* h) {
     if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
     for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 0);
     if (!large.empty()) {
-      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * 2 * large.size() * MAX_PARTS, S, h->pb, 0);
+      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
       KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
     }
     CK(cudaEventRecord(h->ev[13], st));
@@ -411,7 +412,7 @@ int update_links(exb200_handle* h) {
     if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
     for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 1);
     if (!large.empty()) {
-      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * 2 * large.size() * MAX_PARTS, S, h->pb, 1);
+      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
       k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
       h->n_launches++;
     }
@@ -491,6 +492,8 @@ int update_links(exb200_handle* h) {
     CK(cudaStreamSynchronize(st));
     S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
   }
+  // records classified as serial fences by the host loop above are pending too
+  if (S.use_kbounds) KLAUNCH(h, k_bounds_init, nblk(N), TPB, 0, S, n_fence > 0 ? 1 : 0);
   CK(cudaEventRecord(h->ev[11], st));
 
   // dependency rounds
@@ -713,22 +716,41 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     rec_x[(size_t)r * h->RS + h->RS - 1] = f;
   }
   {
-    std::unordered_map<int, int> slot_of; // label -> column of ent_attrs
-    slot_of.reserve((size_t)m->n_entities * 2);
-    for (int e = 0; e < m->n_entities; e++) slot_of[m->ent_ids[e]] = e;
-    std::unordered_map<int, int> rep; // label -> smallest member
-    rep.reserve((size_t)m->n_entities * 2);
+    // label -> column of ent_attrs and label -> smallest member; direct tables when the labels are
+    // small non-negative integers (what exchanger() and this library produce), hash maps otherwise
+    int max_label = -1;
+    bool dense = true;
+    for (int e = 0; e < m->n_entities && dense; e++) {
+      if (m->ent_ids[e] < 0 || m->ent_ids[e] > 8LL * N + 1024) dense = false;
+      else max_label = std::max(max_label, m->ent_ids[e]);
+    }
+    std::vector<int> slot_v, rep_v;
+    std::unordered_map<int, int> slot_m, rep_m;
+    if (dense) { slot_v.assign((size_t)max_label + 1, -1); rep_v.assign((size_t)max_label + 1, -1); }
+    else { slot_m.reserve((size_t)m->n_entities * 2); rep_m.reserve((size_t)m->n_entities * 2); }
+    auto slot_of = [&](int lab) -> int {
+      if (dense) return (lab < 0 || lab > max_label) ? -1 : slot_v[lab];
+      auto it = slot_m.find(lab);
+      return it == slot_m.end() ? -1 : it->second;
+    };
+    for (int e = 0; e < m->n_entities; e++) {
+      if (dense) slot_v[m->ent_ids[e]] = e; else slot_m[m->ent_ids[e]] = e;
+    }
+    int n_linked = 0;
     for (int r = N - 1; r >= 0; r--) {
-      if (!slot_of.count(m->links[r])) return bail(fail(h, EXB200_ERR_INVALID, "links refers to an unknown entity"));
-      rep[m->links[r]] = r;
+      const int lab = m->links[r];
+      if (slot_of(lab) < 0) return bail(fail(h, EXB200_ERR_INVALID, "links refers to an unknown entity"));
+      if (dense) { n_linked += rep_v[lab] < 0; rep_v[lab] = r; }
+      else { n_linked += !rep_m.count(lab); rep_m[lab] = r; }
     }
     std::vector<int> tail(N, -1);
     for (int r = 0; r < N; r++) {
-      const int cidx = rep[m->links[r]];
+      const int lab = m->links[r];
+      const int cidx = dense ? rep_v[lab] : rep_m[lab];
       lambda[r] = cidx;
       if (size[cidx]++ == 0) {
         head[cidx] = r;
-        const int col = slot_of[m->links[r]];
+        const int col = slot_of(lab);
         for (int a = 0; a < A; a++) {
           const int v = m->ent_attrs[a + (size_t)A * col];
           if (v < 0 || v >= m->attrs[a].domain_size) return bail(fail(h, EXB200_ERR_INVALID, "ent_attrs out of range"));
@@ -737,7 +759,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
       } else next[tail[cidx]] = r;
       tail[cidx] = r;
     }
-    h->K = (int)rep.size();
+    h->K = n_linked;
   }
   h->theta.resize((size_t)F * A);
   for (int f = 0; f < F; f++)
@@ -783,6 +805,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.fin, (size_t)N));
   TRY(dalloc(h, &S.rdy_m1, (size_t)N));
   TRY(dalloc(h, &S.rdy_srel, (size_t)N));
+  TRY(dalloc(h, &S.referenced, (size_t)2 * N));
   TRY(dalloc(h, &S.dlo, (size_t)N));
   TRY(dalloc(h, &S.dhi, (size_t)N));
   TRY(dalloc(h, &S.plo, (size_t)N));

@@ -278,9 +278,7 @@ __device__ __forceinline__ bool item_indexed(const DevState& S, int i) {
 // phase 0: partition histogram; phase 1: scatter of the pairs.  Every item tuple is read once per
 // phase for all tables; shared memory holds one histogram (and one slice base) per table.
 __global__ void __launch_bounds__(TPB) k_part_a(DevState S, PartBuild P, int phase) {
-  extern __shared__ int s_dyn[];
-  int* s_cnt = s_dyn;                         // [n_tab][MAX_PARTS]
-  int* s_base = s_dyn + P.n_tab * MAX_PARTS;  // [n_tab][MAX_PARTS] (phase 1)
+  extern __shared__ int s_cnt[]; // [n_tab][MAX_PARTS]: counts, then the running position inside the block's slice
   const int n = 2 * S.N;
   const int per = (n + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
@@ -299,19 +297,17 @@ __global__ void __launch_bounds__(TPB) k_part_a(DevState S, PartBuild P, int pha
       if (s_cnt[q]) atomicAdd(&P.part_cnt[q], s_cnt[q]);
     return;
   }
-  // reserve this block's slice of every partition, then place the pairs
-  for (int q = threadIdx.x; q < nbins; q += TPB) {
-    s_base[q] = s_cnt[q] ? atomicAdd(&P.part_cnt[q], s_cnt[q]) : 0;
-    s_cnt[q] = 0;
-  }
+  // reserve this block's slice of every partition (one global atomic per non-empty bin), then place
+  // the pairs: the shared counter now walks through the slice
+  for (int q = threadIdx.x; q < nbins; q += TPB)
+    if (s_cnt[q]) s_cnt[q] = atomicAdd(&P.part_cnt[q], s_cnt[q]);
   __syncthreads();
   for (int i = i0 + threadIdx.x; i < i1; i += TPB)
     if (item_indexed(S, i)) {
       const int* y = S.ent_y + (size_t)i * S.ES;
       for (int k = 0; k < P.n_tab; k++) {
         const uint32_t b = bucket_of(S, S.tables[P.tabs[k]], y);
-        const int q = k * MAX_PARTS + (b >> PART_BITS);
-        const int pos = s_base[q] + atomicAdd(&s_cnt[q], 1);
+        const int pos = atomicAdd(&s_cnt[k * MAX_PARTS + (b >> PART_BITS)], 1);
         P.pairs[(size_t)k * P.cap + pos] =
             ((unsigned long long)(uint32_t)i << PART_BITS) | (unsigned long long)(b & (PART_SIZE - 1));
       }
@@ -492,8 +488,8 @@ __device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint
   S.dlo[r] = other ? -1 : 0; // while its outcome is unknown the record may lower K only if it can join another entity
   S.dhi[r] = 1;
   if (cnt == -1) S.wide_list[atomicAdd(&S.counters[C_NWIDE], 1)] = r;
-  else if (cnt == -2) atomicAdd(&S.counters[C_NFENCE], 1);
-  else if (cnt == -3) S.unk_list[atomicAdd(&S.counters[C_NUNK], 1)] = r;
+  else if (cnt == -2) { atomicAdd(&S.counters[C_NFENCE], 1); atomicAdd(&S.counters[C_NOLIST], 1); }
+  else if (cnt == -3) { S.unk_list[atomicAdd(&S.counters[C_NUNK], 1)] = r; atomicAdd(&S.counters[C_NOLIST], 1); }
   else if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
 }
 
@@ -594,7 +590,10 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
         if (o + (unsigned long long)cnt > S.pool_cap) overflow = true;
         else {
           off = (uint32_t)o;
-          for (int i = gl; i < cnt; i += GL) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+          for (int i = gl; i < cnt; i += GL) {
+            S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i];
+            if (ids[i] != own) S.referenced[ids[i]] = 1;
+          }
         }
       }
       if (gl == 0) {
@@ -642,7 +641,10 @@ __device__ void stage_sort_store(const DevState& S, int r, int own, int* ids, do
     __syncthreads();
     const unsigned long long o = *s_off;
     const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
-    if (!overflow) for (int i = threadIdx.x; i < cnt; i += blockDim.x) { S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i]; }
+    if (!overflow) for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      S.cand_id[o + i] = ids[i]; S.cand_ll[o + i] = lls[i];
+      if (ids[i] != own) S.referenced[ids[i]] = 1;
+    }
     if (threadIdx.x == 0) {
       const bool other = overflow || cnt > 1 || (cnt == 1 && ids[0] != own);
       finish_candidates(S, r, overflow ? 0u : (uint32_t)o, overflow ? -2 : cnt, other);
@@ -1332,6 +1334,16 @@ __global__ void k_wide_commit(DevState S, int r) {
     if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
   }
   finalize_record(S, r, own, target, single);
+}
+
+// Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares
+// its entity at its turn, i.e. if the entity has other members now or some other record may join
+// it first (the entity is on somebody's candidate list, or a record without a list is pending).
+__global__ void __launch_bounds__(TPB) k_bounds_init(DevState S, int any_nolist) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= S.N || S.fin[r] == 1) return;
+  const int own = S.lambda[r];
+  S.dhi[r] = (any_nolist || S.ent_size[own] > 1 || S.referenced[own]) ? 1 : 0;
 }
 
 // wide records are final before the rounds start and their change of K is folded into K0
