@@ -233,10 +233,9 @@ def run_ours(opt, n_records, kind, desc):
     if rank == 0:
         # ---- roofline of the dominant single kernel (algorithmic bytes: DESIGN.md section 5)
         n, cbar, rho = n_records, cand / opt.steps / n_records, k_ent / n_records
-        items, tbar = 1.2 * n, tables / opt.steps  # indexed entity slots (twins excluded), tables built
+        tbar = tables / opt.steps  # blocking tables built per sweep
+        # single kernels only (the index build, the rounds and the serial path are multi-kernel phases)
         kernels = {
-            "k_index_fill (links: blocking index)": (acc["ms_index_fill"], items * (4 * A + 4 * tbar)),
-            "k_index_count (links: blocking index)": (acc["ms_index_count"], items * 4 * A),
             "k_cand (links: candidate generation)": (acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
             "k_entities (entity attributes)": (acc["ms_entities"], n * (4 + 4 * A + 4 * A * rho)),
             "k_distort (distortion indicators)": (acc["ms_distort"], n * (9 * A + 4)),

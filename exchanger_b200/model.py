@@ -515,6 +515,8 @@ def model_with_state(model: ExchangERModel, state: dict) -> ExchangERModel:
     out.ent_attrs = np.asarray(state["ent_attrs"], np.int32).copy()
     out.rec_distortions = np.asarray(state["rec_distortions"], np.int32).copy()
     out.distort_probs = np.asarray(state["distort_probs"], np.float64).copy()
+    if "distort_dist_concs" in state:
+        out.distort_dist_concs = np.asarray(state["distort_dist_concs"], np.float64).copy()
     cp = copy.copy(model.clust_params)
     cl = state["clust"]
     if isinstance(cp, PitmanYorRP):

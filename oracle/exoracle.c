@@ -14,6 +14,10 @@
  *   attribute tables ....... src/attribute_index.cpp:26-116
  *   cluster prior .......... src/clust_params.cpp:4-31, :37-72, :74-121
  *   distortion probs ....... src/distortion_probs.cpp:30-47
+ *   DP concentrations ...... src/distort_dist_concs.cpp:32-94 (per-cluster value counts; the
+ *                            reference's map that is never cleared between clusters, :53 vs :56,
+ *                            is NOT reproduced - SURVEY.md Appendix B.7)
+ *   entity distributions ... src/entities.cpp:133-156, src/dirichlet.h:12-34
  *
  * The reference draws from R's Mersenne-Twister in program order and iterates
  * std::unordered_* containers, so its draws are not reproducible by any parallel
@@ -51,7 +55,7 @@
 #define REJECT_CAP 100000
 
 enum { PH_LINK_DECIDE = 1, PH_LINK_NEWATTR = 2, PH_ENT_ATTR = 3, PH_DISTORT = 4, PH_CLUST_U = 5,
-       PH_CLUST_V = 6, PH_HOST = 7 };
+       PH_CLUST_V = 6, PH_HOST = 7, PH_CONC_ZETA = 8, PH_CONC_BETA = 9 };
 
 /* ------------------------------------------------------------------ Philox4x32-10 */
 static void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -140,6 +144,9 @@ typedef struct {
   double **g; double G[NMAX_FAST + 1]; alias_t Tg[NMAX_FAST + 1]; /* phi/(1-psi)^n */
   alias_t Tpsi;
   double s1, s2;                  /* Beta prior on theta (<=0: fixed) */
+  double conc;                    /* DP concentration b (INFINITY: none) */
+  double conc_shape, conc_rate;   /* Gamma prior on b (<= 0: fixed) */
+  int dirichlet; double *dir_alpha; /* Dirichlet prior on phi */
 } attr_t;
 
 typedef struct exo {
@@ -156,7 +163,8 @@ typedef struct exo {
   long long n_cand; int n_changed, n_wide;
   /* scratch for the links update */
   double *Lnew; int idx_attr; int *bptr, *bitem;
-  int brute;
+  int *mhead, *mnext;             /* member lists (ascending record id) during the links update */
+  int brute, has_dp;
   int wide_threshold;             /* scan order: records with more possible links go first */
   int *corr;                      /* [F*A] corrected non-distorted counts of the last sweep */
 } exo;
@@ -212,6 +220,39 @@ static double rpois_(exo *s, double lam) {
     if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
   }
 }
+/* gamma / beta variates from keyed uniforms (one stream per (id, attr): slot advances) */
+typedef struct { uint64_t seed; uint32_t id, iter, phase, attr, slot; int half; double ub; } kstream;
+static double ks_u(kstream *k) {
+  if (k->half) { k->half = 0; return k->ub; }
+  double a, b;
+  rng2(k->seed, k->id, k->iter, k->phase, k->attr, k->slot++, &a, &b);
+  k->ub = b; k->half = 1;
+  return a;
+}
+static double ks_norm(kstream *k) {
+  double u1 = ks_u(k), u2 = ks_u(k);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+static double ks_gamma(kstream *k, double a) {
+  if (!(a > 0.0)) return 0.0;
+  if (a < 1.0) { double u = ks_u(k); return ks_gamma(k, a + 1.0) * pow(u, 1.0 / a); }
+  double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (;;) {
+    double x = ks_norm(k), v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = ks_u(k), x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return d * v;
+    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return d * v;
+  }
+}
+static double ks_beta(kstream *k, double a, double b) {
+  if (b == 0.0) return 1.0;
+  if (a == 0.0) return 0.0;
+  double x = ks_gamma(k, a), y = ks_gamma(k, b);
+  return x / (x + y);
+}
+
 /* stands in for R::rnbinom(size, prob): gamma-Poisson mixture */
 static double rnbinom_(exo *s, double size, double prob) {
   if (prob >= 1.0) return 0.0;
@@ -247,6 +288,16 @@ static double log_distortion_prob(const attr_t *t, int v, int w) {
     if (t->col[mid] < v) lo = mid + 1; else hi = mid;
   }
   return (lo < t->row[w + 1] && t->col[lo] == v) ? t->logp[lo] : -INFINITY;
+}
+
+static double distortion_prob(const attr_t *t, int v, int w) {
+  double l = log_distortion_prob(t, v, w);
+  if (!(l > -INFINITY)) return 0.0;
+  if (t->is_const) return t->exclude ? t->psi[w] / t->om[v] : t->psi[w];
+  if (v == w) return 1.0;
+  int64_t lo = t->row[w], hi = t->row[w + 1];
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (t->col[mid] < v) lo = mid + 1; else hi = mid; }
+  return t->p[lo];
 }
 
 /* everything that depends on phi: rebuilt whenever the entity-value pmf changes
@@ -299,6 +350,7 @@ static void set_err(exo *s, int rec, const char *msg) {
 const char *exo_last_error(exo *s) { return s->err; }
 
 void exo_destroy(exo *s);
+static void phase_entity_dists(exo *s);
 
 exo *exo_create(const exb200_model *m) {
   exo *s = (exo *)calloc(1, sizeof(exo));
@@ -313,6 +365,7 @@ exo *exo_create(const exb200_model *m) {
   s->theta = (double *)malloc(sizeof(double) * F * A);
   s->ndist = (int *)calloc(F * A, sizeof(int));
   s->Lnew = (double *)malloc(sizeof(double) * N);
+  s->mhead = (int *)malloc(sizeof(int) * 2 * N); s->mnext = (int *)malloc(sizeof(int) * N);
   s->corr = (int *)calloc(F * A, sizeof(int));
   s->wide_threshold = 4096;
   s->bitem = (int *)malloc(sizeof(int) * 2 * N);
@@ -331,9 +384,12 @@ exo *exo_create(const exb200_model *m) {
     int D = in->domain_size;
     t->D = D; t->is_const = in->is_constant; t->exclude = in->exclude_entity_value;
     t->s1 = in->distort_prob_shape1; t->s2 = in->distort_prob_shape2;
-    if (isfinite(in->distort_dist_conc) || in->conc_prior_shape > 0 ||
-        in->entity_dist_kind != EXB200_ENTDIST_FIXED) {
-      set_err(s, a, "finite DP concentration / Dirichlet entity prior are not restated");
+    t->conc = in->distort_dist_conc; t->conc_shape = in->conc_prior_shape; t->conc_rate = in->conc_prior_rate;
+    t->dirichlet = in->entity_dist_kind == EXB200_ENTDIST_DIRICHLET;
+    if (isfinite(t->conc) && !t->exclude) set_err(s, a, "a finite concentration requires exclude_entity_value");
+    if (t->dirichlet) {
+      t->dir_alpha = (double *)malloc(sizeof(double) * D);
+      for (int v = 0; v < D; v++) t->dir_alpha[v] = in->entity_dist[v];
     }
     t->psi = (double *)malloc(sizeof(double) * D); t->phi = (double *)malloc(sizeof(double) * D);
     t->logpsi = (double *)malloc(sizeof(double) * D); t->log1mpsi = (double *)malloc(sizeof(double) * D);
@@ -343,7 +399,7 @@ exo *exo_create(const exb200_model *m) {
     for (int n = 0; n <= NMAX_FAST; n++) t->g[n] = (double *)malloc(sizeof(double) * D);
     for (int v = 0; v < D; v++) {
       t->psi[v] = in->probs[v];
-      t->phi[v] = in->entity_dist ? in->entity_dist[v] : in->probs[v];
+      t->phi[v] = (in->entity_dist && !t->dirichlet) ? in->entity_dist[v] : in->probs[v];
       t->om[v] = 1.0 - t->psi[v];
       t->logpsi[v] = log(t->psi[v]);
       t->log1mpsi[v] = log(t->om[v]);
@@ -393,6 +449,8 @@ exo *exo_create(const exb200_model *m) {
   }
   s->K = 0;
   for (int e = 0; e < N; e++) s->K += s->esize[e] > 0;
+  s->host_ctr = 0x40000000u; /* the constructor's draw has its own counter range */
+  phase_entity_dists(s);
   for (int r = 0; r < N; r++)
     for (int a = 0; a < A; a++) s->ndist[s->fid[r] * A + a] += s->z[r * A + a];
   return s;
@@ -408,7 +466,7 @@ void exo_destroy(exo *s) {
     free(t->g); if (t->Tpsi.prob) alias_free(&t->Tpsi);
   }
   free(s->x); free(s->z); free(s->fid); free(s->lambda); free(s->ey); free(s->esize); free(s->theta);
-  free(s->ndist); free(s->corr); free(s->Lnew); free(s->bitem); free(s->bptr); free(s->at); free(s);
+  free(s->ndist); free(s->corr); free(s->mhead); free(s->mnext); free(s->Lnew); free(s->bitem); free(s->bptr); free(s->at); free(s);
 }
 
 /* ------------------------------------------------------------------ 1. cluster prior */
@@ -543,15 +601,41 @@ static int compatible(const exo *s, int r, int e) {
   }
   return 1;
 }
-/* logLikelihoodWeightExisting for infinite concentration (links.cpp:216-288) */
+/* logLikelihoodWeightExisting (links.cpp:216-288), the part that does not depend on the other
+   members of e: attributes with infinite concentration */
 static double loglik_existing(const exo *s, int r, int e) {
   const int A = s->A;
   double l = 0.0;
   for (int a = 0; a < A; a++) {
     int xv = s->x[r * A + a];
-    if (xv >= 0 && s->z[r * A + a]) l += log_distortion_prob(&s->at[a], s->ey[(size_t)e * A + a], xv);
+    if (xv >= 0 && s->z[r * A + a] && !isfinite(s->at[a].conc))
+      l += log_distortion_prob(&s->at[a], s->ey[(size_t)e * A + a], xv);
   }
   return l;
+}
+/* ... and the part that does (finite concentration b, links.cpp:251-279): the other members of e
+   whose value of the attribute is distorted and observed form the urn */
+static double loglik_existing_dp(const exo *s, int r, int e) {
+  const int A = s->A;
+  double l = 0.0;
+  for (int a = 0; a < A; a++) {
+    const attr_t *t = &s->at[a];
+    int xv = s->x[r * A + a];
+    if (!(xv >= 0 && s->z[r * A + a] && isfinite(t->conc))) continue;
+    int c_dist = 0, c_same = 0;
+    for (int q = s->mhead[e]; q >= 0; q = s->mnext[q]) {
+      if (q == r) continue;
+      int xq = s->x[q * A + a];
+      if (xq >= 0 && s->z[q * A + a]) { c_dist++; c_same += xq == xv; }
+    }
+    l += log((double)c_same + t->conc * distortion_prob(t, s->ey[(size_t)e * A + a], xv));
+    l += -log((double)c_dist + t->conc);
+  }
+  return l;
+}
+static int any_finite_conc(const exo *s) {
+  for (int a = 0; a < s->A; a++) if (isfinite(s->at[a].conc)) return 1;
+  return 0;
 }
 
 /* Enumerate the conditional of record r (links.cpp:361-399) in the current state:
@@ -577,6 +661,7 @@ static int link_candidates(const exo *s, int r, int **ids, double **lw, int *cap
     }
     (*ids)[n] = e;
     (*lw)[n] = log(prior_existing(&s->cl, sz)) + loglik_existing(s, r, e);
+    if (s->has_dp) (*lw)[n] += loglik_existing_dp(s, r, e);
     n++;
   }
   return n;
@@ -606,6 +691,9 @@ static void phase_links(exo *s) {
   int *ids = NULL, cap = 0; double *lw = NULL;
   links_prepare(s);
   s->n_cand = 0; s->n_changed = 0;
+  s->has_dp = any_finite_conc(s);
+  for (int e = 0; e < 2 * N; e++) s->mhead[e] = -1;
+  for (int r = N - 1; r >= 0; r--) { s->mnext[r] = s->mhead[s->lambda[r]]; s->mhead[s->lambda[r]] = r; }
   /* scan order: records with more than wide_threshold possible links first, then the others */
   int *order = (int *)malloc(sizeof(int) * N), no = 0;
   char *is_wide = (char *)calloc(N, 1);
@@ -651,6 +739,14 @@ static void phase_links(exo *s) {
     if (target == N + r) s->K++;
     s->esize[target]++;
     s->lambda[r] = target;
+    if (target != own) { /* member lists stay sorted by record id */
+      int h = s->mhead[own];
+      if (h == r) s->mhead[own] = s->mnext[r];
+      else { while (s->mnext[h] != r) h = s->mnext[h]; s->mnext[h] = s->mnext[r]; }
+      h = s->mhead[target];
+      if (h < 0 || r < h) { s->mnext[r] = h; s->mhead[target] = r; }
+      else { int nx = s->mnext[h]; while (nx >= 0 && nx < r) { h = nx; nx = s->mnext[h]; } s->mnext[r] = nx; s->mnext[h] = r; }
+    }
     if (!(target == own || (single && target == N + r))) s->n_changed++;
   }
   free(ids); free(lw); free(order);
@@ -685,11 +781,12 @@ static void ks_scan32(double x[32]) {
   }
 }
 
-/* logWeightEntityValue for infinite concentration (entities.cpp:236-296) */
+/* logWeightEntityValue (entities.cpp:236-296) */
 static double log_weight_entity_value(const exo *s, int v, int a, const int *mem, int n) {
   const attr_t *t = &s->at[a];
   const int A = s->A;
   double lw = t->logphi[v], mefv = t->mef[v];
+  int ctr_disagree = 0;
   for (int i = 0; i < n; i++) {
     int r = mem[i], xv = s->x[r * A + a];
     if (xv < 0) continue;
@@ -699,7 +796,20 @@ static double log_weight_entity_value(const exo *s, int v, int a, const int *mem
       else lw += log(1.0 - eff + eff * (t->is_const ? t->psi[v] : 1.0)); /* :270, attribute_index.cpp:45,82 */
     } else {
       lw += log(eff);
-      lw += log_distortion_prob(t, v, xv); /* :290 */
+      if (isfinite(t->conc)) { /* :275-288: Chinese-restaurant terms of the disagreeing values */
+        double b = t->conc;
+        ctr_disagree++;
+        lw += -log((double)ctr_disagree - 1.0 + b);
+        int seen = 0;
+        for (int q = 0; q < i; q++) {
+          int xq = s->x[mem[q] * A + a];
+          if (xq >= 0 && xq != v && xq == xv) seen++;
+        }
+        if (seen) lw += log((double)seen + b * distortion_prob(t, v, xv));
+        else lw += log(b * distortion_prob(t, v, xv));
+      } else {
+        lw += log_distortion_prob(t, v, xv); /* :290 */
+      }
     }
   }
   return lw;
@@ -718,7 +828,7 @@ static int draw_entity_value(exo *s, int e, int a, const int *mem, int n) {
   rng2(s->seed, (uint32_t)e, it, PH_ENT_ATTR, (uint32_t)a, 0, &u, NULL);
   if (nobs == 0) return alias_draw(&t->Tg[0], u); /* entities.cpp:387-389 */
 
-  if (t->is_const && t->exclude && nobs <= NMAX_FAST) {
+  if (t->is_const && t->exclude && nobs <= NMAX_FAST && (nobs == 1 || !isfinite(t->conc))) {
     /* drawEntityValueSequential (entities.cpp:298-348) without touching the whole domain:
        w(v) for v among the members' values explicitly, C * phi(v)/(1-psi(v))^nobs elsewhere */
     int vals[NMAX_FAST]; double w[NMAX_FAST]; int nv = 0;
@@ -848,6 +958,71 @@ static void phase_entities(exo *s) { /* Entities::update_attributes, entities.cp
   free(head); free(next); free(mem);
 }
 
+/* ------------------------------------------------------------------ 3b. entity distributions */
+/* Entities::update_distributions (entities.cpp:133-156) with rdirichlet (dirichlet.h:12-34):
+   phi_a ~ Dirichlet(count_a(v) + alpha_v), then the tables that depend on phi (Cache::update) */
+static void phase_entity_dists(exo *s) {
+  const int N = s->N, A = s->A;
+  for (int a = 0; a < A; a++) {
+    attr_t *t = &s->at[a];
+    if (!t->dirichlet) continue;
+    double *g = (double *)malloc(sizeof(double) * t->D), total = 0.0;
+    int *cnt = (int *)calloc(t->D, sizeof(int));
+    for (int e = 0; e < N; e++) if (s->esize[e] > 0) cnt[s->ey[(size_t)e * A + a]]++;
+    for (int v = 0; v < t->D; v++) { g[v] = rgamma_(s, (double)cnt[v] + t->dir_alpha[v], 1.0); total += g[v]; }
+    for (int v = 0; v < t->D; v++) t->phi[v] = g[v] / total;
+    free(g); free(cnt);
+    if (attr_refresh(t)) set_err(s, a, "invalid entity distribution");
+  }
+}
+
+/* ------------------------------------------------------------------ 3c. DP concentrations */
+/* DistortDistConcs::update (distort_dist_concs.cpp:32-94), value counts per cluster.  Entities in
+   ascending id, members in ascending id; the Bernoulli of member number i of entity e is keyed
+   (e, attribute, i), the cluster's Beta variate has its own keyed stream; log t_e is accumulated in
+   fixed point (2^-40) so that the sum does not depend on the order. */
+static void phase_concs(exo *s) {
+  const int N = s->N, A = s->A;
+  uint32_t it = (uint32_t)s->iteration;
+  int any = 0;
+  for (int a = 0; a < A; a++) any |= s->at[a].conc_shape > 0;
+  if (!any) return;
+  int *head = (int *)malloc(sizeof(int) * N), *next = (int *)malloc(sizeof(int) * N);
+  for (int e = 0; e < N; e++) head[e] = -1;
+  for (int r = N - 1; r >= 0; r--) { next[r] = head[s->lambda[r]]; head[s->lambda[r]] = r; }
+  for (int a = 0; a < A; a++) {
+    attr_t *t = &s->at[a];
+    if (!(t->conc_shape > 0)) continue;
+    long long sum_zeta = 0, sum_logt_fx = 0;
+    for (int e = 0; e < N; e++) {
+      if (s->esize[e] <= 0) continue;
+      int yv = s->ey[(size_t)e * A + a], ctr = 0, idx = 0;
+      for (int r = head[e]; r >= 0; r = next[r], idx++) {
+        int xv = s->x[r * A + a];
+        if (xv < 0 || xv == yv) continue;
+        int seen = 0; /* earlier members of this cluster with the same disagreeing value */
+        for (int q = head[e]; q != r; q = next[q]) seen += s->x[q * A + a] == xv;
+        double prob = 1.0;
+        if (seen) { double zz = t->conc * distortion_prob(t, yv, xv); prob = zz / (zz + (double)seen); }
+        double u;
+        rng2(s->seed, (uint32_t)e, it, PH_CONC_ZETA, (uint32_t)a, (uint32_t)idx, &u, NULL);
+        sum_zeta += u < prob;
+        ctr++;
+      }
+      if (ctr > 0) { /* rbeta(b, 0) = 1 otherwise: log 1 = 0 */
+        kstream k = {s->seed, (uint32_t)e, it, PH_CONC_BETA, (uint32_t)a, 0, 0, 0.0};
+        double te = ks_beta(&k, t->conc, (double)ctr);
+        if (te < 1e-300) te = 1e-300; /* a Beta(b, n) variate can underflow for tiny b */
+        sum_logt_fx += llround(log(te) * 1099511627776.0);
+      }
+    }
+    double shape = t->conc_shape + (double)sum_zeta;
+    double rate = t->conc_rate - (double)sum_logt_fx / 1099511627776.0;
+    t->conc = rgamma_(s, shape, 1.0 / rate);
+  }
+  free(head); free(next);
+}
+
 /* ------------------------------------------------------------------ 4. distortion */
 static void phase_distort(exo *s, int *corr) { /* Records::update_distortion, records.cpp:70-138 */
   const int N = s->N, A = s->A, F = s->F;
@@ -904,7 +1079,7 @@ int exo_sweep_phases(exo *s, int phases) {
   if (s->err[0]) return EXB200_ERR_WEIGHTS;
   if (phases & 1) { s->host_ctr = 0; phase_clust(s); }
   if (phases & 2) { phase_links(s); phase_canon(s); }
-  if (phases & 4) phase_entities(s);
+  if (phases & 4) { phase_entities(s); phase_entity_dists(s); phase_concs(s); }
   if (phases & 8) phase_distort(s, corr);
   if (phases & 16) { phase_theta(s, corr); s->iteration++; }
   return s->err[0] ? EXB200_ERR_WEIGHTS : EXB200_OK;
@@ -939,7 +1114,7 @@ void exo_get_state(exo *s, exb200_state *out) {
       if (out->distort_probs) out->distort_probs[f + F * a] = s->theta[f * A + a];
       if (out->distort_counts) out->distort_counts[f + F * a] = s->ndist[f * A + a];
     }
-  if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = INFINITY;
+  if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = s->at[a].conc;
   out->clust = s->cl;
 }
 void exo_get_stats(exo *s, long long *n_cand, int *n_changed, int *K) {
@@ -953,6 +1128,9 @@ int exo_link_conditional(exo *s, int rid, int cap, int32_t *cand, double *lwout,
   const int N = s->N, A = s->A;
   int save = s->brute; s->brute = 1;
   for (int r = 0; r < N; r++) s->esize[N + r] = 0;
+  s->has_dp = any_finite_conc(s);
+  for (int e = 0; e < 2 * N; e++) s->mhead[e] = -1;
+  for (int r = N - 1; r >= 0; r--) { s->mnext[r] = s->mhead[s->lambda[r]]; s->mhead[s->lambda[r]] = r; }
   double L = 0.0;
   for (int a = 0; a < A; a++) {
     int xv = s->x[rid * A + a];

@@ -269,3 +269,7 @@ double exref_exp_distortion_prob(void *p, int aid, int w) {
   return s.cache_.attr_indices_[aid]->get_exp_distortion_prob(w, s.ents_.get_distribution(aid));
 }
 } // extern "C"
+extern "C" void exref_get_concs(void *p, double *out) {
+  ExRef *h = (ExRef *)p;
+  for (int a = 0; a < h->A; a++) out[a] = h->state->distort_dist_concs_.get(a);
+}
