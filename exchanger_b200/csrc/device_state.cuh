@@ -129,6 +129,8 @@ struct DevState {
   int K0;                       // number of entities at the start of the links update
   int use_kbounds;              // 0 when prior_weight_new does not depend on K
   ClustDev cl;
+  double conc[MAX_ATTRS];       // DP concentration per attribute (infinite: none)
+  int has_dp;                   // some concentration is finite
 };
 
 enum CounterSlot {

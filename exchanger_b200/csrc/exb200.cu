@@ -24,8 +24,11 @@ thread_local std::string g_create_error;
 struct HostAttr {
   int D = 0, is_const = 1, exclude = 1;
   double s1 = 0, s2 = 0; // Beta prior on theta
-  std::vector<double> psi, phi, mef;
-  std::vector<void*> dev; // device allocations owned by this attribute
+  double conc_shape = 0, conc_rate = 0; // Gamma prior on the DP concentration (<= 0: fixed)
+  bool dirichlet = false;               // Dirichlet prior on the entity-value distribution
+  std::vector<double> psi, phi, mef, om, dir_alpha;
+  std::vector<int> row, col;            // inverted neighbourhood CSR (host copy)
+  std::vector<double> p;
 };
 
 struct TableHost {
@@ -47,6 +50,8 @@ struct exb200_handle {
   HostStream hs;
   std::vector<HostAttr> attrs;
   std::vector<double> theta;   // [F*A] f*A + a
+  double conc[MAX_ATTRS];      // DP concentrations (infinite: none)
+  int* d_hist = nullptr;       // [max D] entity-value histogram of one attribute
   std::vector<int> ndist, corr;
   DevState S{};                // device pointers (by-value kernel argument)
   std::vector<void*> allocs;
@@ -139,6 +144,14 @@ double prior_existing_host(const exb200_clust& c, int n) {
   return 1.0;
 }
 
+void refresh_conc_dev(exb200_handle* h) {
+  h->S.has_dp = 0;
+  for (int a = 0; a < MAX_ATTRS; a++) {
+    h->S.conc[a] = a < h->A ? h->conc[a] : std::numeric_limits<double>::infinity();
+    if (a < h->A && std::isfinite(h->conc[a])) h->S.has_dp = 1;
+  }
+}
+
 void refresh_clust_dev(exb200_handle* h) {
   ClustDev& c = h->S.cl;
   c.kind = h->cl.kind; c.alpha = h->cl.alpha; c.d = h->cl.d; c.m = h->cl.m; c.kappa = h->cl.kappa;
@@ -159,37 +172,100 @@ int check_device_error(exb200_handle* h) {
 }
 
 // ---- per-attribute tables (ConstantAttributeIndex / NonConstantAttributeIndex + alias tables)
+// Everything that depends on the entity-value pmf phi of attribute a - what Cache::update
+// (cache.cpp:20-27) refreshes plus the alias tables and prefix sums of the O(1) schemes - computed
+// on the host and copied into the attribute's device buffers.  Called at creation and, with a
+// Dirichlet prior (Entities::update_distributions, entities.cpp:133-156), after every sweep's draw.
+int refresh_phi(exb200_handle* h, int a) {
+  HostAttr& ha = h->attrs[a];
+  DevAttr& da = h->h_attrs[a];
+  const int D = ha.D;
+  std::vector<double> logphi(D), logE(D);
+  double Z = 0.0;
+  for (int v = 0; v < D; v++) {
+    if (!(ha.phi[v] >= 0.0)) return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid pmf");
+    logphi[v] = std::log(ha.phi[v]);
+    Z += ha.phi[v] / ha.om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
+  }
+  std::vector<double> cs(ha.p.size()), csn(ha.p.size());
+  for (int w = 0; w < D && !ha.is_const; w++) {
+    double c = 0.0, cn = 0.0;
+    for (int j = ha.row[w]; j < ha.row[w + 1]; j++) {
+      c += ha.phi[ha.col[j]] * ha.mef[ha.col[j]] * ha.p[j];
+      cs[j] = c;
+      cn += ha.phi[ha.col[j]] * ha.p[j];
+      csn[j] = cn;
+    }
+  }
+  for (int w = 0; w < D; w++) {
+    double e;
+    if (ha.is_const) // get_exp_distortion_prob, attribute_index.cpp:55-62
+      e = ha.exclude ? Z * ha.psi[w] - ha.phi[w] * ha.psi[w] / ha.om[w] : ha.psi[w];
+    else {           // attribute_index.cpp:94-101
+      e = 0.0;
+      for (int j = ha.row[w]; j < ha.row[w + 1]; j++) e += ha.phi[ha.col[j]] * ha.p[j];
+    }
+    logE[w] = std::log(e);
+  }
+  const int nt = ha.is_const ? NMAX_FAST + 1 : 1;
+  std::vector<double> g((size_t)nt * D), aprob((size_t)nt * D);
+  std::vector<int> aalias((size_t)nt * D);
+  for (int n = 0; n < nt; n++) {
+    double G = 0.0;
+    for (int v = 0; v < D; v++) {
+      g[(size_t)n * D + v] = n == 0 ? ha.phi[v] : g[(size_t)(n - 1) * D + v] / ha.om[v];
+      G += g[(size_t)n * D + v];
+    }
+    da.G[n] = G;
+    if (!alias_build(&g[(size_t)n * D], D, &aprob[(size_t)n * D], &aalias[(size_t)n * D]))
+      return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid entity distribution");
+  }
+  cudaStream_t st = h->stream;
+#define PUT(field, vec) if (!(vec).empty()) CK(cudaMemcpyAsync(const_cast<void*>((const void*)da.field), (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, st));
+  PUT(phi, ha.phi) PUT(logphi, logphi) PUT(logE, logE) PUT(cs, cs) PUT(csn, csn) PUT(g, g) PUT(aprob, aprob) PUT(aalias, aalias)
+#undef PUT
+  if (h->d_attrs) CK(cudaMemcpyAsync(h->d_attrs + a, &da, sizeof(DevAttr), cudaMemcpyHostToDevice, st)); // G[] changed
+  CK(cudaStreamSynchronize(st)); // the host vectors go out of scope
+  return EXB200_OK;
+}
+
+// ---- per-attribute tables (ConstantAttributeIndex / NonConstantAttributeIndex + alias tables)
 int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
   HostAttr& ha = h->attrs[a];
   DevAttr& da = h->h_attrs[a];
   const int D = in.domain_size;
   if (D < 1) return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": empty domain");
-  if (!std::isinf(in.distort_dist_conc) || in.conc_prior_shape > 0)
-    return fail(h, EXB200_ERR_UNSUPPORTED, "attribute " + std::to_string(a) +
-                ": finite distort_dist_prior concentration (DistortDistConcs::update) is not built yet");
-  if (in.entity_dist_kind != EXB200_ENTDIST_FIXED)
-    return fail(h, EXB200_ERR_UNSUPPORTED, "attribute " + std::to_string(a) +
-                ": DirichletRV entity_dist_prior (Entities::update_distributions) is not built yet");
+  if (std::isfinite(in.distort_dist_conc) && !in.exclude_entity_value) // comment at links.cpp:251
+    return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": a finite distort_dist_prior requires exclude_entity_value");
+  if (!(in.distort_dist_conc > 0.0)) return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": concentration must be positive");
   ha.D = D; ha.is_const = in.is_constant != 0; ha.exclude = in.exclude_entity_value != 0;
   ha.s1 = in.distort_prob_shape1; ha.s2 = in.distort_prob_shape2;
+  ha.conc_shape = in.conc_prior_shape; ha.conc_rate = in.conc_prior_rate;
+  h->conc[a] = in.distort_dist_conc;
+  ha.dirichlet = in.entity_dist_kind == EXB200_ENTDIST_DIRICHLET;
+  if (ha.dirichlet) {
+    if (!in.entity_dist) return fail(h, EXB200_ERR_INVALID, "Invalid entity_dist_prior"); // entities.cpp:195
+    ha.dir_alpha.assign(in.entity_dist, in.entity_dist + D);
+    for (double al : ha.dir_alpha)
+      if (!(al > 0.0)) return fail(h, EXB200_ERR_INVALID, "rdirichlet: concentration parameter must be positive"); // dirichlet.h:21
+  }
   ha.psi.assign(in.probs, in.probs + D);
-  ha.phi.assign(in.entity_dist ? in.entity_dist : in.probs, (in.entity_dist ? in.entity_dist : in.probs) + D);
+  const double* phi0 = (in.entity_dist && !ha.dirichlet) ? in.entity_dist : in.probs;
+  ha.phi.assign(phi0, phi0 + D);
   ha.mef.assign(D, 1.0);
   if (!ha.is_const) ha.mef.assign(in.max_exp_factor, in.max_exp_factor + D);
-  std::vector<double> om(D), logpsi(D), log1mpsi(D), logphi(D), logE(D);
-  double Z = 0.0;
+  ha.om.resize(D);
+  std::vector<double> logpsi(D), log1mpsi(D);
   for (int v = 0; v < D; v++) {
-    if (!(ha.psi[v] > 0.0 && ha.psi[v] < 1.0) || !(ha.phi[v] >= 0.0))
+    if (!(ha.psi[v] > 0.0 && ha.psi[v] < 1.0))
       return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid pmf");
-    om[v] = 1.0 - ha.psi[v];
+    ha.om[v] = 1.0 - ha.psi[v];
     logpsi[v] = std::log(ha.psi[v]);
-    log1mpsi[v] = std::log(om[v]);
-    logphi[v] = std::log(ha.phi[v]);
-    Z += ha.phi[v] / om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
+    log1mpsi[v] = std::log(ha.om[v]);
   }
   // inverted neighbourhood CSR (attribute_index.cpp:125-140)
-  std::vector<int> row(D + 1, 0), col;
-  std::vector<double> p, logp, cs, csn;
+  ha.row.assign(D + 1, 0);
+  std::vector<double> logp;
   if (!ha.is_const) {
     const int64_t nnz = in.close_row_ptr[D];
     if (nnz >= (int64_t)std::numeric_limits<int>::max())
@@ -197,66 +273,93 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
     for (int64_t j = 0; j < nnz; j++) {
       const int w = in.close_val_ids[j];
       if (w < 0 || w >= D) return fail(h, EXB200_ERR_INVALID, "close_val_ids out of range");
-      row[w + 1]++;
+      ha.row[w + 1]++;
     }
-    for (int w = 0; w < D; w++) row[w + 1] += row[w];
-    col.resize(nnz); p.resize(nnz); logp.resize(nnz);
-    std::vector<int> cur(row.begin(), row.end() - 1);
+    for (int w = 0; w < D; w++) ha.row[w + 1] += ha.row[w];
+    ha.col.resize(nnz); ha.p.resize(nnz); logp.resize(nnz);
+    std::vector<int> cur(ha.row.begin(), ha.row.end() - 1);
     for (int v = 0; v < D; v++)
       for (int64_t j = in.close_row_ptr[v]; j < in.close_row_ptr[v + 1]; j++) {
         const int q = cur[in.close_val_ids[j]]++;
-        col[q] = v; p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
+        ha.col[q] = v; ha.p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
       }
   }
-  cs.resize(p.size());
-  csn.resize(p.size());
-  for (int w = 0; w < D && !ha.is_const; w++) {
-    double c = 0.0, cn = 0.0;
-    for (int j = row[w]; j < row[w + 1]; j++) {
-      c += ha.phi[col[j]] * ha.mef[col[j]] * p[j];
-      cs[j] = c;
-      cn += ha.phi[col[j]] * p[j];
-      csn[j] = cn;
-    }
-  }
-  for (int w = 0; w < D; w++) {
-    double e;
-    if (ha.is_const) // get_exp_distortion_prob, attribute_index.cpp:55-62
-      e = ha.exclude ? Z * ha.psi[w] - ha.phi[w] * ha.psi[w] / om[w] : ha.psi[w];
-    else {           // attribute_index.cpp:94-101
-      e = 0.0;
-      for (int j = row[w]; j < row[w + 1]; j++) e += ha.phi[col[j]] * p[j];
-    }
-    logE[w] = std::log(e);
-  }
-  const int nt = ha.is_const ? NMAX_FAST + 1 : 1;
-  std::vector<double> g((size_t)nt * D), aprob((size_t)nt * D), pprob(D);
-  std::vector<int> aalias((size_t)nt * D), palias(D);
-  for (int n = 0; n < nt; n++) {
-    double G = 0.0;
-    for (int v = 0; v < D; v++) {
-      g[(size_t)n * D + v] = n == 0 ? ha.phi[v] : g[(size_t)(n - 1) * D + v] / om[v];
-      G += g[(size_t)n * D + v];
-    }
-    da.G[n] = G;
-    if (!alias_build(&g[(size_t)n * D], D, &aprob[(size_t)n * D], &aalias[(size_t)n * D]))
-      return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid entity distribution");
-  }
+  std::vector<double> pprob(D);
+  std::vector<int> palias(D);
   if (!alias_build(ha.psi.data(), D, pprob.data(), palias.data()))
     return fail(h, EXB200_ERR_INVALID, "attribute " + std::to_string(a) + ": invalid probs");
   da.D = D; da.is_const = ha.is_const; da.exclude = ha.exclude; da.pad = 0;
+  const int nt = ha.is_const ? NMAX_FAST + 1 : 1;
   int rc = 0;
   double* dp; int* ip;
 #define UPD(field, vec) rc = upload(h, &dp, (vec).data(), (vec).size()); if (rc) return rc; da.field = dp;
 #define UPI(field, vec) rc = upload(h, &ip, (vec).data(), (vec).size()); if (rc) return rc; da.field = ip;
-  UPD(psi, ha.psi) UPD(phi, ha.phi) UPD(om, om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi)
-  UPD(logphi, logphi) UPD(logE, logE) UPD(mef, ha.mef) UPI(row, row) UPI(col, col) UPD(p, p) UPD(logp, logp) UPD(cs, cs) UPD(csn, csn)
-  UPD(g, g) UPD(aprob, aprob) UPI(aalias, aalias) UPD(pprob, pprob) UPI(palias, palias)
+#define NEWD(field, n) rc = dalloc(h, &dp, (size_t)(n)); if (rc) return rc; da.field = dp;
+  UPD(psi, ha.psi) UPD(om, ha.om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi) UPD(mef, ha.mef)
+  UPI(row, ha.row) UPI(col, ha.col) UPD(p, ha.p) UPD(logp, logp) UPD(pprob, pprob) UPI(palias, palias)
+  NEWD(phi, D) NEWD(logphi, D) NEWD(logE, D) NEWD(cs, ha.p.size()) NEWD(csn, ha.p.size())
+  NEWD(g, (size_t)nt * D) NEWD(aprob, (size_t)nt * D)
+  rc = dalloc(h, &ip, (size_t)nt * D); if (rc) return rc; da.aalias = ip;
 #undef UPD
 #undef UPI
+#undef NEWD
   rc = dalloc(h, &da.lt_diff, (size_t)h->F * D); if (rc) return rc;
   rc = dalloc(h, &da.lt_same, (size_t)h->F * D); if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream)); // the host vectors go out of scope
+  return refresh_phi(h, a);
+}
+
+// phi_a ~ Dirichlet(count_a(v) + alpha_v) (entities.cpp:133-156, dirichlet.h:12-34): counts from the
+// device, Gamma variates from the host stream
+int draw_entity_dist(exb200_handle* h, int a, const std::vector<int>& counts) {
+  HostAttr& ha = h->attrs[a];
+  double total = 0.0;
+  std::vector<double> g(ha.D);
+  for (int v = 0; v < ha.D; v++) { g[v] = h->hs.gamma((double)counts[v] + ha.dir_alpha[v], 1.0); total += g[v]; }
+  for (int v = 0; v < ha.D; v++) ha.phi[v] = g[v] / total;
+  return refresh_phi(h, a);
+}
+
+// Entities::update_distributions and DistortDistConcs::update (distort_dist_concs.cpp:32-94; value
+// counts per cluster) after the entity attributes of the sweep are drawn
+int update_dists_and_concs(exb200_handle* h) {
+  DevState& S = h->S;
+  const int N = h->N;
+  cudaStream_t st = h->stream;
+  for (int a = 0; a < h->A; a++) {
+    if (!h->attrs[a].dirichlet) continue;
+    std::vector<int> counts(h->attrs[a].D);
+    CK(cudaMemsetAsync(h->d_hist, 0, sizeof(int) * counts.size(), st));
+    KLAUNCH(h, k_ent_hist, nblk(N), TPB, 0, S, a, h->d_hist);
+    CK(cudaMemcpyAsync(counts.data(), h->d_hist, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc = draw_entity_dist(h, a, counts); if (rc) return rc;
+  }
+  bool changed = false;
+  for (int a = 0; a < h->A; a++) {
+    const HostAttr& ha = h->attrs[a];
+    if (!(ha.conc_shape > 0)) continue;
+    std::vector<int> nd(N);
+    unsigned long long zeta = 0;
+    CK(cudaMemsetAsync(h->d_cl_counts, 0, sizeof(unsigned long long), st));
+    KLAUNCH(h, k_conc_aux, nblk(N), TPB, 0, S, a, S.plo, h->d_cl_counts); // plo is free outside the links update
+    CK(cudaMemcpyAsync(nd.data(), S.plo, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&zeta, h->d_cl_counts, sizeof zeta, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long sum_logt_fx = 0; // fixed point (2^-40): independent of the summation order
+    for (int e = 0; e < N; e++)
+      if (nd[e] > 0) { // rbeta(b, 0) = 1 otherwise: log 1 = 0
+        KeyedStream k{h->seed, (uint32_t)e, (uint32_t)h->iteration, PH_CONC_BETA, (uint32_t)a};
+        double te = k.beta(h->conc[a], (double)nd[e]);
+        if (te < 1e-300) te = 1e-300;
+        sum_logt_fx += std::llround(std::log(te) * 1099511627776.0);
+      }
+    const double shape = ha.conc_shape + (double)zeta;
+    const double rate = ha.conc_rate - (double)sum_logt_fx / 1099511627776.0;
+    h->conc[a] = h->hs.gamma(shape, 1.0 / rate);
+    changed = true;
+  }
+  if (changed) refresh_conc_dev(h);
   return EXB200_OK;
 }
 
@@ -619,8 +722,7 @@ int sweep(exb200_handle* h) {
   rc = update_links(h); if (rc) return rc;              // links_.update(...)
   KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_mask);   // ents_.update_attributes(...)
   KLAUNCH(h, k_entities_general, nblk((N + 31) / 32, TPB / 32), TPB, 0, S, h->d_gen_mask);
-  // ents_.update_distributions(), cache_.update(): phi is fixed (no Dirichlet prior) -> nothing to do
-  // distort_dist_concs_.update(): concentration is infinite -> nothing to do
+  rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
   CK(cudaEventRecord(h->ev[7], st));
   CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
   CK(cudaMemsetAsync(S.corr, 0, sizeof(int) * FA, st));
@@ -785,7 +887,20 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(upload(h, &S.rec_next, next.data(), next.size()));
   TRY(dalloc(h, &h->d_theta, (size_t)F * A)); S.theta = h->d_theta;
   h->attrs.resize(A); h->h_attrs.resize(A);
-  for (int a = 0; a < A; a++) TRY(build_attr(h, m->attrs[a], a));
+  for (int a = 0; a < MAX_ATTRS; a++) h->conc[a] = std::numeric_limits<double>::infinity();
+  int maxD = 1;
+  for (int a = 0; a < A; a++) { TRY(build_attr(h, m->attrs[a], a)); maxD = std::max(maxD, m->attrs[a].domain_size); }
+  TRY(dalloc(h, &h->d_hist, (size_t)maxD));
+  refresh_conc_dev(h);
+  // the reference draws phi in the Entities constructor (entities.cpp:233): same here, from the
+  // entity values of the initial state, with a counter range of its own
+  h->hs.iteration = (uint32_t)m->iteration; h->hs.counter = 0x40000000u;
+  for (int a = 0; a < A; a++)
+    if (h->attrs[a].dirichlet) {
+      std::vector<int> counts(h->attrs[a].D, 0);
+      for (int e = 0; e < N; e++) if (size[e] > 0) counts[ent_y[(size_t)e * h->ES + a]]++;
+      TRY(draw_entity_dist(h, a, counts));
+    }
   TRY(upload(h, &h->d_attrs, h->h_attrs.data(), (size_t)A)); S.attrs = h->d_attrs;
   TRY(dalloc(h, &S.Lnew, (size_t)N));
   TRY(dalloc(h, &S.rec_tab, (size_t)N));
@@ -967,7 +1082,7 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
           if (out->distort_counts) out->distort_counts[(size_t)sample * FA + f + a * h->F] = h->ndist[f * h->A + a];
         }
       if (out->distort_dist_concs)
-        for (int a = 0; a < h->A; a++) out->distort_dist_concs[(size_t)sample * h->A + a] = std::numeric_limits<double>::infinity();
+        for (int a = 0; a < h->A; a++) out->distort_dist_concs[(size_t)sample * h->A + a] = h->conc[a];
       if (out->clust_params) {
         const bool py = h->cl.kind == EXB200_CLUST_PITMAN_YOR;
         out->clust_params[2 * (size_t)sample] = py ? h->cl.alpha : h->cl.kappa;
@@ -1012,7 +1127,7 @@ int exb200_get_state(exb200_handle* h, exb200_state* out) {
       if (out->distort_probs) out->distort_probs[f + (size_t)F * a] = h->theta[f * A + a];
       if (out->distort_counts) out->distort_counts[f + (size_t)F * a] = h->ndist[f * A + a];
     }
-  if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = std::numeric_limits<double>::infinity();
+  if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = h->conc[a];
   out->clust = h->cl;
   return EXB200_OK;
 }

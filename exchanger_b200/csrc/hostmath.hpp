@@ -82,6 +82,44 @@ struct HostStream {
   }
 };
 
+// Gamma / Beta variates from keyed uniforms: one stream per (id, attribute), the slot advances.
+// Used for the per-cluster Beta(b, n) variates of DistortDistConcs::update
+// (src/distort_dist_concs.cpp:87), which must not depend on the order the clusters are visited in.
+struct KeyedStream {
+  uint64_t seed; uint32_t id, iter, phase, attr;
+  uint32_t slot = 0; bool half = false; double ub = 0.0;
+  double next() {
+    if (half) { half = false; return ub; }
+    const U2 u = uniforms(seed, id, iter, phase, attr, slot++);
+    ub = u.b; half = true;
+    return u.a;
+  }
+  double normal() {
+    const double u1 = next(), u2 = next();
+    return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2);
+  }
+  double gamma(double shape) {
+    if (!(shape > 0.0)) return 0.0;
+    if (shape < 1.0) { const double u = next(); return gamma(shape + 1.0) * std::pow(u, 1.0 / shape); }
+    const double d = shape - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
+    for (;;) {
+      const double x = normal();
+      double v = 1.0 + c * x;
+      if (v <= 0.0) continue;
+      v = v * v * v;
+      const double u = next(), x2 = x * x;
+      if (u < 1.0 - 0.0331 * x2 * x2) return d * v;
+      if (std::log(u) < 0.5 * x2 + d * (1.0 - v + std::log(v))) return d * v;
+    }
+  }
+  double beta(double a, double b) {
+    if (b == 0.0) return 1.0;
+    if (a == 0.0) return 0.0;
+    const double x = gamma(a), y = gamma(b);
+    return x / (x + y);
+  }
+};
+
 // Vose's alias construction.  Returns false for the weights AliasSampler rejects
 // (src/alias_sampler.h:76-97: negative / non-finite weight, non-positive total).
 inline bool alias_build(const double* w, int n, double* prob, int* alias) {

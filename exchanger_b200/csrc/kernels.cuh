@@ -50,6 +50,19 @@ __device__ __forceinline__ double log_distortion_prob(const DevAttr& t, int v, i
   return (lo < end && t.col[lo] == v) ? t.logp[lo] : -CUDART_INF;
 }
 
+// p(w | v) itself (only used with a finite concentration, which implies exclude_entity_value)
+__device__ __forceinline__ double distortion_prob(const DevAttr& t, int v, int w) {
+  if (v == w) return t.exclude ? 0.0 : (t.is_const ? t.psi[w] : 1.0);
+  if (t.is_const) return t.exclude ? t.psi[w] / t.om[v] : t.psi[w];
+  int lo = t.row[w], hi = t.row[w + 1];
+  const int end = hi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (t.col[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return (lo < end && t.col[lo] == v) ? t.p[lo] : 0.0;
+}
+
 __device__ __forceinline__ double prior_existing(const ClustDev& c, int n) { // clust_params.cpp:4-27
   if (c.kind == EXB200_CLUST_PITMAN_YOR) return fabs((double)n - c.d);
   if (c.kind == EXB200_CLUST_GEN_COUPON) return (double)n + c.kappa;
@@ -476,9 +489,38 @@ __device__ __forceinline__ double item_loglik(const DevState& S, const int* x, u
   double l = 0.0;
   for (int a = 0; a < S.A; a++) {
     const int xv = x[a];
-    if (xv >= 0 && ((zm >> a) & 1u)) l += log_distortion_prob(S.attrs[a], y[a], xv);
+    // attributes with a finite concentration depend on the entity's other members: dp_loglik
+    if (xv >= 0 && ((zm >> a) & 1u) && isinf(S.conc[a])) l += log_distortion_prob(S.attrs[a], y[a], xv);
   }
   return l;
+}
+// The member-dependent part of logLikelihoodWeightExisting for attributes with a finite
+// concentration b (links.cpp:251-279): the other members of e whose value is distorted and observed
+// form the urn.  Member lists and the members' (x, z) cannot change while r holds e.
+__device__ double dp_loglik(const DevState& S, int r, int e) {
+  const int* x = S.rec_x + (size_t)r * S.RS;
+  const uint32_t zm = S.rec_z[r];
+  const int* y = S.ent_y + (size_t)e * S.ES;
+  double l = 0.0;
+  for (int a = 0; a < S.A; a++) {
+    const int xv = x[a];
+    if (!(xv >= 0 && ((zm >> a) & 1u)) || isinf(S.conc[a])) continue;
+    int c_dist = 0, c_same = 0;
+    for (int q = S.ent_head[e]; q >= 0; q = S.rec_next[q]) {
+      if (q == r) continue;
+      const int xq = S.rec_x[(size_t)q * S.RS + a];
+      if (xq >= 0 && ((S.rec_z[q] >> a) & 1u)) { c_dist++; c_same += xq == xv; }
+    }
+    l += log((double)c_same + S.conc[a] * distortion_prob(S.attrs[a], y[a], xv));
+    l += -log((double)c_dist + S.conc[a]);
+  }
+  return l;
+}
+// log-weight of candidate e (live size sz) for record r from the stored static likelihood
+__device__ __forceinline__ double cand_lw(const DevState& S, int r, int e, int sz, double ll) {
+  double lw = log_prior_existing(S.cl, sz) + ll;
+  if (S.has_dp) lw += dp_loglik(S, r, e);
+  return lw;
 }
 
 // finish one record's candidate list: bounds of its change of K and registration as a long record
@@ -895,7 +937,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         for (int j = 0; j < cnt; j++) {
           const int sz = live_size(S, ids[j], own, single);
           if (sz > 0) {
-            const double lw = log_prior_existing(S.cl, sz) + lls[j];
+            const double lw = cand_lw(S, r, ids[j], sz, lls[j]);
             m1 = lw > m1 ? lw : m1;
           }
         }
@@ -903,7 +945,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         if (m1 > -CUDART_INF)
           for (int j = 0; j < cnt; j++) {
             const int sz = live_size(S, ids[j], own, single);
-            if (sz > 0) srel += exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+            if (sz > 0) srel += exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
           }
         const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
         const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
@@ -917,7 +959,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
             for (int j = 0; j < cnt; j++) {
               const int sz = live_size(S, ids[j], own, single);
               if (sz <= 0) continue;
-              const double w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+              const double w = exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
               if (w > 0.0) lastpos = ids[j];
               c += w;
               if (tt < c) { pick = ids[j]; break; }
@@ -983,7 +1025,7 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
         const int j = 32 * c + lane;
         if (j < cnt) {
           const int sz = live_size(S, ids[j], own, single);
-          if (sz > 0) { const double lw = log_prior_existing(S.cl, sz) + lls[j]; m1 = lw > m1 ? lw : m1; }
+          if (sz > 0) { const double lw = cand_lw(S, r, ids[j], sz, lls[j]); m1 = lw > m1 ? lw : m1; }
         }
       }
       if (!ready) {
@@ -998,7 +1040,7 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
           double w = 0.0;
           if (j < cnt) {
             const int sz = live_size(S, ids[j], own, single);
-            if (sz > 0) w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+            if (sz > 0) w = exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
           }
           for (int k = 0; k < 32; k++) srel += __shfl_sync(FULL, w, k); // candidate order; dead ones add 0
         }
@@ -1018,7 +1060,7 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
             if (j < cnt) {
               e = ids[j];
               const int sz = live_size(S, e, own, single);
-              if (sz > 0) w = exp(log_prior_existing(S.cl, sz) + lls[j] - m1);
+              if (sz > 0) w = exp(cand_lw(S, r, e, sz, lls[j]) - m1);
             }
             for (int k = 0; k < 32 && pick < 0; k++) {
               const double wk = __shfl_sync(FULL, w, k);
@@ -1059,7 +1101,7 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
     const int* y = S.ent_y + (size_t)i * S.ES;
-    if (item_compatible(S, x, zm, y)) out = log_prior_existing(S.cl, sz) + item_loglik(S, x, zm, y);
+    if (item_compatible(S, x, zm, y)) out = cand_lw(S, r, i, sz, item_loglik(S, x, zm, y));
   }
   S.lwbuf[i] = out;
 }
@@ -1084,11 +1126,11 @@ __global__ void __launch_bounds__(TPB) k_eval_batch(DevState S, const int* __res
 }
 
 // log-weight of item i for record r from the batched likelihood and the CURRENT sizes
-__device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, int i, int own, bool single) {
+__device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, int r, int i, int own, bool single) {
   const double v = ll[i];
   if (!(v == v)) return CUDART_NAN;
   const int sz = live_size(S, i, own, single);
-  return sz > 0 ? log_prior_existing(S.cl, sz) + v : CUDART_NAN;
+  return sz > 0 ? cand_lw(S, r, i, sz, v) : CUDART_NAN;
 }
 
 // The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 8
@@ -1113,7 +1155,7 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot
   wide_piece(S, p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
   for (long long i = lo + lane; i < hi; i += 32) {
-    const double v = wide_lw(S, ll, (int)i, own, single);
+    const double v = wide_lw(S, ll, r, (int)i, own, single);
     if (!(v == v) || !(v > -CUDART_INF)) continue;
     if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
   }
@@ -1209,7 +1251,7 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
       const long long i = base + lane;
       double w = 0.0;
       if (i < hi) {
-        const double v = wide_lw(S, ll, (int)i, own, single);
+        const double v = wide_lw(S, ll, r, (int)i, own, single);
         if (v == v) w = exp(v - m1);
       }
       double x = w;
@@ -1399,6 +1441,8 @@ __global__ void __launch_bounds__(TPB) k_canon(DevState S) {
 __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, int a, int v, int head,
                                           int row_first = -1, int row_j = -1) {
   double lw = t.logphi[v];
+  const double b = S.conc[a];
+  int ctr_disagree = 0;
   for (int r = head; r >= 0; r = S.rec_next[r]) {
     const int* x = S.rec_x + (size_t)r * S.RS;
     const int xv = x[a];
@@ -1407,7 +1451,15 @@ __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, i
     if (xv == v) lw += t.lt_same[f * t.D + v];
     else {
       lw += t.lt_diff[f * t.D + v];
-      lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
+      if (isinf(b)) lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
+      else { // entities.cpp:275-288: Chinese-restaurant terms of the disagreeing values
+        ctr_disagree++;
+        lw += -log((double)ctr_disagree - 1.0 + b);
+        int seen = 0; // earlier members with the same disagreeing value
+        for (int q = head; q != r; q = S.rec_next[q]) seen += S.rec_x[(size_t)q * S.RS + a] == xv;
+        const double bp = b * distortion_prob(t, v, xv);
+        lw += seen ? log((double)seen + bp) : log(bp);
+      }
     }
   }
   return lw;
@@ -1423,7 +1475,7 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
   const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
   if (nobs == 0) return alias_draw(t.aprob, t.aalias, t.D, u0.a); // entities.cpp:387-389
 
-  if (t.is_const && t.exclude && nobs <= NMAX_FAST) {
+  if (t.is_const && t.exclude && nobs <= NMAX_FAST && (nobs == 1 || isinf(S.conc[a]))) {
     // whole-domain weights of drawEntityValueSequential (entities.cpp:298-348) in closed form:
     // explicit for the members' values, C phi(v)/(1-psi(v))^nobs for every other value
     int vals[NMAX_FAST];
@@ -1609,6 +1661,45 @@ __global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const uint
       if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Auxiliary variables of DistortDistConcs::update (src/distort_dist_concs.cpp:56-88) for attribute a:
+// per entity the number of disagreeing observed members (for the host's Beta(b, n) variate) and
+// the Bernoulli sum zeta, with the value counts kept per cluster.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_conc_aux(DevState S, int a, int* __restrict__ n_disagree,
+                                                  unsigned long long* __restrict__ sum_zeta) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  int zeta = 0;
+  if (e < S.N) {
+    int ctr = 0;
+    if (S.ent_size[e] > 0) {
+      const DevAttr& t = S.attrs[a];
+      const int head = S.ent_head[e], yv = S.ent_y[(size_t)e * S.ES + a];
+      int idx = 0;
+      for (int r = head; r >= 0; r = S.rec_next[r], idx++) {
+        const int xv = S.rec_x[(size_t)r * S.RS + a];
+        if (xv < 0 || xv == yv) continue;
+        int seen = 0;
+        for (int q = head; q != r; q = S.rec_next[q]) seen += S.rec_x[(size_t)q * S.RS + a] == xv;
+        double prob = 1.0;
+        if (seen) { const double zz = S.conc[a] * distortion_prob(t, yv, xv); prob = zz / (zz + (double)seen); }
+        const U2 u = uniforms(S.seed, e, S.iter, PH_CONC_ZETA, a, idx);
+        zeta += u.a < prob;
+        ctr++;
+      }
+    }
+    n_disagree[e] = ctr;
+  }
+  zeta = warp_sum(zeta);
+  if ((threadIdx.x & 31) == 0 && zeta) atomicAdd(sum_zeta, (unsigned long long)zeta);
+}
+
+// histogram of the entity values of attribute a (Entities::update_distributions, entities.cpp:140-148)
+__global__ void __launch_bounds__(TPB) k_ent_hist(DevState S, int a, int* __restrict__ hist) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < S.N && S.ent_size[e] > 0) atomicAdd(&hist[S.ent_y[(size_t)e * S.ES + a]], 1);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,7 +26,9 @@ enum Phase : uint32_t {
   PH_DISTORT = 4,      // id = record, attr: (indicator, auxiliary)
   PH_CLUST_U = 5,      // id = i: Pitman-Yor u_i
   PH_CLUST_V = 6,      // id = entity, slot = j: per-cluster v_j
-  PH_HOST = 7          // id = counter: host scalar draws (Beta / Gamma / NegBinom)
+  PH_HOST = 7,         // id = counter: host scalar draws (Beta / Gamma / NegBinom)
+  PH_CONC_ZETA = 8,    // id = entity, attr, slot = member index: auxiliary of the DP concentration
+  PH_CONC_BETA = 9     // id = entity, attr: the cluster's Beta variate (drawn on the host)
 };
 
 EXB_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

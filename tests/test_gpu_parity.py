@@ -22,6 +22,7 @@ def assert_same_state(a, b, where=""):
     for k in INT_KEYS:
         assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), f"{k} differs {where}"
     assert np.array_equal(a["distort_probs"], b["distort_probs"]), f"theta differs {where}"
+    assert np.array_equal(a["distort_dist_concs"], b["distort_dist_concs"]), f"DP concentrations differ {where}"
     for k in ("alpha", "d", "m", "kappa"):
         assert a["clust"][k] == b["clust"][k], f"{k} differs {where}"
     assert a["iteration"] == b["iteration"]
@@ -186,15 +187,45 @@ def test_run_inference_schedule_history_and_resume():
     assert b.state.iteration == fit.state.iteration
 
 
-def test_unsupported_model_features_fail_loudly():
-    from exchanger_b200 import DirichletProcess, Attribute, CategoricalAttribute
-    cols, _ = load_rldata("rldata500", 100)
+@pytest.mark.parametrize("gamma_prior", [True, False])
+def test_finite_dp_concentration_lockstep(gamma_prior):
+    """vignette-style model (vignettes/RLdata500.Rmd:45): finite Dirichlet-process concentration on
+    every attribute - the urn terms of links.cpp:251-279, the Chinese-restaurant terms of
+    entities.cpp:275-288 and DistortDistConcs::update (distort_dist_concs.cpp:32-94)."""
+    from exchanger_b200 import DirichletProcess
+    cols, _ = load_rldata("rldata500")
+    ap = readme_attr_params(prior=BetaRV(1, 4))
+    for k in ap:
+        ap[k].distort_dist_prior = DirichletProcess(GammaRV(2, 1e-2) if gamma_prior else 25.0)
+    m = exchanger(cols, ap, PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    lockstep(m, 40, every=2)
+    gpu = Sampler(m, seed=2)
+    gpu.sweeps(30)
+    concs = gpu.state()["distort_dist_concs"]
+    assert np.all(np.isfinite(concs)) and (not gamma_prior or not np.allclose(concs, 200.0))
+    gpu.close()
+
+
+def test_dirichlet_entity_prior_lockstep():
+    """entity_dist_prior = DirichletRV: Entities::update_distributions (entities.cpp:133-156) redraws
+    phi every sweep and every phi-dependent table is rebuilt."""
+    from exchanger_b200 import DirichletRV
+    cols, _ = load_rldata("rldata500", 400)
     ap = readme_attr_params()
-    ap["bm"] = CategoricalAttribute(BetaRV(1, 1), distort_dist_prior=DirichletProcess(GammaRV(2, 1e-4)))
-    m = exchanger(cols, ap, PRIORS["pitman_yor"](100))
+    for k in ("bm", "by", "fname_c1"):
+        ap[k].entity_dist_prior = DirichletRV(1.0)
+    m = exchanger(cols, ap, PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    lockstep(m, 25)
+
+
+def test_invalid_models_fail_loudly():
+    """Errors the reference raises through Rcpp::stop come back as a status and a message."""
+    m, _ = readme_model("rldata500", n=100)
+    m.links = m.links.copy()
+    m.links[3] = 99999  # an entity that does not exist
     with pytest.raises(Exb200Error) as e:
         Sampler(m)
-    assert e.value.status == -2
+    assert e.value.status == -1
 
 
 @pytest.mark.slow
