@@ -615,13 +615,13 @@ int update_links(exb200_handle* h) {
     CK(cudaMemcpyAsync(S.counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(S.counters + C_NACTL_OUT, 0, sizeof(int), st));
     if (n_act > 0) KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
-    if (n_actl > 0) KLAUNCH(h, k_reserve_w, nblk(n_actl, TPB / 32), TPB, 0, S, S.actl_in, n_actl, round);
+    if (n_actl > 0) KLAUNCH(h, k_reserve_w, n_actl, TPB, 0, S, S.actl_in, n_actl, round);
     if (S.use_kbounds) {
       int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
       rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
     }
     if (n_act > 0) KLAUNCH(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
-    if (n_actl > 0) KLAUNCH(h, k_commit_w, nblk(n_actl, TPB / 32), TPB, 0, S, S.actl_in, n_actl, round);
+    if (n_actl > 0) KLAUNCH(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h->trace) std::fprintf(stderr, "[exb200] round %d: short %d long %d -> %d %d%s\n", rounds, n_act, n_actl,
@@ -987,7 +987,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
-  if (cudaFuncSetAttribute(k_index_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_commit_w, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_index_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_part_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_part_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_huge_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||

@@ -825,19 +825,16 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
 }
 
 __global__ void __launch_bounds__(TPB) k_reserve_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-  if (i >= n_act) return;
-  const int r = act[i];
+  const int r = act[blockIdx.x]; // one block per record with a long list
   const unsigned long long key = resv_key(round, r);
   const int cnt = S.cand_cnt[r];
   const int* ids = S.cand_id + S.cand_off[r];
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     atomicMin(&S.owner[S.lambda[r]], key);
     atomicMin(&S.owner[S.N + r], key);
     atomicMin(&S.counters[C_MIN_ACTIVE], r);
   }
-  for (int j = lane; j < cnt; j += 32) atomicMin(&S.owner[ids[j]], key);
+  for (int j = threadIdx.x; j < cnt; j += TPB) atomicMin(&S.owner[ids[j]], key);
 }
 
 // move record r from entity `own` to `target`, keeping member lists sorted (the role of
@@ -988,14 +985,15 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
   }
 }
 
-// One WARP per record with a long candidate list.  Lanes gather sizes and evaluate weights in
-// parallel; the sums are accumulated in candidate order (lane by lane through shuffles), i.e. with
-// exactly the association of the sequential loop in k_commit and in the oracle.
+// One BLOCK per record with a long candidate list.  All threads gather sizes and evaluate weights
+// into shared memory; one thread then accumulates them in candidate order, i.e. with exactly the
+// association of the sequential loop in k_commit and in the oracle.
 __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
-  if (i >= n_act) return;
-  const int r = act[i];
+  extern __shared__ double s_w[]; // [cnt] log-weights, then weights relative to the maximum
+  __shared__ double s_red[TPB];
+  __shared__ double s_m1, s_srel;
+  __shared__ int s_dec, s_target;
+  const int r = act[blockIdx.x];
   const int cnt = S.cand_cnt[r];
   const unsigned long long key = resv_key(round, r);
   const unsigned long long fence = *S.fence;
@@ -1006,83 +1004,81 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
     const int* ids = S.cand_id + S.cand_off[r];
     const double* lls = S.cand_ll + S.cand_off[r];
     // a record that owned all its items once owns them until its turn (earlier unfinalised records
-    // only disappear) and nothing it reads can change: its weights are computed once
+    // only disappear) and nothing it reads can change: its weights are summed once
     const bool ready = S.fin[r] == 2;
-    bool mine = ready;
+    int mine = 1;
     if (!ready) {
       mine = S.owner[own] == key && S.owner[S.N + r] == key;
-      for (int j0 = 0; j0 < cnt && mine; j0 += 32) {
-        const int j = j0 + lane;
-        mine = __all_sync(FULL, j >= cnt || S.owner[ids[j]] == key);
-      }
+      for (int j = threadIdx.x; j < cnt && mine; j += TPB) mine = S.owner[ids[j]] == key;
+      mine = __syncthreads_and(mine);
     }
     if (mine) {
       const bool single = S.ent_size[own] == 1;
-      const int nchunk = (cnt + 31) >> 5;
-      double m1 = -CUDART_INF;
-      if (ready) m1 = S.rdy_m1[r];
-      else for (int c = 0; c < nchunk; c++) {
-        const int j = 32 * c + lane;
-        if (j < cnt) {
+      auto fill_weights = [&](bool need_max) { // s_w[j] = exp(lw_j - m1), 0 for candidates that are not live
+        double m = -CUDART_INF;
+        for (int j = threadIdx.x; j < cnt; j += TPB) {
           const int sz = live_size(S, ids[j], own, single);
-          if (sz > 0) { const double lw = cand_lw(S, r, ids[j], sz, lls[j]); m1 = lw > m1 ? lw : m1; }
+          const double lw = sz > 0 ? cand_lw(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
+          s_w[j] = lw;
+          m = lw > m ? lw : m;
         }
-      }
-      if (!ready) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m1, o); m1 = y > m1 ? y : m1; }
-      }
-      double srel = 0.0;
-      if (ready) srel = S.rdy_srel[r];
-      else if (m1 > -CUDART_INF)
-        for (int c = 0; c < nchunk; c++) {
-          const int j = 32 * c + lane;
-          double w = 0.0;
-          if (j < cnt) {
-            const int sz = live_size(S, ids[j], own, single);
-            if (sz > 0) w = exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
+        if (need_max) {
+          s_red[threadIdx.x] = m;
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            double mm = -CUDART_INF;
+            for (int k = 0; k < TPB; k++) mm = s_red[k] > mm ? s_red[k] : mm;
+            s_m1 = mm;
           }
-          for (int k = 0; k < 32; k++) srel += __shfl_sync(FULL, w, k); // candidate order; dead ones add 0
         }
+        __syncthreads();
+        const double m1 = s_m1;
+        for (int j = threadIdx.x; j < cnt; j += TPB) s_w[j] = s_w[j] > -CUDART_INF ? exp(s_w[j] - m1) : 0.0;
+        __syncthreads();
+      };
+      if (ready) { if (threadIdx.x == 0) { s_m1 = S.rdy_m1[r]; s_srel = S.rdy_srel[r]; } __syncthreads(); }
+      else {
+        fill_weights(true);
+        if (threadIdx.x == 0) {
+          double srel = 0.0;
+          if (s_m1 > -CUDART_INF) for (int j = 0; j < cnt; j++) srel += s_w[j]; // candidate order; dead ones add 0
+          s_srel = srel;
+        }
+        __syncthreads();
+      }
       const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-      const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
+      if (threadIdx.x == 0) s_dec = decide_with_bounds(S, r, single, s_m1, s_srel, u.a);
+      __syncthreads();
+      const int dec = s_dec;
       if (dec != 2) {
-        int target;
-        if (dec == 1) target = S.N + r;
-        else {
-          const double tt = u.b * srel;
-          double cum = 0.0;
-          int pick = -1, lastpos = -1;
-          for (int c = 0; c < nchunk && pick < 0; c++) {
-            const int j = 32 * c + lane;
-            double w = 0.0;
-            int e = -1;
-            if (j < cnt) {
-              e = ids[j];
-              const int sz = live_size(S, e, own, single);
-              if (sz > 0) w = exp(cand_lw(S, r, e, sz, lls[j]) - m1);
+        if (dec == 0 && ready) fill_weights(false); // the weights were not kept: recompute them for the pick
+        if (threadIdx.x == 0) {
+          int target;
+          if (dec == 1) target = S.N + r;
+          else {
+            const double tt = u.b * s_srel;
+            double cum = 0.0;
+            int pick = -1, lastpos = -1;
+            for (int j = 0; j < cnt; j++) {
+              const double w = s_w[j];
+              if (w > 0.0) lastpos = ids[j];
+              cum += w;
+              if (w > 0.0 && tt < cum) { pick = ids[j]; break; }
             }
-            for (int k = 0; k < 32 && pick < 0; k++) {
-              const double wk = __shfl_sync(FULL, w, k);
-              const int ek = __shfl_sync(FULL, e, k);
-              if (wk > 0.0) lastpos = ek;
-              cum += wk;
-              if (wk > 0.0 && tt < cum) pick = ek; // a dead candidate adds 0 and can never be the first to pass tt
-            }
+            target = pick >= 0 ? pick : lastpos;
+            if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
           }
-          target = pick >= 0 ? pick : lastpos;
-          if (target < 0) { if (lane == 0) dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+          finalize_record(S, r, own, target, single);
         }
-        if (lane == 0) finalize_record(S, r, own, target, single);
         stay = false;
-      } else if (lane == 0) {
+      } else if (threadIdx.x == 0) {
         S.dlo[r] = single ? -1 : 0;
         S.dhi[r] = single ? 0 : 1;
-        if (!ready) { S.fin[r] = 2; S.rdy_m1[r] = m1; S.rdy_srel[r] = srel; }
+        if (!ready) { S.fin[r] = 2; S.rdy_m1[r] = s_m1; S.rdy_srel[r] = s_srel; }
       }
     }
   }
-  if (stay && lane == 0) S.actl_out[atomicAdd(&S.counters[C_NACTL_OUT], 1)] = r;
+  if (stay && threadIdx.x == 0) S.actl_out[atomicAdd(&S.counters[C_NACTL_OUT], 1)] = r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1286,96 +1282,6 @@ __global__ void __launch_bounds__(TPB) k_count_all(DevState S, int r) {
   }
   ok = warp_sum(ok);
   if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&S.counters[C_COUNT], ok);
-}
-
-// The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 256
-// contiguous sub-chunks (one thread each).  pass 0: maxima; pass 1: sums of exp(lw - max) per
-// thread and per block.  wide_part layout: [0, WB) block maxima, [WB, 2 WB) block sums,
-// [2 WB, 2 WB + WB*256) thread sums.
-__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int pass) {
-  __shared__ double s_v[TPB];
-  const int n = 2 * S.N;
-  const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
-  const long long b_lo = blockIdx.x * per_b, b_hi = min((long long)n, b_lo + per_b);
-  const long long per_t = (per_b + TPB - 1) / TPB;
-  const long long lo = min(b_hi, b_lo + threadIdx.x * per_t), hi = min(b_hi, lo + per_t);
-  double m1 = -CUDART_INF;
-  if (pass == 1) for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[b] > m1 ? S.wide_part[b] : m1;
-  double acc = pass == 0 ? -CUDART_INF : 0.0;
-  for (long long i = lo; i < hi; i++) {
-    const double v = S.lwbuf[i];
-    if (!(v == v)) continue;
-    if (pass == 0) acc = v > acc ? v : acc;
-    else if (m1 > -CUDART_INF) acc += exp(v - m1);
-  }
-  s_v[threadIdx.x] = acc;
-  if (pass == 1) S.wide_part[2 * WIDE_BLOCKS + blockIdx.x * TPB + threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = pass == 0 ? -CUDART_INF : 0.0;
-    for (int k = 0; k < TPB; k++) t = pass == 0 ? (s_v[k] > t ? s_v[k] : t) : t + s_v[k];
-    S.wide_part[pass * WIDE_BLOCKS + blockIdx.x] = t;
-  }
-}
-
-// decision and commit of the wide record r (one thread walks block sums, thread sums, items)
-__global__ void k_wide_commit(DevState S, int r) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int n = 2 * S.N;
-  double m1 = -CUDART_INF, srel = 0.0;
-  for (int b = 0; b < WIDE_BLOCKS; b++) m1 = S.wide_part[b] > m1 ? S.wide_part[b] : m1;
-  for (int b = 0; b < WIDE_BLOCKS; b++) srel += S.wide_part[WIDE_BLOCKS + b];
-  const int own = S.lambda[r];
-  const bool single = S.ent_size[own] == 1;
-  const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-  const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
-  bool invalid = false;
-  const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
-  if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
-  int target = S.N + r;
-  if (!is_new) {
-    const double tt = u.b * srel;
-    double c = 0.0;
-    int blk = -1, lastb = -1;
-    for (int b = 0; b < WIDE_BLOCKS; b++) {
-      const double sb = S.wide_part[WIDE_BLOCKS + b];
-      if (sb > 0.0) lastb = b;
-      if (tt < c + sb) { blk = b; break; }
-      c += sb;
-    }
-    bool tail = false;
-    if (blk < 0) { blk = lastb; tail = true; } // rounding: the last positive item
-    target = -1;
-    if (blk >= 0) {
-      const long long per_b = ((long long)n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
-      const long long b_lo = blk * per_b, b_hi = min((long long)n, b_lo + per_b);
-      const long long per_t = (per_b + TPB - 1) / TPB;
-      const double* ts = S.wide_part + 2 * WIDE_BLOCKS + (size_t)blk * TPB;
-      int th = -1, lastt = -1;
-      for (int q = 0; q < TPB && !tail; q++) {
-        if (ts[q] > 0.0) lastt = q;
-        if (tt < c + ts[q]) { th = q; break; }
-        c += ts[q];
-      }
-      if (tail) { for (int q = 0; q < TPB; q++) if (ts[q] > 0.0) lastt = q; }
-      if (th < 0) { th = lastt; tail = true; }
-      if (th >= 0) {
-        const long long lo = min(b_hi, b_lo + th * per_t), hi = min(b_hi, lo + per_t);
-        int lastpos = -1;
-        for (long long i = lo; i < hi; i++) {
-          const double v = S.lwbuf[i];
-          if (!(v == v)) continue;
-          const double w = exp(v - m1);
-          if (w > 0.0) lastpos = (int)i;
-          c += w;
-          if (!tail && tt < c) { target = (int)i; break; }
-        }
-        if (target < 0) target = lastpos;
-      }
-    }
-    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
-  }
-  finalize_record(S, r, own, target, single);
 }
 
 // Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares
