@@ -131,6 +131,7 @@ struct DevState {
   ClustDev cl;
   double conc[MAX_ATTRS];       // DP concentration per attribute (infinite: none)
   int has_dp;                   // some concentration is finite
+  uint32_t dp_mask;             // bit a: attribute a has a finite concentration
 };
 
 enum CounterSlot {

@@ -116,6 +116,12 @@ template <class T> int upload(exb200_handle* h, T** p, const T* src, size_t n) {
   if (n) CK(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   return EXB200_OK;
 }
+// kernel with a compile-time switch for finite concentrations, chosen by the model's state
+#define KLAUNCH_DP(h, kern, grid, block, smem, ...)                   \
+  do {                                                                 \
+    if ((h)->S.has_dp) KLAUNCH(h, kern<true>, grid, block, smem, __VA_ARGS__);  \
+    else KLAUNCH(h, kern<false>, grid, block, smem, __VA_ARGS__);      \
+  } while (0)
 #define KLAUNCH(h, kern, grid, block, smem, ...)                      \
   do {                                                                 \
     kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);       \
@@ -146,9 +152,10 @@ double prior_existing_host(const exb200_clust& c, int n) {
 
 void refresh_conc_dev(exb200_handle* h) {
   h->S.has_dp = 0;
+  h->S.dp_mask = 0;
   for (int a = 0; a < MAX_ATTRS; a++) {
     h->S.conc[a] = a < h->A ? h->conc[a] : std::numeric_limits<double>::infinity();
-    if (a < h->A && std::isfinite(h->conc[a])) h->S.has_dp = 1;
+    if (a < h->A && std::isfinite(h->conc[a])) { h->S.has_dp = 1; h->S.dp_mask |= 1u << a; }
   }
 }
 
@@ -584,8 +591,8 @@ int update_links(exb200_handle* h) {
       KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, nb);
       for (int b = 0; b < nb; b++) {
         const int w = wide[g + b];
-        KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, b);
-        KLAUNCH(h, k_wide_commit, 1, TPB, 0, S, w, b);
+        KLAUNCH_DP(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, b);
+        KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, S, w, b);
       }
     }
     CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -620,8 +627,8 @@ int update_links(exb200_handle* h) {
       int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
       rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
     }
-    if (n_act > 0) KLAUNCH(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
-    if (n_actl > 0) KLAUNCH(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
+    if (n_act > 0) KLAUNCH_DP(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
+    if (n_actl > 0) KLAUNCH_DP(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h->trace) std::fprintf(stderr, "[exb200] round %d: short %d long %d -> %d %d%s\n", rounds, n_act, n_actl,
@@ -636,8 +643,8 @@ int update_links(exb200_handle* h) {
       const int w = hc[C_WIDE_READY];
       CK(cudaMemcpyAsync(S.batch_list, &w, sizeof(int), cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, 1);
-      KLAUNCH(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, 0);
-      KLAUNCH(h, k_wide_commit, 1, TPB, 0, S, w, 0);
+      KLAUNCH_DP(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, 0);
+      KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, S, w, 0);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_compact_active, nblk(n_next), TPB, 0, S, next_act, n_next);
@@ -721,7 +728,7 @@ int sweep(exb200_handle* h) {
   refresh_clust_dev(h);
   rc = update_links(h); if (rc) return rc;              // links_.update(...)
   KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_mask);   // ents_.update_attributes(...)
-  KLAUNCH(h, k_entities_general, nblk((N + 31) / 32, TPB / 32), TPB, 0, S, h->d_gen_mask);
+  KLAUNCH_DP(h, k_entities_general, nblk((N + 31) / 32, TPB / 32), TPB, 0, S, h->d_gen_mask);
   rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
   CK(cudaEventRecord(h->ev[7], st));
   CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
@@ -987,7 +994,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
-  if (cudaFuncSetAttribute(k_commit_w, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_commit_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_commit_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_index_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_part_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_part_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess ||

@@ -487,10 +487,11 @@ __device__ __forceinline__ bool item_compatible(const DevState& S, const int* x,
 }
 __device__ __forceinline__ double item_loglik(const DevState& S, const int* x, uint32_t zm, const int* y) {
   double l = 0.0;
+  // attributes with a finite concentration depend on the entity's other members: dp_loglik
+  const uint32_t zs = zm & ~S.dp_mask;
   for (int a = 0; a < S.A; a++) {
     const int xv = x[a];
-    // attributes with a finite concentration depend on the entity's other members: dp_loglik
-    if (xv >= 0 && ((zm >> a) & 1u) && isinf(S.conc[a])) l += log_distortion_prob(S.attrs[a], y[a], xv);
+    if (xv >= 0 && ((zs >> a) & 1u)) l += log_distortion_prob(S.attrs[a], y[a], xv);
   }
   return l;
 }
@@ -517,9 +518,11 @@ __device__ double dp_loglik(const DevState& S, int r, int e) {
   return l;
 }
 // log-weight of candidate e (live size sz) for record r from the stored static likelihood
+// (DP: some attribute has a finite concentration - the b = inf kernels carry none of that code)
+template <bool DP>
 __device__ __forceinline__ double cand_lw(const DevState& S, int r, int e, int sz, double ll) {
   double lw = log_prior_existing(S.cl, sz) + ll;
-  if (S.has_dp) lw += dp_loglik(S, r, e);
+  if (DP) lw += dp_loglik(S, r, e);
   return lw;
 }
 
@@ -906,6 +909,7 @@ __device__ __forceinline__ int live_size(const DevState& S, int e, int own, bool
   return e == own ? (single ? 0 : sz - 1) : sz; // links.cpp:359, :375
 }
 
+template <bool DP>
 __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool stay = false;
@@ -934,7 +938,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         for (int j = 0; j < cnt; j++) {
           const int sz = live_size(S, ids[j], own, single);
           if (sz > 0) {
-            const double lw = cand_lw(S, r, ids[j], sz, lls[j]);
+            const double lw = cand_lw<DP>(S, r, ids[j], sz, lls[j]);
             m1 = lw > m1 ? lw : m1;
           }
         }
@@ -942,7 +946,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
         if (m1 > -CUDART_INF)
           for (int j = 0; j < cnt; j++) {
             const int sz = live_size(S, ids[j], own, single);
-            if (sz > 0) srel += exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
+            if (sz > 0) srel += exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
           }
         const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
         const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
@@ -956,7 +960,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
             for (int j = 0; j < cnt; j++) {
               const int sz = live_size(S, ids[j], own, single);
               if (sz <= 0) continue;
-              const double w = exp(cand_lw(S, r, ids[j], sz, lls[j]) - m1);
+              const double w = exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
               if (w > 0.0) lastpos = ids[j];
               c += w;
               if (tt < c) { pick = ids[j]; break; }
@@ -988,11 +992,12 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
 // One BLOCK per record with a long candidate list.  All threads gather sizes and evaluate weights
 // into shared memory; one thread then accumulates them in candidate order, i.e. with exactly the
 // association of the sequential loop in k_commit and in the oracle.
+template <bool DP>
 __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   extern __shared__ double s_w[]; // [cnt] log-weights, then weights relative to the maximum
   __shared__ double s_red[TPB];
   __shared__ double s_m1, s_srel;
-  __shared__ int s_dec, s_target;
+  __shared__ int s_dec;
   const int r = act[blockIdx.x];
   const int cnt = S.cand_cnt[r];
   const unsigned long long key = resv_key(round, r);
@@ -1018,7 +1023,7 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
         double m = -CUDART_INF;
         for (int j = threadIdx.x; j < cnt; j += TPB) {
           const int sz = live_size(S, ids[j], own, single);
-          const double lw = sz > 0 ? cand_lw(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
+          const double lw = sz > 0 ? cand_lw<DP>(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
           s_w[j] = lw;
           m = lw > m ? lw : m;
         }
@@ -1097,7 +1102,7 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
     const int* y = S.ent_y + (size_t)i * S.ES;
-    if (item_compatible(S, x, zm, y)) out = cand_lw(S, r, i, sz, item_loglik(S, x, zm, y));
+    if (item_compatible(S, x, zm, y)) out = S.has_dp ? cand_lw<true>(S, r, i, sz, item_loglik(S, x, zm, y)) : cand_lw<false>(S, r, i, sz, item_loglik(S, x, zm, y));
   }
   S.lwbuf[i] = out;
 }
@@ -1122,11 +1127,12 @@ __global__ void __launch_bounds__(TPB) k_eval_batch(DevState S, const int* __res
 }
 
 // log-weight of item i for record r from the batched likelihood and the CURRENT sizes
+template <bool DP>
 __device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, int r, int i, int own, bool single) {
   const double v = ll[i];
   if (!(v == v)) return CUDART_NAN;
   const int sz = live_size(S, i, own, single);
-  return sz > 0 ? cand_lw(S, r, i, sz, v) : CUDART_NAN;
+  return sz > 0 ? cand_lw<DP>(S, r, i, sz, v) : CUDART_NAN;
 }
 
 // The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 8
@@ -1141,6 +1147,7 @@ __device__ __forceinline__ void wide_piece(const DevState& S, int p, long long& 
   lo = min(b_hi, b_lo + (p % (TPB / 32)) * per_w);
   hi = min(b_hi, lo + per_w);
 }
+template <bool DP>
 __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot) {
   const int n = 2 * S.N;
   const double* ll = S.lwbuf + (size_t)slot * n;
@@ -1151,7 +1158,7 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot
   wide_piece(S, p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
   for (long long i = lo + lane; i < hi; i += 32) {
-    const double v = wide_lw(S, ll, r, (int)i, own, single);
+    const double v = wide_lw<DP>(S, ll, r, (int)i, own, single);
     if (!(v == v) || !(v > -CUDART_INF)) continue;
     if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
   }
@@ -1167,6 +1174,7 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot
 
 // decision and commit of the serial record r (one block): scale the piece sums to the global max in
 // parallel, walk block sums and piece sums in order, then one warp scans the chosen piece in order
+template <bool DP>
 __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot) {
   __shared__ double s_bsum[WIDE_BLOCKS];
   __shared__ double s_red[TPB];
@@ -1247,7 +1255,7 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
       const long long i = base + lane;
       double w = 0.0;
       if (i < hi) {
-        const double v = wide_lw(S, ll, r, (int)i, own, single);
+        const double v = wide_lw<DP>(S, ll, r, (int)i, own, single);
         if (v == v) w = exp(v - m1);
       }
       double x = w;
@@ -1344,6 +1352,7 @@ __global__ void __launch_bounds__(TPB) k_canon(DevState S) {
 // ------------------------------------------------------------------------------------------
 // `row_first` / `row_j`: when v was taken from position row_j of the neighbourhood row of value
 // row_first, log p(row_first | v) is that row entry - no search for members with this value
+template <bool DP>
 __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, int a, int v, int head,
                                           int row_first = -1, int row_j = -1) {
   double lw = t.logphi[v];
@@ -1357,7 +1366,7 @@ __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, i
     if (xv == v) lw += t.lt_same[f * t.D + v];
     else {
       lw += t.lt_diff[f * t.D + v];
-      if (isinf(b)) lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
+      if (!DP || isinf(b)) lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
       else { // entities.cpp:275-288: Chinese-restaurant terms of the disagreeing values
         ctr_disagree++;
         lw += -log((double)ctr_disagree - 1.0 + b);
@@ -1381,7 +1390,7 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
   const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
   if (nobs == 0) return alias_draw(t.aprob, t.aalias, t.D, u0.a); // entities.cpp:387-389
 
-  if (t.is_const && t.exclude && nobs <= NMAX_FAST && (nobs == 1 || isinf(S.conc[a]))) {
+  if (t.is_const && t.exclude && nobs <= NMAX_FAST && (nobs == 1 || !((S.dp_mask >> a) & 1u))) {
     // whole-domain weights of drawEntityValueSequential (entities.cpp:298-348) in closed form:
     // explicit for the members' values, C phi(v)/(1-psi(v))^nobs for every other value
     int vals[NMAX_FAST];
@@ -1468,6 +1477,7 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
 // neighbourhood row (a subset of entities.cpp:361-383 that holds all the mass).  Lanes take
 // consecutive support entries; weights exp(lw - max) are summed per chunk of 32 with the warp's
 // shuffle scan and chunk totals sequentially - the oracle uses the same association order.
+template <bool DP>
 __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head) {
   const DevAttr& t = S.attrs[a];
   const int lane = threadIdx.x & 31;
@@ -1483,7 +1493,7 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
     if (j >= ns) return -CUDART_INF;
     const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
     if (!t.is_const && j > 0 && v == first) return -CUDART_INF;
-    return log_weight_entity_value(S, t, a, v, head, t.is_const ? -1 : first, (t.is_const || j == 0) ? -1 : lo + j - 1);
+    return log_weight_entity_value<DP>(S, t, a, v, head, t.is_const ? -1 : first, (t.is_const || j == 0) ? -1 : lo + j - 1);
   };
   // the log-weights of the first chunks stay in registers for the two later passes
   constexpr int NC = 4;
@@ -1548,6 +1558,7 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, uint32_t* __restri
 }
 
 // one warp per 32 entity slots: the (entity, attribute) pairs flagged by k_entities
+template <bool DP>
 __global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const uint32_t* __restrict__ gen_mask) {
   const int lane = threadIdx.x & 31;
   const int base = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32;
@@ -1563,7 +1574,7 @@ __global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const uint
     while (mask) {
       const int a = __ffs(mask) - 1;
       mask &= mask - 1;
-      const int v = draw_entity_value_warp(S, e, a, head);
+      const int v = draw_entity_value_warp<DP>(S, e, a, head);
       if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
     }
   }
