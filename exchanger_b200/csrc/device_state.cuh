@@ -27,7 +27,7 @@ constexpr int MAX_ATTRS = 32;
 constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that may form blocking keys
 constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
-constexpr int WIDE_BATCH = 8;       // serial records whose likelihoods are evaluated in one pass over the items
+constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
 constexpr int HUGE_CAP = 16386;     // scratch entries of the grid-wide bucket scan
 
 // Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
@@ -116,13 +116,19 @@ struct DevState {
   int *unk_list;                // records without a usable blocking bucket: classified one by one
   int *huge_list;               // records whose bucket is scanned by the whole grid
   int *huge_id; double *huge_ll;// [HUGE_CAP] scratch of that scan
-  int *batch_list;              // [WIDE_BATCH] records of the current k_eval_batch
+  int *batch_list;              // [WIDE_NB] records of the current k_wide_scan
+  int *wl_sel;                  // [WIDE_NB] batch positions handed to k_wide_store
+  int *wl_cnt;                  // [WIDE_NB][WIDE_PIECES] possible links per record and piece, then their scan
+  int *wl_tot;                  // [WIDE_NB] possible links per record
+  unsigned long long *wl_base;  // [WIDE_NB] start of the record's list in wl_id / wl_ll (~0: not listed)
+  int *wl_id; double *wl_ll;    // [wl_cap] lists of the current batch (carved out of lwbuf)
+  unsigned long long wl_cap;
   int huge_min;                 // bucket length above which the whole grid scans it
   double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path
   int *counters;                // see CounterSlot
   long long *counters64;        // [0] candidates, [1] bucket items visited
   int *dev_err;                 // [0] status, [1] id
-  double *lwbuf;                // [WIDE_BATCH][2N] scratch of the serial path / test hook
+  double *lwbuf;                // [16N] scratch: lists of the serial path / test hook (2N values)
   int *ndist, *corr;            // [F*A] distorted counts, corrected non-distorted counts
   int bucket_cap, cand_cap, long_cap, long_min; // thresholds: see exb200_set_option
   double est_threshold;         // expected bucket size above which the full key is used

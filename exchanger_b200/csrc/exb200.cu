@@ -2,6 +2,12 @@
 // fixes the partially-collapsed order of State::update (src/state.h:60-75), the scalar
 // hyper-parameter updates, history streaming and state read-back.
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <type_traits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -14,6 +20,7 @@
 #include "hostmath.hpp"
 #include "kernels.cuh"
 #include "neighbours.cuh"
+#include "setup.cuh"
 
 using namespace exb;
 
@@ -83,6 +90,12 @@ struct exb200_handle {
   bool poisoned = false;
   bool has_index_events = false;
   long long n_launches = 0; // kernels launched by this handle
+  // saved samples leave the device behind the next sweep: snapshot (D2D) -> pinned buffer on the
+  // copy stream -> the caller's array by a host thread
+  cudaStream_t copy_stream = nullptr;
+  int* d_snap[2] = {nullptr, nullptr};
+  int* pin_snap[2] = {nullptr, nullptr};
+  cudaEvent_t ev_snap[2]{}, ev_d2h[2]{};
 };
 
 namespace {
@@ -101,6 +114,18 @@ int fail(exb200_handle* h, int code, const std::string& msg) {
       return fail(h, EXB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
     }                                                                                              \
   } while (0)
+
+// fn(t, T) on T host threads (table construction at create time; the sweep itself has no host loops
+// over records or domains)
+template <class F> void host_parallel(size_t work, F fn) {
+  int T = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  if (work < (1u << 16)) T = 1;
+  if (T == 1) { fn(0, 1); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back([=] { fn(t, T); });
+  fn(0, T);
+  for (auto& x : th) x.join();
+}
 
 template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
   void* q = nullptr;
@@ -195,25 +220,28 @@ int refresh_phi(exb200_handle* h, int a) {
     Z += ha.phi[v] / ha.om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
   }
   std::vector<double> cs(ha.p.size()), csn(ha.p.size());
-  for (int w = 0; w < D && !ha.is_const; w++) {
-    double c = 0.0, cn = 0.0;
-    for (int j = ha.row[w]; j < ha.row[w + 1]; j++) {
-      c += ha.phi[ha.col[j]] * ha.mef[ha.col[j]] * ha.p[j];
-      cs[j] = c;
-      cn += ha.phi[ha.col[j]] * ha.p[j];
-      csn[j] = cn;
+  host_parallel(ha.p.size() + (size_t)D, [&](int t, int T) {
+    const int w_lo = (int)((int64_t)D * t / T), w_hi = (int)((int64_t)D * (t + 1) / T);
+    for (int w = w_lo; w < w_hi && !ha.is_const; w++) {
+      double c = 0.0, cn = 0.0;
+      for (int j = ha.row[w]; j < ha.row[w + 1]; j++) {
+        c += ha.phi[ha.col[j]] * ha.mef[ha.col[j]] * ha.p[j];
+        cs[j] = c;
+        cn += ha.phi[ha.col[j]] * ha.p[j];
+        csn[j] = cn;
+      }
     }
-  }
-  for (int w = 0; w < D; w++) {
-    double e;
-    if (ha.is_const) // get_exp_distortion_prob, attribute_index.cpp:55-62
-      e = ha.exclude ? Z * ha.psi[w] - ha.phi[w] * ha.psi[w] / ha.om[w] : ha.psi[w];
-    else {           // attribute_index.cpp:94-101
-      e = 0.0;
-      for (int j = ha.row[w]; j < ha.row[w + 1]; j++) e += ha.phi[ha.col[j]] * ha.p[j];
+    for (int w = w_lo; w < w_hi; w++) {
+      double e;
+      if (ha.is_const) // get_exp_distortion_prob, attribute_index.cpp:55-62
+        e = ha.exclude ? Z * ha.psi[w] - ha.phi[w] * ha.psi[w] / ha.om[w] : ha.psi[w];
+      else {           // attribute_index.cpp:94-101
+        e = 0.0;
+        for (int j = ha.row[w]; j < ha.row[w + 1]; j++) e += ha.phi[ha.col[j]] * ha.p[j];
+      }
+      logE[w] = std::log(e);
     }
-    logE[w] = std::log(e);
-  }
+  });
   const int nt = ha.is_const ? NMAX_FAST + 1 : 1;
   std::vector<double> g((size_t)nt * D), aprob((size_t)nt * D);
   std::vector<int> aalias((size_t)nt * D);
@@ -277,19 +305,31 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
     const int64_t nnz = in.close_row_ptr[D];
     if (nnz >= (int64_t)std::numeric_limits<int>::max())
       return fail(h, EXB200_ERR_INVALID, "neighbourhood index too large");
-    for (int64_t j = 0; j < nnz; j++) {
-      const int w = in.close_val_ids[j];
-      if (w < 0 || w >= D) return fail(h, EXB200_ERR_INVALID, "close_val_ids out of range");
-      ha.row[w + 1]++;
-    }
+    // every thread owns a range of output rows w and scans the whole input in order, so the
+    // entries of a row stay in ascending v whatever the number of threads
+    std::vector<int> bad(64, 0);
+    host_parallel((size_t)nnz, [&](int t, int T) {
+      const int w_lo = (int)((int64_t)D * t / T), w_hi = (int)((int64_t)D * (t + 1) / T);
+      for (int64_t j = 0; j < nnz; j++) {
+        const int w = in.close_val_ids[j];
+        if (w < 0 || w >= D) { bad[t] = 1; continue; }
+        if (w >= w_lo && w < w_hi) ha.row[w + 1]++;
+      }
+    });
+    for (int b : bad) if (b) return fail(h, EXB200_ERR_INVALID, "close_val_ids out of range");
     for (int w = 0; w < D; w++) ha.row[w + 1] += ha.row[w];
     ha.col.resize(nnz); ha.p.resize(nnz); logp.resize(nnz);
     std::vector<int> cur(ha.row.begin(), ha.row.end() - 1);
-    for (int v = 0; v < D; v++)
-      for (int64_t j = in.close_row_ptr[v]; j < in.close_row_ptr[v + 1]; j++) {
-        const int q = cur[in.close_val_ids[j]]++;
-        ha.col[q] = v; ha.p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
-      }
+    host_parallel((size_t)nnz, [&](int t, int T) {
+      const int w_lo = (int)((int64_t)D * t / T), w_hi = (int)((int64_t)D * (t + 1) / T);
+      for (int v = 0; v < D; v++)
+        for (int64_t j = in.close_row_ptr[v]; j < in.close_row_ptr[v + 1]; j++) {
+          const int w = in.close_val_ids[j];
+          if (w < w_lo || w >= w_hi) continue;
+          const int q = cur[w]++;
+          ha.col[q] = v; ha.p[q] = in.close_probs[j]; logp[q] = std::log(in.close_probs[j]);
+        }
+    });
   }
   std::vector<double> pprob(D);
   std::vector<int> palias(D);
@@ -427,6 +467,23 @@ int ensure_table(exb200_handle* h, int tab) {
   return EXB200_OK;
 }
 
+// serial path: possible links of up to WIDE_NB records among all the items (counting pass)
+int wide_count(exb200_handle* h, const int* recs, int nb, int* totals, int skip_empty) {
+  DevState& S = h->S;
+  CK(cudaMemcpyAsync(S.batch_list, recs, sizeof(int) * nb, cudaMemcpyHostToDevice, h->stream));
+  KLAUNCH(h, k_wide_scan<false>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, skip_empty);
+  KLAUNCH(h, k_wide_offsets, nb, 1024, 0, S);
+  CK(cudaMemcpyAsync(totals, S.wl_tot, sizeof(int) * nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return EXB200_OK;
+}
+// ... and the turn of one listed record
+void wide_turn(exb200_handle* h, int r, unsigned long long base, int len) {
+  const int n_blocks = std::max(1, std::min(WIDE_BLOCKS, (len + 2047) / 2048));
+  KLAUNCH_DP(h, k_wide_reduce, n_blocks, TPB, 0, h->S, r, base, len);
+  KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, h->S, r, base, len, n_blocks);
+}
+
 // ---- 2. links: Links::update (links.cpp:477-489)
 int update_links(exb200_handle* h) {
   DevState& S = h->S;
@@ -551,24 +608,46 @@ int update_links(exb200_handle* h) {
       CK(cudaStreamSynchronize(st));
     }
   }
-  // records without a usable bucket: count their possible links to classify them
+  // records without a usable bucket: list their possible links among all the items; those with at
+  // most wide_threshold keep the list like everybody else, the others join the wide records
   std::vector<int> wide;
-  int n_fence = hc[C_NFENCE];
   if (hc[C_NUNK] > 0) {
     std::vector<int> unk(hc[C_NUNK]);
     CK(cudaMemcpyAsync(unk.data(), S.unk_list, sizeof(int) * unk.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int r : unk) {
-      int count = 0;
-      CK(cudaMemsetAsync(S.counters + C_COUNT, 0, sizeof(int), st));
-      KLAUNCH(h, k_count_all, nblk(2LL * N), TPB, 0, S, r);
-      CK(cudaMemcpyAsync(&count, S.counters + C_COUNT, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      const int code = count > h->long_cap ? -1 : -2;
-      CK(cudaMemcpyAsync(S.cand_cnt + r, &code, sizeof(int), cudaMemcpyHostToDevice, st));
-      if (code == -1) wide.push_back(r); else n_fence++;
+    std::sort(unk.begin(), unk.end());
+    for (size_t g = 0; g < unk.size(); g += WIDE_NB) {
+      const int nb = (int)std::min<size_t>(WIDE_NB, unk.size() - g);
+      int tot[WIDE_NB];
+      int rc = wide_count(h, unk.data() + g, nb, tot, 1); if (rc) return rc;
+      if (h->trace) for (int q = 0; q < nb; q++) std::fprintf(stderr, "[exb200] record %d without a bucket: %d possible links\n", unk[g + q], tot[q]);
+      int b = 0;
+      while (b < nb) { // groups of short lists that fit the scratch together
+        unsigned long long bases[WIDE_NB], used = 0;
+        int sel[WIDE_NB], n_sel = 0;
+        for (int q = 0; q < nb; q++) bases[q] = ~0ull;
+        for (; b < nb; b++) {
+          if (tot[b] > h->long_cap) {
+            static const int code_wide = -1;
+            CK(cudaMemcpyAsync(S.cand_cnt + unk[g + b], &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
+            wide.push_back(unk[g + b]);
+            continue;
+          }
+          if (used + (unsigned long long)tot[b] > S.wl_cap) break;
+          bases[b] = used; used += (unsigned long long)tot[b]; sel[n_sel++] = b;
+        }
+        if (n_sel == 0) continue;
+        CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
+        KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, 1);
+        KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
+        CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
+      }
     }
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved
+    CK(cudaStreamSynchronize(st));
   }
+  const int n_fence = hc[C_NFENCE]; // candidate pool exhausted: these take their turn serially inside the rounds
   if (hc[C_NWIDE] > 0) {
     const size_t n0 = wide.size();
     wide.resize(n0 + hc[C_NWIDE]);
@@ -579,20 +658,31 @@ int update_links(exb200_handle* h) {
   h->stats.n_wide = (int)wide.size() + n_fence;
   CK(cudaEventRecord(h->ev[4], st));
   // Scan order: records with more than wide_threshold possible links take their turn
-  // first, in ascending id, one at a time against every item; then everybody else in ascending id.
+  // first, in ascending id, one at a time; then everybody else in ascending id.
   int dk_wide = 0;
   if (!wide.empty()) {
     std::sort(wide.begin(), wide.end());
-    for (size_t g = 0; g < wide.size(); g += WIDE_BATCH) {
-      // likelihoods of a batch in one pass over the items, then one record after the other
+    for (size_t g = 0; g < wide.size(); g += WIDE_NB) {
+      // possible links of a batch in two passes over the items, then one record after the other
       // against the sizes its predecessors left
-      const int nb = (int)std::min<size_t>(WIDE_BATCH, wide.size() - g);
-      CK(cudaMemcpyAsync(S.batch_list, wide.data() + g, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
-      KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, nb);
-      for (int b = 0; b < nb; b++) {
-        const int w = wide[g + b];
-        KLAUNCH_DP(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, b);
-        KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, S, w, b);
+      const int nb = (int)std::min<size_t>(WIDE_NB, wide.size() - g);
+      int tot[WIDE_NB];
+      int rc = wide_count(h, wide.data() + g, nb, tot, 0); if (rc) return rc;
+      if (h->trace) for (int q = 0; q < nb; q++) std::fprintf(stderr, "[exb200] wide record %d: %d possible links\n", wide[g + q], tot[q]);
+      int b = 0;
+      while (b < nb) {
+        unsigned long long bases[WIDE_NB], used = 0;
+        for (int q = 0; q < nb; q++) bases[q] = ~0ull;
+        const int b0 = b;
+        for (; b < nb; b++) {
+          if (used + (unsigned long long)tot[b] > S.wl_cap) break;
+          bases[b] = used; used += (unsigned long long)tot[b];
+        }
+        if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
+        CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
+        KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, 0);
+        for (int q = b0; q < b; q++) wide_turn(h, wide[g + q], bases[q], tot[q]);
+        CK(cudaStreamSynchronize(st)); // bases are on the stack
       }
     }
     CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -641,10 +731,12 @@ int update_links(exb200_handle* h) {
     if (hc[C_WIDE_READY] >= 0) {
       // serial path for a record without a stored candidate list
       const int w = hc[C_WIDE_READY];
-      CK(cudaMemcpyAsync(S.batch_list, &w, sizeof(int), cudaMemcpyHostToDevice, st));
-      KLAUNCH(h, k_eval_batch, nblk(2LL * N), TPB, 0, S, S.batch_list, 1);
-      KLAUNCH_DP(h, k_wide_reduce, WIDE_BLOCKS, TPB, 0, S, w, 0);
-      KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, S, w, 0);
+      int tot = 0;
+      int rc = wide_count(h, &w, 1, &tot, 0); if (rc) return rc;
+      const unsigned long long zero_base = 0;
+      CK(cudaMemcpyAsync(S.wl_base, &zero_base, sizeof zero_base, cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1, 0);
+      wide_turn(h, w, 0, tot);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_compact_active, nblk(n_next), TPB, 0, S, next_act, n_next);
@@ -779,6 +871,12 @@ void exb200_destroy(exb200_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  for (int b = 0; b < 2; b++) {
+    if (h->pin_snap[b]) cudaFreeHost(h->pin_snap[b]);
+    if (h->ev_snap[b]) cudaEventDestroy(h->ev_snap[b]);
+    if (h->ev_d2h[b]) cudaEventDestroy(h->ev_d2h[b]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -798,6 +896,13 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
 
   exb200_handle* h = new exb200_handle();
   auto bail = [&](int rc) { g_create_error = h->err; exb200_destroy(h); return rc; };
+  auto t_stage = std::chrono::steady_clock::now();
+  auto stage = [&](const char* what) { // EXB200_TRACE: where the time of create goes
+    if (!h->trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[exb200] create: %-18s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_stage).count());
+    t_stage = now;
+  };
   h->device = device; h->N = N; h->A = A; h->F = F;
   h->RS = ((A + 1 + 7) / 8) * 8; h->ES = ((A + 7) / 8) * 8;
   h->iteration = m->iteration; h->seed = m->seed; h->cl = m->clust; h->hs.seed = m->seed;
@@ -809,94 +914,135 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   if (c.kind != EXB200_CLUST_PITMAN_YOR && c.m < (double)N)
     return bail(fail(h, EXB200_ERR_INVALID, "Coupon collecting parameter m < n_records is currently not supported."));
 
-  // ---- host-side canonical form: entity label = smallest member record
-  std::vector<int> rec_x((size_t)N * h->RS, -1), lambda(N), size(2 * (size_t)N, 0), head(2 * (size_t)N, -1),
-      next(N, -1), ent_y(2 * (size_t)N * h->ES, 0);
-  std::vector<uint32_t> rec_z(N, 0);
-  for (int r = 0; r < N; r++) {
-    for (int a = 0; a < A; a++) {
-      const int v = m->rec_attrs[a + (size_t)A * r];
-      if (v >= m->attrs[a].domain_size) return bail(fail(h, EXB200_ERR_INVALID, "rec_attrs out of range"));
-      rec_x[(size_t)r * h->RS + a] = v < 0 ? -1 : v;
-      if (m->rec_distortions[a + (size_t)A * r]) rec_z[r] |= 1u << a;
-    }
-    const int f = m->file_ids[r];
-    if (f < 0 || f >= F) return bail(fail(h, EXB200_ERR_INVALID, "file_ids out of range"));
-    rec_x[(size_t)r * h->RS + h->RS - 1] = f;
-  }
+  stage("context/stream");
+  // ---- device state.  The caller's arrays are uploaded in their R layout and turned into the
+  // resident layout on the device (setup.cuh): entity label = smallest member record, member lists
+  // in ascending record id.
+  DevState& S = h->S;
+  S.N = N; S.A = A; S.F = F; S.RS = h->RS; S.ES = h->ES; S.seed = h->seed;
+  int rc = 0;
+#define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
   {
-    // label -> column of ent_attrs and label -> smallest member; direct tables when the labels are
-    // small non-negative integers (what exchanger() and this library produce), hash maps otherwise
+    // labels: small non-negative integers (what exchanger() and this library produce) index a
+    // direct table; anything else is first renamed to the column of ent_attrs
+    const int nE = m->n_entities;
     int max_label = -1;
     bool dense = true;
-    for (int e = 0; e < m->n_entities && dense; e++) {
+    for (int e = 0; e < nE && dense; e++) {
       if (m->ent_ids[e] < 0 || m->ent_ids[e] > 8LL * N + 1024) dense = false;
       else max_label = std::max(max_label, m->ent_ids[e]);
     }
-    std::vector<int> slot_v, rep_v;
-    std::unordered_map<int, int> slot_m, rep_m;
-    if (dense) { slot_v.assign((size_t)max_label + 1, -1); rep_v.assign((size_t)max_label + 1, -1); }
-    else { slot_m.reserve((size_t)m->n_entities * 2); rep_m.reserve((size_t)m->n_entities * 2); }
-    auto slot_of = [&](int lab) -> int {
-      if (dense) return (lab < 0 || lab > max_label) ? -1 : slot_v[lab];
-      auto it = slot_m.find(lab);
-      return it == slot_m.end() ? -1 : it->second;
+    std::vector<int> links_slot, ids_slot;
+    const int* links_src = m->links;
+    const int* ids_src = m->ent_ids;
+    if (!dense) {
+      std::unordered_map<int, int> slot_m;
+      slot_m.reserve((size_t)nE * 2);
+      for (int e = 0; e < nE; e++) slot_m[m->ent_ids[e]] = e;
+      links_slot.resize(N);
+      for (int r = 0; r < N; r++) {
+        auto it = slot_m.find(m->links[r]);
+        if (it == slot_m.end()) return bail(fail(h, EXB200_ERR_INVALID, "links refers to an unknown entity"));
+        links_slot[r] = it->second;
+      }
+      ids_slot.resize(nE);
+      for (int e = 0; e < nE; e++) ids_slot[e] = slot_m[m->ent_ids[e]]; // a repeated label keeps its last column
+      links_src = links_slot.data();
+      ids_src = ids_slot.data();
+      max_label = nE - 1;
+    }
+    SetupDomains dom{};
+    for (int a = 0; a < A; a++) dom.D[a] = m->attrs[a].domain_size;
+    int *raw_x = nullptr, *raw_z = nullptr, *raw_f = nullptr, *raw_l = nullptr, *raw_ids = nullptr, *raw_y = nullptr;
+    int *lab2slot = nullptr, *rep = nullptr, *d_misc = nullptr;
+    unsigned long long *keys = nullptr, *keys2 = nullptr;
+    void* cub_tmp = nullptr;
+    std::vector<void*> tmp;
+    auto talloc = [&](auto** p, size_t n) {
+      void* q = nullptr;
+      if (cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(**p)) != cudaSuccess) return false;
+      tmp.push_back(q);
+      *p = (std::remove_reference_t<decltype(**p)>*)q;
+      return true;
     };
-    for (int e = 0; e < m->n_entities; e++) {
-      if (dense) slot_v[m->ent_ids[e]] = e; else slot_m[m->ent_ids[e]] = e;
+    auto release = [&] { for (void* q : tmp) cudaFree(q); tmp.clear(); };
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, keys, keys2, N, 0, 64, h->stream);
+    const bool ok = talloc(&raw_x, (size_t)N * A) && talloc(&raw_z, (size_t)N * A) && talloc(&raw_f, (size_t)N) &&
+                    talloc(&raw_l, (size_t)N) && talloc(&raw_ids, (size_t)nE) && talloc(&raw_y, (size_t)nE * A) &&
+                    talloc(&lab2slot, (size_t)max_label + 1) && talloc(&rep, (size_t)max_label + 1) &&
+                    talloc(&d_misc, 2) && talloc(&keys, (size_t)N) && talloc(&keys2, (size_t)N) &&
+                    cudaMalloc(&cub_tmp, std::max<size_t>(cub_bytes, 1)) == cudaSuccess;
+    if (cub_tmp) tmp.push_back(cub_tmp);
+    if (!ok) { release(); return bail(fail(h, EXB200_ERR_OOM, "cudaMalloc failed while loading the model")); }
+    int* ip; uint32_t* up;
+    auto tbail = [&](int code) { release(); return bail(code); };
+#define TRYT(x) do { rc = (x); if (rc) return tbail(rc); } while (0)
+    TRYT(dalloc(h, &ip, (size_t)N * h->RS)); S.rec_x = ip;
+    TRYT(dalloc(h, &up, (size_t)N)); S.rec_z = up;
+    TRYT(dalloc(h, &S.lambda, (size_t)N));
+    TRYT(dalloc(h, &S.ent_y, 2 * (size_t)N * h->ES));
+    TRYT(dalloc(h, &S.ent_size, 2 * (size_t)N));
+    TRYT(dalloc(h, &S.ent_head, 2 * (size_t)N));
+    TRYT(dalloc(h, &S.ent_size_nx, 2 * (size_t)N));
+    TRYT(dalloc(h, &S.ent_head_nx, 2 * (size_t)N));
+    TRYT(dalloc(h, &S.rec_next, (size_t)N));
+    TRYT(dalloc(h, &S.ndist, (size_t)F * A));
+    TRYT(dalloc(h, &S.corr, (size_t)F * A));
+#undef TRYT
+    cudaStream_t st = h->stream;
+    cudaError_t ce = cudaSuccess;
+    auto H2D = [&](void* d, const void* s, size_t bytes) { if (ce == cudaSuccess && bytes) ce = cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, st); };
+    auto SET = [&](void* d, int v, size_t bytes) { if (ce == cudaSuccess && bytes) ce = cudaMemsetAsync(d, v, bytes, st); };
+    H2D(raw_x, m->rec_attrs, sizeof(int) * (size_t)N * A);
+    H2D(raw_z, m->rec_distortions, sizeof(int) * (size_t)N * A);
+    H2D(raw_f, m->file_ids, sizeof(int) * (size_t)N);
+    H2D(raw_l, links_src, sizeof(int) * (size_t)N);
+    H2D(raw_ids, ids_src, sizeof(int) * (size_t)nE);
+    H2D(raw_y, m->ent_attrs, sizeof(int) * (size_t)nE * A);
+    SET(lab2slot, 0xFF, sizeof(int) * ((size_t)max_label + 1));
+    SET(rep, 0x7F, sizeof(int) * ((size_t)max_label + 1));
+    SET(d_misc, 0, sizeof(int) * 2);
+    SET(S.ndist, 0, sizeof(int) * (size_t)F * A);
+    SET(S.ent_y, 0, sizeof(int) * 2 * (size_t)N * h->ES);
+    SET(S.ent_size, 0, sizeof(int) * 2 * (size_t)N);
+    SET(S.ent_head, 0xFF, sizeof(int) * 2 * (size_t)N);
+    if (ce == cudaSuccess) {
+      KLAUNCH(h, k_setup_records, nblk(N), TPB, 0, S, dom, raw_x, raw_z, raw_f, d_misc);
+      KLAUNCH(h, k_setup_slots, nblk(nE), TPB, 0, raw_ids, nE, lab2slot);
+      KLAUNCH(h, k_setup_rep, nblk(N), TPB, 0, N, raw_l, lab2slot, max_label, rep, d_misc);
     }
-    int n_linked = 0;
-    for (int r = N - 1; r >= 0; r--) {
-      const int lab = m->links[r];
-      if (slot_of(lab) < 0) return bail(fail(h, EXB200_ERR_INVALID, "links refers to an unknown entity"));
-      if (dense) { n_linked += rep_v[lab] < 0; rep_v[lab] = r; }
-      else { n_linked += !rep_m.count(lab); rep_m[lab] = r; }
+    int misc[2] = {0, 0};
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(misc, d_misc, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess && misc[0] == 0) { // every link is valid: entity tables and member lists
+      KLAUNCH(h, k_setup_links, nblk(N), TPB, 0, S, dom, raw_l, lab2slot, rep, raw_y, keys, d_misc + 1, d_misc);
+      ce = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys, keys2, N, 0, 64, st);
+      if (ce == cudaSuccess) KLAUNCH(h, k_setup_next, nblk(N), TPB, 0, N, keys2, S.rec_next);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(S.ent_size_nx, S.ent_size, sizeof(int) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(S.ent_head_nx, S.ent_head, sizeof(int) * 2 * (size_t)N, cudaMemcpyDeviceToDevice, st);
+      h->ndist.assign((size_t)F * A, 0); h->corr.assign((size_t)F * A, 0);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->ndist.data(), S.ndist, sizeof(int) * (size_t)F * A, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(misc, d_misc, sizeof(int) * 2, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     }
-    std::vector<int> tail(N, -1);
-    for (int r = 0; r < N; r++) {
-      const int lab = m->links[r];
-      const int cidx = dense ? rep_v[lab] : rep_m[lab];
-      lambda[r] = cidx;
-      if (size[cidx]++ == 0) {
-        head[cidx] = r;
-        const int col = slot_of(lab);
-        for (int a = 0; a < A; a++) {
-          const int v = m->ent_attrs[a + (size_t)A * col];
-          if (v < 0 || v >= m->attrs[a].domain_size) return bail(fail(h, EXB200_ERR_INVALID, "ent_attrs out of range"));
-          ent_y[(size_t)cidx * h->ES + a] = v;
-        }
-      } else next[tail[cidx]] = r;
-      tail[cidx] = r;
-    }
-    h->K = n_linked;
+    release();
+    if (ce != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, std::string("loading the model: ") + cudaGetErrorString(ce)));
+    static const char* const what[] = {"", "rec_attrs out of range", "file_ids out of range",
+                                       "links refers to an unknown entity", "ent_attrs out of range"};
+    if (misc[0]) return bail(fail(h, EXB200_ERR_INVALID, what[std::min(misc[0], 4)]));
+    h->K = misc[1];
   }
   h->theta.resize((size_t)F * A);
   for (int f = 0; f < F; f++)
     for (int a = 0; a < A; a++) h->theta[f * A + a] = m->distort_probs[f + (size_t)F * a];
-  h->ndist.assign((size_t)F * A, 0); h->corr.assign((size_t)F * A, 0);
-  for (int r = 0; r < N; r++)
-    for (int a = 0; a < A; a++) h->ndist[rec_x[(size_t)r * h->RS + h->RS - 1] * A + a] += (rec_z[r] >> a) & 1u;
-
-  // ---- device state
-  DevState& S = h->S;
-  S.N = N; S.A = A; S.F = F; S.RS = h->RS; S.ES = h->ES; S.seed = h->seed;
-  int rc = 0;
-  int* ip; uint32_t* up;
-#define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
-  TRY(upload(h, &ip, rec_x.data(), rec_x.size())); S.rec_x = ip;
-  TRY(upload(h, &up, rec_z.data(), rec_z.size())); S.rec_z = up;
-  TRY(upload(h, &S.lambda, lambda.data(), lambda.size()));
-  TRY(upload(h, &S.ent_y, ent_y.data(), ent_y.size()));
-  TRY(upload(h, &S.ent_size, size.data(), size.size()));
-  TRY(upload(h, &S.ent_head, head.data(), head.size()));
-  TRY(upload(h, &S.ent_size_nx, size.data(), size.size()));
-  TRY(upload(h, &S.ent_head_nx, head.data(), head.size()));
-  TRY(upload(h, &S.rec_next, next.data(), next.size()));
+  stage("state on device");
   TRY(dalloc(h, &h->d_theta, (size_t)F * A)); S.theta = h->d_theta;
   h->attrs.resize(A); h->h_attrs.resize(A);
   for (int a = 0; a < MAX_ATTRS; a++) h->conc[a] = std::numeric_limits<double>::infinity();
   int maxD = 1;
   for (int a = 0; a < A; a++) { TRY(build_attr(h, m->attrs[a], a)); maxD = std::max(maxD, m->attrs[a].domain_size); }
+  stage("attribute tables");
   TRY(dalloc(h, &h->d_hist, (size_t)maxD));
   refresh_conc_dev(h);
   // the reference draws phi in the Entities constructor (entities.cpp:233): same here, from the
@@ -905,7 +1051,10 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   for (int a = 0; a < A; a++)
     if (h->attrs[a].dirichlet) {
       std::vector<int> counts(h->attrs[a].D, 0);
-      for (int e = 0; e < N; e++) if (size[e] > 0) counts[ent_y[(size_t)e * h->ES + a]]++;
+      cudaMemsetAsync(h->d_hist, 0, sizeof(int) * counts.size(), h->stream);
+      KLAUNCH(h, k_ent_hist, nblk(N), TPB, 0, S, a, h->d_hist);
+      cudaMemcpyAsync(counts.data(), h->d_hist, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, h->stream);
+      if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "entity-value histogram failed"));
       TRY(draw_entity_dist(h, a, counts));
     }
   TRY(upload(h, &h->d_attrs, h->h_attrs.data(), (size_t)A)); S.attrs = h->d_attrs;
@@ -943,13 +1092,17 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
   TRY(dalloc(h, &S.counters64, 2));
   TRY(dalloc(h, &S.dev_err, 2));
-  TRY(dalloc(h, &S.lwbuf, (size_t)WIDE_BATCH * 2 * N));
+  TRY(dalloc(h, &S.lwbuf, (size_t)16 * N));
+  S.wl_cap = 10ull * N; // 10N doubles + 10N ints inside the 16N doubles of lwbuf
+  S.wl_ll = S.lwbuf; S.wl_id = reinterpret_cast<int*>(S.lwbuf + S.wl_cap);
+  TRY(dalloc(h, &S.wl_cnt, (size_t)WIDE_NB * WIDE_PIECES));
+  TRY(dalloc(h, &S.wl_tot, (size_t)WIDE_NB));
+  TRY(dalloc(h, &S.wl_base, (size_t)WIDE_NB));
+  TRY(dalloc(h, &S.wl_sel, (size_t)WIDE_NB));
   TRY(dalloc(h, &S.huge_list, (size_t)N));
   TRY(dalloc(h, &S.huge_id, (size_t)HUGE_CAP));
   TRY(dalloc(h, &S.huge_ll, (size_t)HUGE_CAP));
-  TRY(dalloc(h, &S.batch_list, (size_t)WIDE_BATCH));
-  TRY(dalloc(h, &S.ndist, (size_t)F * A));
-  TRY(dalloc(h, &S.corr, (size_t)F * A));
+  TRY(dalloc(h, &S.batch_list, (size_t)WIDE_NB));
   TRY(dalloc(h, &h->d_active, (size_t)N_TABLES));
   TRY(dalloc(h, &h->d_remap, (size_t)2 * N_TABLES)); S.tab_remap = h->d_remap;
   TRY(dalloc(h, &h->d_part_tabs, (size_t)N_TABLES));
@@ -960,7 +1113,6 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
   cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);
-  cudaMemcpyAsync(S.ndist, h->ndist.data(), sizeof(int) * F * A, cudaMemcpyHostToDevice, h->stream);
   // blocking-table descriptors (storage is allocated when a table is first used).  Key attributes:
   // up to KEY_ATTRS attributes with the largest domains; a table is identified by its key mask.
   {
@@ -1010,6 +1162,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   if (rc) return bail(rc);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess)
     return bail(fail(h, EXB200_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError())));
+  stage("scratch/finish");
   *out = h;
   return EXB200_OK;
 }
@@ -1018,6 +1171,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   if (!h || !name) return EXB200_ERR_INVALID;
   const std::string n(name);
   if (n == "check") h->opt_check = value != 0;
+  else if (n == "trace") h->trace = value != 0;
   else if (n == "bucket_cap") h->bucket_cap = (int)std::max<int64_t>(0, value);
   else if (n == "cand_cap") h->cand_cap = (int)std::min<int64_t>(CAND_SMEM, std::max<int64_t>(0, value));
   else if (n == "wide_threshold") h->long_cap = (int)std::min<int64_t>(16384, std::max<int64_t>(0, value));
@@ -1068,6 +1222,76 @@ int exb200_sweeps_timed(exb200_handle* h, int32_t n_sweeps, float* device_ms, in
   return rc;
 }
 
+namespace {
+// Host side of the sample pipeline of exb200_run: waits for a pinned buffer to be filled and copies
+// it into the caller's history row while the device runs the next sweep.
+struct RowCopier {
+  exb200_handle* h;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::pair<int, int*>> jobs; // (buffer, destination row)
+  bool busy[2] = {false, false};
+  bool stop = false, failed = false;
+  std::thread th;
+  explicit RowCopier(exb200_handle* hh) : h(hh) {
+    th = std::thread([this] {
+      cudaSetDevice(h->device);
+      for (;;) {
+        std::pair<int, int*> job;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || !jobs.empty(); });
+          if (jobs.empty()) return;
+          job = jobs.front();
+          jobs.pop_front();
+        }
+        const bool ok = cudaEventSynchronize(h->ev_d2h[job.first]) == cudaSuccess;
+        if (ok) std::memcpy(job.second, h->pin_snap[job.first], sizeof(int) * (size_t)h->N);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          busy[job.first] = false;
+          failed |= !ok;
+        }
+        cv.notify_all();
+      }
+    });
+  }
+  void acquire(int b) { // blocks until the previous use of buffer b has reached the caller's array
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !busy[b]; });
+    busy[b] = true;
+  }
+  void submit(int b, int* dst) {
+    { std::lock_guard<std::mutex> lk(mu); jobs.emplace_back(b, dst); }
+    cv.notify_all();
+  }
+  bool drain() { // true if every row arrived
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return jobs.empty() && !busy[0] && !busy[1]; });
+    return !failed;
+  }
+  ~RowCopier() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv.notify_all();
+    th.join();
+  }
+};
+
+int ensure_sample_pipeline(exb200_handle* h) {
+  if (h->copy_stream) return EXB200_OK;
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    int rc = dalloc(h, &h->d_snap[b], (size_t)h->N);
+    if (rc) return rc;
+    if (cudaMallocHost((void**)&h->pin_snap[b], sizeof(int) * (size_t)h->N) != cudaSuccess)
+      return fail(h, EXB200_ERR_OOM, "cannot allocate pinned staging for the history");
+    CK(cudaEventCreateWithFlags(&h->ev_snap[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
+  }
+  return EXB200_OK;
+}
+} // namespace
+
 int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin, exb200_history* out,
                int (*abort_cb)(void*), void (*progress_cb)(void*, int32_t), void* ctx) {
   if (!h || !out) return EXB200_ERR_INVALID;
@@ -1076,14 +1300,34 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
   cudaSetDevice(h->device);
   const int N = h->N, FA = h->F * h->A;
   out->n_saved = 0;
+  if (out->links && n_samples > 0) { int rc = ensure_sample_pipeline(h); if (rc) return rc; }
+  RowCopier copier(h);
+  auto finish = [&](int rc, int sample) { // rows still in flight land before the call returns
+    if (!copier.drain() && !rc) { h->poisoned = true; rc = fail(h, EXB200_ERR_CUDA, "copying a saved sample failed"); }
+    out->n_saved = sample;
+    return rc;
+  };
   int sample = 0;
   const int initial = h->iteration;
   while (sample < n_samples) { // src/sample.cpp:171-202
     int rc = sweep(h);
-    if (rc) return rc;
+    if (rc) return finish(rc, sample);
     const int completed = h->iteration - initial;
     if (completed >= burnin && (completed - burnin) % thin == 0) {
-      if (out->links) CK(cudaMemcpyAsync(out->links + (size_t)sample * N, h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+      if (out->links) {
+        const int b = sample & 1;
+        copier.acquire(b);
+        cudaError_t e = cudaMemcpyAsync(h->d_snap[b], h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_snap[b], h->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream, h->ev_snap[b], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->pin_snap[b], h->d_snap[b], sizeof(int) * N, cudaMemcpyDeviceToHost, h->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_d2h[b], h->copy_stream);
+        copier.submit(b, out->links + (size_t)sample * N); // also releases the buffer on failure
+        if (e != cudaSuccess) {
+          h->poisoned = true;
+          return finish(fail(h, EXB200_ERR_CUDA, std::string("history copy: ") + cudaGetErrorString(e)), sample);
+        }
+      }
       if (out->n_linked_ents) out->n_linked_ents[sample] = h->K;
       for (int f = 0; f < h->F; f++)
         for (int a = 0; a < h->A; a++) {
@@ -1097,40 +1341,47 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
         out->clust_params[2 * (size_t)sample] = py ? h->cl.alpha : h->cl.kappa;
         out->clust_params[2 * (size_t)sample + 1] = py ? h->cl.d : h->cl.m;
       }
-      CK(cudaStreamSynchronize(h->stream));
       sample++;
-      out->n_saved = sample;
     }
-    if (abort_cb && abort_cb(ctx)) return fail(h, EXB200_ERR_ABORTED, "aborted by the caller");
+    if (abort_cb && abort_cb(ctx)) return finish(fail(h, EXB200_ERR_ABORTED, "aborted by the caller"), sample);
     if (progress_cb) progress_cb(ctx, completed);
   }
-  return EXB200_OK;
+  return finish(EXB200_OK, sample);
 }
 
 int exb200_get_state(exb200_handle* h, exb200_state* out) {
   if (!h || !out) return EXB200_ERR_INVALID;
   cudaSetDevice(h->device);
   const int N = h->N, A = h->A, F = h->F;
-  std::vector<int> lam(N), size(N), y((size_t)N * h->ES);
-  std::vector<uint32_t> z(N);
-  CK(cudaMemcpyAsync(lam.data(), h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(size.data(), h->S.ent_size, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(y.data(), h->S.ent_y, sizeof(int) * (size_t)N * h->ES, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(z.data(), h->S.rec_z, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  cudaStream_t st = h->stream;
+  DevState& S = h->S;
+  // packed on the device in the R layout, then straight into the caller's arrays (the links-update
+  // scratch is free between sweeps: plo = flags, phi_ = positions, cand_id = packed values)
   out->iteration = h->iteration;
-  int k = 0;
-  for (int e = 0; e < N; e++)
-    if (size[e] > 0) {
-      if (out->ent_ids) out->ent_ids[k] = e;
-      if (out->ent_attrs) for (int a = 0; a < A; a++) out->ent_attrs[a + (size_t)A * k] = y[(size_t)e * h->ES + a];
-      k++;
-    }
-  out->n_entities = k;
-  if (out->links) std::memcpy(out->links, lam.data(), sizeof(int) * N);
-  if (out->rec_distortions)
-    for (int r = 0; r < N; r++)
-      for (int a = 0; a < A; a++) out->rec_distortions[a + (size_t)A * r] = (z[r] >> a) & 1u;
+  out->n_entities = h->K;
+  int* pack = S.cand_id;
+  void* big = nullptr;
+  if ((unsigned long long)N * (unsigned long long)A > S.pool_cap) { // many attributes: a buffer of its own
+    if (cudaMalloc(&big, sizeof(int) * (size_t)N * A) != cudaSuccess) return fail(h, EXB200_ERR_OOM, "cudaMalloc failed in get_state");
+    pack = (int*)big;
+  }
+  struct Release { void* p; ~Release() { if (p) cudaFree(p); } } release{big};
+  if (out->links) CK(cudaMemcpyAsync(out->links, S.lambda, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+  if (out->ent_ids || out->ent_attrs) {
+    KLAUNCH(h, k_pack_flags, nblk(N), TPB, 0, S, S.plo);
+    int rc = scan_exclusive(h, S.plo, S.phi_, N); if (rc) return rc;
+    int* ids = S.act_in;      // [N]
+    int* attrs = pack;        // [>= N * A]
+    KLAUNCH(h, k_pack_entities, nblk(N), TPB, 0, S, S.phi_, out->ent_ids ? ids : nullptr, out->ent_attrs ? attrs : nullptr);
+    if (out->ent_ids) CK(cudaMemcpyAsync(out->ent_ids, ids, sizeof(int) * (size_t)h->K, cudaMemcpyDeviceToHost, st));
+    if (out->ent_attrs) CK(cudaMemcpyAsync(out->ent_attrs, attrs, sizeof(int) * (size_t)h->K * A, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); // the packing buffer is reused below
+  }
+  if (out->rec_distortions) {
+    KLAUNCH(h, k_pack_distortions, nblk((long long)N * A), TPB, 0, S, pack);
+    CK(cudaMemcpyAsync(out->rec_distortions, pack, sizeof(int) * (size_t)N * A, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
   for (int f = 0; f < F; f++)
     for (int a = 0; a < A; a++) {
       if (out->distort_probs) out->distort_probs[f + (size_t)F * a] = h->theta[f * A + a];

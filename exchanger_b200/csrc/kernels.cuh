@@ -1107,58 +1107,171 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
   S.lwbuf[i] = out;
 }
 
-// The size-independent part for up to WIDE_BATCH records at once (each item tuple is read once):
-// lwbuf[b][i] = logLikelihoodWeightExisting of record list[b] with item i, NaN if incompatible.
-__global__ void __launch_bounds__(TPB) k_eval_batch(DevState S, const int* __restrict__ list, int nb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = 2 * S.N;
-  if (i >= n) return;
-  int y[MAX_ATTRS];
-  const int* yp = S.ent_y + (size_t)i * S.ES;
-  for (int a = 0; a < S.A; a++) y[a] = yp[a];
-  for (int b = 0; b < nb; b++) {
+// Records without a stored candidate list (more than wide_threshold possible links, or no usable
+// blocking bucket): their possible links among ALL the items of the sweep are listed here, up to
+// WIDE_NB records per pass over the item tuples.  The item range is cut into WIDE_PIECES contiguous
+// pieces, one warp each; a counting pass, a scan per record and a filling pass leave every record's
+// (item, log-likelihood) list in ascending item order - no sort.  Items are static during the links
+// update; sizes are read when the record's turn comes (k_wide_reduce / k_wide_commit).
+constexpr int WIDE_PIECES = WIDE_BLOCKS * (TPB / 32);
+__device__ __forceinline__ void wide_piece(long long n, int n_pieces, int p, long long& lo, long long& hi) {
+  const long long per = (n + n_pieces - 1) / n_pieces;
+  lo = min(n, (long long)p * per);
+  hi = min(n, lo + per);
+}
+// FILL = false: wl_cnt[b][piece] = possible links of record list[b] in the piece
+// FILL = true : entries of the records with a base (wl_base[b] != ~0) written at
+//               wl_base[b] + (scanned) wl_cnt[b][piece]
+// skip_empty: leave out the slots [0,N) that hold no entity.  That is the specification's count of
+// possible links, valid while no record has moved in this sweep; once records move, sizes change
+// between the two passes, so the serial turns list those slots too (their size is checked again
+// at the record's turn anyway).
+template <bool FILL>
+__global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __restrict__ list, int nb, int skip_empty) {
+  __shared__ int s_x[WIDE_NB][8];            // pinned value of the first 8 attributes (-1: free)
+  __shared__ int s_r[WIDE_NB];
+  __shared__ uint8_t s_more[WIDE_NB];        // the record pins an attribute beyond the eighth
+  __shared__ int s_run[TPB / 32][WIDE_NB];
+  __shared__ uint8_t s_skip[WIDE_NB];
+  for (int q = threadIdx.x; q < nb * 8; q += TPB) {
+    const int b = q >> 3, a = q & 7, r = list[b];
+    const int xv = a < S.A ? S.rec_x[(size_t)r * S.RS + a] : -1;
+    s_x[b][a] = (xv >= 0 && !((S.rec_z[r] >> a) & 1u)) ? xv : -1;
+  }
+  for (int b = threadIdx.x; b < nb; b += TPB) {
     const int r = list[b];
-    const int* x = S.rec_x + (size_t)r * S.RS;
-    const uint32_t zm = S.rec_z[r];
-    double out = CUDART_NAN;
-    if (i != S.N + r && item_compatible(S, x, zm, y)) out = item_loglik(S, x, zm, y);
-    S.lwbuf[(size_t)b * n + i] = out;
+    s_r[b] = r;
+    bool more = false;
+    for (int a = 8; a < S.A; a++) more |= S.rec_x[(size_t)r * S.RS + a] >= 0 && !((S.rec_z[r] >> a) & 1u);
+    s_more[b] = more;
+    s_skip[b] = FILL && S.wl_base[b] == ~0ull;
+  }
+  for (int q = threadIdx.x; q < (TPB / 32) * WIDE_NB; q += TPB) (&s_run[0][0])[q] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, p = blockIdx.x * (TPB / 32) + wp;
+  long long lo, hi;
+  wide_piece(2LL * S.N, WIDE_PIECES, p, lo, hi);
+  for (long long base = lo; base < hi; base += 32) {
+    const long long i = base + lane;
+    bool live = i < hi;
+    int y[8];
+    const int* yp = S.ent_y + (size_t)(live ? i : lo) * S.ES;
+    {
+      const int4 y0 = *reinterpret_cast<const int4*>(yp), y1 = *reinterpret_cast<const int4*>(yp + 4);
+      y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+    }
+    if (skip_empty && live && i < S.N) live = S.ent_size[i] > 0;
+    for (int b = 0; b < nb; b++) {
+      if (s_skip[b]) continue;
+      bool hit = live;
+#pragma unroll
+      for (int a = 0; a < 8; a++) { const int xv = s_x[b][a]; hit &= (xv < 0) | (y[a] == xv); }
+      double ll = 0.0;
+      if (hit) {
+        const int r = s_r[b];
+        hit = i != (long long)S.N + r;
+        if (hit) {
+          const int* x = S.rec_x + (size_t)r * S.RS;
+          const uint32_t zm = S.rec_z[r];
+          if (s_more[b]) hit = item_compatible(S, x, zm, yp);
+          if (hit) { ll = item_loglik(S, x, zm, yp); hit = ll > -CUDART_INF; }
+        }
+      }
+      const unsigned m = __ballot_sync(FULL, hit);
+      if (m) {
+        if (FILL && hit) {
+          const unsigned long long pos = S.wl_base[b] + (unsigned long long)S.wl_cnt[(size_t)b * WIDE_PIECES + p] +
+                                         (unsigned long long)(s_run[wp][b] + __popc(m & ((1u << lane) - 1u)));
+          S.wl_id[pos] = (int)i;
+          S.wl_ll[pos] = ll;
+        }
+        __syncwarp();
+        if (lane == 0) s_run[wp][b] += __popc(m);
+        __syncwarp();
+      }
+    }
+  }
+  if (!FILL) {
+    __syncwarp();
+    for (int b = lane; b < nb; b += 32) S.wl_cnt[(size_t)b * WIDE_PIECES + p] = s_run[wp][b];
+  }
+}
+// one block per record of the batch: exclusive scan of its piece counts, total in wl_tot
+__global__ void __launch_bounds__(1024) k_wide_offsets(DevState S) {
+  __shared__ int s_w[32];
+  int* c = S.wl_cnt + (size_t)blockIdx.x * WIDE_PIECES;
+  constexpr int PER = WIDE_PIECES / 1024;
+  int v[PER], t = 0;
+#pragma unroll
+  for (int k = 0; k < PER; k++) { v[k] = c[threadIdx.x * PER + k]; t += v[k]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_w[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int z = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, z, o); if (lane >= o) z += y; }
+    s_w[lane] = z;
+  }
+  __syncthreads();
+  int excl = x - t + (w ? s_w[w - 1] : 0);
+#pragma unroll
+  for (int k = 0; k < PER; k++) { c[threadIdx.x * PER + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 1023) S.wl_tot[blockIdx.x] = excl;
+}
+// records that turned out to have at most wide_threshold possible links keep their list like
+// everybody else (one block per record; the list is sorted already)
+__global__ void __launch_bounds__(TPB) k_wide_store(DevState S, const int* __restrict__ list, const int* __restrict__ sel, int cap) {
+  __shared__ unsigned long long s_off;
+  const int b = sel[blockIdx.x], r = list[b];
+  const int cnt = S.wl_tot[b];
+  const unsigned long long base = S.wl_base[b];
+  const int own = S.lambda[r];
+  if (threadIdx.x == 0) s_off = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+  __syncthreads();
+  const unsigned long long o = s_off;
+  const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
+  if (!overflow) for (int i = threadIdx.x; i < cnt; i += TPB) {
+    const int id = S.wl_id[base + i];
+    S.cand_id[o + i] = id; S.cand_ll[o + i] = S.wl_ll[base + i];
+    if (id != own) S.referenced[id] = 1;
+  }
+  if (threadIdx.x == 0) {
+    const bool other = overflow || cnt > 1 || (cnt == 1 && S.wl_id[base] != own);
+    S.cand_off[r] = overflow ? 0u : (uint32_t)o;
+    S.cand_cnt[r] = overflow ? -2 : cnt;
+    S.dlo[r] = other ? -1 : 0;
+    S.dhi[r] = 1;
+    if (overflow) atomicAdd(&S.counters[C_NFENCE], 1);
+    else {
+      atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
+      if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
+    }
   }
 }
 
-// log-weight of item i for record r from the batched likelihood and the CURRENT sizes
+// Turn of record r, listed at wl_base = `base` with `len` entries: every warp of the grid reduces a
+// contiguous piece (lanes strided: coalesced) to (max, sum of exp(lw - max)) in wide_part[2p], [2p+1].
 template <bool DP>
-__device__ __forceinline__ double wide_lw(const DevState& S, const double* ll, int r, int i, int own, bool single) {
-  const double v = ll[i];
-  if (!(v == v)) return CUDART_NAN;
-  const int sz = live_size(S, i, own, single);
-  return sz > 0 ? cand_lw<DP>(S, r, i, sz, v) : CUDART_NAN;
-}
-
-// The item range is cut into WIDE_BLOCKS contiguous chunks (one block each), every chunk into 8
-// contiguous pieces (one warp each, lanes strided: coalesced).  Every warp leaves
-// (max, sum of exp(lw - max)) of its piece in wide_part[2p], wide_part[2p+1], p = 8 block + warp.
-constexpr int WIDE_PIECES = WIDE_BLOCKS * (TPB / 32);
-__device__ __forceinline__ void wide_piece(const DevState& S, int p, long long& lo, long long& hi) {
-  const long long n = 2LL * S.N;
-  const long long per_b = (n + WIDE_BLOCKS - 1) / WIDE_BLOCKS;
-  const long long per_w = (per_b + (TPB / 32) - 1) / (TPB / 32);
-  const long long b_lo = (p / (TPB / 32)) * per_b, b_hi = min(n, b_lo + per_b);
-  lo = min(b_hi, b_lo + (p % (TPB / 32)) * per_w);
-  hi = min(b_hi, lo + per_w);
+__device__ __forceinline__ double wide_lw(const DevState& S, int r, int item, double ll, int own, bool single) {
+  const int sz = live_size(S, item, own, single);
+  return sz > 0 ? cand_lw<DP>(S, r, item, sz, ll) : CUDART_NAN;
 }
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot) {
-  const int n = 2 * S.N;
-  const double* ll = S.lwbuf + (size_t)slot * n;
+__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len) {
+  const int* ids = S.wl_id + base;
+  const double* ll = S.wl_ll + base;
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
   const int lane = threadIdx.x & 31, p = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
   long long lo, hi;
-  wide_piece(S, p, lo, hi);
+  wide_piece(len, gridDim.x * (TPB / 32), p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
   for (long long i = lo + lane; i < hi; i += 32) {
-    const double v = wide_lw<DP>(S, ll, r, (int)i, own, single);
+    const double v = wide_lw<DP>(S, r, ids[i], ll[i], own, single);
     if (!(v == v) || !(v > -CUDART_INF)) continue;
     if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
   }
@@ -1172,21 +1285,23 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, int slot
   if (lane == 0) { S.wide_part[2 * p] = m; S.wide_part[2 * p + 1] = sum; }
 }
 
-// decision and commit of the serial record r (one block): scale the piece sums to the global max in
-// parallel, walk block sums and piece sums in order, then one warp scans the chosen piece in order
+// decision and commit of record r (one block; n_blocks = grid of the k_wide_reduce before it):
+// scale the piece sums to the global max in parallel, walk block sums and piece sums in order,
+// then one warp scans the chosen piece in order
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot) {
+__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks) {
   __shared__ double s_bsum[WIDE_BLOCKS];
   __shared__ double s_red[TPB];
   __shared__ double s_m1, s_tt, s_c;
   __shared__ int s_piece, s_target, s_tail;
-  const int n = 2 * S.N;
-  const double* ll = S.lwbuf + (size_t)slot * n;
+  const int* ids = S.wl_id + base;
+  const double* ll = S.wl_ll + base;
+  const int n_pieces = n_blocks * (TPB / 32);
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
   double* scaled = S.wide_part + 2 * WIDE_PIECES;
   double m = -CUDART_INF;
-  for (int p = threadIdx.x; p < WIDE_PIECES; p += TPB) m = S.wide_part[2 * p] > m ? S.wide_part[2 * p] : m;
+  for (int p = threadIdx.x; p < n_pieces; p += TPB) m = S.wide_part[2 * p] > m ? S.wide_part[2 * p] : m;
   s_red[threadIdx.x] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1196,7 +1311,7 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
   }
   __syncthreads();
   const double m1 = s_m1;
-  for (int b = threadIdx.x; b < WIDE_BLOCKS; b += TPB) {
+  for (int b = threadIdx.x; b < n_blocks; b += TPB) {
     double t = 0.0;
     for (int w = 0; w < TPB / 32; w++) {
       const int p = b * (TPB / 32) + w;
@@ -1210,7 +1325,7 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
   __syncthreads();
   if (threadIdx.x == 0) {
     double srel = 0.0;
-    for (int b = 0; b < WIDE_BLOCKS; b++) srel += s_bsum[b];
+    for (int b = 0; b < n_blocks; b++) srel += s_bsum[b];
     const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
     const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
     bool invalid = false;
@@ -1221,7 +1336,7 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
       const double tt = u.b * srel;
       double c = 0.0;
       int blk = -1, lastb = -1;
-      for (int b = 0; b < WIDE_BLOCKS; b++) {
+      for (int b = 0; b < n_blocks; b++) {
         if (s_bsum[b] > 0.0) lastb = b;
         if (tt < c + s_bsum[b]) { blk = b; break; }
         c += s_bsum[b];
@@ -1246,25 +1361,27 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
   if (s_piece >= 0 && threadIdx.x < 32) {
     const int lane = threadIdx.x;
     long long lo, hi;
-    wide_piece(S, s_piece, lo, hi);
+    wide_piece(len, n_pieces, s_piece, lo, hi);
     const double tt = s_tt;
     const bool tail = s_tail != 0;
     double c = s_c;
     int target = -1, lastpos = -1;
-    for (long long base = lo; base < hi && target < 0; base += 32) {
-      const long long i = base + lane;
+    for (long long base_i = lo; base_i < hi && target < 0; base_i += 32) {
+      const long long i = base_i + lane;
       double w = 0.0;
+      int item = -1;
       if (i < hi) {
-        const double v = wide_lw<DP>(S, ll, r, (int)i, own, single);
+        item = ids[i];
+        const double v = wide_lw<DP>(S, r, item, ll[i], own, single);
         if (v == v) w = exp(v - m1);
       }
       double x = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
       const unsigned pos = __ballot_sync(FULL, w > 0.0);
-      if (pos) lastpos = (int)base + (31 - __clz(pos));
+      if (pos) lastpos = __shfl_sync(FULL, item, 31 - __clz(pos));
       const unsigned hit = __ballot_sync(FULL, !tail && w > 0.0 && tt < c + x);
-      if (hit) target = (int)base + (__ffs(hit) - 1);
+      if (hit) target = __shfl_sync(FULL, item, __ffs(hit) - 1);
       c += __shfl_sync(FULL, x, 31);
     }
     if (lane == 0) s_target = target >= 0 ? target : lastpos;
@@ -1275,21 +1392,6 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, int slot
     if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
     finalize_record(S, r, own, target, single);
   }
-}
-
-// number of possible links of record r (compatible items of non-zero likelihood among all the
-// items of the sweep, whatever their size): classifies records that have no usable bucket
-__global__ void __launch_bounds__(TPB) k_count_all(DevState S, int r) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int ok = 0;
-  if (i < 2 * S.N && i != S.N + r && !(i < S.N && S.ent_size[i] <= 0)) {
-    const int* x = S.rec_x + (size_t)r * S.RS;
-    const uint32_t zm = S.rec_z[r];
-    const int* y = S.ent_y + (size_t)i * S.ES;
-    ok = item_compatible(S, x, zm, y) && item_loglik(S, x, zm, y) > -CUDART_INF;
-  }
-  ok = warp_sum(ok);
-  if ((threadIdx.x & 31) == 0 && ok) atomicAdd(&S.counters[C_COUNT], ok);
 }
 
 // Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares

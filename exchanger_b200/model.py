@@ -348,6 +348,12 @@ class ExchangERModel:
     clust_prior: object          # RP possibly holding RVs
     attr_indices: list           # list[AttributeIndex]
 
+    def __post_init__(self):
+        # matrices are held column-major, as R holds them: the C ABI reads them in place
+        for name in ("rec_attrs", "rec_distortions", "ent_attrs"):
+            setattr(self, name, np.asfortranarray(getattr(self, name), dtype=np.int32))
+        self.distort_probs = np.asfortranarray(self.distort_probs, dtype=np.float64)
+
     @property
     def n_records(self) -> int:
         return self.rec_attrs.shape[1]
@@ -512,9 +518,9 @@ def model_with_state(model: ExchangERModel, state: dict) -> ExchangERModel:
     out.iteration = int(state["iteration"])
     out.links = np.asarray(state["links"], np.int32).copy()
     out.ent_ids = np.asarray(state["ent_ids"], np.int32).copy()
-    out.ent_attrs = np.asarray(state["ent_attrs"], np.int32).copy()
-    out.rec_distortions = np.asarray(state["rec_distortions"], np.int32).copy()
-    out.distort_probs = np.asarray(state["distort_probs"], np.float64).copy()
+    out.ent_attrs = np.array(state["ent_attrs"], np.int32, order="F")
+    out.rec_distortions = np.array(state["rec_distortions"], np.int32, order="F")
+    out.distort_probs = np.array(state["distort_probs"], np.float64, order="F")
     if "distort_dist_concs" in state:
         out.distort_dist_concs = np.asarray(state["distort_dist_concs"], np.float64).copy()
     cp = copy.copy(model.clust_params)

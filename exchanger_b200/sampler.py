@@ -6,6 +6,7 @@ path: without the library or without a GPU every call raises :class:`Exb200Error
 """
 from __future__ import annotations
 
+import time
 import ctypes as C
 import warnings
 from dataclasses import dataclass, field
@@ -24,7 +25,9 @@ class Sampler:
         self.lib = capi.load_library()
         self.model = model
         self.N, self.A, self.F = model.n_records, model.n_attrs, model.n_files
+        t0 = time.perf_counter()
         self.flat = FlatModel(model, seed)
+        self.t_flat = time.perf_counter() - t0   # host-side flattening, for the end-to-end breakdown
         self.h = C.c_void_p()
         rc = self.lib.exb200_create(C.byref(self.flat.c), device, C.byref(self.h))
         if rc != capi.EXB200_OK:
@@ -87,10 +90,10 @@ class Sampler:
     def state(self) -> dict:
         from_c = CState()
         N, A, F = self.N, self.A, self.F
-        links = np.zeros(N, np.int32)
-        ent_ids = np.zeros(N, np.int32)
-        ent_attrs = np.zeros((N, A), np.int32)
-        rec_dist = np.zeros((N, A), np.int32)
+        links = np.empty(N, np.int32)
+        ent_ids = np.empty(N, np.int32)
+        ent_attrs = np.empty((N, A), np.int32)
+        rec_dist = np.empty((N, A), np.int32)
         theta = np.zeros((A, F))
         counts = np.zeros((A, F), np.int32)
         concs = np.zeros(A)
@@ -104,8 +107,9 @@ class Sampler:
         self._check(self.lib.exb200_get_state(self.h, C.byref(from_c)))
         K = from_c.n_entities
         cl = from_c.clust
-        return dict(iteration=from_c.iteration, links=links, ent_ids=ent_ids[:K].copy(),
-                    ent_attrs=ent_attrs[:K].T.copy(), rec_distortions=rec_dist.T.copy(),
+        # [A, K] / [A, N] matrices are column-major views of what the library wrote (R's layout)
+        return dict(iteration=from_c.iteration, links=links, ent_ids=ent_ids[:K],
+                    ent_attrs=ent_attrs[:K].T, rec_distortions=rec_dist.T,
                     distort_probs=theta.T.copy(), distort_counts=counts.T.copy(),
                     distort_dist_concs=concs,
                     clust=dict(alpha=cl.alpha, d=cl.d, m=cl.m, kappa=cl.kappa, kind=cl.kind))
