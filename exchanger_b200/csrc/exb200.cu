@@ -667,8 +667,15 @@ int update_links(exb200_handle* h) {
       // against the sizes its predecessors left
       const int nb = (int)std::min<size_t>(WIDE_NB, wide.size() - g);
       int tot[WIDE_NB];
+      const auto t_a = std::chrono::steady_clock::now();
       int rc = wide_count(h, wide.data() + g, nb, tot, 0); if (rc) return rc;
-      if (h->trace) for (int q = 0; q < nb; q++) std::fprintf(stderr, "[exb200] wide record %d: %d possible links\n", wide[g + q], tot[q]);
+      const auto t_b = std::chrono::steady_clock::now();
+      if (h->trace) {
+        long long sum = 0;
+        for (int q = 0; q < nb; q++) sum += tot[q];
+        std::fprintf(stderr, "[exb200] wide batch of %d: count pass %.2f ms, %lld possible links\n", nb,
+                     std::chrono::duration<double, std::milli>(t_b - t_a).count(), sum);
+      }
       int b = 0;
       while (b < nb) {
         unsigned long long bases[WIDE_NB], used = 0;
@@ -681,8 +688,15 @@ int update_links(exb200_handle* h) {
         if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
         CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
         KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, 0);
+        const auto t_c = std::chrono::steady_clock::now();
+        if (h->trace) CK(cudaStreamSynchronize(st));
+        const auto t_d = std::chrono::steady_clock::now();
         for (int q = b0; q < b; q++) wide_turn(h, wide[g + q], bases[q], tot[q]);
         CK(cudaStreamSynchronize(st)); // bases are on the stack
+        if (h->trace)
+          std::fprintf(stderr, "[exb200] wide group of %d: fill pass %.2f ms, turns %.2f ms\n", b - b0,
+                       std::chrono::duration<double, std::milli>(t_d - t_c).count(),
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_d).count());
       }
     }
     CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));

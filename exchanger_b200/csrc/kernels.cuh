@@ -1114,6 +1114,7 @@ __global__ void __launch_bounds__(TPB) k_eval_all(DevState S, int r, int n_items
 // (item, log-likelihood) list in ascending item order - no sort.  Items are static during the links
 // update; sizes are read when the record's turn comes (k_wide_reduce / k_wide_commit).
 constexpr int WIDE_PIECES = WIDE_BLOCKS * (TPB / 32);
+constexpr int WIDE_Q = 256; // a group of four records adds at most 128 pairs to fewer than 32 waiting ones
 __device__ __forceinline__ void wide_piece(long long n, int n_pieces, int p, long long& lo, long long& hi) {
   const long long per = (n + n_pieces - 1) / n_pieces;
   lo = min(n, (long long)p * per);
@@ -1126,31 +1127,51 @@ __device__ __forceinline__ void wide_piece(long long n, int n_pieces, int p, lon
 // possible links, valid while no record has moved in this sweep; once records move, sizes change
 // between the two passes, so the serial turns list those slots too (their size is checked again
 // at the record's turn anyway).
+// W-bit hash of an attribute value; W = 64 / (attributes in the packed word), at most 16
+__device__ __forceinline__ unsigned long long hash_w(int v, int W) { return (unsigned long long)(((uint32_t)v * 0x9E3779B1u) >> (32 - W)); }
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __restrict__ list, int nb, int skip_empty) {
+  // records taking part in this pass, compacted: k -> batch position s_b[k]
+  __shared__ ulonglong2 s_mv[WIDE_NB];       // field a of .x: all ones if attribute a is pinned; of .y: hash of the pinned value
   __shared__ int s_x[WIDE_NB][8];            // pinned value of the first 8 attributes (-1: free)
-  __shared__ int s_r[WIDE_NB];
+  __shared__ int s_r[WIDE_NB], s_b[WIDE_NB];
   __shared__ uint8_t s_more[WIDE_NB];        // the record pins an attribute beyond the eighth
   __shared__ int s_run[TPB / 32][WIDE_NB];
-  __shared__ uint8_t s_skip[WIDE_NB];
-  for (int q = threadIdx.x; q < nb * 8; q += TPB) {
-    const int b = q >> 3, a = q & 7, r = list[b];
-    const int xv = a < S.A ? S.rec_x[(size_t)r * S.RS + a] : -1;
-    s_x[b][a] = (xv >= 0 && !((S.rec_z[r] >> a) & 1u)) ? xv : -1;
+  __shared__ uint16_t s_q[TPB / 32][WIDE_Q]; // per-warp queue of (record << 5 | lane) pairs waiting for their likelihood
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int b = 0; b < nb; b++) if (!FILL || S.wl_base[b] != ~0ull) s_b[n++] = b;
+    s_n = n;
   }
-  for (int b = threadIdx.x; b < nb; b += TPB) {
-    const int r = list[b];
-    s_r[b] = r;
+  __syncthreads();
+  const int n_act = s_n;
+  const int W = min(16, 64 / min(S.A, 8));
+  const unsigned long long field = (1ull << W) - 1ull;
+  for (int k = threadIdx.x; k < WIDE_NB; k += TPB) {
+    if (k >= n_act) { s_mv[k] = make_ulonglong2(~0ull, 0ull); continue; } // padding of the last group of four: matches (almost) nothing
+
+    const int r = list[s_b[k]];
+    s_r[k] = r;
+    const uint32_t zm = S.rec_z[r];
+    unsigned long long M = 0, V = 0;
+    for (int a = 0; a < 8; a++) {
+      const int xv = a < S.A ? S.rec_x[(size_t)r * S.RS + a] : -1;
+      const bool pinned = xv >= 0 && !((zm >> a) & 1u);
+      s_x[k][a] = pinned ? xv : -1;
+      if (pinned) { M |= field << (W * a); V |= hash_w(xv, W) << (W * a); }
+    }
+    s_mv[k] = make_ulonglong2(M, V);
     bool more = false;
-    for (int a = 8; a < S.A; a++) more |= S.rec_x[(size_t)r * S.RS + a] >= 0 && !((S.rec_z[r] >> a) & 1u);
-    s_more[b] = more;
-    s_skip[b] = FILL && S.wl_base[b] == ~0ull;
+    for (int a = 8; a < S.A; a++) more |= S.rec_x[(size_t)r * S.RS + a] >= 0 && !((zm >> a) & 1u);
+    s_more[k] = more;
   }
   for (int q = threadIdx.x; q < (TPB / 32) * WIDE_NB; q += TPB) (&s_run[0][0])[q] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, p = blockIdx.x * (TPB / 32) + wp;
   long long lo, hi;
   wide_piece(2LL * S.N, WIDE_PIECES, p, lo, hi);
+  int qh = 0, qn = 0; // queue head and length (warp-uniform)
   for (long long base = lo; base < hi; base += 32) {
     const long long i = base + lane;
     bool live = i < hi;
@@ -1161,39 +1182,78 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
       y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
     }
     if (skip_empty && live && i < S.N) live = S.ent_size[i] > 0;
-    for (int b = 0; b < nb; b++) {
-      if (s_skip[b]) continue;
-      bool hit = live;
+    unsigned long long P = 0;
 #pragma unroll
-      for (int a = 0; a < 8; a++) { const int xv = s_x[b][a]; hit &= (xv < 0) | (y[a] == xv); }
+    for (int a = 0; a < 8; a++) if (a * W < 64) P |= hash_w(y[a], W) << (W * a);
+    // Pairs that pass the pinned attributes are queued per warp and their likelihoods evaluated 32
+    // at a time, one pair per lane: the evaluation is a chain of dependent loads (neighbourhood
+    // search), far too slow to run with a lane or two active.  The queue is filled in (record,
+    // item) order and emptied before the next 32 items, so every record sees its items in order.
+    auto drain = [&](int cnt) {
+      int k = -1 - lane, rank = 0; // inactive lanes: distinct keys that match nobody
+      long long it = 0;
       double ll = 0.0;
-      if (hit) {
-        const int r = s_r[b];
-        hit = i != (long long)S.N + r;
+      bool hit = false;
+      if (lane < cnt) {
+        const unsigned e = s_q[wp][(qh + lane) & (WIDE_Q - 1)];
+        k = (int)(e >> 5);
+        it = base + (long long)(e & 31u);
+        const int r = s_r[k];
+        hit = it != (long long)S.N + r;
         if (hit) {
           const int* x = S.rec_x + (size_t)r * S.RS;
           const uint32_t zm = S.rec_z[r];
-          if (s_more[b]) hit = item_compatible(S, x, zm, yp);
-          if (hit) { ll = item_loglik(S, x, zm, yp); hit = ll > -CUDART_INF; }
+          const int* yq = S.ent_y + (size_t)it * S.ES;
+          if (s_more[k]) hit = item_compatible(S, x, zm, yq);
+          if (hit) { ll = item_loglik(S, x, zm, yq); hit = ll > -CUDART_INF; }
         }
       }
-      const unsigned m = __ballot_sync(FULL, hit);
-      if (m) {
-        if (FILL && hit) {
-          const unsigned long long pos = S.wl_base[b] + (unsigned long long)S.wl_cnt[(size_t)b * WIDE_PIECES + p] +
-                                         (unsigned long long)(s_run[wp][b] + __popc(m & ((1u << lane) - 1u)));
-          S.wl_id[pos] = (int)i;
-          S.wl_ll[pos] = ll;
+      const unsigned hm = __ballot_sync(FULL, hit);
+      if (hm) {
+        const unsigned peers = __match_any_sync(FULL, k) & hm;
+        if (hit) {
+          rank = __popc(peers & ((1u << lane) - 1u));
+          if (FILL) {
+            const int b = s_b[k];
+            const unsigned long long pos = S.wl_base[b] + (unsigned long long)S.wl_cnt[(size_t)b * WIDE_PIECES + p] +
+                                           (unsigned long long)(s_run[wp][k] + rank);
+            S.wl_id[pos] = (int)it;
+            S.wl_ll[pos] = ll;
+          }
         }
         __syncwarp();
-        if (lane == 0) s_run[wp][b] += __popc(m);
-        __syncwarp();
+        if (hit && rank == 0) s_run[wp][k] += __popc(peers);
       }
+      __syncwarp();
+      qh += cnt; qn -= cnt;
+    };
+    for (int k4 = 0; k4 < n_act; k4 += 4) {
+      // hashed pre-test of four records at once: exact for nearly every pair
+      const ulonglong2 mv0 = s_mv[k4], mv1 = s_mv[k4 + 1], mv2 = s_mv[k4 + 2], mv3 = s_mv[k4 + 3];
+      const bool h0 = ((P ^ mv0.y) & mv0.x) == 0, h1 = ((P ^ mv1.y) & mv1.x) == 0;
+      const bool h2 = ((P ^ mv2.y) & mv2.x) == 0, h3 = ((P ^ mv3.y) & mv3.x) == 0;
+      if (!__any_sync(FULL, live && (h0 | h1 | h2 | h3))) continue;
+      for (int k = k4; k < min(k4 + 4, n_act); k++) {
+        const int kk = k - k4;
+        bool hit = live && (kk == 0 ? h0 : kk == 1 ? h1 : kk == 2 ? h2 : h3);
+        if (hit) {
+#pragma unroll
+          for (int a = 0; a < 8; a++) { const int xv = s_x[k][a]; hit &= (xv < 0) | (y[a] == xv); }
+        }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m) {
+          if (hit) s_q[wp][(qh + qn + __popc(m & ((1u << lane) - 1u))) & (WIDE_Q - 1)] = (uint16_t)((k << 5) | lane);
+          qn += __popc(m);
+        }
+      }
+      __syncwarp();
+      while (qn >= 32) drain(32);
     }
+    if (qn) drain(qn);
   }
   if (!FILL) {
     __syncwarp();
-    for (int b = lane; b < nb; b += 32) S.wl_cnt[(size_t)b * WIDE_PIECES + p] = s_run[wp][b];
+    for (int k = lane; k < n_act; k += 32) S.wl_cnt[(size_t)s_b[k] * WIDE_PIECES + p] = s_run[wp][k];
   }
 }
 // one block per record of the batch: exclusive scan of its piece counts, total in wl_tot
@@ -1256,11 +1316,6 @@ __global__ void __launch_bounds__(TPB) k_wide_store(DevState S, const int* __res
 // Turn of record r, listed at wl_base = `base` with `len` entries: every warp of the grid reduces a
 // contiguous piece (lanes strided: coalesced) to (max, sum of exp(lw - max)) in wide_part[2p], [2p+1].
 template <bool DP>
-__device__ __forceinline__ double wide_lw(const DevState& S, int r, int item, double ll, int own, bool single) {
-  const int sz = live_size(S, item, own, single);
-  return sz > 0 ? cand_lw<DP>(S, r, item, sz, ll) : CUDART_NAN;
-}
-template <bool DP>
 __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len) {
   const int* ids = S.wl_id + base;
   const double* ll = S.wl_ll + base;
@@ -1270,10 +1325,24 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned
   long long lo, hi;
   wide_piece(len, gridDim.x * (TPB / 32), p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
-  for (long long i = lo + lane; i < hi; i += 32) {
-    const double v = wide_lw<DP>(S, r, ids[i], ll[i], own, single);
-    if (!(v == v) || !(v > -CUDART_INF)) continue;
-    if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
+  for (long long i0 = lo; i0 < hi; i0 += 256) { // 8 entries per lane in flight (a piece has at most 256 unless the grid is capped)
+    int id[8], sz[8];
+    double l[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const long long i = i0 + j * 32 + lane;
+      id[j] = i < hi ? ids[i] : -1;
+      l[j] = i < hi ? ll[i] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) sz[j] = id[j] >= 0 ? live_size(S, id[j], own, single) : 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (sz[j] <= 0) continue;
+      const double v = cand_lw<DP>(S, r, id[j], sz[j], l[j]);
+      if (!(v > -CUDART_INF)) continue;
+      if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1366,23 +1435,31 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned
     const bool tail = s_tail != 0;
     double c = s_c;
     int target = -1, lastpos = -1;
-    for (long long base_i = lo; base_i < hi && target < 0; base_i += 32) {
-      const long long i = base_i + lane;
-      double w = 0.0;
-      int item = -1;
-      if (i < hi) {
-        item = ids[i];
-        const double v = wide_lw<DP>(S, r, item, ll[i], own, single);
-        if (v == v) w = exp(v - m1);
-      }
-      double x = w;
+    for (long long i0 = lo; i0 < hi && target < 0; i0 += 256) {
+      int id[8], sz[8];
+      double l[8];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
-      const unsigned pos = __ballot_sync(FULL, w > 0.0);
-      if (pos) lastpos = __shfl_sync(FULL, item, 31 - __clz(pos));
-      const unsigned hit = __ballot_sync(FULL, !tail && w > 0.0 && tt < c + x);
-      if (hit) target = __shfl_sync(FULL, item, __ffs(hit) - 1);
-      c += __shfl_sync(FULL, x, 31);
+      for (int j = 0; j < 8; j++) {
+        const long long i = i0 + j * 32 + lane;
+        id[j] = i < hi ? ids[i] : -1;
+        l[j] = i < hi ? ll[i] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) sz[j] = id[j] >= 0 ? live_size(S, id[j], own, single) : 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (target >= 0 || i0 + j * 32 >= hi) break; // warp-uniform
+        double w = 0.0;
+        if (sz[j] > 0) w = exp(cand_lw<DP>(S, r, id[j], sz[j], l[j]) - m1);
+        double x = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
+        const unsigned pos = __ballot_sync(FULL, w > 0.0);
+        if (pos) lastpos = __shfl_sync(FULL, id[j], 31 - __clz(pos));
+        const unsigned hit = __ballot_sync(FULL, !tail && w > 0.0 && tt < c + x);
+        if (hit) target = __shfl_sync(FULL, id[j], __ffs(hit) - 1);
+        c += __shfl_sync(FULL, x, 31);
+      }
     }
     if (lane == 0) s_target = target >= 0 ? target : lastpos;
   }
