@@ -591,11 +591,20 @@ int update_links(exb200_handle* h) {
   int hc[C_NSLOTS];
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  auto t_tr = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what, int n) { // EXB200_TRACE: host-side laps between synchronisation points
+    if (!h->trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[exb200] %-28s %6d records %8.2f ms\n", what, n, std::chrono::duration<double, std::milli>(now - t_tr).count());
+    t_tr = now;
+  };
   if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
     const size_t smem = (size_t)h->long_cap * (sizeof(double) + sizeof(int));
+    const int n_todo = hc[C_NLONG_TODO];
     KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 8), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    lap("block-staged candidate lists", n_todo);
     if (hc[C_NHUGE] > 0) { // buckets so long that the whole grid scans them, one record at a time
       std::vector<int> huge(hc[C_NHUGE]);
       CK(cudaMemcpyAsync(huge.data(), S.huge_list, sizeof(int) * huge.size(), cudaMemcpyDeviceToHost, st));
@@ -606,6 +615,7 @@ int update_links(exb200_handle* h) {
       }
       CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      lap("grid-scanned huge buckets", (int)huge.size());
     }
   }
   // records without a usable bucket: list their possible links among all the items; those with at
@@ -646,6 +656,7 @@ int update_links(exb200_handle* h) {
     }
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved
     CK(cudaStreamSynchronize(st));
+    lap("records without a bucket", (int)unk.size());
   }
   const int n_fence = hc[C_NFENCE]; // candidate pool exhausted: these take their turn serially inside the rounds
   if (hc[C_NWIDE] > 0) {

@@ -1198,13 +1198,19 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
         const unsigned e = s_q[wp][(qh + lane) & (WIDE_Q - 1)];
         k = (int)(e >> 5);
         it = base + (long long)(e & 31u);
-        const int r = s_r[k];
-        hit = it != (long long)S.N + r;
+        const int r = k < n_act ? s_r[k] : 0;
+        hit = k < n_act && it != (long long)S.N + r;
         if (hit) {
           const int* x = S.rec_x + (size_t)r * S.RS;
           const uint32_t zm = S.rec_z[r];
           const int* yq = S.ent_y + (size_t)it * S.ES;
-          if (s_more[k]) hit = item_compatible(S, x, zm, yq);
+          { // the hashed pre-test let it through: now the pinned attributes themselves
+            const int4 q0 = *reinterpret_cast<const int4*>(yq), q1 = *reinterpret_cast<const int4*>(yq + 4);
+            const int yv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int a = 0; a < 8; a++) { const int xv = s_x[k][a]; hit &= (xv < 0) | (yv[a] == xv); }
+          }
+          if (hit && s_more[k]) hit = item_compatible(S, x, zm, yq);
           if (hit) { ll = item_loglik(S, x, zm, yq); hit = ll > -CUDART_INF; }
         }
       }
@@ -1233,19 +1239,14 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
       const bool h0 = ((P ^ mv0.y) & mv0.x) == 0, h1 = ((P ^ mv1.y) & mv1.x) == 0;
       const bool h2 = ((P ^ mv2.y) & mv2.x) == 0, h3 = ((P ^ mv3.y) & mv3.x) == 0;
       if (!__any_sync(FULL, live && (h0 | h1 | h2 | h3))) continue;
-      for (int k = k4; k < min(k4 + 4, n_act); k++) {
-        const int kk = k - k4;
-        bool hit = live && (kk == 0 ? h0 : kk == 1 ? h1 : kk == 2 ? h2 : h3);
-        if (hit) {
-#pragma unroll
-          for (int a = 0; a < 8; a++) { const int xv = s_x[k][a]; hit &= (xv < 0) | (y[a] == xv); }
-        }
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (m) {
-          if (hit) s_q[wp][(qh + qn + __popc(m & ((1u << lane) - 1u))) & (WIDE_Q - 1)] = (uint16_t)((k << 5) | lane);
-          qn += __popc(m);
-        }
-      }
+      const unsigned lt = (1u << lane) - 1u;
+      const unsigned m0 = __ballot_sync(FULL, live && h0), m1 = __ballot_sync(FULL, live && h1);
+      const unsigned m2 = __ballot_sync(FULL, live && h2), m3 = __ballot_sync(FULL, live && h3);
+      // (the padding records of the last group match next to nothing and are dropped in drain)
+      if (m0) { if (live && h0) s_q[wp][(qh + qn + __popc(m0 & lt)) & (WIDE_Q - 1)] = (uint16_t)((k4 << 5) | lane); qn += __popc(m0); }
+      if (m1) { if (live && h1) s_q[wp][(qh + qn + __popc(m1 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 1) << 5) | lane); qn += __popc(m1); }
+      if (m2) { if (live && h2) s_q[wp][(qh + qn + __popc(m2 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 2) << 5) | lane); qn += __popc(m2); }
+      if (m3) { if (live && h3) s_q[wp][(qh + qn + __popc(m3 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 3) << 5) | lane); qn += __popc(m3); }
       __syncwarp();
       while (qn >= 32) drain(32);
     }

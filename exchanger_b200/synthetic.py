@@ -60,9 +60,17 @@ def _name_domain(rng, base_count: int):
 
 
 def synth_rldata(n_records: int, seed: int = 20260101, dup_frac: float = 0.1, distort: float = 0.03,
-                 na_frac: float = 0.01, d_fname: int | None = None, d_lname: int | None = None):
+                 na_frac: float = 0.01, d_fname: int | None = None, d_lname: int | None = None,
+                 name_skew: float = 0.5):
     """Returns ``(codes [5, N] int32, domains, attr_names, identity [N])`` with attributes ordered
-    by, bm, bd, fname, lname (categorical first, as ``exchanger()`` sorts them)."""
+    by, bm, bd, fname, lname (categorical first, as ``exchanger()`` sorts them).
+
+    ``name_skew`` is the Zipf exponent of the name frequencies.  It sets how many DISTINCT entities
+    share both names: at 9 M entities about 6.4 others per entity for 0.9, 0.04 for 0.5.  The model
+    treats a shared rare full name as overwhelming evidence (dates are cheap to distort), so with
+    dense name collisions its posterior merges all namesakes, theta of the dates drifts to 0.2-0.3
+    over a few hundred sweeps and a sweep costs 30x more (profiles/README.md, "chain drift").
+    0.5 keeps the collision density below RLdata10000's, where the reference reaches F1 0.94."""
     rng = np.random.default_rng(seed)
     N = int(n_records)
     M = max(1, int(round((1.0 - dup_frac) * N)))
@@ -72,7 +80,7 @@ def synth_rldata(n_records: int, seed: int = 20260101, dup_frac: float = 0.1, di
     dom_l, var_l = _name_domain(rng, d_lname)
 
     def zipf(d):
-        w = 1.0 / (np.arange(d) + 10.0) ** 0.9
+        w = 1.0 / (np.arange(d) + 10.0) ** name_skew
         return w / w.sum()
 
     years = np.arange(1920, 2010)
