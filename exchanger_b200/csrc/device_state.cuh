@@ -27,6 +27,7 @@ constexpr int MAX_ATTRS = 32;
 constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that may form blocking keys
 constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
+constexpr int CAND_INLINE = 4;      // candidate lists up to this length are stored at pool[CAND_INLINE * record]
 constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
 constexpr int HUGE_CAP = 16386;     // scratch entries of the grid-wide bucket scan
 

@@ -494,7 +494,10 @@ int update_links(exb200_handle* h) {
   CK(cudaMemsetAsync(S.tab_est, 0, sizeof(float) * N_TABLES, st));
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
   CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
-  CK(cudaMemsetAsync(S.pool_cursor, 0, sizeof(unsigned long long), st));
+  {
+    const unsigned long long shared_from = (unsigned long long)CAND_INLINE * (unsigned long long)N; // after the per-record slots
+    CK(cudaMemcpyAsync(S.pool_cursor, &shared_from, sizeof shared_from, cudaMemcpyHostToDevice, st));
+  }
   CK(cudaMemsetAsync(S.referenced, 0, (size_t)2 * N, st));
   CK(cudaEventRecord(h->ev[1], st));
   KLAUNCH(h, k_prep, nblk(N), TPB, 0, S);
@@ -1092,7 +1095,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.twin, (size_t)N));
   TRY(dalloc(h, &S.cand_off, (size_t)N));
   TRY(dalloc(h, &S.cand_cnt, (size_t)N));
-  S.pool_cap = std::min<unsigned long long>(8ull * N + (1ull << 20), 0xFFFFFFF0ull);
+  S.pool_cap = std::min<unsigned long long>((8ull + CAND_INLINE) * N + (1ull << 20), 0xFFFFFFF0ull);
   TRY(dalloc(h, &S.cand_id, (size_t)S.pool_cap));
   TRY(dalloc(h, &S.cand_ll, (size_t)S.pool_cap));
   TRY(dalloc(h, &S.pool_cursor, 1));

@@ -629,9 +629,13 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
             }
             __syncwarp(gmask);
           }
-        unsigned long long o = 0;
-        if (gl == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
-        o = __shfl_sync(gmask, o, gsh);
+        // lists of up to CAND_INLINE entries live in the record's own slot of the pool; only longer
+        // ones take space from the shared cursor (one global atomic per record stalled this kernel)
+        unsigned long long o = (unsigned long long)CAND_INLINE * (unsigned long long)r;
+        if (cnt > CAND_INLINE) {
+          if (gl == 0) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+          o = __shfl_sync(gmask, o, gsh);
+        }
         if (o + (unsigned long long)cnt > S.pool_cap) overflow = true;
         else {
           off = (uint32_t)o;
