@@ -83,6 +83,7 @@ struct exb200_handle {
   int huge_min = 65536;
   int index_partitioned = 1;
   double table_full_cost = 1.0, table_pair_cost = 0.25; // cost of building a table, in bucket visits per item
+  int table_min_usage = 16;     // a key mask wanted by at most this many records never gets a table of its own
   int n_tab = 0; // 2^n_key
   exb200_stats stats{};
   cudaEvent_t ev[16]{};
@@ -529,12 +530,27 @@ int update_links(exb200_handle* h) {
         if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
       // expected bucket visits through the substitute versus the cost of a table of its own
       if (best && (double)usage[N_TABLES + t] * items / keys_of(best) > h->table_pair_cost * items) best = 0;
+      if (best == 0 && usage[N_TABLES + t] <= h->table_min_usage && !built[t]) {
+        // a handful of records: no table for them (remap 0: their possible links are listed by the
+        // batched scan over all the items, like records without any usable key)
+        for (int b : active)
+          if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
+        remap[N_TABLES + t] = (uint16_t)best;
+        continue;
+      }
       if (best == 0) { best = t; if (!built[t]) { built[t] = 1; active.push_back(t); } }
       remap[N_TABLES + t] = (uint16_t)best;
     }
   }
   for (int t : active) {
     int rc = ensure_table(h, t); if (rc) return rc;
+  }
+  if (h->trace) {
+    for (int t = 1; t < NT; t++)
+      if (usage[t] > 0 || usage[N_TABLES + t] > 0)
+        std::fprintf(stderr, "[exb200] key mask %2d: wanted as full key by %8d (pair cost %.3g visits), as pair by %8d -> served by %d / %d%s, %u buckets\n",
+                     t, usage[t], (double)est[t], usage[N_TABLES + t], (int)remap[t], (int)remap[N_TABLES + t],
+                     std::find(active.begin(), active.end(), t) != active.end() ? " (built)" : "", h->tables[t].d.B);
   }
   CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * remap.size(), cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
@@ -1207,6 +1223,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "est_threshold") h->est_threshold = (double)value;
   else if (n == "huge_min") h->huge_min = (int)std::max<int64_t>(0, value);
   else if (n == "index_partitioned") h->index_partitioned = value != 0;
+  else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
   h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap; h->S.long_cap = h->long_cap;
