@@ -524,21 +524,36 @@ int update_links(exb200_handle* h) {
     for (int t = 1; t < NT; t++) if (usage[N_TABLES + t] > 0) wanted.push_back(t);
     std::sort(wanted.begin(), wanted.end(), [&](int a, int b) { return usage[N_TABLES + a] > usage[N_TABLES + b]; });
     auto keys_of = [&](int t) { return (double)h->tables[t].keys; };
+    // a built table b serves the pair mask t directly if b is a subset of t, or by probing every
+    // value of ONE extra key attribute e with a small domain (b = subset of t + e).  Expected
+    // bucket visits per record: D_e probes of at least one visit each.
+    auto visits_via = [&](int b, int t) -> double {
+      const int extra = b & ~t;
+      const double per_bucket = std::max(1.0, items / keys_of(b));
+      if (extra == 0) return per_bucket;
+      if ((extra & (extra - 1)) || (b & t) == 0) return -1.0; // not served
+      int pos = 0;
+      while (!((extra >> pos) & 1)) pos++;
+      const int D = h->attrs[S.key_attr[pos]].D;
+      // (one thread walks each probed bucket: short buckets only)
+      return D <= 256 && per_bucket <= 32.0 ? (double)D * per_bucket : -1.0;
+    };
     for (int t : wanted) {
       int best = 0;
-      for (int b : active)
-        if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
+      double best_visits = 0.0;
+      for (int b : active) {
+        const double v = visits_via(b, t);
+        if (v > 0.0 && (best == 0 || v < best_visits)) { best_visits = v; best = b; }
+      }
       // expected bucket visits through the substitute versus the cost of a table of its own
-      if (best && (double)usage[N_TABLES + t] * items / keys_of(best) > h->table_pair_cost * items) best = 0;
-      if (best == 0 && usage[N_TABLES + t] <= h->table_min_usage && !built[t]) {
-        // a handful of records: no table for them (remap 0: their possible links are listed by the
-        // batched scan over all the items, like records without any usable key)
-        for (int b : active)
-          if ((b & t) == b && (best == 0 || keys_of(b) > keys_of(best))) best = b;
-        remap[N_TABLES + t] = (uint16_t)best;
+      const bool too_slow = !best || (double)usage[N_TABLES + t] * best_visits > h->table_pair_cost * items;
+      if (too_slow && usage[N_TABLES + t] <= h->table_min_usage && !built[t]) {
+        // a handful of records: no table for them (remap 0 if nothing serves them: their possible
+        // links are then listed by the batched scan over all the items)
+        remap[N_TABLES + t] = (uint16_t)(best && best_visits <= 65536.0 ? best : 0);
         continue;
       }
-      if (best == 0) { best = t; if (!built[t]) { built[t] = 1; active.push_back(t); } }
+      if (too_slow) { best = t; if (!built[t]) { built[t] = 1; active.push_back(t); } }
       remap[N_TABLES + t] = (uint16_t)best;
     }
   }
@@ -618,7 +633,7 @@ int update_links(exb200_handle* h) {
     t_tr = now;
   };
   if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
-    const size_t smem = (size_t)h->long_cap * (sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)pow2_ceil(std::max(h->long_cap, 1)) * (sizeof(double) + sizeof(int)); // padded for the bitonic sort
     const int n_todo = hc[C_NLONG_TODO];
     KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 8), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));

@@ -25,13 +25,24 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 }
 // bucket of an attribute tuple y under the key mask of table t (mixed-radix key over the key
 // attributes in the mask; hashed when the key space is larger than the bucket array)
-__device__ __forceinline__ uint32_t bucket_of(const DevState& S, const DevTable& t, const int* y) {
+// (attribute `ea`, if any, takes the value `ev` instead of y[ea])
+__device__ __forceinline__ uint32_t bucket_of(const DevState& S, const DevTable& t, const int* y, int ea = -1, int ev = 0) {
   uint64_t key = 0;
   for (uint32_t m = t.mask; m; m &= m - 1) {
     const int a = S.key_attr[__ffs(m) - 1];
-    key = key * (uint64_t)S.attrs[a].D + (uint64_t)y[a];
+    key = key * (uint64_t)S.attrs[a].D + (uint64_t)(a == ea ? ev : y[a]);
   }
   return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
+}
+// A record may be served by a table with ONE key attribute it cannot pin (missing or distorted):
+// it then probes the bucket of every value of that attribute (a few dozen for the categorical
+// ones), which saves building a table of its own for a rare key mask.  Returns that attribute or -1.
+__device__ __forceinline__ int unpinned_key(const DevState& S, uint32_t mask, const int* x, uint32_t zm) {
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const int a = S.key_attr[__ffs(m) - 1];
+    if (x[a] < 0 || ((zm >> a) & 1u)) return a;
+  }
+  return -1;
 }
 
 // log p(w | v) = log get_distortion_prob(v, w)   (src/attribute_index.cpp:36-47, 77-92)
@@ -564,11 +575,14 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     int lo = 0, hi = 0;
     if (!wide) {
       const DevTable& t = S.tables[tab];
-      const uint32_t b = bucket_of(S, t, x);
-      if (gl == 0) S.rec_bkt[r] = b;
-      lo = b ? t.ptr[b - 1] : 0;
-      hi = t.ptr[b];
-      spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
+      if (unpinned_key(S, t.mask, x, zm) >= 0) spill = true; // several buckets to probe: k_cand_long
+      else {
+        const uint32_t b = bucket_of(S, t, x);
+        if (gl == 0) S.rec_bkt[r] = b;
+        lo = b ? t.ptr[b - 1] : 0;
+        hi = t.ptr[b];
+        spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
+      }
     }
     if (!wide && !spill) {
       const int* bucket = S.tables[tab].ids;
@@ -661,6 +675,8 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
 }
 
+__host__ __device__ __forceinline__ int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
 // Block-wide tail of candidate staging: sort `cnt` staged (id, ll) pairs by id, append them to the
 // pool and register the record (cnt > cap: more than wide_threshold possible links).
 __device__ void stage_sort_store(const DevState& S, int r, int own, int* ids, double* lls, int cnt, int cap,
@@ -711,7 +727,7 @@ __device__ void stage_sort_store(const DevState& S, int r, int own, int* ids, do
 __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int cap) {
   extern __shared__ unsigned char s_raw[];
   double* lls = reinterpret_cast<double*>(s_raw);
-  int* ids = reinterpret_cast<int*>(lls + cap);
+  int* ids = reinterpret_cast<int*>(lls + pow2_ceil(cap)); // the sort pads the list to a power of two
   __shared__ int s_cnt;
   __shared__ unsigned long long s_off;
   for (int w = blockIdx.x; w < n_todo; w += gridDim.x) {
@@ -723,28 +739,45 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
     int tab = S.tab_remap[S.rec_tab[r]];
     if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
     const DevTable& t = S.tables[tab];
-    const uint32_t b = S.rec_bkt[r];
-    const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
     const int own = S.lambda[r];
-    if (hi - lo > S.huge_min) {
-      if (threadIdx.x == 0) S.huge_list[atomicAdd(&S.counters[C_NHUGE], 1)] = r;
-      __syncthreads();
-      continue;
+    const int ea = unpinned_key(S, t.mask, x, zm);
+    const int n_probe = ea >= 0 ? S.attrs[ea].D : 1;
+    if (ea < 0) {
+      const uint32_t b = S.rec_bkt[r];
+      const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+      if (hi - lo > S.huge_min) {
+        if (threadIdx.x == 0) S.huge_list[atomicAdd(&S.counters[C_NHUGE], 1)] = r;
+        __syncthreads();
+        continue;
+      }
     }
-    for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
-      if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
-      const int q = q0 + threadIdx.x;
-      if (q >= hi) continue;
-      const int item = t.ids[q];
-      if (item == S.N + r) continue;
+    auto visit = [&](int item, int v) {
+      if (item == S.N + r) return;
       const int* y = S.ent_y + (size_t)item * S.ES;
-      if (!item_compatible(S, x, zm, y)) continue;
+      if (ea >= 0 && y[ea] != v) return; // hashed buckets: an item counts in the probe of its own value only
+      if (!item_compatible(S, x, zm, y)) return;
       const double ll = item_loglik(S, x, zm, y);
-      if (!(ll > -CUDART_INF)) continue;
+      if (!(ll > -CUDART_INF)) return;
       const bool tw = item < S.N && item != r && S.twin[item];
       const int pos = atomicAdd(&s_cnt, tw ? 2 : 1);
       if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
       if (tw && pos + 1 < cap) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
+    };
+    if (ea >= 0) {
+      // one thread per probed value: the buckets are short, the probes independent
+      for (int v = threadIdx.x; v < n_probe; v += blockDim.x) {
+        const uint32_t b = bucket_of(S, t, x, ea, v);
+        const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v);
+      }
+    } else {
+      const uint32_t b = S.rec_bkt[r];
+      const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+      for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
+        if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
+        const int q = q0 + threadIdx.x;
+        if (q < hi) visit(t.ids[q], 0);
+      }
     }
     __syncthreads();
     stage_sort_store(S, r, own, ids, lls, s_cnt, cap, &s_off);
@@ -778,7 +811,7 @@ __global__ void __launch_bounds__(TPB) k_huge_scan(DevState S, int r, int cap) {
 __global__ void __launch_bounds__(TPB) k_huge_finish(DevState S, int r, int cap) {
   extern __shared__ unsigned char s_raw[];
   double* lls = reinterpret_cast<double*>(s_raw);
-  int* ids = reinterpret_cast<int*>(lls + cap);
+  int* ids = reinterpret_cast<int*>(lls + pow2_ceil(cap)); // the sort pads the list to a power of two
   __shared__ unsigned long long s_off;
   const int cnt = S.counters[C_COUNT];
   if (cnt <= cap)
