@@ -90,6 +90,7 @@ struct DevState {
   uint16_t *rec_alt;            // [N] key mask of its best pair
   uint8_t *twin;                // [N] 1: potential entity N+r has the same attributes as entity slot r (a
                                 //     singleton of r); it is then not indexed but implied by slot r
+  uint8_t *live0;               // [N] 1: entity slot r held an entity when the sweep started
   uint32_t *rec_bkt;            // [N] bucket inside that table
   const DevTable *tables;       // [2^n_key] indexed by key mask
   int *tab_usage;               // [2][2^n_key] records wanting each full mask / each pair mask
@@ -113,6 +114,7 @@ struct DevState {
   int *act_in, *act_out;        // active records with short candidate lists (thread per record)
   int *actl_in, *actl_out;      // active records with long candidate lists (warp per record)
   int *long_todo;               // records whose candidates did not fit a warp's staging area
+  int *probe_list;              // records that probe several buckets of their table (warp per record)
   int *wide_list;               // records with more than wide_threshold possible links (taken first)
   int *unk_list;                // records without a usable blocking bucket: classified one by one
   int *huge_list;               // records whose bucket is scanned by the whole grid
@@ -157,6 +159,7 @@ enum CounterSlot {
   C_COUNT = 12,     // scratch of k_count_all / k_huge_scan
   C_NHUGE = 13,     // size of huge_list
   C_NOLIST = 14,    // records without a stored list (wide / serial): they may join any entity
+  C_NPROBE = 15,    // size of probe_list
   C_NSLOTS = 16
 };
 

@@ -469,10 +469,10 @@ int ensure_table(exb200_handle* h, int tab) {
 }
 
 // serial path: possible links of up to WIDE_NB records among all the items (counting pass)
-int wide_count(exb200_handle* h, const int* recs, int nb, int* totals, int skip_empty) {
+int wide_count(exb200_handle* h, const int* recs, int nb, int* totals) {
   DevState& S = h->S;
   CK(cudaMemcpyAsync(S.batch_list, recs, sizeof(int) * nb, cudaMemcpyHostToDevice, h->stream));
-  KLAUNCH(h, k_wide_scan<false>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, skip_empty);
+  KLAUNCH(h, k_wide_scan<false>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb);
   KLAUNCH(h, k_wide_offsets, nb, 1024, 0, S);
   CK(cudaMemcpyAsync(totals, S.wl_tot, sizeof(int) * nb, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -620,7 +620,7 @@ int update_links(exb200_handle* h) {
     h->has_index_events = true;
   } else h->has_index_events = false;
   CK(cudaEventRecord(h->ev[3], st));
-  KLAUNCH(h, k_cand, nblk((long long)N, TPB / GL), TPB, 0, S);
+  KLAUNCH(h, k_cand<8>, nblk((long long)N, TPB / 8), TPB, 0, S, (const int*)nullptr, N);
   CK(cudaEventRecord(h->ev[10], st));
   int hc[C_NSLOTS];
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -632,6 +632,12 @@ int update_links(exb200_handle* h) {
     std::fprintf(stderr, "[exb200] %-28s %6d records %8.2f ms\n", what, n, std::chrono::duration<double, std::milli>(now - t_tr).count());
     t_tr = now;
   };
+  if (hc[C_NPROBE] > 0) { // records that probe several buckets: a warp each
+    KLAUNCH(h, k_cand<32>, nblk((long long)hc[C_NPROBE], TPB / 32), TPB, 0, S, (const int*)S.probe_list, hc[C_NPROBE]);
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    lap("multi-bucket probes", hc[C_NPROBE]);
+  }
   if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
     const size_t smem = (size_t)pow2_ceil(std::max(h->long_cap, 1)) * (sizeof(double) + sizeof(int)); // padded for the bitonic sort
     const int n_todo = hc[C_NLONG_TODO];
@@ -652,98 +658,78 @@ int update_links(exb200_handle* h) {
       lap("grid-scanned huge buckets", (int)huge.size());
     }
   }
-  // records without a usable bucket: list their possible links among all the items; those with at
-  // most wide_threshold keep the list like everybody else, the others join the wide records
-  std::vector<int> wide;
+  // Records without a stored list: no usable bucket (their possible links still have to be counted)
+  // or more than wide_threshold possible links in their bucket.  Their possible links among all the
+  // items are listed in batches (k_wide_scan).  Scan order: those with more than
+  // wide_threshold take their turn first, in ascending id, one at a time; the others keep their list
+  // like everybody else and wait for the rounds.
+  std::vector<int> serial; // (record << 1) | needs classification
   if (hc[C_NUNK] > 0) {
     std::vector<int> unk(hc[C_NUNK]);
     CK(cudaMemcpyAsync(unk.data(), S.unk_list, sizeof(int) * unk.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::sort(unk.begin(), unk.end());
-    for (size_t g = 0; g < unk.size(); g += WIDE_NB) {
-      const int nb = (int)std::min<size_t>(WIDE_NB, unk.size() - g);
-      int tot[WIDE_NB];
-      int rc = wide_count(h, unk.data() + g, nb, tot, 1); if (rc) return rc;
-      if (h->trace) for (int q = 0; q < nb; q++) std::fprintf(stderr, "[exb200] record %d without a bucket: %d possible links\n", unk[g + q], tot[q]);
-      int b = 0;
-      while (b < nb) { // groups of short lists that fit the scratch together
-        unsigned long long bases[WIDE_NB], used = 0;
-        int sel[WIDE_NB], n_sel = 0;
-        for (int q = 0; q < nb; q++) bases[q] = ~0ull;
-        for (; b < nb; b++) {
-          if (tot[b] > h->long_cap) {
-            static const int code_wide = -1;
-            CK(cudaMemcpyAsync(S.cand_cnt + unk[g + b], &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
-            wide.push_back(unk[g + b]);
-            continue;
-          }
-          if (used + (unsigned long long)tot[b] > S.wl_cap) break;
-          bases[b] = used; used += (unsigned long long)tot[b]; sel[n_sel++] = b;
-        }
-        if (n_sel == 0) continue;
-        CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
-        KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, 1);
-        KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
-        CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
-      }
+    for (int r : unk) serial.push_back((r << 1) | 1);
+  }
+  if (hc[C_NWIDE] > 0) {
+    std::vector<int> w(hc[C_NWIDE]);
+    CK(cudaMemcpyAsync(w.data(), S.wide_list, sizeof(int) * w.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r : w) serial.push_back(r << 1);
+  }
+  std::sort(serial.begin(), serial.end());
+  CK(cudaEventRecord(h->ev[4], st));
+  std::vector<int> wide; // the records that took their turn first
+  int dk_wide = 0;
+  for (size_t g = 0; g < serial.size(); g += WIDE_NB) {
+    const int nb = (int)std::min<size_t>(WIDE_NB, serial.size() - g);
+    int recs[WIDE_NB], tot[WIDE_NB];
+    for (int q = 0; q < nb; q++) recs[q] = serial[g + q] >> 1;
+    const auto t_a = std::chrono::steady_clock::now();
+    int rc = wide_count(h, recs, nb, tot); if (rc) return rc;
+    if (h->trace) {
+      long long sum = 0;
+      for (int q = 0; q < nb; q++) sum += tot[q];
+      std::fprintf(stderr, "[exb200] serial batch of %d: count pass %.2f ms, %lld possible links\n", nb,
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum);
     }
+    int b = 0;
+    while (b < nb) { // groups whose lists fit the scratch together
+      unsigned long long bases[WIDE_NB], used = 0;
+      int sel[WIDE_NB], n_sel = 0;
+      for (int q = 0; q < nb; q++) bases[q] = ~0ull;
+      const int b0 = b;
+      for (; b < nb; b++) {
+        if (used + (unsigned long long)tot[b] > S.wl_cap) break;
+        bases[b] = used; used += (unsigned long long)tot[b];
+        if ((serial[g + b] & 1) && tot[b] <= h->long_cap) sel[n_sel++] = b; // keeps its list
+      }
+      if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
+      CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb);
+      if (n_sel > 0) {
+        CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
+        KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
+      }
+      for (int q = b0; q < b; q++) {
+        if ((serial[g + q] & 1) && tot[q] <= h->long_cap) continue;
+        if (serial[g + q] & 1) { // no bucket and more than wide_threshold possible links
+          static const int code_wide = -1;
+          CK(cudaMemcpyAsync(S.cand_cnt + recs[q], &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        wide_turn(h, recs[q], bases[q], tot[q]);
+        wide.push_back(recs[q]);
+      }
+      CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
+    }
+  }
+  if (!serial.empty()) {
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved
     CK(cudaStreamSynchronize(st));
-    lap("records without a bucket", (int)unk.size());
   }
   const int n_fence = hc[C_NFENCE]; // candidate pool exhausted: these take their turn serially inside the rounds
-  if (hc[C_NWIDE] > 0) {
-    const size_t n0 = wide.size();
-    wide.resize(n0 + hc[C_NWIDE]);
-    CK(cudaMemcpyAsync(wide.data() + n0, S.wide_list, sizeof(int) * hc[C_NWIDE], cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-  }
   h->stats.n_long = hc[C_NACTL_INIT];
   h->stats.n_wide = (int)wide.size() + n_fence;
-  CK(cudaEventRecord(h->ev[4], st));
-  // Scan order: records with more than wide_threshold possible links take their turn
-  // first, in ascending id, one at a time; then everybody else in ascending id.
-  int dk_wide = 0;
   if (!wide.empty()) {
-    std::sort(wide.begin(), wide.end());
-    for (size_t g = 0; g < wide.size(); g += WIDE_NB) {
-      // possible links of a batch in two passes over the items, then one record after the other
-      // against the sizes its predecessors left
-      const int nb = (int)std::min<size_t>(WIDE_NB, wide.size() - g);
-      int tot[WIDE_NB];
-      const auto t_a = std::chrono::steady_clock::now();
-      int rc = wide_count(h, wide.data() + g, nb, tot, 0); if (rc) return rc;
-      const auto t_b = std::chrono::steady_clock::now();
-      if (h->trace) {
-        long long sum = 0;
-        for (int q = 0; q < nb; q++) sum += tot[q];
-        std::fprintf(stderr, "[exb200] wide batch of %d: count pass %.2f ms, %lld possible links\n", nb,
-                     std::chrono::duration<double, std::milli>(t_b - t_a).count(), sum);
-      }
-      int b = 0;
-      while (b < nb) {
-        unsigned long long bases[WIDE_NB], used = 0;
-        for (int q = 0; q < nb; q++) bases[q] = ~0ull;
-        const int b0 = b;
-        for (; b < nb; b++) {
-          if (used + (unsigned long long)tot[b] > S.wl_cap) break;
-          bases[b] = used; used += (unsigned long long)tot[b];
-        }
-        if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
-        CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
-        KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb, 0);
-        const auto t_c = std::chrono::steady_clock::now();
-        if (h->trace) CK(cudaStreamSynchronize(st));
-        const auto t_d = std::chrono::steady_clock::now();
-        for (int q = b0; q < b; q++) wide_turn(h, wide[g + q], bases[q], tot[q]);
-        CK(cudaStreamSynchronize(st)); // bases are on the stack
-        if (h->trace)
-          std::fprintf(stderr, "[exb200] wide group of %d: fill pass %.2f ms, turns %.2f ms\n", b - b0,
-                       std::chrono::duration<double, std::milli>(t_d - t_c).count(),
-                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_d).count());
-      }
-    }
     CK(cudaMemcpyAsync(&dk_wide, S.counters + C_DK_TOTAL, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(S.act_out, wide.data(), sizeof(int) * wide.size(), cudaMemcpyHostToDevice, st));
     KLAUNCH(h, k_clear_bounds, nblk((long long)wide.size()), TPB, 0, S, S.act_out, (int)wide.size());
@@ -791,10 +777,10 @@ int update_links(exb200_handle* h) {
       // serial path for a record without a stored candidate list
       const int w = hc[C_WIDE_READY];
       int tot = 0;
-      int rc = wide_count(h, &w, 1, &tot, 0); if (rc) return rc;
+      int rc = wide_count(h, &w, 1, &tot); if (rc) return rc;
       const unsigned long long zero_base = 0;
       CK(cudaMemcpyAsync(S.wl_base, &zero_base, sizeof zero_base, cudaMemcpyHostToDevice, st));
-      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1, 0);
+      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1);
       wide_turn(h, w, 0, tot);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
@@ -1124,6 +1110,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.tab_est, (size_t)N_TABLES));
   TRY(dalloc(h, &S.rec_alt, (size_t)N));
   TRY(dalloc(h, &S.twin, (size_t)N));
+  TRY(dalloc(h, &S.live0, (size_t)N));
   TRY(dalloc(h, &S.cand_off, (size_t)N));
   TRY(dalloc(h, &S.cand_cnt, (size_t)N));
   S.pool_cap = std::min<unsigned long long>((8ull + CAND_INLINE) * N + (1ull << 20), 0xFFFFFFF0ull);
@@ -1145,6 +1132,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.actl_in, (size_t)N));
   TRY(dalloc(h, &S.actl_out, (size_t)N));
   TRY(dalloc(h, &S.long_todo, (size_t)N));
+  TRY(dalloc(h, &S.probe_list, (size_t)N));
   TRY(dalloc(h, &S.wide_list, (size_t)N));
   TRY(dalloc(h, &S.unk_list, (size_t)N));
   TRY(dalloc(h, &S.wide_part, (size_t)3 * WIDE_PIECES));

@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
       for (int a = 0; a < S.A; a++) tw &= ye[a] == yn[a];
     }
     S.twin[r] = tw;
+    S.live0[r] = S.ent_size[r] > 0;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < AA; i += blockDim.x) {
@@ -551,17 +552,23 @@ __device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint
 
 // Eight lanes per record (four records per warp): candidate lists are short (1.2-1.4 entries on
 // average), so narrow groups keep four times as many independent gather chains in flight.
-constexpr int GL = 8;
-__global__ void __launch_bounds__(TPB) k_cand(DevState S) {
+// Records served by a table with an unpinned key attribute probe one bucket per value of that
+// attribute: they are listed (probe_list) and taken by a second launch with a whole warp per record
+// (GL = 32, `list` = probe_list), so that their dozens of probes do not hold up a block of ordinary
+// records.
+template <int GL>
+__global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict__ list, int n_rec) {
   __shared__ int s_id[TPB / GL][CAND_SMEM];
   __shared__ double s_ll[TPB / GL][CAND_SMEM];
   __shared__ long long s_stat[2];
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gsh = lane & ~(GL - 1);
-  const unsigned gmask = 0xFFu << gsh;
+  constexpr unsigned GM = GL == 32 ? 0xFFFFFFFFu : (1u << GL) - 1u;
+  const unsigned gmask = GM << gsh;
   const int gib = threadIdx.x / GL;
-  const int r = blockIdx.x * (TPB / GL) + gib;
+  const int gi = blockIdx.x * (TPB / GL) + gib;
+  const int r = gi < n_rec ? (list ? list[gi] : gi) : S.N;
   if (r < S.N) {
     int* ids = s_id[gib];
     double* lls = s_ll[gib];
@@ -573,10 +580,12 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
     int cnt = 0;
     bool wide = tab == 0, spill = false, overflow = false;
     int lo = 0, hi = 0;
+    int ea = -1;
+    bool deferred = false;
     if (!wide) {
       const DevTable& t = S.tables[tab];
-      if (unpinned_key(S, t.mask, x, zm) >= 0) spill = true; // several buckets to probe: k_cand_long
-      else {
+      ea = unpinned_key(S, t.mask, x, zm); // >= 0: the bucket of every value of that attribute is probed
+      if (ea < 0) {
         const uint32_t b = bucket_of(S, t, x);
         if (gl == 0) S.rec_bkt[r] = b;
         lo = b ? t.ptr[b - 1] : 0;
@@ -584,7 +593,22 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
         spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
       }
     }
-    if (!wide && !spill) {
+    // stage the group's hits of one step (lane: item / ok / ll), twins expanded
+    auto stage = [&](int item, bool ok, double ll) {
+      // an indexed slot whose potential entity is its twin stands for both items
+      const bool tw = ok && item < S.N && item != r && S.twin[item];
+      const unsigned m = (__ballot_sync(gmask, ok) >> gsh) & GM, m2 = (__ballot_sync(gmask, tw) >> gsh) & GM;
+      const unsigned below = (1u << gl) - 1u;
+      const int pos = cnt + __popc(m & below) + __popc(m2 & below);
+      const int add = __popc(m) + __popc(m2);
+      if (cnt + add > S.cand_cap) spill = true;
+      else if (ok) {
+        ids[pos] = item; lls[pos] = ll;
+        if (tw) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
+      }
+      cnt += add;
+    };
+    if (!wide && !spill && ea < 0) {
       const int* bucket = S.tables[tab].ids;
       for (int base = lo; base < hi && !spill; base += GL) {
         const int q = base + gl;
@@ -602,22 +626,49 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S) {
             }
           }
         }
-        // an indexed slot whose potential entity is its twin stands for both items
-        const bool tw = ok && item < S.N && item != r && S.twin[item];
-        const unsigned m = (__ballot_sync(gmask, ok) >> gsh) & 0xFFu, m2 = (__ballot_sync(gmask, tw) >> gsh) & 0xFFu;
-        const unsigned below = (1u << gl) - 1u;
-        const int pos = cnt + __popc(m & below) + __popc(m2 & below);
-        const int add = __popc(m) + __popc(m2);
-        if (cnt + add > S.cand_cap) spill = true;
-        else if (ok) {
-          ids[pos] = item; lls[pos] = ll;
-          if (tw) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
-        }
-        cnt += add;
+        stage(item, ok, ll);
       }
       if (gl == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
+    } else if (!wide && ea >= 0 && GL != 32) {
+      if (gl == 0) S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; // a warp of the second launch takes it
+      deferred = true;
+    } else if (!wide && ea >= 0) {
+      // lanes take the probed values round-robin and walk their own (short) buckets
+      const DevTable& t = S.tables[tab];
+      const int D = S.attrs[ea].D;
+      int v_next = gl, v_cur = 0, q = 0, q_end = 0, visited = 0;
+      for (;;) {
+        while (q >= q_end && v_next < D) {
+          const uint32_t b = bucket_of(S, t, x, ea, v_next);
+          q = b ? t.ptr[b - 1] : 0;
+          q_end = t.ptr[b];
+          v_cur = v_next;
+          v_next += GL;
+        }
+        const bool active = q < q_end;
+        if (spill || !__any_sync(gmask, active)) break;
+        int item = -1;
+        bool ok = false;
+        double ll = 0.0;
+        if (active) {
+          item = t.ids[q++];
+          visited++;
+          if (item != S.N + r) {
+            const int* y = S.ent_y + (size_t)item * S.ES;
+            // hashed buckets: an item counts in the probe of its own value only
+            ok = y[ea] == v_cur && item_compatible(S, x, zm, y);
+            if (ok) {
+              ll = item_loglik(S, x, zm, y);
+              ok = ll > -CUDART_INF;
+            }
+          }
+        }
+        stage(item, ok, ll);
+      }
+      atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)visited);
     }
-    if (spill) {
+    if (deferred) {
+    } else if (spill) {
       // long bucket or more candidates than a group can stage: a whole block takes the record
       if (gl == 0) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r;
     } else {
@@ -1160,14 +1211,13 @@ __device__ __forceinline__ void wide_piece(long long n, int n_pieces, int p, lon
 // FILL = false: wl_cnt[b][piece] = possible links of record list[b] in the piece
 // FILL = true : entries of the records with a base (wl_base[b] != ~0) written at
 //               wl_base[b] + (scanned) wl_cnt[b][piece]
-// skip_empty: leave out the slots [0,N) that hold no entity.  That is the specification's count of
-// possible links, valid while no record has moved in this sweep; once records move, sizes change
-// between the two passes, so the serial turns list those slots too (their size is checked again
-// at the record's turn anyway).
+// Slots [0,N) that held no entity when the sweep started (live0) are left out: that is the
+// specification's count of possible links, and it does not change while records move between the
+// two passes (sizes are checked again at the record's turn).
 // W-bit hash of an attribute value; W = 64 / (attributes in the packed word), at most 16
 __device__ __forceinline__ unsigned long long hash_w(int v, int W) { return (unsigned long long)(((uint32_t)v * 0x9E3779B1u) >> (32 - W)); }
 template <bool FILL>
-__global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __restrict__ list, int nb, int skip_empty) {
+__global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __restrict__ list, int nb) {
   // records taking part in this pass, compacted: k -> batch position s_b[k]
   __shared__ ulonglong2 s_mv[WIDE_NB];       // field a of .x: all ones if attribute a is pinned; of .y: hash of the pinned value
   __shared__ int s_x[WIDE_NB][8];            // pinned value of the first 8 attributes (-1: free)
@@ -1218,7 +1268,7 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
       const int4 y0 = *reinterpret_cast<const int4*>(yp), y1 = *reinterpret_cast<const int4*>(yp + 4);
       y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
     }
-    if (skip_empty && live && i < S.N) live = S.ent_size[i] > 0;
+    if (live && i < S.N) live = S.live0[i] != 0;
     unsigned long long P = 0;
 #pragma unroll
     for (int a = 0; a < 8; a++) if (a * W < 64) P |= hash_w(y[a], W) << (W * a);
