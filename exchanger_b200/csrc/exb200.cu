@@ -74,7 +74,8 @@ struct exb200_handle {
   int* d_bsum = nullptr; size_t bsum_cap = 0;
   unsigned long long* d_cl_counts = nullptr;
   double* d_theta = nullptr;
-  uint32_t* d_gen_mask = nullptr; // [N] attributes of each entity that need the general scheme
+  unsigned long long* d_gen_list = nullptr; // (entity << 8 | attribute) pairs that need the general scheme
+  int* d_gen_count = nullptr;
   uint32_t round_ctr = 1;
   int opt_check = 0;
   int trace = std::getenv("EXB200_TRACE") ? 1 : 0;
@@ -864,8 +865,9 @@ int sweep(exb200_handle* h) {
   int rc = update_clust(h); if (rc) return rc;          // clust_params_->update(links_)
   refresh_clust_dev(h);
   rc = update_links(h); if (rc) return rc;              // links_.update(...)
-  KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_mask);   // ents_.update_attributes(...)
-  KLAUNCH_DP(h, k_entities_general, nblk((N + 31) / 32, TPB / 32), TPB, 0, S, h->d_gen_mask);
+  CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), st));
+  KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_list, h->d_gen_count);   // ents_.update_attributes(...)
+  KLAUNCH_DP(h, k_entities_general, 148 * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
   rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
   CK(cudaEventRecord(h->ev[7], st));
   CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
@@ -1156,7 +1158,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &h->pb.part_cnt, (size_t)PA_MAX_TABS * MAX_PARTS));
   TRY(dalloc(h, &h->pb.part_start, (size_t)PA_MAX_TABS * (MAX_PARTS + 1)));
   TRY(dalloc(h, &h->d_cl_counts, 2));
-  TRY(dalloc(h, &h->d_gen_mask, (size_t)N));
+  TRY(dalloc(h, &h->d_gen_list, (size_t)N * (size_t)A)); // worst case (include mode): every entity, every attribute
+  TRY(dalloc(h, &h->d_gen_count, 1));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
   cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);

@@ -1744,26 +1744,57 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
 // neighbourhood row (a subset of entities.cpp:361-383 that holds all the mass).  Lanes take
 // consecutive support entries; weights exp(lw - max) are summed per chunk of 32 with the warp's
 // shuffle scan and chunk totals sequentially - the oracle uses the same association order.
+// logWeightEntityValue for a warp that holds the entity's members in its lanes (lane k: value and
+// file of the k-th member, n_mem <= 32; infinite concentration): the terms of
+// log_weight_entity_value in the same order, without walking the member list again for every
+// candidate value.  Called by all 32 lanes.
+__device__ __forceinline__ double log_weight_members(const DevAttr& t, int v, bool valid, int n_mem, int mx, int mf,
+                                                     int row_first, int row_j) {
+  double lw = valid ? t.logphi[v] : -CUDART_INF;
+  for (int k = 0; k < n_mem; k++) {
+    const int xv = __shfl_sync(FULL, mx, k), f = __shfl_sync(FULL, mf, k);
+    if (xv < 0 || !valid) continue;
+    if (xv == v) lw += t.lt_same[f * t.D + v];
+    else {
+      lw += t.lt_diff[f * t.D + v];
+      lw += (xv == row_first && row_j >= 0) ? t.logp[row_j] : log_distortion_prob(t, v, xv);
+    }
+  }
+  return lw;
+}
+
 template <bool DP>
 __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head) {
   const DevAttr& t = S.attrs[a];
   const int lane = threadIdx.x & 31;
-  int first = -1;
-  for (int r = head; r >= 0 && first < 0; r = S.rec_next[r]) {
-    const int xv = S.rec_x[(size_t)r * S.RS + a];
-    if (xv >= 0) first = xv;
+  // members into lanes (every lane walks the list: the loads are broadcasts)
+  int first = -1, n_mem = 0, mx = -1, mf = 0;
+  for (int r = head; r >= 0; r = S.rec_next[r], n_mem++) {
+    if ((n_mem & 31) == lane || first < 0) {
+      const int* x = S.rec_x + (size_t)r * S.RS;
+      const int xv = x[a];
+      if (first < 0 && xv >= 0) first = xv;
+      if ((n_mem & 31) == lane) { mx = xv; mf = x[S.RS - 1]; }
+    }
   }
+  const bool in_lanes = n_mem <= 32 && !(DP && isfinite(S.conc[a])); // a finite concentration needs the urn terms: list walk
   const int lo = t.is_const ? 0 : t.row[first];
   const int ns = t.is_const ? t.D : 1 + (t.row[first + 1] - lo);
   const int nchunk = (ns + 31) >> 5;
-  auto weight_log = [&](int j) -> double {
-    if (j >= ns) return -CUDART_INF;
-    const int v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
-    if (!t.is_const && j > 0 && v == first) return -CUDART_INF;
-    return log_weight_entity_value<DP>(S, t, a, v, head, t.is_const ? -1 : first, (t.is_const || j == 0) ? -1 : lo + j - 1);
+  auto weight_log = [&](int j) -> double { // called by all lanes
+    const bool valid = j < ns;
+    int v = 0;
+    if (valid) v = t.is_const ? j : (j == 0 ? first : t.col[lo + j - 1]);
+    const bool dup = valid && !t.is_const && j > 0 && v == first;
+    const int rf = t.is_const ? -1 : first, rj = (t.is_const || j == 0) ? -1 : lo + j - 1;
+    if (in_lanes) {
+      return log_weight_members(t, v, valid && !dup, n_mem, mx, mf, rf, rj);
+    }
+    if (!valid || dup) return -CUDART_INF;
+    return log_weight_entity_value<DP>(S, t, a, v, head, rf, rj);
   };
-  // the log-weights of the first chunks stay in registers for the two later passes
-  constexpr int NC = 4;
+  // the log-weights of the first chunks stay in registers for the later passes
+  constexpr int NC = 8;
   double lwc[NC];
   double m = -CUDART_INF;
   for (int c = 0; c < nchunk; c++) {
@@ -1774,33 +1805,49 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m, o); m = y > m ? y : m; }
   if (!(m > -CUDART_INF)) { if (lane == 0) dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
-  double total = 0.0;
-  for (int c = 0; c < nchunk; c++) {
-    const double lw = c < NC ? lwc[c] : weight_log(32 * c + lane);
-    double x = lw > -CUDART_INF ? exp(lw - m) : 0.0;
+  auto chunk_lw = [&](int c) -> double {
+    double lw = 0.0;
+    bool cached = false;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
-    total += __shfl_sync(FULL, x, 31);
-  }
-  const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
-  const double tt = u0.a * total;
-  double run = 0.0;
+    for (int k = 0; k < NC; k++) if (c == k) { lw = lwc[k]; cached = true; }
+    return cached ? lw : weight_log(32 * c + lane);
+  };
+  // chunk totals (lane c % 32 keeps the total of chunk c), summed in chunk order
+  double total = 0.0, tcs = 0.0;
   int lastpos = -1;
   for (int c = 0; c < nchunk; c++) {
-    const int j = 32 * c + lane;
-    const double lw = c < NC ? lwc[c] : weight_log(j);
+    const double lw = chunk_lw(c);
     const double w = lw > -CUDART_INF ? exp(lw - m) : 0.0;
     double x = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
     const double tc = __shfl_sync(FULL, x, 31);
+    if ((c & 31) == lane && c < 32) tcs = tc;
+    total += tc;
     const unsigned pos = __ballot_sync(FULL, w > 0.0);
     if (pos) lastpos = 32 * c + (31 - __clz(pos));
-    if (tt < run + tc) {
-      const unsigned hit = __ballot_sync(FULL, j < ns && tt < run + x);
-      if (hit) {
-        const int jj = 32 * c + (__ffs(hit) - 1);
-        return t.is_const ? jj : (jj == 0 ? first : t.col[lo + jj - 1]);
+  }
+  const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
+  const double tt = u0.a * total;
+  double run = 0.0;
+  for (int c = 0; c < nchunk; c++) {
+    double tc;
+    bool look = true;
+    if (c < 32) { tc = __shfl_sync(FULL, tcs, c); look = tt < run + tc; }
+    if (look) { // the chunk that holds the draw (beyond 32 chunks: every chunk is looked at again)
+      const int j = 32 * c + lane;
+      const double lw = chunk_lw(c);
+      const double w = lw > -CUDART_INF ? exp(lw - m) : 0.0;
+      double x = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
+      tc = __shfl_sync(FULL, x, 31);
+      if (tt < run + tc) {
+        const unsigned hit = __ballot_sync(FULL, j < ns && tt < run + x);
+        if (hit) {
+          const int jj = 32 * c + (__ffs(hit) - 1);
+          return t.is_const ? jj : (jj == 0 ? first : t.col[lo + jj - 1]);
+        }
       }
     }
     run += tc;
@@ -1809,11 +1856,12 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
   return t.is_const ? lastpos : (lastpos == 0 ? first : t.col[lo + lastpos - 1]);
 }
 
-__global__ void __launch_bounds__(TPB) k_entities(DevState S, uint32_t* __restrict__ gen_mask) {
+__global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count) {
+  __shared__ int s_warp[TPB / 32];
+  __shared__ int s_base;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= S.N) return;
   uint32_t need = 0;
-  if (S.ent_size[e] > 0) {
+  if (e < S.N && S.ent_size[e] > 0) {
     const int head = S.ent_head[e];
     int* y = S.ent_y + (size_t)e * S.ES;
     for (int a = 0; a < S.A; a++) {
@@ -1821,29 +1869,37 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, uint32_t* __restri
       if (v >= 0) y[a] = v; else need |= 1u << a;
     }
   }
-  gen_mask[e] = need;
+  // the (entity, attribute) pairs left to the general scheme are listed (one atomic per block)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int mine = __popc(need);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < TPB / 32; k++) { const int c = s_warp[k]; s_warp[k] = t; t += c; }
+    s_base = t ? atomicAdd(gen_count, t) : 0;
+  }
+  __syncthreads();
+  int pos = s_base + s_warp[w] + incl - mine;
+  for (uint32_t m = need; m; m &= m - 1)
+    gen_list[pos++] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)(__ffs(m) - 1);
 }
 
-// one warp per 32 entity slots: the (entity, attribute) pairs flagged by k_entities
+// one warp per listed (entity, attribute) pair, whatever the launch shape
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const uint32_t* __restrict__ gen_mask) {
+__global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const unsigned long long* __restrict__ gen_list,
+                                                          const int* __restrict__ gen_count) {
   const int lane = threadIdx.x & 31;
-  const int base = (blockIdx.x * (TPB / 32) + (threadIdx.x >> 5)) * 32;
-  if (base >= S.N) return;
-  const uint32_t mine = base + lane < S.N ? gen_mask[base + lane] : 0u;
-  unsigned todo = __ballot_sync(FULL, mine != 0u);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int e = base + src;
-    uint32_t mask = __shfl_sync(FULL, mine, src);
-    const int head = S.ent_head[e];
-    while (mask) {
-      const int a = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int v = draw_entity_value_warp<DP>(S, e, a, head);
-      if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
-    }
+  const int n = *gen_count;
+  const int n_warps = gridDim.x * (TPB / 32);
+  for (int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); i < n; i += n_warps) {
+    const unsigned long long p = gen_list[i];
+    const int e = (int)(p >> 8), a = (int)(p & 0xFFu);
+    const int v = draw_entity_value_warp<DP>(S, e, a, S.ent_head[e]);
+    if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
   }
 }
 
