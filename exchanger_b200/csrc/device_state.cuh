@@ -43,6 +43,7 @@ struct DevAttr {
   const int *row, *col;                    // inverted neighbourhood CSR: row w -> entity values v, ascending
   const double *p, *logp;                  // p(w | v) and its log
   const double *cs;                        // per row: inclusive prefix sums of phi(v) mef(v) p(w|v)
+  const double *cs2;                       // ... and of phi(v) (mef(v) p(w|v))^2 (two members with the same value)
   const double *csn;                       // per row: inclusive prefix sums of phi(v) p(w|v) (new-entity draw)
   const double *g;                         // [(NMAX_FAST+1)][D]  phi(v) / (1-psi(v))^n
   const double *aprob; const int *aalias;  // alias tables of g_n, same shape

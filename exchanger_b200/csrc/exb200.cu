@@ -221,14 +221,17 @@ int refresh_phi(exb200_handle* h, int a) {
     logphi[v] = std::log(ha.phi[v]);
     Z += ha.phi[v] / ha.om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
   }
-  std::vector<double> cs(ha.p.size()), csn(ha.p.size());
+  std::vector<double> cs(ha.p.size()), cs2(ha.p.size()), csn(ha.p.size());
   host_parallel(ha.p.size() + (size_t)D, [&](int t, int T) {
     const int w_lo = (int)((int64_t)D * t / T), w_hi = (int)((int64_t)D * (t + 1) / T);
     for (int w = w_lo; w < w_hi && !ha.is_const; w++) {
-      double c = 0.0, cn = 0.0;
+      double c = 0.0, c2 = 0.0, cn = 0.0;
       for (int j = ha.row[w]; j < ha.row[w + 1]; j++) {
-        c += ha.phi[ha.col[j]] * ha.mef[ha.col[j]] * ha.p[j];
+        const double base = ha.phi[ha.col[j]] * ha.mef[ha.col[j]] * ha.p[j];
+        c += base;
         cs[j] = c;
+        c2 += base * (ha.mef[ha.col[j]] * ha.p[j]);
+        cs2[j] = c2;
         cn += ha.phi[ha.col[j]] * ha.p[j];
         csn[j] = cn;
       }
@@ -259,7 +262,7 @@ int refresh_phi(exb200_handle* h, int a) {
   }
   cudaStream_t st = h->stream;
 #define PUT(field, vec) if (!(vec).empty()) CK(cudaMemcpyAsync(const_cast<void*>((const void*)da.field), (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, st));
-  PUT(phi, ha.phi) PUT(logphi, logphi) PUT(logE, logE) PUT(cs, cs) PUT(csn, csn) PUT(g, g) PUT(aprob, aprob) PUT(aalias, aalias)
+  PUT(phi, ha.phi) PUT(logphi, logphi) PUT(logE, logE) PUT(cs, cs) PUT(cs2, cs2) PUT(csn, csn) PUT(g, g) PUT(aprob, aprob) PUT(aalias, aalias)
 #undef PUT
   if (h->d_attrs) CK(cudaMemcpyAsync(h->d_attrs + a, &da, sizeof(DevAttr), cudaMemcpyHostToDevice, st)); // G[] changed
   CK(cudaStreamSynchronize(st)); // the host vectors go out of scope
@@ -346,7 +349,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
 #define NEWD(field, n) rc = dalloc(h, &dp, (size_t)(n)); if (rc) return rc; da.field = dp;
   UPD(psi, ha.psi) UPD(om, ha.om) UPD(logpsi, logpsi) UPD(log1mpsi, log1mpsi) UPD(mef, ha.mef)
   UPI(row, ha.row) UPI(col, ha.col) UPD(p, ha.p) UPD(logp, logp) UPD(pprob, pprob) UPI(palias, palias)
-  NEWD(phi, D) NEWD(logphi, D) NEWD(logE, D) NEWD(cs, ha.p.size()) NEWD(csn, ha.p.size())
+  NEWD(phi, D) NEWD(logphi, D) NEWD(logE, D) NEWD(cs, ha.p.size()) NEWD(cs2, ha.p.size()) NEWD(csn, ha.p.size())
   NEWD(g, (size_t)nt * D) NEWD(aprob, (size_t)nt * D)
   rc = dalloc(h, &ip, (size_t)nt * D); if (rc) return rc; da.aalias = ip;
 #undef UPD

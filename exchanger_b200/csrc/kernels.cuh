@@ -1710,28 +1710,39 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
     return first;
   }
 
-  if (!t.is_const && t.exclude && nobs == 1) {
-    // one observed member value x (singletons above all): every v != x has weight
-    // theta phi(v) mef(v) p(x|v) whose row sums are static, so drawEntityValueIndex
-    // (entities.cpp:351-431) reduces to "keep x" versus a search in the row's prefix sums
-    double th = 0.0;
+  bool same = true; // every observed member value equals the first one
+  if (nobs == 2)
+    for (int r = head; r >= 0; r = S.rec_next[r]) {
+      const int xv = S.rec_x[(size_t)r * S.RS + a];
+      same &= xv < 0 || xv == first;
+    }
+  if (!t.is_const && t.exclude && (nobs == 1 || (nobs == 2 && same && !((S.dp_mask >> a) & 1u)))) {
+    // one observed member value x, held by one member (singletons above all) or by two: every
+    // v != x has weight (prod_m theta_m) phi(v) (mef(v) p(x|v))^nobs whose row sums are static, so
+    // drawEntityValueIndex (entities.cpp:351-431) reduces to "keep x" versus a search in the
+    // row's prefix sums
+    double th = 1.0, wx = t.phi[first];
     for (int r = head; r >= 0; r = S.rec_next[r]) {
       const int* x = S.rec_x + (size_t)r * S.RS;
-      if (x[a] >= 0) th = S.theta[x[S.RS - 1] * S.A + a];
+      if (x[a] >= 0) {
+        const double thm = S.theta[x[S.RS - 1] * S.A + a];
+        th *= thm;
+        wx *= 1.0 - thm * t.mef[first];
+      }
     }
+    const double* cs = nobs == 1 ? t.cs : t.cs2;
     const int lo = t.row[first], hi = t.row[first + 1];
-    const double wx = t.phi[first] * (1.0 - th * t.mef[first]);
-    const double rsum = hi > lo ? t.cs[hi - 1] : 0.0;
+    const double rsum = hi > lo ? cs[hi - 1] : 0.0;
     const double total = wx + th * rsum;
     if (!(total > 0.0) || !isfinite(total)) { dev_fail(S, EXB200_ERR_WEIGHTS, e); return first; }
     const double tt = u0.a * total;
     if (tt < wx || hi == lo) return first;
     const double t2 = tt - wx;
     int a0 = lo, b0 = hi; // first j with t2 < th * cs[j]
-    while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t2 < th * t.cs[mid]) b0 = mid; else a0 = mid + 1; }
+    while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t2 < th * cs[mid]) b0 = mid; else a0 = mid + 1; }
     if (a0 == hi) { // rounding: the first entry that reaches the row total
       a0 = lo; b0 = hi - 1;
-      while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t.cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
+      while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
     }
     return t.col[a0];
   }

@@ -140,6 +140,7 @@ typedef struct {
   int64_t *row;                   /* inverted neighbourhood: row w -> (v, p(w|v)), v ascending */
   int *col; double *p, *logp;
   double *cs;                     /* per row: inclusive prefix sums of phi(v) mef(v) p(w|v) */
+  double *cs2;                    /* ... and of phi(v) (mef(v) p(w|v))^2: two members with the same value */
   double *mef;                    /* max_exp_factor (1 for constant, attribute_index.cpp:49) */
   double **g; double G[NMAX_FAST + 1]; alias_t Tg[NMAX_FAST + 1]; /* phi/(1-psi)^n */
   alias_t Tpsi;
@@ -321,10 +322,13 @@ static int attr_refresh(attr_t *t) {
   }
   if (!t->is_const)
     for (int w = 0; w < D; w++) {
-      double c = 0.0;
+      double c = 0.0, c2 = 0.0;
       for (int64_t j = t->row[w]; j < t->row[w + 1]; j++) {
-        c += t->phi[t->col[j]] * t->mef[t->col[j]] * t->p[j];
+        const double base = t->phi[t->col[j]] * t->mef[t->col[j]] * t->p[j];
+        c += base;
         t->cs[j] = c;
+        c2 += base * (t->mef[t->col[j]] * t->p[j]);
+        t->cs2[j] = c2;
       }
     }
   for (int n = 0; n <= NMAX_FAST; n++) {
@@ -411,6 +415,7 @@ exo *exo_create(const exb200_model *m) {
       t->col = (int *)malloc(sizeof(int) * (nnz + 1)); t->p = (double *)malloc(sizeof(double) * (nnz + 1));
       t->logp = (double *)malloc(sizeof(double) * (nnz + 1));
       t->cs = (double *)malloc(sizeof(double) * (nnz + 1));
+      t->cs2 = (double *)malloc(sizeof(double) * (nnz + 1));
       for (int64_t j = 0; j < nnz; j++) t->row[in->close_val_ids[j] + 1]++;
       for (int w = 0; w < D; w++) t->row[w + 1] += t->row[w];
       int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * D);
@@ -461,7 +466,7 @@ void exo_destroy(exo *s) {
   for (int a = 0; a < s->A; a++) {
     attr_t *t = &s->at[a];
     free(t->psi); free(t->phi); free(t->logpsi); free(t->log1mpsi); free(t->om); free(t->logphi);
-    free(t->logE); free(t->mef); free(t->row); free(t->col); free(t->p); free(t->logp); free(t->cs);
+    free(t->logE); free(t->mef); free(t->row); free(t->col); free(t->p); free(t->logp); free(t->cs); free(t->cs2);
     for (int n = 0; n <= NMAX_FAST; n++) { free(t->g[n]); if (t->Tg[n].prob) alias_free(&t->Tg[n]); }
     free(t->g); if (t->Tpsi.prob) alias_free(&t->Tpsi);
   }
@@ -872,26 +877,33 @@ static int draw_entity_value(exo *s, int e, int a, const int *mem, int n) {
     return first;
   }
 
-  if (!t->is_const && t->exclude && nobs == 1) {
-    /* one observed member value x (singletons above all): every v != x has weight
-       theta * phi(v) mef(v) p(x|v), whose row sums are static, so drawEntityValueIndex
-       (entities.cpp:351-431) reduces to "keep x" versus a search in the row's prefix sums */
-    double th = 0.0;
+  int same = 1; /* every observed member value equals the first one */
+  for (int i = 0; i < n; i++) { int xv = s->x[mem[i] * A + a]; if (xv >= 0 && xv != first) same = 0; }
+  if (!t->is_const && t->exclude && (nobs == 1 || (nobs == 2 && same && !isfinite(t->conc)))) {
+    /* one observed member value x, held by one member (singletons above all) or by two: every
+       v != x has weight (prod_m theta_m) phi(v) (mef(v) p(x|v))^nobs, whose row sums are static, so
+       drawEntityValueIndex (entities.cpp:351-431) reduces to "keep x" versus a search in the row's
+       prefix sums */
+    double th = 1.0, wx = t->phi[first];
     for (int i = 0; i < n; i++)
-      if (s->x[mem[i] * A + a] >= 0) th = s->theta[s->fid[mem[i]] * A + a];
+      if (s->x[mem[i] * A + a] >= 0) {
+        double thm = s->theta[s->fid[mem[i]] * A + a];
+        th *= thm;
+        wx *= 1.0 - thm * t->mef[first];
+      }
+    const double *cs = nobs == 1 ? t->cs : t->cs2;
     int64_t lo = t->row[first], hi = t->row[first + 1];
-    double wx = t->phi[first] * (1.0 - th * t->mef[first]);
-    double rsum = hi > lo ? t->cs[hi - 1] : 0.0;
+    double rsum = hi > lo ? cs[hi - 1] : 0.0;
     double total = wx + th * rsum;
     if (!(total > 0.0) || !isfinite(total)) { set_err(s, e, "no valid entity values for attribute"); return first; }
     double tt = u * total;
     if (tt < wx || hi == lo) return first;
     double t2 = tt - wx;
     int64_t a0 = lo, b0 = hi; /* first j with t2 < th * cs[j] */
-    while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (t2 < th * t->cs[mid]) b0 = mid; else a0 = mid + 1; }
+    while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (t2 < th * cs[mid]) b0 = mid; else a0 = mid + 1; }
     if (a0 == hi) { /* rounding: the first entry that reaches the row total */
       a0 = lo; b0 = hi - 1;
-      while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (t->cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
+      while (a0 < b0) { int64_t mid = (a0 + b0) >> 1; if (cs[mid] >= rsum) b0 = mid; else a0 = mid + 1; }
     }
     return t->col[a0];
   }
