@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -28,14 +29,29 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// array of n values left uninitialised (the neighbourhood-sized host arrays are written in full by
+// several threads: no single-threaded zero fill, pages are first touched in parallel)
+template <class T> struct RawVec {
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  void resize(size_t m) { p.reset(m ? new T[m] : nullptr); n = m; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* data() { return p.get(); }
+  const T* data() const { return p.get(); }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct HostAttr {
   int D = 0, is_const = 1, exclude = 1;
   double s1 = 0, s2 = 0; // Beta prior on theta
   double conc_shape = 0, conc_rate = 0; // Gamma prior on the DP concentration (<= 0: fixed)
   bool dirichlet = false;               // Dirichlet prior on the entity-value distribution
   std::vector<double> psi, phi, mef, om, dir_alpha;
-  std::vector<int> row, col;            // inverted neighbourhood CSR (host copy)
-  std::vector<double> p;
+  std::vector<int> row;                 // inverted neighbourhood CSR (host copy)
+  RawVec<int> col;
+  RawVec<double> p;
 };
 
 struct TableHost {
@@ -62,6 +78,7 @@ struct exb200_handle {
   std::vector<int> ndist, corr;
   DevState S{};                // device pointers (by-value kernel argument)
   std::vector<void*> allocs;
+  std::mutex alloc_mu;          // attribute tables are built by concurrent host threads at create time
   DevAttr* d_attrs = nullptr;
   std::vector<DevAttr> h_attrs;
   std::vector<TableHost> tables; // [2^n_key] indexed by key mask
@@ -103,6 +120,8 @@ struct exb200_handle {
 namespace {
 
 int fail(exb200_handle* h, int code, const std::string& msg) {
+  static std::mutex mu; // attribute tables are built by concurrent threads
+  std::lock_guard<std::mutex> lk(mu);
   if (h) { h->err = msg; }
   else g_create_error = msg;
   return code;
@@ -133,7 +152,7 @@ template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
   if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  h->allocs.push_back(q);
+  { std::lock_guard<std::mutex> lk(h->alloc_mu); h->allocs.push_back(q); }
   *p = (T*)q;
   return EXB200_OK;
 }
@@ -221,7 +240,8 @@ int refresh_phi(exb200_handle* h, int a) {
     logphi[v] = std::log(ha.phi[v]);
     Z += ha.phi[v] / ha.om[v]; // ConstantAttributeIndex::update, attribute_index.cpp:26-34
   }
-  std::vector<double> cs(ha.p.size()), cs2(ha.p.size()), csn(ha.p.size());
+  RawVec<double> cs, cs2, csn;
+  cs.resize(ha.p.size()); cs2.resize(ha.p.size()); csn.resize(ha.p.size());
   host_parallel(ha.p.size() + (size_t)D, [&](int t, int T) {
     const int w_lo = (int)((int64_t)D * t / T), w_hi = (int)((int64_t)D * (t + 1) / T);
     for (int w = w_lo; w < w_hi && !ha.is_const; w++) {
@@ -305,7 +325,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
   }
   // inverted neighbourhood CSR (attribute_index.cpp:125-140)
   ha.row.assign(D + 1, 0);
-  std::vector<double> logp;
+  RawVec<double> logp;
   if (!ha.is_const) {
     const int64_t nnz = in.close_row_ptr[D];
     if (nnz >= (int64_t)std::numeric_limits<int>::max())
@@ -1091,7 +1111,17 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   h->attrs.resize(A); h->h_attrs.resize(A);
   for (int a = 0; a < MAX_ATTRS; a++) h->conc[a] = std::numeric_limits<double>::infinity();
   int maxD = 1;
-  for (int a = 0; a < A; a++) { TRY(build_attr(h, m->attrs[a], a)); maxD = std::max(maxD, m->attrs[a].domain_size); }
+  {
+    // one host thread per attribute (each spreads its neighbourhood work over more threads)
+    std::vector<int> rcs(A, 0);
+    std::vector<std::thread> th;
+    for (int a = 0; a < A; a++) th.emplace_back([&, a] { cudaSetDevice(device); rcs[a] = build_attr(h, m->attrs[a], a); });
+    for (auto& t : th) t.join();
+    for (int a = 0; a < A; a++) {
+      if (rcs[a]) return bail(rcs[a]);
+      maxD = std::max(maxD, m->attrs[a].domain_size);
+    }
+  }
   stage("attribute tables");
   TRY(dalloc(h, &h->d_hist, (size_t)maxD));
   refresh_conc_dev(h);
