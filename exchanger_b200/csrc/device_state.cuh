@@ -29,7 +29,7 @@ constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
 constexpr int CAND_INLINE = 4;      // candidate lists up to this length are stored at pool[CAND_INLINE * record]
 constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
-constexpr int HUGE_CAP = 16386;     // scratch entries of the grid-wide bucket scan
+constexpr int HUGE_BATCH = 512;     // records with a huge bucket scanned per launch
 
 // Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
 // (src/attribute_index.h:12-146) plus the alias tables that replace IndexNonUniformDiscreteDist
@@ -119,7 +119,8 @@ struct DevState {
   int *wide_list;               // records with more than wide_threshold possible links (taken first)
   int *unk_list;                // records without a usable blocking bucket: classified one by one
   int *huge_list;               // records whose bucket is scanned by the whole grid
-  int *huge_id; double *huge_ll;// [HUGE_CAP] scratch of that scan
+  int *huge_id; double *huge_ll;// [HUGE_BATCH][wide_threshold + 2] scratch lists of that scan
+  int *huge_tiles, *huge_cnt;   // [HUGE_BATCH + 1] first tile of each record of the batch, [HUGE_BATCH] list lengths
   int *batch_list;              // [WIDE_NB] records of the current k_wide_scan
   int *wl_sel;                  // [WIDE_NB] batch positions handed to k_wide_store
   int *wl_cnt;                  // [WIDE_NB][WIDE_PIECES] possible links per record and piece, then their scan

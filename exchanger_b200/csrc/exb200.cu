@@ -88,6 +88,7 @@ struct exb200_handle {
   PartBuild pb{};              // partitioned build of the large tables
   int* d_part_tabs = nullptr;
   int pb_tables_cap = 0;
+  int huge_cap_alloc = -1;     // wide_threshold the huge-bucket scratch lists were sized for
   int* d_bsum = nullptr; size_t bsum_cap = 0;
   unsigned long long* d_cl_counts = nullptr;
   double* d_theta = nullptr;
@@ -669,17 +670,25 @@ int update_links(exb200_handle* h) {
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     lap("block-staged candidate lists", n_todo);
-    if (hc[C_NHUGE] > 0) { // buckets so long that the whole grid scans them, one record at a time
-      std::vector<int> huge(hc[C_NHUGE]);
-      CK(cudaMemcpyAsync(huge.data(), S.huge_list, sizeof(int) * huge.size(), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      for (int r : huge) {
-        KLAUNCH(h, k_huge_scan, 148 * 4, TPB, 0, S, r, h->long_cap);
-        KLAUNCH(h, k_huge_finish, 1, TPB, smem, S, r, h->long_cap);
+    if (hc[C_NHUGE] > 0) { // buckets so long that many blocks scan them, HUGE_BATCH records per launch
+      const size_t n_huge = (size_t)hc[C_NHUGE];
+      if (h->huge_cap_alloc < h->long_cap) { // scratch lists sized by the current wide_threshold
+        int rc = dalloc(h, &S.huge_id, (size_t)HUGE_BATCH * (h->long_cap + 2)); if (rc) return rc;
+        rc = dalloc(h, &S.huge_ll, (size_t)HUGE_BATCH * (h->long_cap + 2)); if (rc) return rc;
+        h->huge_cap_alloc = h->long_cap;
+      }
+      for (size_t g = 0; g < n_huge; g += HUGE_BATCH) {
+        const int nb = (int)std::min<size_t>(HUGE_BATCH, n_huge - g);
+        int n_tiles = 0;
+        KLAUNCH(h, k_huge_plan, 1, 1024, 0, S, S.huge_list + g, nb, S.huge_tiles, S.huge_cnt);
+        CK(cudaMemcpyAsync(&n_tiles, S.huge_tiles + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (n_tiles > 0) KLAUNCH(h, k_huge_scan, n_tiles, TPB, 0, S, S.huge_list + g, nb, S.huge_tiles, S.huge_cnt, h->long_cap);
+        KLAUNCH(h, k_huge_finish, nb, TPB, smem, S, S.huge_list + g, S.huge_cnt, h->long_cap);
       }
       CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
-      lap("grid-scanned huge buckets", (int)huge.size());
+      lap("grid-scanned huge buckets", (int)n_huge);
     }
   }
   // Records without a stored list: no usable bucket (their possible links still have to be counted)
@@ -1182,8 +1191,8 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.wl_base, (size_t)WIDE_NB));
   TRY(dalloc(h, &S.wl_sel, (size_t)WIDE_NB));
   TRY(dalloc(h, &S.huge_list, (size_t)N));
-  TRY(dalloc(h, &S.huge_id, (size_t)HUGE_CAP));
-  TRY(dalloc(h, &S.huge_ll, (size_t)HUGE_CAP));
+  TRY(dalloc(h, &S.huge_tiles, (size_t)HUGE_BATCH + 1));
+  TRY(dalloc(h, &S.huge_cnt, (size_t)HUGE_BATCH));
   TRY(dalloc(h, &S.batch_list, (size_t)WIDE_NB));
   TRY(dalloc(h, &h->d_active, (size_t)N_TABLES));
   TRY(dalloc(h, &h->d_remap, (size_t)2 * N_TABLES)); S.tab_remap = h->d_remap;

@@ -835,41 +835,96 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
   }
 }
 
-// A huge bucket is scanned by the whole grid: compatible items of non-zero likelihood go to a
-// scratch list (unordered), then one block sorts and stores it (k_huge_finish).
-__global__ void __launch_bounds__(TPB) k_huge_scan(DevState S, int r, int cap) {
-  const int* x = S.rec_x + (size_t)r * S.RS;
-  const uint32_t zm = S.rec_z[r];
+// Huge buckets (longer than huge_min) are scanned by many blocks at once, HUGE_BATCH records per
+// launch: k_huge_plan cuts every record's bucket into tiles, k_huge_scan takes one tile per block
+// and appends the possible links to the record's scratch list (unordered), k_huge_finish sorts and
+// stores each list with one block per record (or finds the record wide).
+constexpr int HUGE_TILE = 8192;
+__device__ __forceinline__ void huge_bucket(const DevState& S, int r, const DevTable*& t, int& lo, int& hi) {
   int tab = S.tab_remap[S.rec_tab[r]];
   if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
-  const DevTable& t = S.tables[tab];
+  t = &S.tables[tab];
   const uint32_t b = S.rec_bkt[r];
-  const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
-  for (int q = lo + blockIdx.x * blockDim.x + threadIdx.x; q < hi; q += gridDim.x * blockDim.x) {
-    if (S.counters[C_COUNT] > cap) return;
-    const int item = t.ids[q];
+  lo = b ? t->ptr[b - 1] : 0;
+  hi = t->ptr[b];
+}
+// tile_start[i] = first tile of record i of the batch (exclusive scan, one block), [n] = total
+__global__ void __launch_bounds__(1024) k_huge_plan(DevState S, const int* __restrict__ recs, int n, int* __restrict__ tile_start,
+                                                    int* __restrict__ cnt) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    int tiles = 0;
+    if (i < n) {
+      const DevTable* t; int lo, hi;
+      huge_bucket(S, recs[i], t, lo, hi);
+      tiles = (hi - lo + HUGE_TILE - 1) / HUGE_TILE;
+      cnt[i] = 0;
+    }
+    int x = tiles;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int z = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, z, o); if (lane >= o) z += y; }
+      s_w[lane] = z;
+    }
+    __syncthreads();
+    const int excl = s_carry + x - tiles + (w ? s_w[w - 1] : 0);
+    if (i < n) tile_start[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + tiles;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_start[n] = s_carry;
+}
+__global__ void __launch_bounds__(TPB) k_huge_scan(DevState S, const int* __restrict__ recs, int n, const int* __restrict__ tile_start,
+                                                   int* __restrict__ cnt, int cap) {
+  // which record does this tile belong to
+  int a0 = 0, b0 = n; // last i with tile_start[i] <= blockIdx.x
+  while (b0 - a0 > 1) { const int mid = (a0 + b0) >> 1; if (tile_start[mid] <= (int)blockIdx.x) a0 = mid; else b0 = mid; }
+  const int i = a0, r = recs[i];
+  const DevTable* t; int lo, hi;
+  huge_bucket(S, r, t, lo, hi);
+  const int q_lo = lo + ((int)blockIdx.x - tile_start[i]) * HUGE_TILE, q_hi = min(hi, q_lo + HUGE_TILE);
+  const int* x = S.rec_x + (size_t)r * S.RS;
+  const uint32_t zm = S.rec_z[r];
+  int* ids = S.huge_id + (size_t)i * (cap + 2);
+  double* lls = S.huge_ll + (size_t)i * (cap + 2);
+  for (int q = q_lo + threadIdx.x; q < q_hi; q += TPB) {
+    if (cnt[i] > cap) return; // already wide (benign race: any exit is a valid exit)
+    const int item = t->ids[q];
     if (item == S.N + r) continue;
     const int* y = S.ent_y + (size_t)item * S.ES;
     if (!item_compatible(S, x, zm, y)) continue;
     const double ll = item_loglik(S, x, zm, y);
     if (!(ll > -CUDART_INF)) continue;
     const bool tw = item < S.N && item != r && S.twin[item];
-    const int pos = atomicAdd(&S.counters[C_COUNT], tw ? 2 : 1);
-    if (pos < cap) { S.huge_id[pos] = item; S.huge_ll[pos] = ll; }
-    if (tw && pos + 1 < cap) { S.huge_id[pos + 1] = S.N + item; S.huge_ll[pos + 1] = ll; }
+    const int pos = atomicAdd(&cnt[i], tw ? 2 : 1);
+    if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
+    if (tw && pos + 1 < cap) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
   }
 }
-__global__ void __launch_bounds__(TPB) k_huge_finish(DevState S, int r, int cap) {
+__global__ void __launch_bounds__(TPB) k_huge_finish(DevState S, const int* __restrict__ recs, const int* __restrict__ cnt, int cap) {
   extern __shared__ unsigned char s_raw[];
   double* lls = reinterpret_cast<double*>(s_raw);
   int* ids = reinterpret_cast<int*>(lls + pow2_ceil(cap)); // the sort pads the list to a power of two
   __shared__ unsigned long long s_off;
-  const int cnt = S.counters[C_COUNT];
-  if (cnt <= cap)
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { ids[i] = S.huge_id[i]; lls[i] = S.huge_ll[i]; }
+  const int i = blockIdx.x, r = recs[i];
+  const int n = cnt[i];
+  const int* gid = S.huge_id + (size_t)i * (cap + 2);
+  const double* gll = S.huge_ll + (size_t)i * (cap + 2);
+  if (n <= cap)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { ids[k] = gid[k]; lls[k] = gll[k]; }
   __syncthreads();
-  stage_sort_store(S, r, S.lambda[r], ids, lls, cnt, cap, &s_off);
-  if (threadIdx.x == 0) S.counters[C_COUNT] = 0;
+  stage_sort_store(S, r, S.lambda[r], ids, lls, n, cap, &s_off);
 }
 
 // ------------------------------------------------------------------------------------------
