@@ -550,6 +550,7 @@ __device__ __forceinline__ void finish_candidates(const DevState& S, int r, uint
   else if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
 }
 
+constexpr int WARP_BUCKET_MAX = 8192; // buckets up to this length are scanned by one warp
 // Eight lanes per record (four records per warp): candidate lists are short (1.2-1.4 entries on
 // average), so narrow groups keep four times as many independent gather chains in flight.
 // Records served by a table with an unpinned key attribute probe one bucket per value of that
@@ -590,7 +591,15 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict_
         if (gl == 0) S.rec_bkt[r] = b;
         lo = b ? t.ptr[b - 1] : 0;
         hi = t.ptr[b];
-        spill = hi - lo > S.bucket_cap; // a long bucket is scanned by a whole block (k_cand_long)
+        // a bucket longer than bucket_cap is left to a whole warp (second launch), a very long one
+        // to a whole block (k_cand_long)
+        if (GL == 32) spill = hi - lo > WARP_BUCKET_MAX;
+        else if (hi - lo > S.bucket_cap) {
+          if (hi - lo <= WARP_BUCKET_MAX && S.bucket_cap > 0) {
+            if (gl == 0) S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r;
+            deferred = true;
+          } else spill = true;
+        }
       }
     }
     // stage the group's hits of one step (lane: item / ok / ll), twins expanded
@@ -608,7 +617,7 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict_
       }
       cnt += add;
     };
-    if (!wide && !spill && ea < 0) {
+    if (!wide && !spill && !deferred && ea < 0) {
       const int* bucket = S.tables[tab].ids;
       for (int base = lo; base < hi && !spill; base += GL) {
         const int q = base + gl;
