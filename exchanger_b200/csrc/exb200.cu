@@ -645,7 +645,7 @@ int update_links(exb200_handle* h) {
     h->has_index_events = true;
   } else h->has_index_events = false;
   CK(cudaEventRecord(h->ev[3], st));
-  KLAUNCH(h, k_cand<8>, nblk((long long)N, TPB / 8), TPB, 0, S, (const int*)nullptr, N);
+  KLAUNCH(h, (k_cand<8, 64>), nblk((long long)N, 64 / 8), 64, 0, S, (const int*)nullptr, N);
   CK(cudaEventRecord(h->ev[10], st));
   int hc[C_NSLOTS];
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -658,7 +658,7 @@ int update_links(exb200_handle* h) {
     t_tr = now;
   };
   if (hc[C_NPROBE] > 0) { // records that probe several buckets: a warp each
-    KLAUNCH(h, k_cand<32>, nblk((long long)hc[C_NPROBE], TPB / 32), TPB, 0, S, (const int*)S.probe_list, hc[C_NPROBE]);
+    KLAUNCH(h, (k_cand<32, 128>), nblk((long long)hc[C_NPROBE], 128 / 32), 128, 0, S, (const int*)S.probe_list, hc[C_NPROBE]);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     lap("multi-bucket probes", hc[C_NPROBE]);

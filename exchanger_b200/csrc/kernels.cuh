@@ -557,18 +557,20 @@ constexpr int WARP_BUCKET_MAX = 8192; // buckets up to this length are scanned b
 // attribute: they are listed (probe_list) and taken by a second launch with a whole warp per record
 // (GL = 32, `list` = probe_list), so that their dozens of probes do not hold up a block of ordinary
 // records.
-template <int GL>
-__global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict__ list, int n_rec) {
-  __shared__ int s_id[TPB / GL][CAND_SMEM];
-  __shared__ double s_ll[TPB / GL][CAND_SMEM];
-  __shared__ long long s_stat[2];
+// Small blocks (BT threads) for the first launch: a block lives as long as its slowest record.
+template <int GL, int BT>
+__global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__ list, int n_rec) {
+  __shared__ int s_id[BT / GL][CAND_SMEM];
+  __shared__ double s_ll[BT / GL][CAND_SMEM];
+  __shared__ unsigned s_stat[2], s_done; // candidates stored / bucket items visited by this block; warps finished
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  if (threadIdx.x == 2) s_done = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, gl = lane & (GL - 1), gsh = lane & ~(GL - 1);
   constexpr unsigned GM = GL == 32 ? 0xFFFFFFFFu : (1u << GL) - 1u;
   const unsigned gmask = GM << gsh;
   const int gib = threadIdx.x / GL;
-  const int gi = blockIdx.x * (TPB / GL) + gib;
+  const int gi = blockIdx.x * (BT / GL) + gib;
   const int r = gi < n_rec ? (list ? list[gi] : gi) : S.N;
   if (r < S.N) {
     int* ids = s_id[gib];
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict_
         }
         stage(item, ok, ll);
       }
-      if (gl == 0) { atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)(hi - lo)); }
+      if (gl == 0) atomicAdd(&s_stat[1], (unsigned)(hi - lo));
     } else if (!wide && ea >= 0 && GL != 32) {
       if (gl == 0) S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; // a warp of the second launch takes it
       deferred = true;
@@ -674,7 +676,7 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict_
         }
         stage(item, ok, ll);
       }
-      atomicAdd((unsigned long long*)&s_stat[1], (unsigned long long)visited);
+      atomicAdd(&s_stat[1], (unsigned)visited);
     }
     if (deferred) {
     } else if (spill) {
@@ -726,13 +728,22 @@ __global__ void __launch_bounds__(TPB) k_cand(DevState S, const int* __restrict_
         bool other = code < 0;
         if (code >= 0) for (int i = 0; i < cnt; i++) other |= ids[i] != own;
         finish_candidates(S, r, off, code, other);
-        if (code >= 0) atomicAdd((unsigned long long*)&s_stat[0], (unsigned long long)cnt);
+        if (code >= 0) atomicAdd(&s_stat[0], (unsigned)cnt);
       }
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 2 && s_stat[threadIdx.x])
-    atomicAdd((unsigned long long*)&S.counters64[threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+  // the last warp to finish adds the block's statistics to the global counters (no barrier: the
+  // other warps are gone by then)
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    if (atomicAdd(&s_done, 1u) == BT / 32 - 1) {
+      for (int k = 0; k < 2; k++) {
+        const unsigned v = atomicAdd(&s_stat[k], 0u);
+        if (v) atomicAdd((unsigned long long*)&S.counters64[k], (unsigned long long)v);
+      }
+    }
+  }
 }
 
 __host__ __device__ __forceinline__ int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
