@@ -898,7 +898,7 @@ int sweep(exb200_handle* h) {
   refresh_clust_dev(h);
   rc = update_links(h); if (rc) return rc;              // links_.update(...)
   CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), st));
-  KLAUNCH(h, k_entities, nblk(N), TPB, 0, S, h->d_gen_list, h->d_gen_count);   // ents_.update_attributes(...)
+  KLAUNCH(h, k_entities, nblk(N, 64), 64, 0, S, h->d_gen_list, h->d_gen_count);   // ents_.update_attributes(...)
   KLAUNCH_DP(h, k_entities_general, 148 * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
   rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
   CK(cudaEventRecord(h->ev[7], st));

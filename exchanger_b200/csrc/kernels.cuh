@@ -1943,7 +1943,7 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
 }
 
 __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count) {
-  __shared__ int s_warp[TPB / 32];
+  __shared__ int s_warp[TPB / 32]; // (launched with blocks of up to TPB threads)
   __shared__ int s_base;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t need = 0;
@@ -1965,7 +1965,7 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
-    for (int k = 0; k < TPB / 32; k++) { const int c = s_warp[k]; s_warp[k] = t; t += c; }
+    for (int k = 0; k < (int)blockDim.x / 32; k++) { const int c = s_warp[k]; s_warp[k] = t; t += c; }
     s_base = t ? atomicAdd(gen_count, t) : 0;
   }
   __syncthreads();
