@@ -264,7 +264,7 @@ def run_ours(opt, n_records, kind, desc):
             "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": 1e3 * t_max / opt.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind,
-                       "distort_prior": "Beta(1,50)", "parallelism": f"{world} independent chain(s)",
+                       "distort_prior": "Beta(1,50)", "name_frequencies": "Zipf exponent 0.5 (synthetic.py)", "parallelism": f"{world} independent chain(s)",
                        "burnin_sweeps": opt.burnin, "model_build_s": round(t_build, 1),
                        "l2": f"inputs larger than L2: resident state {n_records * 150 / 1e6:.0f} MB streamed every sweep"},
             "clocks": clk, "gpu_launches": int(launches),
