@@ -164,7 +164,7 @@ typedef struct exb200_stats {
   int32_t n_entities;     /* K after the sweep                                     */
   int32_t n_links_changed;/* records whose cluster changed                         */
   int32_t n_tables;       /* blocking tables built                                 */
-  int32_t n_long;         /* records handled by the warp-per-record path (long lists)      */
+  int32_t n_long;         /* records whose turn is taken by a block (lists longer than long_min) */
   float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
       ms_distort, ms_total, ms_cand_long, ms_wide, ms_index_count, ms_index_fill; /* CUDA-event times */
 } exb200_stats;
@@ -183,7 +183,11 @@ int exb200_create(const exb200_model* model, int device, exb200_handle** out);
 
 /* Run the sampling loop of sample() (sample.cpp:171-202): sweeps until n_samples
    are saved.  abort_cb (may be NULL) replaces Progress::check_abort (sample.cpp:200);
-   progress_cb (may be NULL) replaces p.increment() (sample.cpp:201). */
+   progress_cb (may be NULL) replaces p.increment() (sample.cpp:201).
+   A saved links row leaves the device behind the next sweep (snapshot -> pinned buffer on a copy
+   stream -> the caller's array, written by a helper thread of the library); every row has landed
+   when the call returns, and out->n_saved tells how many did if it returns an error.  The
+   callbacks are only ever called on the calling thread. */
 int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin_interval,
                int32_t burnin_interval, exb200_history* out,
                int (*abort_cb)(void*), void (*progress_cb)(void*, int32_t), void* ctx);
@@ -217,14 +221,19 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
      "wide_threshold" (default 4096, <= 16384): records with more possible links than this
                  take their turn first, in ascending id, before all other records
    The others change no result, only how the work is scheduled:
-     "cand_cap"  candidates a warp stages per record (<= 256); more go to a block-wide kernel
-     "long_min"  list length above which a record's turn is taken by a warp instead of a thread
-     "bucket_cap" bucket length above which a block instead of a warp scans the bucket
-     "huge_min"  bucket length above which the whole grid scans the bucket
+     "cand_cap"  candidates a group of lanes stages per record (<= 64); more go to a block-wide kernel
+     "long_min"  list length above which a record's turn is taken by a block instead of a thread
+     "bucket_cap" bucket length above which a whole warp (up to 8192 items) or a block scans the
+                 bucket; 0 sends every record to the block-wide kernel
+     "huge_min"  bucket length above which the bucket is cut into tiles scanned by many blocks
      "est_threshold" expected bucket size above which the blocking key uses every usable attribute
      "table_cost_permille" assumed cost of building one blocking table, in bucket visits per item
                  x 1000 (default 1000); 0 builds every table that some record wants
-     "check"     recompute sizes / member lists / K from the links after every sweep and compare */
+     "table_min_usage" (default 16) a key mask wanted by at most this many records gets no table of
+                 its own: another table serves them, or the batched scan over all items
+     "index_partitioned" 0 builds every table with global atomics (debugging)
+     "check"     recompute sizes / member lists / K from the links after every sweep and compare
+     "trace"     print the phases of every sweep to stderr (also: environment EXB200_TRACE) */
 int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
 
 void exb200_destroy(exb200_handle* h);
