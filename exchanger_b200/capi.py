@@ -88,7 +88,7 @@ class CStats(C.Structure):
         ("ms_cand", C.c_float), ("ms_rounds", C.c_float), ("ms_canon", C.c_float),
         ("ms_entities", C.c_float), ("ms_distort", C.c_float), ("ms_total", C.c_float),
         ("ms_cand_long", C.c_float), ("ms_wide", C.c_float), ("ms_index_count", C.c_float),
-        ("ms_index_fill", C.c_float),
+        ("ms_index_fill", C.c_float), ("n_probe", C.c_int32), ("n_huge", C.c_int32),
     ]
 
 

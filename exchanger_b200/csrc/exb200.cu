@@ -657,6 +657,8 @@ int update_links(exb200_handle* h) {
     std::fprintf(stderr, "[exb200] %-28s %6d records %8.2f ms\n", what, n, std::chrono::duration<double, std::milli>(now - t_tr).count());
     t_tr = now;
   };
+  h->stats.n_probe = hc[C_NPROBE];
+  h->stats.n_huge = 0;
   if (hc[C_NPROBE] > 0) { // records that probe several buckets: a warp each
     KLAUNCH(h, (k_cand<32, 128>), nblk((long long)hc[C_NPROBE], 128 / 32), 128, 0, S, (const int*)S.probe_list, hc[C_NPROBE]);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -672,6 +674,7 @@ int update_links(exb200_handle* h) {
     lap("block-staged candidate lists", n_todo);
     if (hc[C_NHUGE] > 0) { // buckets so long that many blocks scan them, HUGE_BATCH records per launch
       const size_t n_huge = (size_t)hc[C_NHUGE];
+      h->stats.n_huge = hc[C_NHUGE];
       if (h->huge_cap_alloc < h->long_cap) { // scratch lists sized by the current wide_threshold
         int rc = dalloc(h, &S.huge_id, (size_t)HUGE_BATCH * (h->long_cap + 2)); if (rc) return rc;
         rc = dalloc(h, &S.huge_ll, (size_t)HUGE_BATCH * (h->long_cap + 2)); if (rc) return rc;

@@ -167,6 +167,9 @@ typedef struct exb200_stats {
   int32_t n_long;         /* records whose turn is taken by a block (lists longer than long_min) */
   float ms_clust, ms_prep, ms_index, ms_cand, ms_rounds, ms_canon, ms_entities,
       ms_distort, ms_total, ms_cand_long, ms_wide, ms_index_count, ms_index_fill; /* CUDA-event times */
+  int32_t n_probe;        /* records taken by a whole warp in the second candidate launch (several
+                             buckets to probe, or one bucket of 513..8192 items)                  */
+  int32_t n_huge;         /* records whose bucket was cut into tiles (longer than huge_min)       */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;

@@ -64,10 +64,11 @@ def test_wide_records_take_their_turn_first(threshold):
     assert sum(s["n_wide"] for s in stats) > (50 if threshold == 0 else 0)
 
 
-def test_serial_fence_inside_the_rounds():
+def test_records_without_a_usable_blocking_attribute():
     """Records without any usable blocking attribute (here: every attribute missing or distorted
-    in a data set with many NAs) but few possible links are not wide by the specification: they
-    take their turn serially, in id order, inside the rounds."""
+    in a data set with many NAs): their possible links are listed by the batched scan over all the
+    items; those with few of them keep that list and wait for the rounds like everybody else, the
+    others are wide by the specification and go first."""
     cols, _ = load_rldata("rldata500", 200)
     rng = np.random.default_rng(1)
     for k in ("fname_c1", "lname_c1", "by", "bm", "bd"):
@@ -159,6 +160,21 @@ def test_results_do_not_depend_on_batching_thresholds():
             states.append(g.state())
     for s in states[1:]:
         assert_same_state(states[0], s)
+
+
+def test_multi_bucket_probes_and_warp_scanned_buckets():
+    """Expensive tables (table_cost_permille high) leave rare key masks to tables with one extra
+    small-domain attribute whose every value is probed; bucket_cap=8 sends mid-sized buckets to the
+    warp-per-record launch.  Same chain as the oracle either way."""
+    cols, _ = load_rldata("rldata10000", 3000)
+    rng = np.random.default_rng(5)
+    for k in ("fname_c1", "lname_c1", "by"):  # missing values make rare key masks
+        cols[k] = [None if rng.random() < 0.15 else v for v in cols[k]]
+    m = exchanger(cols, readme_attr_params(), PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    stats = lockstep(m, 6, table_cost_permille=20000, table_min_usage=0, bucket_cap=8)
+    assert sum(s["n_probe"] for s in stats) > 100
+    stats = lockstep(m, 4, bucket_cap=0, huge_min=4)  # block-staged lists and tiled buckets
+    assert sum(s["n_huge"] for s in stats) > 10
 
 
 def test_run_inference_schedule_history_and_resume():
