@@ -977,7 +977,11 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EXB200_ERR_NO_DEVICE, "cudaSetDevice failed");
 
   exb200_handle* h = new exb200_handle();
-  auto bail = [&](int rc) { g_create_error = h->err; exb200_destroy(h); return rc; };
+  // the attribute tables are built by host threads while the records are loaded on the device
+  std::vector<std::thread> attr_threads;
+  std::vector<int> attr_rc(A, 0);
+  auto join_attr = [&] { for (auto& t : attr_threads) if (t.joinable()) t.join(); };
+  auto bail = [&](int rc) { join_attr(); g_create_error = h->err; exb200_destroy(h); return rc; };
   auto t_stage = std::chrono::steady_clock::now();
   auto stage = [&](const char* what) { // EXB200_TRACE: where the time of create goes
     if (!h->trace) return;
@@ -1004,6 +1008,11 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   S.N = N; S.A = A; S.F = F; S.RS = h->RS; S.ES = h->ES; S.seed = h->seed;
   int rc = 0;
 #define TRY(x) do { rc = (x); if (rc) return bail(rc); } while (0)
+  h->attrs.resize(A); h->h_attrs.resize(A);
+  for (int a = 0; a < MAX_ATTRS; a++) h->conc[a] = std::numeric_limits<double>::infinity();
+  // one host thread per attribute (each spreads its neighbourhood work over more threads)
+  for (int a = 0; a < A; a++)
+    attr_threads.emplace_back([&, a] { cudaSetDevice(device); attr_rc[a] = build_attr(h, m->attrs[a], a); });
   {
     // labels: small non-negative integers (what exchanger() and this library produce) index a
     // direct table; anything else is first renamed to the column of ent_attrs
@@ -1120,19 +1129,11 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     for (int a = 0; a < A; a++) h->theta[f * A + a] = m->distort_probs[f + (size_t)F * a];
   stage("state on device");
   TRY(dalloc(h, &h->d_theta, (size_t)F * A)); S.theta = h->d_theta;
-  h->attrs.resize(A); h->h_attrs.resize(A);
-  for (int a = 0; a < MAX_ATTRS; a++) h->conc[a] = std::numeric_limits<double>::infinity();
   int maxD = 1;
-  {
-    // one host thread per attribute (each spreads its neighbourhood work over more threads)
-    std::vector<int> rcs(A, 0);
-    std::vector<std::thread> th;
-    for (int a = 0; a < A; a++) th.emplace_back([&, a] { cudaSetDevice(device); rcs[a] = build_attr(h, m->attrs[a], a); });
-    for (auto& t : th) t.join();
-    for (int a = 0; a < A; a++) {
-      if (rcs[a]) return bail(rcs[a]);
-      maxD = std::max(maxD, m->attrs[a].domain_size);
-    }
+  join_attr();
+  for (int a = 0; a < A; a++) {
+    if (attr_rc[a]) return bail(attr_rc[a]);
+    maxD = std::max(maxD, m->attrs[a].domain_size);
   }
   stage("attribute tables");
   TRY(dalloc(h, &h->d_hist, (size_t)maxD));
