@@ -25,24 +25,73 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 }
 // bucket of an attribute tuple y under the key mask of table t (mixed-radix key over the key
 // attributes in the mask; hashed when the key space is larger than the bucket array)
-// (attribute `ea`, if any, takes the value `ev` instead of y[ea])
-__device__ __forceinline__ uint32_t bucket_of(const DevState& S, const DevTable& t, const int* y, int ea = -1, int ev = 0) {
+// (attributes `ea` / `eb`, if any, take the values `ev` / `fv` instead of y[.])
+__device__ __forceinline__ uint32_t bucket_of(const DevState& S, const DevTable& t, const int* y, int ea = -1, int ev = 0,
+                                              int eb = -1, int fv = 0) {
   uint64_t key = 0;
   for (uint32_t m = t.mask; m; m &= m - 1) {
     const int a = S.key_attr[__ffs(m) - 1];
-    key = key * (uint64_t)S.attrs[a].D + (uint64_t)(a == ea ? ev : y[a]);
+    key = key * (uint64_t)S.attrs[a].D + (uint64_t)(a == ea ? ev : (a == eb ? fv : y[a]));
   }
   return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
 }
 // A record may be served by a table with ONE key attribute it cannot pin (missing or distorted):
 // it then probes the bucket of every value of that attribute (a few dozen for the categorical
 // ones), which saves building a table of its own for a rare key mask.  Returns that attribute or -1.
-__device__ __forceinline__ int unpinned_key(const DevState& S, uint32_t mask, const int* x, uint32_t zm) {
+// The values of an unpinned attribute whose buckets the record probes: when the record's value is
+// observed but distorted and the attribute has a neighbourhood index (string attribute, infinite
+// concentration), only the entity values v with p(x|v) > 0 can give a possible link - the
+// neighbourhood row of x (what getPossibleLinks unions, links.cpp:132-171); otherwise every value of
+// the (small) domain.
+struct ProbeValues {
+  const int* col; // row entries (nullptr: the whole domain 0..n-1)
+  int n;
+  __device__ __forceinline__ int value(int j) const { return col ? col[j] : j; }
+};
+__device__ __forceinline__ ProbeValues probe_values(const DevState& S, int ea, const int* x, uint32_t zm) {
+  const DevAttr& t = S.attrs[ea];
+  ProbeValues p;
+  if (x[ea] >= 0 && ((zm >> ea) & 1u) && !t.is_const && !((S.dp_mask >> ea) & 1u)) {
+    p.col = t.col + t.row[x[ea]];
+    p.n = t.row[x[ea] + 1] - t.row[x[ea]];
+  } else { p.col = nullptr; p.n = t.D; }
+  return p;
+}
+// The probes of one record in one table: up to two unpinned key attributes, every combination of
+// their possible values (n_un = 3: more than two, or too many combinations - the table cannot
+// serve the record and its possible links are listed by the batched scan over all the items).
+constexpr int MAX_PROBES = 16384;
+struct Probe {
+  int n_un, a1, a2, count;
+  ProbeValues p1, p2;
+  __device__ __forceinline__ void values(int j, int& v1, int& v2) const {
+    v1 = p1.value(j % p1.n);
+    v2 = n_un == 2 ? p2.value(j / p1.n) : 0;
+  }
+  __device__ __forceinline__ uint32_t bucket(const DevState& S, const DevTable& t, const int* x, int v1, int v2) const {
+    return bucket_of(S, t, x, a1, v1, n_un == 2 ? a2 : -1, v2);
+  }
+  __device__ __forceinline__ bool own_probe(const int* y, int v1, int v2) const { // hashed buckets: an item counts in the probe of its own values only
+    return y[a1] == v1 && (n_un < 2 || y[a2] == v2);
+  }
+};
+__device__ __forceinline__ Probe make_probe(const DevState& S, uint32_t mask, const int* x, uint32_t zm) {
+  Probe p;
+  p.n_un = 0; p.a1 = p.a2 = -1; p.count = 1;
+  p.p1.col = p.p2.col = nullptr; p.p1.n = p.p2.n = 1;
   for (uint32_t m = mask; m; m &= m - 1) {
     const int a = S.key_attr[__ffs(m) - 1];
-    if (x[a] < 0 || ((zm >> a) & 1u)) return a;
+    if (x[a] >= 0 && !((zm >> a) & 1u)) continue;
+    if (p.n_un == 0) { p.a1 = a; p.p1 = probe_values(S, a, x, zm); }
+    else if (p.n_un == 1) { p.a2 = a; p.p2 = probe_values(S, a, x, zm); }
+    p.n_un++;
   }
-  return -1;
+  if (p.n_un > 2) p.n_un = 3;
+  else if (p.n_un >= 1) {
+    const long long c = (long long)p.p1.n * (long long)(p.n_un == 2 ? p.p2.n : 1);
+    if (c > MAX_PROBES) p.n_un = 3; else p.count = (int)c;
+  }
+  return p;
 }
 
 // log p(w | v) = log get_distortion_prob(v, w)   (src/attribute_index.cpp:36-47, 77-92)
@@ -133,6 +182,8 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
     int b1 = -1, b2 = -1;        // key positions of the most selective observed non-distorted attributes
     uint32_t nd_mask = 0;
     double s1 = 2.0, s2 = 2.0;
+    bool pinned_string = false;  // some string attribute is observed and not distorted
+    int soft = -1, soft_len = 0; // key position of the distorted string attribute with the shortest neighbourhood row
     for (int a = 0; a < S.A; a++) {
       const DevAttr& t = S.attrs[a];
       const int xv = x[a];
@@ -146,6 +197,7 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
         if (!zz) { // links.cpp:440-442
           yv = xv;
           if (S.key_pos[a] >= 0) {
+            pinned_string |= !t.is_const;
             nd_mask |= 1u << S.key_pos[a];
             const double sel = t.psi[xv];
             if (sel < s1) { s2 = s1; b2 = b1; s1 = sel; b1 = S.key_pos[a]; }
@@ -166,6 +218,7 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
           }
         } else { // links.cpp:454-461: phi(v) p(x | v) over the neighbourhood of x (static prefix sums)
           const int lo = t.row[xv], hi = t.row[xv + 1];
+          if (S.key_pos[a] >= 0 && !((S.dp_mask >> a) & 1u) && (soft < 0 || hi - lo < soft_len)) { soft = S.key_pos[a]; soft_len = hi - lo; }
           const double tot = hi > lo ? t.csn[hi - 1] : 0.0;
           yv = xv;
           if (tot > 0.0) {
@@ -189,7 +242,14 @@ __global__ void __launch_bounds__(TPB) k_prep(DevState S) {
     S.fin[r] = 0;
     // blocking table
     uint32_t tab = 0, pair = 0;
-    if (b1 >= 0) {
+    if (b1 >= 0 && !pinned_string && soft >= 0 && soft_len <= 1024) {
+      // No pinned name, but a distorted one: only entity values in its neighbourhood row can be
+      // linked (links.cpp:132-171), so the record probes those buckets of the (name, best pinned
+      // attribute) table instead of scanning the long buckets of the date-only tables.
+      pair = (1u << b1) | (1u << soft);
+      tab = pair;
+      atomicAdd(&s_usage[AA + pair], 1);
+    } else if (b1 >= 0) {
       pair = (1u << b1) | (b2 >= 0 ? 1u << b2 : 0u);
       const double est = 2.0 * (double)S.N * s1 * (b2 >= 0 ? s2 : 1.0);
       tab = est > S.est_threshold ? nd_mask : pair;
@@ -583,12 +643,14 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
     int cnt = 0;
     bool wide = tab == 0, spill = false, overflow = false;
     int lo = 0, hi = 0;
-    int ea = -1;
     bool deferred = false;
+    Probe pr;
+    pr.n_un = 0;
     if (!wide) {
       const DevTable& t = S.tables[tab];
-      ea = unpinned_key(S, t.mask, x, zm); // >= 0: the bucket of every value of that attribute is probed
-      if (ea < 0) {
+      pr = make_probe(S, t.mask, x, zm); // n_un >= 1: the buckets of the unpinned attributes' possible values are probed
+      if (pr.n_un == 3) { wide = true; pr.n_un = 0; } // not served by this table after all: batched scan over all items
+      else if (pr.n_un == 0) {
         const uint32_t b = bucket_of(S, t, x);
         if (gl == 0) S.rec_bkt[r] = b;
         lo = b ? t.ptr[b - 1] : 0;
@@ -619,7 +681,7 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
       }
       cnt += add;
     };
-    if (!wide && !spill && !deferred && ea < 0) {
+    if (!wide && !spill && !deferred && pr.n_un == 0) {
       const int* bucket = S.tables[tab].ids;
       for (int base = lo; base < hi && !spill; base += GL) {
         const int q = base + gl;
@@ -640,21 +702,23 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
         stage(item, ok, ll);
       }
       if (gl == 0) atomicAdd(&s_stat[1], (unsigned)(hi - lo));
-    } else if (!wide && ea >= 0 && GL != 32) {
-      if (gl == 0) S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; // a warp of the second launch takes it
-      deferred = true;
-    } else if (!wide && ea >= 0) {
+    } else if (!wide && pr.n_un > 0 && GL != 32) {
+      if (pr.count > 512) spill = true; // thousands of probes: a whole block, one thread per probe
+      else {
+        if (gl == 0) S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; // a warp of the second launch takes it
+        deferred = true;
+      }
+    } else if (!wide && pr.n_un > 0) {
       // lanes take the probed values round-robin and walk their own (short) buckets
       const DevTable& t = S.tables[tab];
-      const int D = S.attrs[ea].D;
-      int v_next = gl, v_cur = 0, q = 0, q_end = 0, visited = 0;
+      int j_next = gl, v_cur = 0, w_cur = 0, q = 0, q_end = 0, visited = 0;
       for (;;) {
-        while (q >= q_end && v_next < D) {
-          const uint32_t b = bucket_of(S, t, x, ea, v_next);
+        while (q >= q_end && j_next < pr.count) {
+          pr.values(j_next, v_cur, w_cur);
+          const uint32_t b = pr.bucket(S, t, x, v_cur, w_cur);
           q = b ? t.ptr[b - 1] : 0;
           q_end = t.ptr[b];
-          v_cur = v_next;
-          v_next += GL;
+          j_next += GL;
         }
         const bool active = q < q_end;
         if (spill || !__any_sync(gmask, active)) break;
@@ -667,7 +731,7 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
           if (item != S.N + r) {
             const int* y = S.ent_y + (size_t)item * S.ES;
             // hashed buckets: an item counts in the probe of its own value only
-            ok = y[ea] == v_cur && item_compatible(S, x, zm, y);
+            ok = pr.own_probe(y, v_cur, w_cur) && item_compatible(S, x, zm, y);
             if (ok) {
               ll = item_loglik(S, x, zm, y);
               ok = ll > -CUDART_INF;
@@ -811,9 +875,8 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
     if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
     const DevTable& t = S.tables[tab];
     const int own = S.lambda[r];
-    const int ea = unpinned_key(S, t.mask, x, zm);
-    const int n_probe = ea >= 0 ? S.attrs[ea].D : 1;
-    if (ea < 0) {
+    const Probe pr = make_probe(S, t.mask, x, zm); // (n_un = 3 never gets here: k_cand sends those to the batched scan)
+    if (pr.n_un == 0) {
       const uint32_t b = S.rec_bkt[r];
       const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
       if (hi - lo > S.huge_min) {
@@ -822,10 +885,10 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
         continue;
       }
     }
-    auto visit = [&](int item, int v) {
+    auto visit = [&](int item, int v, int w2) {
       if (item == S.N + r) return;
       const int* y = S.ent_y + (size_t)item * S.ES;
-      if (ea >= 0 && y[ea] != v) return; // hashed buckets: an item counts in the probe of its own value only
+      if (pr.n_un > 0 && !pr.own_probe(y, v, w2)) return;
       if (!item_compatible(S, x, zm, y)) return;
       const double ll = item_loglik(S, x, zm, y);
       if (!(ll > -CUDART_INF)) return;
@@ -834,12 +897,14 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
       if (tw && pos + 1 < cap) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
     };
-    if (ea >= 0) {
-      // one thread per probed value: the buckets are short, the probes independent
-      for (int v = threadIdx.x; v < n_probe; v += blockDim.x) {
-        const uint32_t b = bucket_of(S, t, x, ea, v);
+    if (pr.n_un > 0) {
+      // one thread per probe: the buckets are short, the probes independent
+      for (int j = threadIdx.x; j < pr.count; j += blockDim.x) {
+        int v, w2;
+        pr.values(j, v, w2);
+        const uint32_t b = pr.bucket(S, t, x, v, w2);
         const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
-        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v);
+        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, w2);
       }
     } else {
       const uint32_t b = S.rec_bkt[r];
@@ -847,7 +912,7 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
         if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
         const int q = q0 + threadIdx.x;
-        if (q < hi) visit(t.ids[q], 0);
+        if (q < hi) visit(t.ids[q], 0, 0);
       }
     }
     __syncthreads();
