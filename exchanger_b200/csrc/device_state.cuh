@@ -127,6 +127,9 @@ struct DevState {
   int *wl_tot;                  // [WIDE_NB] possible links per record
   unsigned long long *wl_base;  // [WIDE_NB] start of the record's list in wl_id / wl_ll (~0: not listed)
   int *wl_id; double *wl_ll;    // [wl_cap] lists of the current batch (carved out of lwbuf)
+  uint8_t *wl_log_k; int *wl_log_item; double *wl_log_ll; // [WIDE_PIECES][wl_logcap] hits of the counting pass, per piece
+  int *wl_logn;                 // [WIDE_PIECES] entries logged (-1: the piece's log overflowed)
+  int wl_logcap;
   unsigned long long wl_cap;
   int huge_min;                 // bucket length above which the whole grid scans it
   double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path

@@ -496,6 +496,15 @@ int ensure_table(exb200_handle* h, int tab) {
 // serial path: possible links of up to WIDE_NB records among all the items (counting pass)
 int wide_count(exb200_handle* h, const int* recs, int nb, int* totals) {
   DevState& S = h->S;
+  if (!S.wl_log_k) { // the hit logs of the counting pass, allocated when the serial path is first used
+    const long long per_piece = (2LL * h->N + WIDE_PIECES - 1) / WIDE_PIECES;
+    S.wl_logcap = (int)std::min<long long>(4096, std::max<long long>(64, 8 * per_piece));
+    const size_t n = (size_t)WIDE_PIECES * S.wl_logcap;
+    int rc = dalloc(h, &S.wl_log_k, n); if (rc) return rc;
+    rc = dalloc(h, &S.wl_log_item, n); if (rc) return rc;
+    rc = dalloc(h, &S.wl_log_ll, n); if (rc) return rc;
+    rc = dalloc(h, &S.wl_logn, (size_t)WIDE_PIECES); if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(S.batch_list, recs, sizeof(int) * nb, cudaMemcpyHostToDevice, h->stream));
   KLAUNCH(h, k_wide_scan<false>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb);
   KLAUNCH(h, k_wide_offsets, nb, 1024, 0, S);
@@ -741,7 +750,8 @@ int update_links(exb200_handle* h) {
       }
       if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
       CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
-      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb);
+      KLAUNCH(h, k_wide_fill_log, WIDE_BLOCKS, TPB, 0, S, nb);
+      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb); // pieces whose log overflowed
       if (n_sel > 0) {
         CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
         KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
@@ -816,6 +826,7 @@ int update_links(exb200_handle* h) {
       int rc = wide_count(h, &w, 1, &tot); if (rc) return rc;
       const unsigned long long zero_base = 0;
       CK(cudaMemcpyAsync(S.wl_base, &zero_base, sizeof zero_base, cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_wide_fill_log, WIDE_BLOCKS, TPB, 0, S, 1);
       KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1);
       wide_turn(h, w, 0, tot);
       const int zero = 0;

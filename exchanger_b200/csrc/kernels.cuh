@@ -1399,6 +1399,11 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
   long long lo, hi;
   wide_piece(2LL * S.N, WIDE_PIECES, p, lo, hi);
   int qh = 0, qn = 0; // queue head and length (warp-uniform)
+  // The counting pass logs its hits per piece (record, item, log-likelihood; in the order they are
+  // found), so that the filling pass only replays the log (k_wide_fill_log); a piece whose log
+  // overflows is filled by repeating the scan.
+  int lg = 0;
+  if (FILL && S.wl_logn[p] >= 0) hi = lo; // logged piece: nothing to do here
   for (long long base = lo; base < hi; base += 32) {
     const long long i = base + lane;
     bool live = i < hi;
@@ -1454,6 +1459,14 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
             S.wl_ll[pos] = ll;
           }
         }
+        if (!FILL) {
+          const int lpos = lg + __popc(hm & ((1u << lane) - 1u));
+          if (hit && lpos < S.wl_logcap) {
+            const size_t o = (size_t)p * S.wl_logcap + lpos;
+            S.wl_log_k[o] = (uint8_t)s_b[k]; S.wl_log_item[o] = (int)it; S.wl_log_ll[o] = ll;
+          }
+          lg += __popc(hm);
+        }
         __syncwarp();
         if (hit && rank == 0) s_run[wp][k] += __popc(peers);
       }
@@ -1482,6 +1495,42 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
   if (!FILL) {
     __syncwarp();
     for (int k = lane; k < n_act; k += 32) S.wl_cnt[(size_t)s_b[k] * WIDE_PIECES + p] = s_run[wp][k];
+    if (lane == 0) S.wl_logn[p] = lg <= S.wl_logcap ? lg : -1;
+  }
+}
+// filling pass from the logs: one warp per piece replays its hits in order
+__global__ void __launch_bounds__(TPB) k_wide_fill_log(DevState S, int nb) {
+  __shared__ int s_run[TPB / 32][WIDE_NB];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, p = blockIdx.x * (TPB / 32) + wp;
+  for (int b = lane; b < nb; b += 32) s_run[wp][b] = 0;
+  __syncwarp();
+  const int n = S.wl_logn[p];
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    int b = -1 - lane, item = 0;
+    double ll = 0.0;
+    bool act = false;
+    if (e < n) {
+      const size_t o = (size_t)p * S.wl_logcap + e;
+      b = (int)S.wl_log_k[o]; item = S.wl_log_item[o]; ll = S.wl_log_ll[o];
+      act = S.wl_base[b] != ~0ull;
+      if (!act) b = -1 - lane;
+    }
+    const unsigned am = __ballot_sync(FULL, act);
+    if (am) {
+      const unsigned peers = __match_any_sync(FULL, b) & am;
+      int rank = 0;
+      if (act) {
+        rank = __popc(peers & ((1u << lane) - 1u));
+        const unsigned long long pos = S.wl_base[b] + (unsigned long long)S.wl_cnt[(size_t)b * WIDE_PIECES + p] +
+                                       (unsigned long long)(s_run[wp][b] + rank);
+        S.wl_id[pos] = item;
+        S.wl_ll[pos] = ll;
+      }
+      __syncwarp();
+      if (act && rank == 0) s_run[wp][b] += __popc(peers);
+    }
+    __syncwarp();
   }
 }
 // one block per record of the batch: exclusive scan of its piece counts, total in wl_tot
