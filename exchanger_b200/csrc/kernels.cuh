@@ -1222,10 +1222,10 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
 // association of the sequential loop in k_commit and in the oracle.
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
-  extern __shared__ double s_w[]; // [cnt] log-weights, then weights relative to the maximum
-  __shared__ double s_red[TPB];
+  extern __shared__ double s_w[]; // [cnt] log-weights, then weights relative to the maximum, then their running sums
+  __shared__ double s_red[TPB / 32];
   __shared__ double s_m1, s_srel;
-  __shared__ int s_dec;
+  __shared__ int s_dec, s_pick, s_last;
   const int r = act[blockIdx.x];
   const int cnt = S.cand_cnt[r];
   const unsigned long long key = resv_key(round, r);
@@ -1247,7 +1247,10 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
     }
     if (mine) {
       const bool single = S.ent_size[own] == 1;
-      auto fill_weights = [&](bool need_max) { // s_w[j] = exp(lw_j - m1), 0 for candidates that are not live
+      // s_w[j] = running sum (candidate order, summed by one thread: the association of the
+      // sequential loop in k_commit and in the oracle) of exp(lw_j - m1), 0 for candidates that are
+      // not live; s_last = last candidate of positive weight; s_srel = the total
+      auto fill_weights = [&](bool need_max) {
         double m = -CUDART_INF;
         for (int j = threadIdx.x; j < cnt; j += TPB) {
           const int sz = live_size(S, ids[j], own, single);
@@ -1255,50 +1258,59 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
           s_w[j] = lw;
           m = lw > m ? lw : m;
         }
+        if (threadIdx.x == 0) s_last = -1;
         if (need_max) {
-          s_red[threadIdx.x] = m;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m, o); m = y > m ? y : m; }
+          if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
           __syncthreads();
           if (threadIdx.x == 0) {
             double mm = -CUDART_INF;
-            for (int k = 0; k < TPB; k++) mm = s_red[k] > mm ? s_red[k] : mm;
+            for (int k = 0; k < TPB / 32; k++) mm = s_red[k] > mm ? s_red[k] : mm;
             s_m1 = mm;
           }
         }
         __syncthreads();
         const double m1 = s_m1;
-        for (int j = threadIdx.x; j < cnt; j += TPB) s_w[j] = s_w[j] > -CUDART_INF ? exp(s_w[j] - m1) : 0.0;
+        int last = -1;
+        for (int j = threadIdx.x; j < cnt; j += TPB) {
+          const double w = s_w[j] > -CUDART_INF ? exp(s_w[j] - m1) : 0.0;
+          s_w[j] = w;
+          if (w > 0.0) last = j;
+        }
+        if (last >= 0) atomicMax(&s_last, last);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double c = 0.0;
+          if (m1 > -CUDART_INF) for (int j = 0; j < cnt; j++) { c += s_w[j]; s_w[j] = c; } // dead ones add 0
+          s_srel = c;
+        }
         __syncthreads();
       };
       if (ready) { if (threadIdx.x == 0) { s_m1 = S.rdy_m1[r]; s_srel = S.rdy_srel[r]; } __syncthreads(); }
-      else {
-        fill_weights(true);
-        if (threadIdx.x == 0) {
-          double srel = 0.0;
-          if (s_m1 > -CUDART_INF) for (int j = 0; j < cnt; j++) srel += s_w[j]; // candidate order; dead ones add 0
-          s_srel = srel;
-        }
-        __syncthreads();
-      }
+      else fill_weights(true);
       const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
       if (threadIdx.x == 0) s_dec = decide_with_bounds(S, r, single, s_m1, s_srel, u.a);
       __syncthreads();
       const int dec = s_dec;
       if (dec != 2) {
-        if (dec == 0 && ready) fill_weights(false); // the weights were not kept: recompute them for the pick
+        if (dec == 0) {
+          if (ready) { const double keep = s_srel; fill_weights(false); if (threadIdx.x == 0) s_srel = keep; __syncthreads(); } // the sums were not kept
+          // the first candidate whose running sum exceeds the threshold (it has a positive weight:
+          // a zero weight leaves the sum where it was); the running sums never decrease
+          if (threadIdx.x == 0) s_pick = 0x7FFFFFFF;
+          __syncthreads();
+          const double tt = u.b * s_srel;
+          for (int j = threadIdx.x; j < cnt; j += TPB)
+            if (tt < s_w[j] && (j == 0 || !(tt < s_w[j - 1]))) atomicMin(&s_pick, j);
+          __syncthreads();
+        }
         if (threadIdx.x == 0) {
           int target;
           if (dec == 1) target = S.N + r;
           else {
-            const double tt = u.b * s_srel;
-            double cum = 0.0;
-            int pick = -1, lastpos = -1;
-            for (int j = 0; j < cnt; j++) {
-              const double w = s_w[j];
-              if (w > 0.0) lastpos = ids[j];
-              cum += w;
-              if (w > 0.0 && tt < cum) { pick = ids[j]; break; }
-            }
-            target = pick >= 0 ? pick : lastpos;
+            const int j = s_pick != 0x7FFFFFFF ? s_pick : s_last;
+            target = j >= 0 ? ids[j] : -1;
             if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
           }
           finalize_record(S, r, own, target, single);
