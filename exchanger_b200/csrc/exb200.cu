@@ -1354,7 +1354,15 @@ struct RowCopier {
           jobs.pop_front();
         }
         const bool ok = cudaEventSynchronize(h->ev_d2h[job.first]) == cudaSuccess;
-        if (ok) std::memcpy(job.second, h->pin_snap[job.first], sizeof(int) * (size_t)h->N);
+        if (ok) { // the destination is usually untouched memory: several threads take the page faults
+          const size_t n = (size_t)h->N;
+          const int parts = n >= (1u << 20) ? 4 : 1;
+          std::vector<std::thread> th;
+          for (int q = 1; q < parts; q++)
+            th.emplace_back([=] { std::memcpy(job.second + n * q / parts, h->pin_snap[job.first] + n * q / parts, sizeof(int) * (n * (q + 1) / parts - n * q / parts)); });
+          std::memcpy(job.second, h->pin_snap[job.first], sizeof(int) * (n / parts));
+          for (auto& t : th) t.join();
+        }
         {
           std::lock_guard<std::mutex> lk(mu);
           busy[job.first] = false;
