@@ -161,9 +161,9 @@ enum CounterSlot {
   C_NACTL_INIT = 9, // long records found by candidate generation
   C_NUNK = 10,      // size of unk_list
   C_NFENCE = 11,    // records that take their turn serially inside the rounds
-  C_COUNT = 12,     // scratch of k_count_all / k_huge_scan
+  C_COUNT = 12,     // (free)
   C_NHUGE = 13,     // size of huge_list
-  C_NOLIST = 14,    // records without a stored list (wide / serial): they may join any entity
+  C_NOLIST = 14,    // records without a stored list after candidate generation (diagnostic)
   C_NPROBE = 15,    // size of probe_list
   C_NSLOTS = 16
 };

@@ -177,6 +177,16 @@ def test_multi_bucket_probes_and_warp_scanned_buckets():
     assert sum(s["n_huge"] for s in stats) > 10
 
 
+def test_synthetic_records_at_scale_lockstep():
+    """The generator of the 1 M / 10 M workloads at a size the oracle still finishes in seconds
+    (120 k records, GeneralizedCoupon as in config C4): identical states sweep by sweep."""
+    from bench import DATA_SEED, clust_prior
+    from exchanger_b200.synthetic import synth_model
+    m, _ = synth_model(120_000, clust_prior("gen_coupon", 120_000), seed=DATA_SEED)
+    stats = lockstep(m, 3)
+    assert stats[-1]["n_entities"] < 120_000 and stats[-1]["n_tables"] >= 2
+
+
 def test_run_inference_schedule_history_and_resume():
     """Save schedule of sample() (src/sample.cpp:171-197) and resuming from fit.state
     (R/run_inference.R:104-115): 3 + 3 resumed samples equal one run of 6."""
