@@ -228,6 +228,12 @@ def load_library(path: str | None = None):
     lib.exb200_destroy.restype = None
     lib.exb200_last_error.argtypes = [H]
     lib.exb200_last_error.restype = C.c_char_p
+    lib.exb200_shard_links.argtypes = [H]
+    lib.exb200_shard_entities.argtypes = [H, C.c_int32, C.c_int32]
+    lib.exb200_shard_distort.argtypes = [H, C.c_int32, C.c_int32, c_i32p, c_i32p]
+    lib.exb200_shard_finish.argtypes = [H, c_i32p, c_i32p]
+    lib.exb200_device_buffer.argtypes = [H, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.exb200_stream_sync.argtypes = [H]
     lib.exb200_neighbours_create.argtypes = [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                                              C.POINTER(H)]
     lib.exb200_neighbours_nnz.argtypes = [H]
@@ -277,4 +283,6 @@ EXPORTED_SYMBOLS = [
     "exb200_get_state", "exb200_get_stats", "exb200_link_conditional", "exb200_set_option",
     "exb200_destroy", "exb200_last_error", "exb200_neighbours_create", "exb200_neighbours_nnz",
     "exb200_neighbours_get", "exb200_neighbours_destroy",
+    "exb200_shard_links", "exb200_shard_entities", "exb200_shard_distort", "exb200_shard_finish",
+    "exb200_device_buffer", "exb200_stream_sync",
 ]

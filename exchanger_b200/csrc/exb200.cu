@@ -901,29 +901,52 @@ int check_state(exb200_handle* h) {
 }
 
 // ---- one application of State::update (state.h:60-75)
-int sweep(exb200_handle* h) {
-  DevState& S = h->S;
-  cudaStream_t st = h->stream;
-  const int N = h->N, FA = h->F * h->A;
-  S.iter = (uint32_t)h->iteration;
+// One sweep = State::update() (src/state.h:60-75), in the pieces within-chain sharding needs
+// (DESIGN.md section 7): the links update runs on every GPU, the entity attributes and the
+// distortion indicators on a slice of the entity slots / records.
+int sweep_links(exb200_handle* h) {
+  h->S.iter = (uint32_t)h->iteration;
   h->hs.begin_sweep((uint32_t)h->iteration);
-  CK(cudaEventRecord(h->ev[0], st));
+  CK(cudaEventRecord(h->ev[0], h->stream));
   int rc = update_clust(h); if (rc) return rc;          // clust_params_->update(links_)
   refresh_clust_dev(h);
-  rc = update_links(h); if (rc) return rc;              // links_.update(...)
-  CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), st));
-  KLAUNCH(h, k_entities, nblk(N, 64), 64, 0, S, h->d_gen_list, h->d_gen_count);   // ents_.update_attributes(...)
+  return update_links(h);                               // links_.update(...)
+}
+int sweep_entities(exb200_handle* h, int lo, int hi) {
+  DevState& S = h->S;
+  CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), h->stream));
+  if (hi > lo) KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
   KLAUNCH_DP(h, k_entities_general, 148 * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
-  rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
+  return EXB200_OK;
+}
+int sweep_distort(exb200_handle* h, int lo, int hi) {
+  DevState& S = h->S;
+  cudaStream_t st = h->stream;
+  const int FA = h->F * h->A;
   CK(cudaEventRecord(h->ev[7], st));
   CK(cudaMemsetAsync(S.ndist, 0, sizeof(int) * FA, st));
   CK(cudaMemsetAsync(S.corr, 0, sizeof(int) * FA, st));
   const int use_smem = 2 * FA * (int)sizeof(int) <= 32768;
-  KLAUNCH(h, k_distort, nblk(N), TPB, use_smem ? 2 * FA * sizeof(int) : 0, S, use_smem); // recs_.update_distortion
+  if (hi > lo) KLAUNCH(h, k_distort, nblk(hi - lo), TPB, use_smem ? 2 * FA * sizeof(int) : 0, S, use_smem, lo, hi); // recs_.update_distortion
   CK(cudaMemcpyAsync(h->ndist.data(), S.ndist, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(h->corr.data(), S.corr, sizeof(int) * FA, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[8], st));
-  rc = check_device_error(h); if (rc) return rc;        // also synchronises
+  return check_device_error(h);                         // also synchronises
+}
+int sweep_finish(exb200_handle* h);
+
+int sweep(exb200_handle* h) {
+  int rc = sweep_links(h); if (rc) return rc;
+  rc = sweep_entities(h, 0, h->N); if (rc) return rc;
+  rc = update_dists_and_concs(h); if (rc) return rc;    // ents_.update_distributions(); cache_.update(); distort_dist_concs_.update()
+  rc = sweep_distort(h, 0, h->N); if (rc) return rc;
+  return sweep_finish(h);
+}
+
+// distort_probs_.update from the (global) counts in h->ndist / h->corr, end of the sweep
+int sweep_finish(exb200_handle* h) {
+  cudaStream_t st = h->stream;
+  int rc = 0;
   // distort_probs_.update (distortion_probs.cpp:30-47): file-major, attribute-minor order
   for (int f = 0; f < h->F; f++)
     for (int a = 0; a < h->A; a++)
@@ -1505,6 +1528,60 @@ int exb200_get_state(exb200_handle* h, exb200_state* out) {
     }
   if (out->distort_dist_concs) for (int a = 0; a < A; a++) out->distort_dist_concs[a] = h->conc[a];
   out->clust = h->cl;
+  return EXB200_OK;
+}
+
+namespace {
+int shard_ready(exb200_handle* h) {
+  if (!h) return EXB200_ERR_INVALID;
+  if (h->poisoned) return fail(h, EXB200_ERR_CUDA, "handle unusable after an earlier error: " + h->err);
+  cudaSetDevice(h->device);
+  for (int a = 0; a < h->A; a++)
+    if (h->attrs[a].dirichlet || h->attrs[a].conc_shape > 0)
+      return fail(h, EXB200_ERR_UNSUPPORTED, "within-chain sharding: DirichletRV entity priors and GammaRV concentration priors are not supported");
+  return EXB200_OK;
+}
+} // namespace
+
+int exb200_shard_links(exb200_handle* h) {
+  int rc = shard_ready(h); if (rc) return rc;
+  return sweep_links(h);
+}
+int exb200_shard_entities(exb200_handle* h, int32_t lo, int32_t hi) {
+  int rc = shard_ready(h); if (rc) return rc;
+  if (lo < 0 || hi > h->N || lo > hi) return fail(h, EXB200_ERR_INVALID, "slice out of range");
+  return sweep_entities(h, lo, hi);
+}
+int exb200_shard_distort(exb200_handle* h, int32_t lo, int32_t hi, int32_t* ndist, int32_t* corr) {
+  int rc = shard_ready(h); if (rc) return rc;
+  if (lo < 0 || hi > h->N || lo > hi || !ndist || !corr) return fail(h, EXB200_ERR_INVALID, "slice out of range");
+  rc = sweep_distort(h, lo, hi); if (rc) return rc;
+  std::memcpy(ndist, h->ndist.data(), sizeof(int) * h->ndist.size());
+  std::memcpy(corr, h->corr.data(), sizeof(int) * h->corr.size());
+  return EXB200_OK;
+}
+int exb200_shard_finish(exb200_handle* h, const int32_t* ndist, const int32_t* corr) {
+  int rc = shard_ready(h); if (rc) return rc;
+  if (!ndist || !corr) return EXB200_ERR_INVALID;
+  std::memcpy(h->ndist.data(), ndist, sizeof(int) * h->ndist.size());
+  std::memcpy(h->corr.data(), corr, sizeof(int) * h->corr.size());
+  // the device copies of the counts are only read back by the host; keep them in step anyway
+  CK(cudaMemcpyAsync(h->S.ndist, h->ndist.data(), sizeof(int) * h->ndist.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->S.corr, h->corr.data(), sizeof(int) * h->corr.size(), cudaMemcpyHostToDevice, h->stream));
+  return sweep_finish(h);
+}
+int exb200_device_buffer(exb200_handle* h, const char* name, void** ptr, int64_t* bytes, int32_t* row_bytes) {
+  if (!h || !name || !ptr || !bytes || !row_bytes) return EXB200_ERR_INVALID;
+  const std::string n(name);
+  if (n == "ent_y") { *ptr = h->S.ent_y; *row_bytes = (int32_t)(sizeof(int) * h->ES); *bytes = (int64_t)2 * h->N * *row_bytes; }
+  else if (n == "rec_z") { *ptr = const_cast<uint32_t*>(h->S.rec_z); *row_bytes = (int32_t)sizeof(uint32_t); *bytes = (int64_t)h->N * *row_bytes; }
+  else return fail(h, EXB200_ERR_INVALID, "unknown buffer " + n);
+  return EXB200_OK;
+}
+int exb200_stream_sync(exb200_handle* h) {
+  if (!h) return EXB200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));
   return EXB200_OK;
 }
 

@@ -2068,12 +2068,14 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
   return t.is_const ? lastpos : (lastpos == 0 ? first : t.col[lo + lastpos - 1]);
 }
 
-__global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count) {
+// (entity slots [e_lo, e_hi): the whole range on one GPU, a slice under within-chain sharding)
+__global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count,
+                                                  int e_lo, int e_hi) {
   __shared__ int s_warp[TPB / 32]; // (launched with blocks of up to TPB threads)
   __shared__ int s_base;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = e_lo + blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t need = 0;
-  if (e < S.N && S.ent_size[e] > 0) {
+  if (e < e_hi && S.ent_size[e] > 0) {
     const int head = S.ent_head[e];
     int* y = S.ent_y + (size_t)e * S.ES;
     for (int a = 0; a < S.A; a++) {
@@ -2159,15 +2161,16 @@ __global__ void __launch_bounds__(TPB) k_ent_hist(DevState S, int a, int* __rest
 // elementwise over records x attributes, counts reduced per (file, attribute) with warp
 // ballots into shared memory and one global atomic per block and bin.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_distort(DevState S, int use_smem) {
+// (records [r_lo, r_hi): the whole range on one GPU, a slice under within-chain sharding)
+__global__ void __launch_bounds__(TPB) k_distort(DevState S, int use_smem, int r_lo, int r_hi) {
   extern __shared__ int s_cnt[]; // [2][F*A] when use_smem
   const int FA = S.F * S.A;
   if (use_smem) {
     for (int i = threadIdx.x; i < 2 * FA; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
   }
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = r < S.N;
+  const int r = r_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < r_hi;
   const int* x = S.rec_x + (size_t)(live ? r : 0) * S.RS;
   const int f = live ? x[S.RS - 1] : -1;
   const int* y = S.ent_y + (size_t)(live ? S.lambda[r] : 0) * S.ES;

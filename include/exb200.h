@@ -209,6 +209,34 @@ int exb200_get_state(exb200_handle* h, exb200_state* out);
 int exb200_get_stats(exb200_handle* h, exb200_stats* out);
 
 /*
+ * Within-chain sharding over several GPUs of one node.  Every GPU holds the
+ * whole state and runs the links update (steps 1-2 of State::update, state.h:60-67) identically -
+ * the randomness is keyed, so the replicas agree bit for bit.  The entity attributes
+ * (Entities::update_attributes, state.h:68) and the distortion indicators
+ * (Records::update_distortion, state.h:72) are computed on a slice of the entity slots / records
+ * per GPU; the host exchanges the slices between the calls (all-gather of the device buffers
+ * "ent_y" rows [lo, hi) and "rec_z" entries [lo, hi), sum of the two count matrices):
+ *
+ *   exb200_shard_links(h);
+ *   exb200_shard_entities(h, lo, hi);   exb200_stream_sync(h);   all-gather "ent_y"
+ *   exb200_shard_distort(h, lo, hi, ndist, corr);                all-gather "rec_z", sum counts
+ *   exb200_shard_finish(h, ndist_sum, corr_sum);
+ *
+ * Models with a DirichletRV entity prior or a GammaRV concentration prior (steps 4-6) are not
+ * supported in this mode (EXB200_ERR_UNSUPPORTED).  Count matrices are [F x A], file-major
+ * (f * A + a).  One call sequence with lo = 0, hi = n_records equals exb200_sweeps(h, 1).
+ */
+int exb200_shard_links(exb200_handle* h);
+int exb200_shard_entities(exb200_handle* h, int32_t lo, int32_t hi);
+int exb200_shard_distort(exb200_handle* h, int32_t lo, int32_t hi, int32_t* ndist, int32_t* corr);
+int exb200_shard_finish(exb200_handle* h, const int32_t* ndist, const int32_t* corr);
+/* device address and size of a state buffer: "ent_y" ([2N][row] int32, row = *row_bytes / 4
+   values per entity slot), "rec_z" ([N] uint32, one distortion bit per attribute) */
+int exb200_device_buffer(exb200_handle* h, const char* name, void** ptr, int64_t* bytes, int32_t* row_bytes);
+/* wait until the library's stream has finished everything queued so far */
+int exb200_stream_sync(exb200_handle* h);
+
+/*
  * Test hook: the conditional of one record's link in the CURRENT state, without
  * changing it: what Links::update_link computes at src/links.cpp:361-399.
  * cand_ids/log_weights receive up to `cap` existing candidates in ascending entity
