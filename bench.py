@@ -295,6 +295,48 @@ def run_ours(opt, n_records, kind, desc):
         dist.destroy_process_group()
 
 
+def run_sharded(opt, n_records, kind, desc):
+    """--mode shard: ONE chain over all the GPUs (within-chain sharding) -
+    strong scaling.  The default mode (independent chains, weak scaling) is what the driver runs."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29512")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    dist.barrier()
+    from exchanger_b200.sharded import ShardedSampler
+    from exchanger_b200.synthetic import synth_model
+    model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED)
+    g = ShardedSampler(model, seed=1000, device=local)
+    g.sweeps(opt.burnin + opt.warmup)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    t0 = time.perf_counter()
+    g.sweeps(opt.steps)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    secs = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    clk = clocks.stop()
+    if rank == 0:
+        t = float(secs.item())
+        print(json.dumps({
+            "metric": "gibbs_sweeps_per_s", "value": opt.steps / t, "unit": "sweeps/s",
+            "link_updates_per_s": opt.steps * n_records / t, "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
+            "ms_per_step": 1e3 * t / opt.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind,
+                       "parallelism": f"one chain sharded over {world} GPU(s): links replicated, entity attributes and "
+                                      "distortion indicators on slices, all-gather + all-reduce per sweep",
+                       "burnin_sweeps": opt.burnin},
+            "clocks": clk, "timing": "wall clock around the timed sweeps, max over ranks (collectives included)",
+        }), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +347,8 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the record count (debugging)")
     ap.add_argument("--burnin", type=int, default=20, help="untimed sweeps before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="chains", choices=["chains", "shard"],
+                    help="N > 1: independent chains (default, weak scaling) or one chain sharded over the GPUs")
     opt = ap.parse_args()
     opt.warmup = max(opt.warmup, 3)
     n_records, kind, desc = WORKLOADS[opt.workload]
@@ -313,6 +357,8 @@ def main():
         desc += f" (records overridden to {n_records})"
     if opt.impl == "reference":
         run_reference(opt, n_records, kind, desc)
+    elif opt.mode == "shard":
+        run_sharded(opt, n_records, kind, desc)
     else:
         run_ours(opt, n_records, kind, desc)
 

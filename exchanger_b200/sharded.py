@@ -25,6 +25,23 @@ def slice_bounds(n: int, world: int, rank: int) -> tuple[int, int, int]:
     return chunk, lo, min(n, lo + chunk)
 
 
+def exchange_slices(dist, full, chunk: int, rank: int, world: int, group=None):
+    """All-gather of equal slices in place: on return rows ``[r * chunk, (r + 1) * chunk)`` of
+    ``full`` hold what rank ``r`` had there.  ``full`` has at least ``world * chunk`` rows."""
+    out = full[: world * chunk]
+    dist.all_gather_into_tensor(out, out[rank * chunk:(rank + 1) * chunk].clone(), group=group)
+    return out
+
+
+def exchange_ragged(dist, values, stage, chunk: int, lo: int, hi: int, rank: int, world: int, group=None):
+    """All-gather of the slices ``values[lo:hi]`` of an array whose length is not a multiple of the
+    slice size, through the padded staging array ``stage`` (``world * chunk`` entries)."""
+    stage[rank * chunk: rank * chunk + (hi - lo)] = values[lo:hi]
+    exchange_slices(dist, stage, chunk, rank, world, group)
+    values.copy_(stage[: values.shape[0]])
+    return values
+
+
 class _DeviceArray:
     """Zero-copy view of a library buffer for ``torch.as_tensor`` (``__cuda_array_interface__``)."""
 
@@ -64,15 +81,11 @@ class ShardedSampler:
             chk(lib.exb200_shard_entities(h, self.lo, self.hi))
             chk(lib.exb200_stream_sync(h))
             if self.world > 1:   # entity tuples of every slice, in place
-                full = self.ent_y[: self.world * self.chunk]
-                dist.all_gather_into_tensor(full, full[self.rank * self.chunk:(self.rank + 1) * self.chunk], group=self.group)
+                exchange_slices(dist, self.ent_y, self.chunk, self.rank, self.world, self.group)
                 torch.cuda.synchronize(self.device)
             chk(lib.exb200_shard_distort(h, self.lo, self.hi, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
             if self.world > 1:   # distortion masks of every slice, counts summed
-                self.z_stage[self.rank * self.chunk: self.rank * self.chunk + (self.hi - self.lo)] = self.rec_z[self.lo:self.hi]
-                dist.all_gather_into_tensor(self.z_stage, self.z_stage[self.rank * self.chunk:(self.rank + 1) * self.chunk].clone(),
-                                            group=self.group)
-                self.rec_z.copy_(self.z_stage[: self.N])
+                exchange_ragged(dist, self.rec_z, self.z_stage, self.chunk, self.lo, self.hi, self.rank, self.world, self.group)
                 self.counts.copy_(torch.from_numpy(np.concatenate([nd, co]).astype(np.int64)))
                 dist.all_reduce(self.counts, group=self.group)
                 torch.cuda.synchronize(self.device)

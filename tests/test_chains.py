@@ -47,3 +47,46 @@ def test_merged_coreference_probs_two_ranks_gloo():
     both = np.concatenate([out[0][0], out[1][0]], axis=0)
     expect = coreference_probs(both, pairs)
     assert np.allclose(out[0][1], expect) and np.allclose(out[1][1], expect)
+
+
+# ---- within-chain sharding: slice arithmetic and the exchange pattern (two ranks over gloo)
+def test_slice_bounds_cover_the_range():
+    from exchanger_b200.sharded import slice_bounds
+    for n in (2, 7, 500, 10_000_019):
+        for world in (1, 2, 3, 8):
+            if world > n:
+                continue
+            chunks = [slice_bounds(n, world, r) for r in range(world)]
+            assert all(c[0] == chunks[0][0] for c in chunks) and chunks[0][0] * world <= 2 * n
+            covered = np.concatenate([np.arange(lo, hi) for _, lo, hi in chunks])
+            assert np.array_equal(covered, np.arange(n))
+
+
+def _shard_worker(rank, world, port, out):
+    import torch
+    from exchanger_b200.sharded import exchange_ragged, exchange_slices, slice_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 11
+    chunk, lo, hi = slice_bounds(n, world, rank)
+    truth_rows = torch.arange(2 * n * 8, dtype=torch.int32).reshape(2 * n, 8)
+    rows = torch.zeros_like(truth_rows)
+    rows[lo:hi] = truth_rows[lo:hi]                     # what this rank computed
+    rows[n:] = truth_rows[n:]                           # slots beyond N are replicated anyway
+    exchange_slices(dist, rows, chunk, rank, world)
+    truth_z = torch.arange(100, 100 + n, dtype=torch.int32)
+    z = torch.zeros(n, dtype=torch.int32)
+    z[lo:hi] = truth_z[lo:hi]
+    exchange_ragged(dist, z, torch.zeros(world * chunk, dtype=torch.int32), chunk, lo, hi, rank, world)
+    out[rank] = (bool(torch.equal(rows, truth_rows)), bool(torch.equal(z, truth_z)))
+    dist.destroy_process_group()
+
+
+def test_slice_exchange_two_ranks_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_shard_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == (True, True) and out[1] == (True, True)

@@ -187,6 +187,47 @@ def test_synthetic_records_at_scale_lockstep():
     assert stats[-1]["n_entities"] < 120_000 and stats[-1]["n_tables"] >= 2
 
 
+def test_sweep_in_slices_equals_the_sweep():
+    """The slice calls of within-chain sharding (exb200_shard_*): two slices per phase on one GPU,
+    and the ShardedSampler with a single rank, give the chain of exb200_sweeps."""
+    import ctypes as C
+    import socket
+    import torch.distributed as dist
+    from exchanger_b200.capi import c_i32p
+    from exchanger_b200.sharded import ShardedSampler
+    m, _ = readme_model("rldata10000", n=3000, clust_prior=PRIORS["gen_coupon"](3000))
+    whole, sliced = Sampler(m, seed=21), Sampler(m, seed=21)
+    FA = whole.F * whole.A
+    for _ in range(5):
+        whole.sweeps(1)
+        lib, h = sliced.lib, sliced.h
+        sliced._check(lib.exb200_shard_links(h))
+        for lo, hi in ((0, 1700), (1700, 3000)):
+            sliced._check(lib.exb200_shard_entities(h, lo, hi))
+        total = np.zeros((2, FA), np.int32)
+        for lo, hi in ((0, 1200), (1200, 3000)):
+            nd, co = np.zeros(FA, np.int32), np.zeros(FA, np.int32)
+            sliced._check(lib.exb200_shard_distort(h, lo, hi, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
+            total += np.stack([nd, co])
+        sliced._check(lib.exb200_shard_finish(h, total[0].ctypes.data_as(c_i32p), total[1].ctypes.data_as(c_i32p)))
+        assert_same_state(whole.state(), sliced.state())
+    sliced.close()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        sh = ShardedSampler(m, seed=21)
+        sh.sweeps(5)
+        whole2 = Sampler(m, seed=21)
+        whole2.sweeps(5)
+        assert_same_state(whole2.state(), sh.state())
+        sh.close(); whole2.close()
+    finally:
+        dist.destroy_process_group()
+    whole.close()
+
+
 def test_run_inference_schedule_history_and_resume():
     """Save schedule of sample() (src/sample.cpp:171-197) and resuming from fit.state
     (R/run_inference.R:104-115): 3 + 3 resumed samples equal one run of 6."""
