@@ -1694,9 +1694,7 @@ int exb200_neighbours_create(const uint8_t* chars, const int32_t* lens, int32_t 
   r->probs.resize((size_t)nnz);
   r->mef.assign((size_t)n, 0.0);
   double max_d = 0.0;
-  bool any = false;
-  for (int64_t j = 0; j < nnz; j++) { max_d = std::max(max_d, (double)dist[j]); any = true; }
-  (void)any;
+  for (int64_t j = 0; j < nnz; j++) max_d = std::max(max_d, (double)dist[j]);
   for (int i = 0; i < n; i++) {
     double sum = 0.0, min_d = std::numeric_limits<double>::infinity();
     for (int64_t j = r->row_ptr[i]; j < r->row_ptr[i + 1]; j++) {
