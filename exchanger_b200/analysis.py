@@ -3,6 +3,8 @@
 reports (README.md:117-144, computed there with the ``clevr`` package).
 
 Host post-processing that runs once per fit; it is outside the Gibbs sweep.
+:class:`DevicePointEstimate` computes the same estimates on the GPU from the stream of saved link
+vectors, without the ``n_samples x N`` history.
 """
 from __future__ import annotations
 
@@ -83,3 +85,85 @@ def pairwise_measures(true_membership: np.ndarray, pred_membership: np.ndarray) 
     rec = tp / true_pairs if true_pairs else 1.0
     f1 = 2 * prec * rec / (prec + rec) if prec + rec else 0.0
     return dict(precision=prec, recall=rec, f1score=f1, true_pairs=true_pairs, pred_pairs=pred_pairs, tp=tp)
+
+
+class DevicePointEstimate:
+    """``mp_clusters`` / ``smp_clusters`` on the device (``exb200_pe_*`` of the C ABI): add the saved
+    samples one at a time - rows of a history (``add``) or the current links of a running chain
+    (``add_chain``, nothing leaves the GPU) - then ``finish``.
+
+    A cluster is identified by a 128-bit fingerprint of its member set.  When two clusters of a
+    record are equally frequent the reference keeps the lexicographically smaller member set
+    (``std::map<set<int>, int>`` order, point_estimate.cpp:65-87); the device keeps the smaller
+    fingerprint and flags the record in ``tied``.  With the history at hand (``finish(history=...)``)
+    tied records are settled on the host exactly as the reference does."""
+
+    def __init__(self, n_records: int, slots: int = 8, device: int = 0):
+        import ctypes as C
+        from . import capi
+        self._C, self._capi = C, capi
+        self.lib = capi.load_library()
+        self.n = int(n_records)
+        self.h = C.c_void_p()
+        rc = self.lib.exb200_pe_create(self.n, int(slots), int(device), C.byref(self.h))
+        if rc != capi.EXB200_OK:
+            self.h = None
+            raise capi.Exb200Error(rc, self.lib.exb200_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != self._capi.EXB200_OK:
+            raise self._capi.Exb200Error(rc, self.lib.exb200_last_error(None).decode())
+
+    def add(self, links: np.ndarray):
+        row = np.ascontiguousarray(links, dtype=np.int32)
+        if row.shape != (self.n,):
+            raise ValueError("one link per record expected")
+        self._check(self.lib.exb200_pe_add(self.h, row.ctypes.data_as(self._capi.c_i32p)))
+
+    def add_chain(self, sampler):
+        self._check(self.lib.exb200_pe_add_chain(self.h, sampler.h))
+
+    def finish(self, history: np.ndarray | None = None) -> dict:
+        """``membership`` (records with equal values form one shared most probable cluster),
+        ``probabilities`` (of each record's most probable cluster), ``first_sample``, ``tied``,
+        ``n_overflow``."""
+        C, capi = self._C, self._capi
+        memb, prob = np.empty(self.n, np.int32), np.empty(self.n)
+        first, tied = np.empty(self.n, np.int32), np.empty(self.n, np.int32)
+        over = C.c_int64()
+        self._check(self.lib.exb200_pe_finish(self.h, memb.ctypes.data_as(capi.c_i32p), prob.ctypes.data_as(capi.c_f64p),
+                                              first.ctypes.data_as(capi.c_i32p), tied.ctypes.data_as(capi.c_i32p), C.byref(over)))
+        if history is not None and tied.any():
+            # the reference's tie-break needs the member sets: only the tied records' clusters are rebuilt
+            history = np.asarray(history)
+
+            def members(s, r):
+                return tuple(np.flatnonzero(history[s] == history[s, r]).tolist())
+
+            group = {int(r): ("device", int(memb[r])) for r in range(self.n) if not tied[r]}
+            for r in np.flatnonzero(tied):
+                freq = Counter(members(s, r) for s in range(history.shape[0]))
+                top = max(freq.values())
+                cl = min(c for c, f in freq.items() if f == top)
+                key = ("set", cl)
+                for q in cl:   # an untied record whose most probable cluster is this very set
+                    if not tied[q] and members(int(first[q]), q) == cl:
+                        key = group[q]
+                        break
+                group[int(r)] = key
+            heads = {}
+            for r in range(self.n):
+                heads.setdefault(group[r], r)
+            memb = np.array([heads[group[r]] for r in range(self.n)], np.int32)
+        return dict(membership=memb, probabilities=prob, first_sample=first, tied=tied.astype(bool), n_overflow=int(over.value))
+
+    def close(self):
+        if self.h is not None:
+            self.lib.exb200_pe_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

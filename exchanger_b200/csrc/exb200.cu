@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "neighbours.cuh"
 #include "setup.cuh"
+#include "point_estimate.cuh"
 
 using namespace exb;
 
@@ -1706,6 +1707,125 @@ int exb200_neighbours_create(const uint8_t* chars, const int32_t* lens, int32_t 
     r->mef[i] = std::isfinite(min_d) ? std::exp(-0.5 * min_d / max_d) : 0.0;
   }
   *out = r;
+  return EXB200_OK;
+}
+
+// ---------------------------------------------------------------- point estimates on the device
+struct exb200_pe {
+  int device = 0, N = 0, slots = 8, n_samples = 0;
+  cudaStream_t stream = nullptr;
+  PeSlot* table = nullptr;
+  unsigned long long *fp1 = nullptr, *fp2 = nullptr;
+  int* links = nullptr;
+  int* misc = nullptr; // [0] label out of range, [1] overflow count
+};
+
+void exb200_pe_destroy(exb200_pe* pe) {
+  if (!pe) return;
+  cudaSetDevice(pe->device);
+  if (pe->stream) cudaStreamSynchronize(pe->stream);
+  cudaFree(pe->table); cudaFree(pe->fp1); cudaFree(pe->fp2); cudaFree(pe->links); cudaFree(pe->misc);
+  if (pe->stream) cudaStreamDestroy(pe->stream);
+  delete pe;
+}
+
+int exb200_pe_create(int32_t n_records, int32_t slots, int device, exb200_pe** out) {
+  if (!out || n_records < 1 || slots < 1 || slots > 64) return fail(nullptr, EXB200_ERR_INVALID, "point estimate: need n_records >= 1, 1 <= slots <= 64");
+  *out = nullptr;
+  if (exb200_device_count() <= 0) return fail(nullptr, EXB200_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU path");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, EXB200_ERR_NO_DEVICE, "invalid device index");
+  exb200_pe* pe = new exb200_pe();
+  pe->device = device; pe->N = n_records; pe->slots = slots;
+  const size_t n = (size_t)n_records;
+  bool ok = cudaStreamCreateWithFlags(&pe->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc((void**)&pe->table, sizeof(PeSlot) * n * slots) == cudaSuccess &&
+            cudaMalloc((void**)&pe->fp1, sizeof(unsigned long long) * 2 * n) == cudaSuccess &&
+            cudaMalloc((void**)&pe->fp2, sizeof(unsigned long long) * 2 * n) == cudaSuccess &&
+            cudaMalloc((void**)&pe->links, sizeof(int) * n) == cudaSuccess &&
+            cudaMalloc((void**)&pe->misc, sizeof(int) * 2) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(pe->table, 0, sizeof(PeSlot) * n * slots, pe->stream) == cudaSuccess &&
+               cudaMemsetAsync(pe->misc, 0, sizeof(int) * 2, pe->stream) == cudaSuccess &&
+               cudaStreamSynchronize(pe->stream) == cudaSuccess;
+  if (!ok) { exb200_pe_destroy(pe); return fail(nullptr, EXB200_ERR_OOM, "point estimate: device allocation failed"); }
+  *out = pe;
+  return EXB200_OK;
+}
+
+namespace {
+int pe_add_device(exb200_pe* pe, const int* d_links) {
+  const int N = pe->N;
+  cudaStream_t st = pe->stream;
+  cudaMemsetAsync(pe->fp1, 0, sizeof(unsigned long long) * 2 * (size_t)N, st);
+  cudaMemsetAsync(pe->fp2, 0, sizeof(unsigned long long) * 2 * (size_t)N, st);
+  k_pe_fingerprint<<<nblk(N), TPB, 0, st>>>(N, 2 * N, d_links, pe->fp1, pe->fp2, pe->misc);
+  int bad = 0;
+  cudaMemcpyAsync(&bad, pe->misc, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, "point estimate: fingerprint kernel failed");
+  if (bad) {
+    cudaMemsetAsync(pe->misc, 0, sizeof(int), st);
+    return fail(nullptr, EXB200_ERR_INVALID, "point estimate: labels must lie in [0, 2 * n_records)");
+  }
+  k_pe_count<<<nblk(N), TPB, 0, st>>>(N, pe->slots, pe->n_samples, d_links, pe->fp1, pe->fp2, pe->table, pe->misc + 1);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, "point estimate: counting kernel failed");
+  pe->n_samples++;
+  return EXB200_OK;
+}
+} // namespace
+
+int exb200_pe_add(exb200_pe* pe, const int32_t* links) {
+  if (!pe || !links) return EXB200_ERR_INVALID;
+  cudaSetDevice(pe->device);
+  if (cudaMemcpyAsync(pe->links, links, sizeof(int) * (size_t)pe->N, cudaMemcpyHostToDevice, pe->stream) != cudaSuccess)
+    return fail(nullptr, EXB200_ERR_CUDA, "point estimate: upload failed");
+  return pe_add_device(pe, pe->links);
+}
+
+int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h) {
+  if (!pe || !h) return EXB200_ERR_INVALID;
+  if (h->N != pe->N || h->device != pe->device) return fail(nullptr, EXB200_ERR_INVALID, "point estimate: chain of another size or device");
+  cudaSetDevice(pe->device);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, "point estimate: chain stream failed");
+  return pe_add_device(pe, h->S.lambda);
+}
+
+int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, int32_t* mp_sample, int32_t* tied,
+                     int64_t* n_overflow) {
+  if (!pe) return EXB200_ERR_INVALID;
+  if (pe->n_samples < 1) return fail(nullptr, EXB200_ERR_INVALID, "point estimate: no sample added");
+  cudaSetDevice(pe->device);
+  const int N = pe->N;
+  const size_t n = (size_t)N;
+  cudaStream_t st = pe->stream;
+  unsigned long long *k1 = nullptr, *k2 = nullptr, *k1s = nullptr;
+  int *cnt = nullptr, *smp = nullptr, *tie = nullptr, *ids = nullptr, *ids_s = nullptr, *head = nullptr, *memb = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k1, k1s, ids, ids_s, N, 0, 64, st);
+  std::vector<void*> held;
+  auto dal = [&](auto** p, size_t bytes) { void* q = nullptr; if (cudaMalloc(&q, std::max<size_t>(bytes, 1)) != cudaSuccess) return false; held.push_back(q); *p = (std::remove_reference_t<decltype(**p)>*)q; return true; };
+  auto release = [&] { for (void* q : held) cudaFree(q); };
+  bool ok = dal(&k1, 8 * n) && dal(&k2, 8 * n) && dal(&k1s, 8 * n) && dal(&cnt, 4 * n) && dal(&smp, 4 * n) && dal(&tie, 4 * n) &&
+            dal(&ids, 4 * n) && dal(&ids_s, 4 * n) && dal(&head, 4 * n) && dal(&memb, 4 * n);
+  if (ok) { ok = cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 1)) == cudaSuccess; if (ok) held.push_back(tmp); }
+  if (!ok) { release(); return fail(nullptr, EXB200_ERR_OOM, "point estimate: device allocation failed"); }
+  k_pe_best<<<nblk(N), TPB, 0, st>>>(N, pe->slots, pe->table, k1, k2, cnt, smp, tie, ids);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k1, k1s, ids, ids_s, N, 0, 64, st);
+  if (e == cudaSuccess) {
+    k_pe_heads<<<nblk(N), TPB, 0, st>>>(N, k1s, ids_s, k2, head);
+    k_pe_membership<<<nblk(N), TPB, 0, st>>>(N, ids_s, head, memb);
+  }
+  std::vector<int> h_cnt;
+  if (e == cudaSuccess && smp_membership) e = cudaMemcpyAsync(smp_membership, memb, 4 * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && mp_sample) e = cudaMemcpyAsync(mp_sample, smp, 4 * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && tied) e = cudaMemcpyAsync(tied, tie, 4 * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && mp_prob) { h_cnt.resize(n); e = cudaMemcpyAsync(h_cnt.data(), cnt, 4 * n, cudaMemcpyDeviceToHost, st); }
+  int over = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&over, pe->misc + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  release();
+  if (e != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, std::string("point estimate: ") + cudaGetErrorString(e));
+  if (mp_prob) for (size_t r = 0; r < n; r++) mp_prob[r] = 1.0 / (double)pe->n_samples * (double)h_cnt[r]; // point_estimate.cpp:97
+  if (n_overflow) *n_overflow = over;
   return EXB200_OK;
 }
 

@@ -270,6 +270,30 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value);
 void exb200_destroy(exb200_handle* h);
 
 /*
+ * Point estimates on the device from the stream of saved link vectors, without the n_samples x N
+ * history: what mp_clusters / smp_clusters compute from it (src/point_estimate.cpp:58-136,
+ * R/analysis.R:53-186).  Samples are added one at a time, from a host row of the history or
+ * straight from a chain's current links.  Labels must lie in [0, 2 * n_records).
+ *   smp_membership[r] : smallest record of r's shared most probable cluster (records with equal
+ *                       values form one cluster of smp_clusters)
+ *   mp_prob[r]        : relative frequency of r's most probable cluster (mp_clusters()$probabilities)
+ *   mp_sample[r]      : index of the first added sample in which that cluster appeared (its members
+ *                       are the records linked like r in that sample)
+ *   tied[r]           : 1 if another cluster of r is as frequent (the reference then takes the
+ *                       lexicographically smallest member set; here the smaller fingerprint)
+ *   *n_overflow       : occurrences not counted because a record was seen in more than `slots`
+ *                       distinct clusters
+ * Any output pointer may be NULL.
+ */
+typedef struct exb200_pe exb200_pe;
+int exb200_pe_create(int32_t n_records, int32_t slots, int device, exb200_pe** out);
+int exb200_pe_add(exb200_pe* pe, const int32_t* links);
+int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h);
+int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, int32_t* mp_sample,
+                     int32_t* tied, int64_t* n_overflow);
+void exb200_pe_destroy(exb200_pe* pe);
+
+/*
  * One-off model preparation on the GPU: the value neighbourhoods of a string attribute under
  * transform_dist_fn(Levenshtein(), threshold) - what compute_close_values builds in R
  * (R/AttributeIndex.R:117-137; the result fills exb200_attr.close_* and max_exp_factor).

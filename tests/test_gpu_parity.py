@@ -304,3 +304,39 @@ def test_rldata500_posterior_f1():
     pm = pairwise_measures(ident, clusters_to_membership(smp_clusters(fit.history["links"]), 500))
     assert 0.96 <= pm["f1score"] <= 1.0 and pm["tp"] >= 48
     assert abs(fit.history["n_linked_ents"].mean() - 449.65) < 1.5
+
+
+def test_device_point_estimates_match_the_host_restatement():
+    """mp_clusters / smp_clusters on the device (no history on the GPU side) against the host
+    restatement of src/point_estimate.cpp on a real chain, from history rows and straight from the
+    running chain."""
+    from exchanger_b200.analysis import DevicePointEstimate, mp_clusters
+    m, _ = readme_model("rldata500")
+    g = Sampler(m, seed=5)
+    g.sweeps(200)
+    rows = []
+    with DevicePointEstimate(500) as from_rows, DevicePointEstimate(500) as from_chain:
+        for _ in range(40):
+            g.sweeps(5)
+            from_chain.add_chain(g)
+            rows.append(g.state()["links"].copy())
+            from_rows.add(rows[-1])
+        hist = np.stack(rows)
+        a, b = from_rows.finish(history=hist), from_chain.finish(history=hist)
+    g.close()
+    best, prob = mp_clusters(hist)
+    want = clusters_to_membership(smp_clusters((best, prob)), 500)
+    for got in (a, b):
+        assert got["n_overflow"] == 0
+        assert np.allclose(got["probabilities"], prob)
+        # same partition: a bijection between the two labelings
+        pairs = set(zip(got["membership"].tolist(), want.tolist()))
+        assert len(pairs) == len(set(got["membership"].tolist())) == len(set(want.tolist()))
+        # the first sample in which the most probable cluster appeared holds exactly that cluster
+        for r in (0, 17, 250, 499):
+            if not got["tied"][r]:
+                s = got["first_sample"][r]
+                assert tuple(np.flatnonzero(hist[s] == hist[s, r]).tolist()) == best[r]
+    with pytest.raises(Exb200Error):
+        with DevicePointEstimate(4) as pe:
+            pe.add(np.array([0, 1, 9, 3], np.int32))  # label outside [0, 2N)
