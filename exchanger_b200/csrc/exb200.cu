@@ -111,6 +111,7 @@ struct exb200_handle {
   bool poisoned = false;
   bool has_index_events = false;
   long long n_launches = 0; // kernels launched by this handle
+  struct exb200_pe* pe = nullptr; // point estimate fed by exb200_run (not owned)
   // saved samples leave the device behind the next sweep: snapshot (D2D) -> pinned buffer on the
   // copy stream -> the caller's array by a host thread
   cudaStream_t copy_stream = nullptr;
@@ -1354,6 +1355,8 @@ int exb200_sweeps_timed(exb200_handle* h, int32_t n_sweeps, float* device_ms, in
   return rc;
 }
 
+int pe_add_chain_links(struct exb200_pe* pe, exb200_handle* h); // point estimates below
+
 namespace {
 // Host side of the sample pipeline of exb200_run: waits for a pinned buffer to be filled and copies
 // it into the caller's history row while the device runs the next sweep.
@@ -1468,6 +1471,7 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
           return finish(fail(h, EXB200_ERR_CUDA, std::string("history copy: ") + cudaGetErrorString(e)), sample);
         }
       }
+      if (h->pe) { const int rc2 = pe_add_chain_links(h->pe, h); if (rc2) return finish(rc2, sample); }
       if (out->n_linked_ents) out->n_linked_ents[sample] = h->K;
       for (int f = 0; f < h->F; f++)
         for (int a = 0; a < h->A; a++) {
@@ -1778,6 +1782,15 @@ int exb200_pe_add(exb200_pe* pe, const int32_t* links) {
   if (cudaMemcpyAsync(pe->links, links, sizeof(int) * (size_t)pe->N, cudaMemcpyHostToDevice, pe->stream) != cudaSuccess)
     return fail(nullptr, EXB200_ERR_CUDA, "point estimate: upload failed");
   return pe_add_device(pe, pe->links);
+}
+
+int pe_add_chain_links(exb200_pe* pe, exb200_handle* h) { return exb200_pe_add_chain(pe, h); }
+
+int exb200_attach_point_estimate(exb200_handle* h, exb200_pe* pe) {
+  if (!h) return EXB200_ERR_INVALID;
+  if (pe && (pe->N != h->N || pe->device != h->device)) return fail(h, EXB200_ERR_INVALID, "point estimate of another size or device");
+  h->pe = pe;
+  return EXB200_OK;
 }
 
 int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h) {

@@ -52,11 +52,16 @@ class Sampler:
         self._check(self.lib.exb200_sweeps_timed(self.h, int(n), C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
 
-    def run(self, n_samples: int, thin_interval: int = 1, burnin_interval: int = 0) -> dict:
-        """The sampling loop of ``sample()`` (src/sample.cpp:171-202) into fresh host arrays."""
+    def run(self, n_samples: int, thin_interval: int = 1, burnin_interval: int = 0, *,
+            keep_links: bool = True, point_estimate=None) -> dict:
+        """The sampling loop of ``sample()`` (src/sample.cpp:171-202) into fresh host arrays.
+        ``point_estimate`` (an ``analysis.DevicePointEstimate``) receives every saved sample on the
+        device; with ``keep_links=False`` the link vectors then never leave the GPU (``links`` of the
+        history is empty)."""
         N, FA, A = self.N, self.F * self.A, self.A
+        self._check(self.lib.exb200_attach_point_estimate(self.h, point_estimate.h if point_estimate is not None else None))
         hist = dict(
-            links=np.zeros((n_samples, N), np.int32),
+            links=np.zeros((n_samples if keep_links else 0, N), np.int32),
             distort_probs=np.zeros((n_samples, FA)),
             distort_counts=np.zeros((n_samples, FA), np.int32),
             distort_dist_concs=np.zeros((n_samples, A)),
@@ -64,7 +69,7 @@ class Sampler:
             clust_params=np.zeros((n_samples, 2)),
         )
         ch = CHistory()
-        ch.links = hist["links"].ctypes.data_as(c_i32p)
+        ch.links = hist["links"].ctypes.data_as(c_i32p) if keep_links else None
         ch.distort_probs = hist["distort_probs"].ctypes.data_as(c_f64p)
         ch.distort_counts = hist["distort_counts"].ctypes.data_as(c_i32p)
         ch.distort_dist_concs = hist["distort_dist_concs"].ctypes.data_as(c_f64p)
@@ -156,6 +161,7 @@ class ExchangERFit:
     history: dict
     state: ExchangERModel
     mcpar: tuple = field(default=(0, 0, 1))
+    point_estimate: dict | None = None   # run_inference(point_estimate=True): DevicePointEstimate.finish()
 
 
 def _is_integer(x) -> bool:
@@ -163,13 +169,17 @@ def _is_integer(x) -> bool:
 
 
 def run_inference(x, n_samples: int, thin_interval: int = 1, burnin_interval: int = 0, *,
-                  seed: int = 0, device: int = 0) -> ExchangERFit:
+                  seed: int = 0, device: int = 0, point_estimate: bool = False, keep_links: bool = True) -> ExchangERFit:
     """Mirror of ``run_inference`` (R/run_inference.R:60-115).
 
     ``x`` is an :class:`ExchangERModel` (new chain, or a chain resumed from ``fit.state``) or an
     :class:`ExchangERFit` (resume and concatenate the histories, :104-115).  ``seed`` plays the
     role of ``set.seed()``: it is the Philox key of the chain; the absolute iteration is part of
     every counter, so a resumed chain continues the same stream.
+
+    ``point_estimate=True`` also accumulates ``mp_clusters`` / ``smp_clusters`` on the device while the
+    chain runs (``fit.point_estimate``: ``analysis.DevicePointEstimate.finish()``); with
+    ``keep_links=False`` the ``n_samples x N`` link history is then not kept at all.
     """
     if isinstance(x, ExchangERFit):
         if burnin_interval != 0:
@@ -198,10 +208,20 @@ def run_inference(x, n_samples: int, thin_interval: int = 1, burnin_interval: in
         start_iter = burnin_interval if burnin_interval else thin_interval
     else:
         start_iter = x.iteration + thin_interval
+    pe_result = None
     with Sampler(x, seed=seed, device=device) as s:
-        history = s.run(n_samples, thin_interval, burnin_interval)
+        if point_estimate:
+            from .analysis import DevicePointEstimate
+            with DevicePointEstimate(s.N, device=device) as pe:
+                history = s.run(n_samples, thin_interval, burnin_interval, keep_links=keep_links, point_estimate=pe)
+                s._check(s.lib.exb200_attach_point_estimate(s.h, None))
+                pe_result = pe.finish(history["links"] if keep_links and n_samples else None) if n_samples else None
+        else:
+            history = s.run(n_samples, thin_interval, burnin_interval, keep_links=keep_links)
         final = model_with_state(x, s.state())
-    return ExchangERFit(history=history, state=final, mcpar=(start_iter, final.iteration, thin_interval))
+    fit = ExchangERFit(history=history, state=final, mcpar=(start_iter, final.iteration, thin_interval))
+    fit.point_estimate = pe_result
+    return fit
 
 
 def combine_results(a: ExchangERFit, b: ExchangERFit) -> ExchangERFit:

@@ -292,6 +292,9 @@ int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h);
 int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, int32_t* mp_sample,
                      int32_t* tied, int64_t* n_overflow);
 void exb200_pe_destroy(exb200_pe* pe);
+/* Every sample exb200_run saves from now on is also added to `pe` (NULL: detach), on the device;
+   with exb200_history.links = NULL the link vectors then never leave the GPU. */
+int exb200_attach_point_estimate(exb200_handle* h, exb200_pe* pe);
 
 /*
  * One-off model preparation on the GPU: the value neighbourhoods of a string attribute under

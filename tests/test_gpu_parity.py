@@ -340,3 +340,19 @@ def test_device_point_estimates_match_the_host_restatement():
     with pytest.raises(Exb200Error):
         with DevicePointEstimate(4) as pe:
             pe.add(np.array([0, 1, 9, 3], np.int32))  # label outside [0, 2N)
+
+
+def test_run_inference_with_device_point_estimate_and_no_link_history():
+    """run_inference(point_estimate=True): the estimates accumulated on the device while the chain
+    runs equal those computed from the history; with keep_links=False no link history is kept."""
+    m, _ = readme_model("rldata500", n=300)
+    fit = run_inference(m, n_samples=30, thin_interval=3, burnin_interval=60, seed=2, point_estimate=True)
+    want = clusters_to_membership(smp_clusters(fit.history["links"]), 300)
+    got = fit.point_estimate["membership"]
+    assert len(set(zip(got.tolist(), want.tolist()))) == len(set(got.tolist())) == len(set(want.tolist()))
+    lean = run_inference(m, n_samples=30, thin_interval=3, burnin_interval=60, seed=2, point_estimate=True, keep_links=False)
+    assert lean.history["links"].shape == (0, 300)
+    assert np.array_equal(lean.point_estimate["probabilities"], fit.point_estimate["probabilities"])
+    assert np.array_equal(lean.history["n_linked_ents"], fit.history["n_linked_ents"])
+    if not fit.point_estimate["tied"].any():  # ties are settled from the history, which `lean` does not have
+        assert np.array_equal(lean.point_estimate["membership"], fit.point_estimate["membership"])
