@@ -78,7 +78,10 @@ struct exb200_handle {
   int* d_hist = nullptr;       // [max D] entity-value histogram of one attribute
   std::vector<int> ndist, corr;
   DevState S{};                // device pointers (by-value kernel argument)
-  std::vector<void*> allocs;
+  // device memory comes from a few large slabs (bump allocation, freed together: a handle makes
+  // about a hundred allocations and cudaFree is slow per call)
+  struct Slab { char* base; size_t size, used; };
+  std::vector<Slab> slabs;
   std::mutex alloc_mu;          // attribute tables are built by concurrent host threads at create time
   DevAttr* d_attrs = nullptr;
   std::vector<DevAttr> h_attrs;
@@ -152,11 +155,21 @@ template <class F> void host_parallel(size_t work, F fn) {
 }
 
 template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
-  if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  { std::lock_guard<std::mutex> lk(h->alloc_mu); h->allocs.push_back(q); }
-  *p = (T*)q;
+  const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+  std::lock_guard<std::mutex> lk(h->alloc_mu);
+  if (h->slabs.empty() || h->slabs.back().size - h->slabs.back().used < bytes) {
+    // slabs double from 64 MiB to 2 GiB; a larger request gets a slab of its own size
+    size_t want = h->slabs.empty() ? ((size_t)64 << 20) : std::min<size_t>(h->slabs.back().size * 2, (size_t)2 << 30);
+    want = std::max(want, bytes);
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess && want > bytes) { want = bytes; e = cudaMalloc(&q, want); }
+    if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->slabs.push_back({(char*)q, want, 0});
+  }
+  exb200_handle::Slab& sl = h->slabs.back();
+  *p = (T*)(sl.base + sl.used);
+  sl.used += bytes;
   return EXB200_OK;
 }
 template <class T> int upload(exb200_handle* h, T** p, const T* src, size_t n) {
@@ -988,7 +1001,7 @@ void exb200_destroy(exb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (void* p : h->allocs) cudaFree(p);
+  for (auto& sl : h->slabs) cudaFree(sl.base);
   for (int b = 0; b < 2; b++) {
     if (h->pin_snap[b]) cudaFreeHost(h->pin_snap[b]);
     if (h->ev_snap[b]) cudaEventDestroy(h->ev_snap[b]);

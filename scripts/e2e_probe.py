@@ -35,3 +35,17 @@ for rep in range(2):
     t4 = time.perf_counter()
     print(f"rep {rep}: create {t1-t0:.3f}s (flat {getattr(g2,'t_flat',float('nan')):.3f}) run {t2-t1:.3f}s "
           f"({(t2-t1)/steps*1e3:.1f} ms/sweep) state {t3-t2:.3f}s close {t4-t3:.3f}s total {t4-t0:.3f}s")
+
+# the same call sequence with the point estimate accumulated on the device instead of a link history
+from exchanger_b200.analysis import DevicePointEstimate
+t0 = time.perf_counter()
+g4 = Sampler(hm, seed=2, device=0)
+pe = DevicePointEstimate(n)
+t1 = time.perf_counter()
+hist = g4.run(steps, 1, 0, keep_links=False, point_estimate=pe)
+t2 = time.perf_counter()
+res = pe.finish()
+t3 = time.perf_counter()
+pe.close(); g4.close()
+print(f"device point estimate instead of the link history: create {t1-t0:.3f}s run {t2-t1:.3f}s ({(t2-t1)/steps*1e3:.1f} ms/sweep) "
+      f"finish {t3-t2:.3f}s; {len(set(res['membership'].tolist()))} shared most probable clusters, overflow {res['n_overflow']}")
