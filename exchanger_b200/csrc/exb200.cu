@@ -1464,6 +1464,7 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
     return rc;
   };
   int sample = 0;
+  double wait_ms = 0.0; // time spent waiting for a staging buffer (EXB200_TRACE)
   const int initial = h->iteration;
   while (sample < n_samples) { // src/sample.cpp:171-202
     int rc = sweep(h);
@@ -1472,7 +1473,9 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
     if (completed >= burnin && (completed - burnin) % thin == 0) {
       if (out->links) {
         const int b = sample & 1;
+        const auto t_w = std::chrono::steady_clock::now();
         copier.acquire(b);
+        wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_w).count();
         cudaError_t e = cudaMemcpyAsync(h->d_snap[b], h->S.lambda, sizeof(int) * N, cudaMemcpyDeviceToDevice, h->stream);
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_snap[b], h->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream, h->ev_snap[b], 0);
@@ -1503,6 +1506,7 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
     if (abort_cb && abort_cb(ctx)) return finish(fail(h, EXB200_ERR_ABORTED, "aborted by the caller"), sample);
     if (progress_cb) progress_cb(ctx, completed);
   }
+  if (h->trace) std::fprintf(stderr, "[exb200] run: %d samples, %.1f ms waiting for staging buffers\n", sample, wait_ms);
   return finish(EXB200_OK, sample);
 }
 
