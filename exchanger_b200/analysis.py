@@ -123,6 +123,23 @@ class DevicePointEstimate:
     def add_chain(self, sampler):
         self._check(self.lib.exb200_pe_add_chain(self.h, sampler.h))
 
+    def set_pairs(self, pairs: np.ndarray):
+        """Record pairs (0-based, ``[n_pairs, 2]``) whose coreference is counted from now on
+        (``coreference_probs``, R/coreference_probs.R:54-82)."""
+        self._pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        self._check(self.lib.exb200_pe_set_pairs(self.h, self._pairs.ctypes.data_as(self._capi.c_i32p), len(self._pairs)))
+
+    def coreference_counts(self):
+        """``(counts, n_samples)`` for the pairs of :meth:`set_pairs`."""
+        counts = np.zeros(len(self._pairs), np.int32)
+        ns = self._C.c_int32()
+        self._check(self.lib.exb200_pe_pair_counts(self.h, counts.ctypes.data_as(self._capi.c_i32p), self._C.byref(ns)))
+        return counts.astype(np.int64), int(ns.value)
+
+    def coreference_probs(self) -> np.ndarray:
+        counts, ns = self.coreference_counts()
+        return counts / float(ns)
+
     def finish(self, history: np.ndarray | None = None) -> dict:
         """``membership`` (records with equal values form one shared most probable cluster),
         ``probabilities`` (of each record's most probable cluster), ``first_sample``, ``tied``,

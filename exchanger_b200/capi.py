@@ -241,6 +241,8 @@ def load_library(path: str | None = None):
     lib.exb200_pe_destroy.argtypes = [H]
     lib.exb200_pe_destroy.restype = None
     lib.exb200_attach_point_estimate.argtypes = [H, H]
+    lib.exb200_pe_set_pairs.argtypes = [H, c_i32p, C.c_int64]
+    lib.exb200_pe_pair_counts.argtypes = [H, c_i32p, c_i32p]
     lib.exb200_neighbours_create.argtypes = [C.c_void_p, c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int,
                                              C.POINTER(H)]
     lib.exb200_neighbours_nnz.argtypes = [H]
@@ -293,5 +295,5 @@ EXPORTED_SYMBOLS = [
     "exb200_shard_links", "exb200_shard_entities", "exb200_shard_distort", "exb200_shard_finish",
     "exb200_device_buffer", "exb200_stream_sync",
     "exb200_pe_create", "exb200_pe_add", "exb200_pe_add_chain", "exb200_pe_finish", "exb200_pe_destroy",
-    "exb200_attach_point_estimate",
+    "exb200_attach_point_estimate", "exb200_pe_set_pairs", "exb200_pe_pair_counts",
 ]

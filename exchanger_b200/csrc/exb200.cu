@@ -1739,6 +1739,9 @@ struct exb200_pe {
   unsigned long long *fp1 = nullptr, *fp2 = nullptr;
   int* links = nullptr;
   int* misc = nullptr; // [0] label out of range, [1] overflow count
+  int* pairs = nullptr; int* pair_counts = nullptr; // coreference counting (exb200_pe_set_pairs)
+  long long n_pairs = 0;
+  int pair_samples = 0;
 };
 
 void exb200_pe_destroy(exb200_pe* pe) {
@@ -1746,6 +1749,7 @@ void exb200_pe_destroy(exb200_pe* pe) {
   cudaSetDevice(pe->device);
   if (pe->stream) cudaStreamSynchronize(pe->stream);
   cudaFree(pe->table); cudaFree(pe->fp1); cudaFree(pe->fp2); cudaFree(pe->links); cudaFree(pe->misc);
+  cudaFree(pe->pairs); cudaFree(pe->pair_counts);
   if (pe->stream) cudaStreamDestroy(pe->stream);
   delete pe;
 }
@@ -1787,11 +1791,44 @@ int pe_add_device(exb200_pe* pe, const int* d_links) {
     return fail(nullptr, EXB200_ERR_INVALID, "point estimate: labels must lie in [0, 2 * n_records)");
   }
   k_pe_count<<<nblk(N), TPB, 0, st>>>(N, pe->slots, pe->n_samples, d_links, pe->fp1, pe->fp2, pe->table, pe->misc + 1);
+  if (pe->n_pairs > 0) {
+    k_pe_pairs<<<nblk(pe->n_pairs), TPB, 0, st>>>(pe->n_pairs, pe->pairs, d_links, pe->pair_counts);
+    pe->pair_samples++;
+  }
   if (cudaStreamSynchronize(st) != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, "point estimate: counting kernel failed");
   pe->n_samples++;
   return EXB200_OK;
 }
 } // namespace
+
+int exb200_pe_set_pairs(exb200_pe* pe, const int32_t* pairs, int64_t n_pairs) {
+  if (!pe || n_pairs < 0 || (n_pairs > 0 && !pairs)) return EXB200_ERR_INVALID;
+  cudaSetDevice(pe->device);
+  for (int64_t i = 0; i < 2 * n_pairs; i++)
+    if (pairs[i] < 0 || pairs[i] >= pe->N) return fail(nullptr, EXB200_ERR_INVALID, "point estimate: `pairs` refers to records that are not there");
+  cudaStreamSynchronize(pe->stream);
+  cudaFree(pe->pairs); cudaFree(pe->pair_counts);
+  pe->pairs = pe->pair_counts = nullptr; pe->n_pairs = 0; pe->pair_samples = 0;
+  if (n_pairs == 0) return EXB200_OK;
+  if (cudaMalloc((void**)&pe->pairs, sizeof(int) * 2 * (size_t)n_pairs) != cudaSuccess ||
+      cudaMalloc((void**)&pe->pair_counts, sizeof(int) * (size_t)n_pairs) != cudaSuccess)
+    return fail(nullptr, EXB200_ERR_OOM, "point estimate: device allocation failed");
+  cudaMemcpyAsync(pe->pairs, pairs, sizeof(int) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice, pe->stream);
+  cudaMemsetAsync(pe->pair_counts, 0, sizeof(int) * (size_t)n_pairs, pe->stream);
+  if (cudaStreamSynchronize(pe->stream) != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, "point estimate: upload failed");
+  pe->n_pairs = n_pairs;
+  return EXB200_OK;
+}
+
+int exb200_pe_pair_counts(exb200_pe* pe, int32_t* counts, int32_t* n_samples) {
+  if (!pe || !counts) return EXB200_ERR_INVALID;
+  cudaSetDevice(pe->device);
+  if (pe->n_pairs > 0 && (cudaMemcpyAsync(counts, pe->pair_counts, sizeof(int) * (size_t)pe->n_pairs, cudaMemcpyDeviceToHost, pe->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(pe->stream) != cudaSuccess))
+    return fail(nullptr, EXB200_ERR_CUDA, "point estimate: download failed");
+  if (n_samples) *n_samples = pe->pair_samples;
+  return EXB200_OK;
+}
 
 int exb200_pe_add(exb200_pe* pe, const int32_t* links) {
   if (!pe || !links) return EXB200_ERR_INVALID;

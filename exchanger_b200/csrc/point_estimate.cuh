@@ -89,4 +89,11 @@ __global__ void __launch_bounds__(TPB) k_pe_membership(int n, const int* __restr
   membership[ids_sorted[i]] = ids_sorted[j];
 }
 
+// coreference counts of given record pairs (numerator of coreference_probs, R/coreference_probs.R:77-79)
+__global__ void __launch_bounds__(TPB) k_pe_pairs(long long n_pairs, const int* __restrict__ pairs, const int* __restrict__ links,
+                                                  int* __restrict__ counts) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs && links[pairs[2 * p]] == links[pairs[2 * p + 1]]) counts[p]++;
+}
+
 } // namespace exb

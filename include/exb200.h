@@ -291,6 +291,12 @@ int exb200_pe_add(exb200_pe* pe, const int32_t* links);
 int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h);
 int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, int32_t* mp_sample,
                      int32_t* tied, int64_t* n_overflow);
+/* Record pairs ([n_pairs][2], 0-based) whose coreference is counted in every sample added from
+   now on: counts[p] = samples in which both records had the same entity, the numerator of
+   coreference_probs (R/coreference_probs.R:54-82); *n_samples = samples added since the pairs
+   were set. */
+int exb200_pe_set_pairs(exb200_pe* pe, const int32_t* pairs, int64_t n_pairs);
+int exb200_pe_pair_counts(exb200_pe* pe, int32_t* counts, int32_t* n_samples);
 void exb200_pe_destroy(exb200_pe* pe);
 /* Every sample exb200_run saves from now on is also added to `pe` (NULL: detach), on the device;
    with exb200_history.links = NULL the link vectors then never leave the GPU. */

@@ -315,7 +315,9 @@ def test_device_point_estimates_match_the_host_restatement():
     g = Sampler(m, seed=5)
     g.sweeps(200)
     rows = []
+    pairs = np.array([[0, 1], [10, 11], [3, 250], [498, 499], [42, 42]])
     with DevicePointEstimate(500) as from_rows, DevicePointEstimate(500) as from_chain:
+        from_chain.set_pairs(pairs)
         for _ in range(40):
             g.sweeps(5)
             from_chain.add_chain(g)
@@ -323,6 +325,8 @@ def test_device_point_estimates_match_the_host_restatement():
             from_rows.add(rows[-1])
         hist = np.stack(rows)
         a, b = from_rows.finish(history=hist), from_chain.finish(history=hist)
+        from exchanger_b200.chains import coreference_probs
+        assert np.array_equal(from_chain.coreference_probs(), coreference_probs(hist, pairs))
     g.close()
     best, prob = mp_clusters(hist)
     want = clusters_to_membership(smp_clusters((best, prob)), 500)
