@@ -167,10 +167,11 @@ __global__ void k_theta_tables(DevState S, int a) {
 //     are rarest, or all of them when that pair is expected to match many items (replaces the
 //     set-size ordering of getPossibleLinks, links.cpp:187-189)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_prep(DevState S) {
-  __shared__ int s_usage[2 * N_TABLES];
-  __shared__ float s_est[N_TABLES];
+__global__ void __launch_bounds__(TPB, 4) k_prep(DevState S) {
+  extern __shared__ int s_prep[]; // [2][2^n_key] usage counts, [2^n_key] expected visits (float)
   const int AA = 1 << S.n_key;
+  int* s_usage = s_prep;
+  float* s_est = reinterpret_cast<float*>(s_prep + 2 * AA);
   for (int i = threadIdx.x; i < AA; i += blockDim.x) { s_usage[i] = 0; s_usage[AA + i] = 0; s_est[i] = 0.f; }
   __syncthreads();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
