@@ -440,32 +440,44 @@ __global__ void __launch_bounds__(TPB) k_part_b(DevState S, PartBuild P) {
   const unsigned long long* pairs = P.pairs + (size_t)k * P.cap;
   for (int b = threadIdx.x; b < PART_SIZE; b += TPB) s_cnt[b] = 0;
   __syncthreads();
-  for (int q = lo + threadIdx.x; q < hi; q += TPB) atomicAdd(&s_cnt[(int)(pairs[q] & (PART_SIZE - 1))], 1);
-  __syncthreads();
-  // exclusive scan of the counters (each thread owns PART_SIZE / TPB consecutive ones)
-  constexpr int PER = PART_SIZE / TPB;
-  int tsum = 0;
-  for (int j = 0; j < PER; j++) tsum += s_cnt[threadIdx.x * PER + j];
-  s_w[threadIdx.x] = tsum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int q = 0; q < TPB; q++) { const int x = s_w[q]; s_w[q] = run; run += x; }
+  // four loads in flight per thread: the kernel waits on these loads and on nothing else
+  for (int q0 = lo; q0 < hi; q0 += 4 * TPB) {
+    unsigned long long v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int q = q0 + u * TPB + threadIdx.x; v[u] = q < hi ? pairs[q] : ~0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (q0 + u * TPB + (int)threadIdx.x < hi) atomicAdd(&s_cnt[(int)(v[u] & (PART_SIZE - 1))], 1);
   }
   __syncthreads();
-  int run = lo + s_w[threadIdx.x];
+  // exclusive scan of the counters, TPB consecutive ones at a time (thread = counter: no bank
+  // conflicts), with a running carry; s_cnt[b] becomes the start of bucket b, ptr[b] its end
   const uint32_t b0 = (uint32_t)p << PART_BITS;
-  for (int j = 0; j < PER; j++) {
-    const int b = threadIdx.x * PER + j;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int carry = lo;
+  for (int c0 = 0; c0 < PART_SIZE; c0 += TPB) {
+    const int b = c0 + threadIdx.x;
     const int c = s_cnt[b];
-    s_cnt[b] = run;           // start of the bucket: cursor of the fill below
-    run += c;
-    if (b0 + b < t.B) t.ptr[b0 + b] = run; // END offset of the bucket
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[w] = x;
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int k2 = 0; k2 < TPB / 32; k2++) { const int sv = s_w[k2]; if (k2 < w) off += sv; total += sv; }
+    const int end = carry + off + x;
+    s_cnt[b] = end - c;       // start of the bucket: cursor of the fill below
+    if (b0 + b < t.B) t.ptr[b0 + b] = end; // END offset of the bucket
+    carry += total;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int q = lo + threadIdx.x; q < hi; q += TPB) {
-    const unsigned long long v = pairs[q];
-    t.ids[atomicAdd(&s_cnt[(int)(v & (PART_SIZE - 1))], 1)] = (int)(v >> PART_BITS);
+  for (int q0 = lo; q0 < hi; q0 += 4 * TPB) {
+    unsigned long long v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int q = q0 + u * TPB + threadIdx.x; v[u] = q < hi ? pairs[q] : ~0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (q0 + u * TPB + (int)threadIdx.x < hi) t.ids[atomicAdd(&s_cnt[(int)(v[u] & (PART_SIZE - 1))], 1)] = (int)(v[u] >> PART_BITS);
   }
 }
 
