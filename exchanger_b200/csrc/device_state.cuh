@@ -161,7 +161,7 @@ enum CounterSlot {
   C_NACTL_INIT = 9, // long records found by candidate generation
   C_NUNK = 10,      // size of unk_list
   C_NFENCE = 11,    // records that take their turn serially inside the rounds
-  C_COUNT = 12,     // (free)
+  C_LONG_NEXT = 12, // next entry of long_todo to hand out (k_cand_long)
   C_NHUGE = 13,     // size of huge_list
   C_NOLIST = 14,    // records without a stored list after candidate generation (diagnostic)
   C_NPROBE = 15,    // size of probe_list

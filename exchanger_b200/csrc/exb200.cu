@@ -692,7 +692,7 @@ int update_links(exb200_handle* h) {
   if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
     const size_t smem = (size_t)pow2_ceil(std::max(h->long_cap, 1)) * (sizeof(double) + sizeof(int)); // padded for the bitonic sort
     const int n_todo = hc[C_NLONG_TODO];
-    KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 8), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
+    KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 4), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     lap("block-staged candidate lists", n_todo);

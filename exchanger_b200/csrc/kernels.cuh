@@ -878,10 +878,13 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
   int* ids = reinterpret_cast<int*>(lls + pow2_ceil(cap)); // the sort pads the list to a power of two
   __shared__ int s_cnt;
   __shared__ unsigned long long s_off;
-  for (int w = blockIdx.x; w < n_todo; w += gridDim.x) {
-    const int r = S.long_todo[w];
-    if (threadIdx.x == 0) s_cnt = 0;
+  __shared__ int s_next;
+  for (;;) { // records are handed out one at a time: their costs differ by orders of magnitude
+    if (threadIdx.x == 0) { s_next = atomicAdd(&S.counters[C_LONG_NEXT], 1); s_cnt = 0; }
     __syncthreads();
+    const int w = s_next;
+    if (w >= n_todo) break;
+    const int r = S.long_todo[w];
     const int* x = S.rec_x + (size_t)r * S.RS;
     const uint32_t zm = S.rec_z[r];
     int tab = S.tab_remap[S.rec_tab[r]];
