@@ -300,3 +300,54 @@ def test_dirichlet_entity_prior_runs_and_moves_phi():
     b.sweeps(15)
     assert np.array_equal(a.state()["links"], b.state()["links"])
     assert 200 < len(a.state()["ent_ids"]) <= 300
+
+
+def test_closed_form_string_schemes_draw_from_the_reference_law():
+    """The closed-form draws for string attributes (one observed member value held by one or by two
+    members: static row prefix sums instead of the explicit support) against the law defined by the
+    REFERENCE's logWeightEntityValue (src/entities.cpp:236-296): 600 independent draws per entity
+    and attribute, chi-square on the cells with enough mass."""
+    from scipy.stats import chisquare
+    m, _ = readme_model("rldata500")
+    o = OracleSampler(m, seed=3)
+    o.sweeps(40)
+    st = o.state()
+    m2 = model_with_state(m, st)
+    ref = RefSampler(m2)
+    links, ents = st["links"], st["ent_ids"]
+    picks = []   # (entity, column of ent_attrs, attribute, number of members)
+    for want in (2, 1):
+        for col, e in enumerate(ents):
+            mem = np.flatnonzero(links == e)
+            if len(mem) != want:
+                continue
+            for a in (3, 4):
+                x = m.rec_attrs[a, mem]
+                if (x >= 0).all() and len(set(x.tolist())) == 1:
+                    picks.append((int(e), col, a, want))
+            if sum(p[3] == want for p in picks) >= 6:
+                break
+    assert sum(p[3] == 2 for p in picks) >= 4 and sum(p[3] == 1 for p in picks) >= 4
+    n_draws = 600
+    counts = {p: np.zeros(len(m.attr_indices[p[2]].probs)) for p in picks}
+    for seed in range(n_draws):
+        o2 = OracleSampler(m2, seed=1000 + seed)
+        o2.phases(4)   # entity attributes only
+        y = o2.state()["ent_attrs"]
+        for p in picks:
+            counts[p][y[p[2], p[1]]] += 1
+    worst_p = 1.0
+    for p in picks:
+        e, _, a, _ = p
+        D = len(counts[p])
+        lw = np.array([ref.lib.exref_log_weight_entity_value(ref.h, e, a, v) for v in range(D)])
+        pmf = np.exp(lw - lw.max())
+        pmf /= pmf.sum()
+        assert counts[p][pmf == 0].sum() == 0          # never a value of zero weight
+        big = pmf * n_draws >= 5
+        obs = np.append(counts[p][big], counts[p][~big].sum())
+        exp = np.append(pmf[big], pmf[~big].sum()) * n_draws
+        keep = exp > 0
+        if keep.sum() > 1:
+            worst_p = min(worst_p, chisquare(obs[keep], exp[keep]).pvalue)
+    assert worst_p > 1e-4   # a dozen tests: a false alarm once in a thousand runs
