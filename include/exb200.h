@@ -35,7 +35,9 @@
 extern "C" {
 #endif
 
-#define EXB200_ABI_VERSION 1
+/* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
+   estimates (exb200_pe_*) added */
+#define EXB200_ABI_VERSION 2
 
 enum {
   EXB200_OK = 0,
