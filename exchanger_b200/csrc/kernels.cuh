@@ -554,9 +554,10 @@ __global__ void __launch_bounds__(TPB) k_scan_apply(const T_IN* __restrict__ in,
 }
 
 // ------------------------------------------------------------------------------------------
-// K1c  candidate generation: one WARP per record (replaces getPossibleLinks, src/links.cpp:90-212,
-// and the per-candidate likelihood logLikelihoodWeightExisting, src/links.cpp:216-288).
-// The warp streams the record's bucket, gathers each item's attribute tuple (one 32-byte sector),
+// K1c  candidate generation: a group of lanes per record - eight in the first launch, a whole warp
+// for the records listed for the second (replaces getPossibleLinks, src/links.cpp:90-212, and the
+// per-candidate likelihood logLikelihoodWeightExisting, src/links.cpp:216-288).
+// The group streams the record's bucket(s), gathers each item's attribute tuple (one 32-byte sector),
 // keeps the items that agree with the record on every observed non-distorted attribute
 // (links.cpp:122-131) and stores them, sorted by id, with the log-likelihood of the distorted
 // attributes.  Attribute tuples do not change during the links update, so this list is computed
