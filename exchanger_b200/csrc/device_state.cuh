@@ -102,7 +102,8 @@ struct DevState {
   int key_attr[KEY_ATTRS];      // key position -> attribute
   int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
   uint32_t *cand_off;           // [N]
-  int *cand_cnt;                // [N] >= 0: stored list; -1: wide (turn taken first); -2: serial fence; -3: unclassified
+  int *cand_cnt;                // [N] >= 0: stored list; -1: wide (turn taken first); -2: list did not fit the pool
+                                //     (serial turn inside the rounds); -3: no usable bucket yet (batched scan)
   int *cand_id; double *cand_ll;// candidate pool
   unsigned long long *pool_cursor; unsigned long long pool_cap;
   unsigned long long *owner;    // [2N] reservation words
@@ -131,7 +132,7 @@ struct DevState {
   int *wl_logn;                 // [WIDE_PIECES] entries logged (-1: the piece's log overflowed)
   int wl_logcap;
   unsigned long long wl_cap;
-  int huge_min;                 // bucket length above which the whole grid scans it
+  int huge_min;                 // bucket length above which the bucket is cut into tiles (k_huge_*)
   double *wide_part;            // [WIDE_BLOCKS * 257 + WIDE_BLOCKS] partial maxima / sums of the wide path
   int *counters;                // see CounterSlot
   long long *counters64;        // [0] candidates, [1] bucket items visited

@@ -798,7 +798,7 @@ int update_links(exb200_handle* h) {
     CK(cudaStreamSynchronize(st));
     S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
   }
-  // records classified as serial fences by the host loop above are pending too
+  // records whose list did not fit the candidate pool (n_fence) are pending too
   if (S.use_kbounds) KLAUNCH(h, k_bounds_init, nblk(N), TPB, 0, S, n_fence > 0 ? 1 : 0);
   CK(cudaEventRecord(h->ev[11], st));
 

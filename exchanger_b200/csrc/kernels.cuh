@@ -1035,7 +1035,8 @@ __global__ void __launch_bounds__(TPB) k_huge_finish(DevState S, const int* __re
 // all the items its conditional reads or may write: its entity, its potential entity and its
 // candidates.  A record whose reservations all carry its own id has no earlier unfinalised
 // record that could change what it reads, so its conditional is already the one the sequential
-// scan would see.  Wide records (no stored candidate list) act as a fence.
+// scan would see.  A record whose list did not fit the candidate pool (cand_cnt = -2) acts as a
+// fence: it takes its turn serially when every earlier record is final.
 // Records with short lists take one thread each; records with more than long_min candidates take
 // a warp each (k_reserve_w / k_commit_w) - same arithmetic in the same order.
 // ------------------------------------------------------------------------------------------
