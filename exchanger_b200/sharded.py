@@ -42,6 +42,30 @@ def exchange_ragged(dist, values, stage, chunk: int, lo: int, hi: int, rank: int
     return values
 
 
+def sharded_sweep(chain, dist, rank: int, world: int, group=None):
+    """One sweep of a chain held by every rank.  ``chain`` provides the slice
+    calls (``links()``, ``entities(lo, hi)``, ``distort(lo, hi) -> (ndist, corr)``,
+    ``finish(ndist, corr)``, ``fence()``), the exchanged arrays (``ent_y`` [rows, ints], ``rec_z`` [N],
+    staging ``z_stage`` [world * chunk], ``counts`` [2 * FA] int64) and ``N``, ``FA``, ``chunk``,
+    ``lo``, ``hi``.  Collectives: one all-gather of the entity tuples, one of the distortion masks,
+    one all-reduce of the two count matrices."""
+    chain.links()                                   # replicated: keyed randomness, identical on every rank
+    chain.entities(chain.lo, chain.hi)
+    chain.fence()
+    if world > 1:
+        exchange_slices(dist, chain.ent_y, chain.chunk, rank, world, group)
+        chain.fence()
+    nd, co = chain.distort(chain.lo, chain.hi)
+    if world > 1:
+        exchange_ragged(dist, chain.rec_z, chain.z_stage, chain.chunk, chain.lo, chain.hi, rank, world, group)
+        chain.counts.copy_(chain.counts.new_tensor(np.concatenate([nd, co]).astype(np.int64)))
+        dist.all_reduce(chain.counts, group=group)
+        chain.fence()
+        both = chain.counts.cpu().numpy()
+        nd, co = both[: chain.FA].astype(np.int32), both[chain.FA:].astype(np.int32)
+    chain.finish(nd, co)
+
+
 class _DeviceArray:
     """Zero-copy view of a library buffer for ``torch.as_tensor`` (``__cuda_array_interface__``)."""
 
@@ -73,25 +97,30 @@ class ShardedSampler:
         self.z_stage = torch.zeros(self.world * self.chunk, dtype=torch.int32, device=self.device)
         self.counts = torch.zeros(2 * self.FA, dtype=torch.int64, device=self.device)
 
-    def sweeps(self, n: int = 1):
-        torch, dist, lib, h, chk = self.torch, self.dist, self.lib, self.h, self.sampler._check
+    # ---- the slice calls of the C ABI, as the backend of `sharded_sweep`
+    def links(self):
+        self.sampler._check(self.lib.exb200_shard_links(self.h))
+
+    def entities(self, lo: int, hi: int):
+        self.sampler._check(self.lib.exb200_shard_entities(self.h, lo, hi))
+
+    def distort(self, lo: int, hi: int):
         nd, co = np.zeros(self.FA, np.int32), np.zeros(self.FA, np.int32)
+        self.sampler._check(self.lib.exb200_shard_distort(self.h, lo, hi, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
+        return nd, co
+
+    def finish(self, nd: np.ndarray, co: np.ndarray):
+        nd, co = np.ascontiguousarray(nd, np.int32), np.ascontiguousarray(co, np.int32)
+        self.sampler._check(self.lib.exb200_shard_finish(self.h, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
+
+    def fence(self):
+        """The library's stream and torch's: nothing of either is in flight afterwards."""
+        self.sampler._check(self.lib.exb200_stream_sync(self.h))
+        self.torch.cuda.synchronize(self.device)
+
+    def sweeps(self, n: int = 1):
         for _ in range(n):
-            chk(lib.exb200_shard_links(h))
-            chk(lib.exb200_shard_entities(h, self.lo, self.hi))
-            chk(lib.exb200_stream_sync(h))
-            if self.world > 1:   # entity tuples of every slice, in place
-                exchange_slices(dist, self.ent_y, self.chunk, self.rank, self.world, self.group)
-                torch.cuda.synchronize(self.device)
-            chk(lib.exb200_shard_distort(h, self.lo, self.hi, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
-            if self.world > 1:   # distortion masks of every slice, counts summed
-                exchange_ragged(dist, self.rec_z, self.z_stage, self.chunk, self.lo, self.hi, self.rank, self.world, self.group)
-                self.counts.copy_(torch.from_numpy(np.concatenate([nd, co]).astype(np.int64)))
-                dist.all_reduce(self.counts, group=self.group)
-                torch.cuda.synchronize(self.device)
-                both = self.counts.cpu().numpy().astype(np.int32)
-                nd, co = np.ascontiguousarray(both[: self.FA]), np.ascontiguousarray(both[self.FA:])
-            chk(lib.exb200_shard_finish(h, nd.ctypes.data_as(c_i32p), co.ctypes.data_as(c_i32p)))
+            sharded_sweep(self, self.dist, self.rank, self.world, self.group)
 
     def state(self):
         return self.sampler.state()

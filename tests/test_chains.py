@@ -90,3 +90,71 @@ def test_slice_exchange_two_ranks_gloo():
     out = mp.Manager().dict()
     mp.spawn(_shard_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] == (True, True) and out[1] == (True, True)
+
+
+class _ToyChain:
+    """Stand-in for the library behind `sharded_sweep`: deterministic toy phases whose results depend
+    on the other ranks' slices, so a missing or misplaced exchange changes the outcome."""
+
+    def __init__(self, n, world, rank):
+        import torch
+        from exchanger_b200.sharded import slice_bounds
+        self.N, self.FA, self.it = n, 5, 0
+        self.chunk, self.lo, self.hi = slice_bounds(n, world, rank)
+        self.ent_y = torch.zeros(2 * n, 8, dtype=torch.int32)
+        self.rec_z = torch.zeros(n, dtype=torch.int32)
+        self.z_stage = torch.zeros(world * self.chunk, dtype=torch.int32)
+        self.counts = torch.zeros(2 * self.FA, dtype=torch.int64)
+        self.theta = []
+
+    def links(self):
+        import torch
+        self.ent_y[self.N:] = (torch.arange(self.N, dtype=torch.int32)[:, None] + self.it) % 97   # replicated part
+
+    def entities(self, lo, hi):
+        import torch
+        rows = torch.arange(lo, hi, dtype=torch.int32)
+        self.ent_y[lo:hi] = (rows[:, None] * 7 + self.it * 3 + torch.arange(8, dtype=torch.int32) + self.rec_z[lo:hi, None]) % 1000
+
+    def distort(self, lo, hi):
+        import torch
+        r = torch.arange(lo, hi)
+        self.rec_z[lo:hi] = (self.ent_y[(r * 13 + 5) % self.N, 0] + self.ent_y[r, 1] + self.it) & 31   # reads other slices
+        z = self.rec_z[lo:hi]
+        nd = np.array([int(((z >> a) & 1).sum()) for a in range(self.FA)], np.int32)
+        return nd, (nd[::-1] * 2).astype(np.int32)   # both count matrices are sums over records
+
+    def finish(self, nd, co):
+        self.theta.append((int(nd.sum()), int(co.sum())))
+        self.it += 1
+
+    def fence(self):
+        pass
+
+
+def _toy_worker(rank, world, port, out):
+    from exchanger_b200.sharded import sharded_sweep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chain = _ToyChain(23, world, rank)
+    for _ in range(4):
+        sharded_sweep(chain, dist, rank, world)
+    out[rank] = (chain.ent_y[:23].numpy().copy(), chain.rec_z.numpy().copy(), chain.theta)
+    dist.destroy_process_group()
+
+
+def test_sharded_sweep_equals_the_unsharded_one_two_ranks_gloo():
+    from exchanger_b200.sharded import sharded_sweep
+    whole = _ToyChain(23, 1, 0)
+    for _ in range(4):
+        sharded_sweep(whole, None, 0, 1)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_toy_worker, args=(2, port, out), nprocs=2, join=True)
+    for rank in (0, 1):
+        y, z, theta = out[rank]
+        assert np.array_equal(y, whole.ent_y[:23].numpy()) and np.array_equal(z, whole.rec_z.numpy())
+        assert theta == whole.theta
