@@ -135,6 +135,10 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.Exb200Error) as e:
         run_inference(m, n_samples=1)
     assert e.value.status == -3
+    from exchanger_b200.analysis import DevicePointEstimate
+    with pytest.raises(capi.Exb200Error) as e:   # the device point estimates have no host path either
+        DevicePointEstimate(50)
+    assert e.value.status == -3
     src = ""
     for root, _, files in os.walk(os.path.join(ROOT, "exchanger_b200")):
         for f in files:
