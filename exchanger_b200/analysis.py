@@ -150,21 +150,31 @@ class DevicePointEstimate:
         over = C.c_int64()
         self._check(self.lib.exb200_pe_finish(self.h, memb.ctypes.data_as(capi.c_i32p), prob.ctypes.data_as(capi.c_f64p),
                                               first.ctypes.data_as(capi.c_i32p), tied.ctypes.data_as(capi.c_i32p), C.byref(over)))
-        if history is not None and tied.any():
-            # the reference's tie-break needs the member sets: only the tied records' clusters are rebuilt
+        overflowed = np.zeros(self.n, np.uint8)
+        if over.value:
+            # records seen in more than `slots` distinct clusters: some occurrences were dropped, so
+            # their most probable cluster may be wrong - redone below when the history is at hand
+            self._check(self.lib.exb200_pe_overflowed(self.h, overflowed.ctypes.data_as(C.POINTER(C.c_uint8))))
+        redo = (tied != 0) | (overflowed != 0)
+        if history is not None and redo.any():
+            # the reference's tie-break needs the member sets: only these records' clusters are rebuilt
+            # (point_estimate.cpp:65-99 restated for single records)
             history = np.asarray(history)
 
             def members(s, r):
                 return tuple(np.flatnonzero(history[s] == history[s, r]).tolist())
 
-            group = {int(r): ("device", int(memb[r])) for r in range(self.n) if not tied[r]}
-            for r in np.flatnonzero(tied):
-                freq = Counter(members(s, r) for s in range(history.shape[0]))
+            group = {int(r): ("device", int(memb[r])) for r in range(self.n) if not redo[r]}
+            for r in np.flatnonzero(redo):
+                seen = [members(s, r) for s in range(history.shape[0])]
+                freq = Counter(seen)
                 top = max(freq.values())
                 cl = min(c for c, f in freq.items() if f == top)
+                prob[r] = top / float(history.shape[0])
+                first[r] = seen.index(cl)
                 key = ("set", cl)
-                for q in cl:   # an untied record whose most probable cluster is this very set
-                    if not tied[q] and members(int(first[q]), q) == cl:
+                for q in cl:   # a settled record whose most probable cluster is this very set
+                    if not redo[q] and members(int(first[q]), q) == cl:
                         key = group[q]
                         break
                 group[int(r)] = key
@@ -172,7 +182,15 @@ class DevicePointEstimate:
             for r in range(self.n):
                 heads.setdefault(group[r], r)
             memb = np.array([heads[group[r]] for r in range(self.n)], np.int32)
-        return dict(membership=memb, probabilities=prob, first_sample=first, tied=tied.astype(bool), n_overflow=int(over.value))
+            overflowed[:] = 0
+        elif over.value:
+            import warnings
+            warnings.warn(f"device point estimate: {int(overflowed.sum())} records were seen in more than the table's "
+                          f"slots of distinct clusters ({int(over.value)} occurrences dropped); their estimates are "
+                          "unreliable - pass the link history to finish() or create the estimate with more slots "
+                          "(slots >= n_samples cannot overflow)", RuntimeWarning, stacklevel=2)
+        return dict(membership=memb, probabilities=prob, first_sample=first, tied=tied.astype(bool), n_overflow=int(over.value),
+                    overflowed=overflowed.astype(bool))
 
     def close(self):
         if self.h is not None:

@@ -17,6 +17,7 @@ from .model import BetaRV, DirichletRV, ExchangERModel, GammaRV, GeneralizedCoup
     PitmanYorRP, ShiftedNegBinomRV
 
 EXB200_OK = 0
+EXB200_ERR_WEIGHTS, EXB200_ERR_ABORTED = -5, -6
 ERR_NAMES = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "WEIGHTS",
              -6: "ABORTED", -7: "OOM"}
 CLUST_PITMAN_YOR, CLUST_GEN_COUPON, CLUST_COUPON = 0, 1, 2
@@ -25,6 +26,9 @@ ENTDIST_FIXED, ENTDIST_DIRICHLET = 0, 1
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
+# callbacks of exb200_run: int abort_cb(void* ctx), void progress_cb(void* ctx, int32_t completed)
+ABORT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int32)
 
 
 class CAttr(C.Structure):
@@ -238,6 +242,7 @@ def load_library(path: str | None = None):
     lib.exb200_pe_add.argtypes = [H, c_i32p]
     lib.exb200_pe_add_chain.argtypes = [H, H]
     lib.exb200_pe_finish.argtypes = [H, c_i32p, c_f64p, c_i32p, c_i32p, c_i64p]
+    lib.exb200_pe_overflowed.argtypes = [H, C.POINTER(C.c_uint8)]
     lib.exb200_pe_destroy.argtypes = [H]
     lib.exb200_pe_destroy.restype = None
     lib.exb200_attach_point_estimate.argtypes = [H, H]
@@ -295,5 +300,5 @@ EXPORTED_SYMBOLS = [
     "exb200_shard_links", "exb200_shard_entities", "exb200_shard_distort", "exb200_shard_finish",
     "exb200_device_buffer", "exb200_stream_sync",
     "exb200_pe_create", "exb200_pe_add", "exb200_pe_add_chain", "exb200_pe_finish", "exb200_pe_destroy",
-    "exb200_attach_point_estimate", "exb200_pe_set_pairs", "exb200_pe_pair_counts",
+    "exb200_attach_point_estimate", "exb200_pe_set_pairs", "exb200_pe_pair_counts", "exb200_pe_overflowed",
 ]

@@ -118,6 +118,8 @@ struct exb200_handle {
   // saved samples leave the device behind the next sweep: snapshot (D2D) -> pinned buffer on the
   // copy stream -> the caller's array by a host thread
   cudaStream_t copy_stream = nullptr;
+  bool pipeline_ready = false;  // every buffer and event of the sample pipeline exists
+  int n_sm = 148;               // multiprocessors of the device (grid sizes of the persistent kernels)
   int* d_snap[2] = {nullptr, nullptr};
   int* pin_snap[2] = {nullptr, nullptr};
   cudaEvent_t ev_snap[2]{}, ev_d2h[2]{};
@@ -142,8 +144,7 @@ int fail(exb200_handle* h, int code, const std::string& msg) {
     }                                                                                              \
   } while (0)
 
-// fn(t, T) on T host threads (table construction at create time; the sweep itself has no host loops
-// over records or domains)
+// fn(t, T) on T host threads (table construction at create time)
 template <class F> void host_parallel(size_t work, F fn) {
   int T = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
   if (work < (1u << 16)) T = 1;
@@ -692,7 +693,7 @@ int update_links(exb200_handle* h) {
   if (hc[C_NLONG_TODO] > 0) { // records whose candidates need a whole block to stage and sort
     const size_t smem = (size_t)pow2_ceil(std::max(h->long_cap, 1)) * (sizeof(double) + sizeof(int)); // padded for the bitonic sort
     const int n_todo = hc[C_NLONG_TODO];
-    KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], 148 * 4), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
+    KLAUNCH(h, k_cand_long, std::min(hc[C_NLONG_TODO], h->n_sm * 4), TPB, smem, S, hc[C_NLONG_TODO], h->long_cap);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     lap("block-staged candidate lists", n_todo);
@@ -931,7 +932,7 @@ int sweep_entities(exb200_handle* h, int lo, int hi) {
   DevState& S = h->S;
   CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), h->stream));
   if (hi > lo) KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
-  KLAUNCH_DP(h, k_entities_general, 148 * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
+  KLAUNCH_DP(h, k_entities_general, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
   return EXB200_OK;
 }
 int sweep_distort(exb200_handle* h, int lo, int hi) {
@@ -1043,6 +1044,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   h->iteration = m->iteration; h->seed = m->seed; h->cl = m->clust; h->hs.seed = m->seed;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     return bail(fail(h, EXB200_ERR_NO_DEVICE, "cudaStreamCreate failed"));
+  if (cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->n_sm < 1) h->n_sm = 148;
   for (auto& e : h->ev) cudaEventCreate(&e);
   const exb200_clust& c = m->clust;
   if (c.kind < 0 || c.kind > 2) return bail(fail(h, EXB200_ERR_INVALID, "Unrecognized clust_prior"));
@@ -1393,8 +1395,9 @@ struct RowCopier {
           job = jobs.front();
           jobs.pop_front();
         }
-        const bool ok = cudaEventSynchronize(h->ev_d2h[job.first]) == cudaSuccess;
-        if (ok) { // the destination is usually untouched memory: several threads take the page faults
+        // (a null destination only releases the buffer: the enqueue of this row failed)
+        const bool ok = !job.second || cudaEventSynchronize(h->ev_d2h[job.first]) == cudaSuccess;
+        if (ok && job.second) { // the destination is usually untouched memory: several threads take the page faults
           const size_t n = (size_t)h->N;
           const int parts = n >= (1u << 20) ? 4 : 1;
           std::vector<std::thread> th;
@@ -1434,16 +1437,20 @@ struct RowCopier {
 };
 
 int ensure_sample_pipeline(exb200_handle* h) {
-  if (h->copy_stream) return EXB200_OK;
-  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (h->pipeline_ready) return EXB200_OK;
+  // (a failed earlier attempt leaves what it allocated in place: only the missing pieces are made)
+  if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int b = 0; b < 2; b++) {
-    int rc = dalloc(h, &h->d_snap[b], (size_t)h->N);
-    if (rc) return rc;
-    if (cudaMallocHost((void**)&h->pin_snap[b], sizeof(int) * (size_t)h->N) != cudaSuccess)
+    if (!h->d_snap[b]) { int rc = dalloc(h, &h->d_snap[b], (size_t)h->N); if (rc) return rc; }
+    if (!h->pin_snap[b] && cudaMallocHost((void**)&h->pin_snap[b], sizeof(int) * (size_t)h->N) != cudaSuccess) {
+      h->pin_snap[b] = nullptr;
+      cudaGetLastError();
       return fail(h, EXB200_ERR_OOM, "cannot allocate pinned staging for the history");
-    CK(cudaEventCreateWithFlags(&h->ev_snap[b], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
+    }
+    if (!h->ev_snap[b]) CK(cudaEventCreateWithFlags(&h->ev_snap[b], cudaEventDisableTiming));
+    if (!h->ev_d2h[b]) CK(cudaEventCreateWithFlags(&h->ev_d2h[b], cudaEventDisableTiming));
   }
+  h->pipeline_ready = true;
   return EXB200_OK;
 }
 } // namespace
@@ -1481,7 +1488,8 @@ int exb200_run(exb200_handle* h, int32_t n_samples, int32_t thin, int32_t burnin
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_stream, h->ev_snap[b], 0);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h->pin_snap[b], h->d_snap[b], sizeof(int) * N, cudaMemcpyDeviceToHost, h->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_d2h[b], h->copy_stream);
-        copier.submit(b, out->links + (size_t)sample * N); // also releases the buffer on failure
+        // a failed enqueue releases the buffer without copying stale pinned data into the caller's row
+        copier.submit(b, e == cudaSuccess ? out->links + (size_t)sample * N : nullptr);
         if (e != cudaSuccess) {
           h->poisoned = true;
           return finish(fail(h, EXB200_ERR_CUDA, std::string("history copy: ") + cudaGetErrorString(e)), sample);
@@ -1739,6 +1747,7 @@ struct exb200_pe {
   unsigned long long *fp1 = nullptr, *fp2 = nullptr;
   int* links = nullptr;
   int* misc = nullptr; // [0] label out of range, [1] overflow count
+  uint8_t* over_flag = nullptr; // [N] 1: the record was seen in more than `slots` distinct clusters
   int* pairs = nullptr; int* pair_counts = nullptr; // coreference counting (exb200_pe_set_pairs)
   long long n_pairs = 0;
   int pair_samples = 0;
@@ -1748,7 +1757,7 @@ void exb200_pe_destroy(exb200_pe* pe) {
   if (!pe) return;
   cudaSetDevice(pe->device);
   if (pe->stream) cudaStreamSynchronize(pe->stream);
-  cudaFree(pe->table); cudaFree(pe->fp1); cudaFree(pe->fp2); cudaFree(pe->links); cudaFree(pe->misc);
+  cudaFree(pe->table); cudaFree(pe->fp1); cudaFree(pe->fp2); cudaFree(pe->links); cudaFree(pe->misc); cudaFree(pe->over_flag);
   cudaFree(pe->pairs); cudaFree(pe->pair_counts);
   if (pe->stream) cudaStreamDestroy(pe->stream);
   delete pe;
@@ -1767,8 +1776,10 @@ int exb200_pe_create(int32_t n_records, int32_t slots, int device, exb200_pe** o
             cudaMalloc((void**)&pe->fp1, sizeof(unsigned long long) * 2 * n) == cudaSuccess &&
             cudaMalloc((void**)&pe->fp2, sizeof(unsigned long long) * 2 * n) == cudaSuccess &&
             cudaMalloc((void**)&pe->links, sizeof(int) * n) == cudaSuccess &&
-            cudaMalloc((void**)&pe->misc, sizeof(int) * 2) == cudaSuccess;
+            cudaMalloc((void**)&pe->misc, sizeof(int) * 2) == cudaSuccess &&
+            cudaMalloc((void**)&pe->over_flag, n) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(pe->table, 0, sizeof(PeSlot) * n * slots, pe->stream) == cudaSuccess &&
+               cudaMemsetAsync(pe->over_flag, 0, n, pe->stream) == cudaSuccess &&
                cudaMemsetAsync(pe->misc, 0, sizeof(int) * 2, pe->stream) == cudaSuccess &&
                cudaStreamSynchronize(pe->stream) == cudaSuccess;
   if (!ok) { exb200_pe_destroy(pe); return fail(nullptr, EXB200_ERR_OOM, "point estimate: device allocation failed"); }
@@ -1790,7 +1801,7 @@ int pe_add_device(exb200_pe* pe, const int* d_links) {
     cudaMemsetAsync(pe->misc, 0, sizeof(int), st);
     return fail(nullptr, EXB200_ERR_INVALID, "point estimate: labels must lie in [0, 2 * n_records)");
   }
-  k_pe_count<<<nblk(N), TPB, 0, st>>>(N, pe->slots, pe->n_samples, d_links, pe->fp1, pe->fp2, pe->table, pe->misc + 1);
+  k_pe_count<<<nblk(N), TPB, 0, st>>>(N, pe->slots, pe->n_samples, d_links, pe->fp1, pe->fp2, pe->table, pe->misc + 1, pe->over_flag);
   if (pe->n_pairs > 0) {
     k_pe_pairs<<<nblk(pe->n_pairs), TPB, 0, st>>>(pe->n_pairs, pe->pairs, d_links, pe->pair_counts);
     pe->pair_samples++;
@@ -1893,6 +1904,15 @@ int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, in
   if (e != cudaSuccess) return fail(nullptr, EXB200_ERR_CUDA, std::string("point estimate: ") + cudaGetErrorString(e));
   if (mp_prob) for (size_t r = 0; r < n; r++) mp_prob[r] = 1.0 / (double)pe->n_samples * (double)h_cnt[r]; // point_estimate.cpp:97
   if (n_overflow) *n_overflow = over;
+  return EXB200_OK;
+}
+
+int exb200_pe_overflowed(exb200_pe* pe, uint8_t* flags) {
+  if (!pe || !flags) return EXB200_ERR_INVALID;
+  cudaSetDevice(pe->device);
+  if (cudaMemcpyAsync(flags, pe->over_flag, (size_t)pe->N, cudaMemcpyDeviceToHost, pe->stream) != cudaSuccess ||
+      cudaStreamSynchronize(pe->stream) != cudaSuccess)
+    return fail(nullptr, EXB200_ERR_CUDA, "point estimate: download failed");
   return EXB200_OK;
 }
 

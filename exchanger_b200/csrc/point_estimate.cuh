@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(TPB) k_pe_fingerprint(int n, int n_labels, con
 // every record counts the cluster it is in (its own table: no atomics)
 __global__ void __launch_bounds__(TPB) k_pe_count(int n, int slots, int sample, const int* __restrict__ links,
                                                   const unsigned long long* __restrict__ fp1, const unsigned long long* __restrict__ fp2,
-                                                  PeSlot* __restrict__ table, int* __restrict__ overflow) {
+                                                  PeSlot* __restrict__ table, int* __restrict__ overflow,
+                                                  uint8_t* __restrict__ over_flag) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int lab = links[r];
@@ -45,7 +46,8 @@ __global__ void __launch_bounds__(TPB) k_pe_count(int n, int slots, int sample, 
     if (t[s].count == 0) { t[s].k1 = k1; t[s].k2 = k2; t[s].count = 1; t[s].first_sample = sample; return; }
     if (t[s].k1 == k1 && t[s].k2 == k2) { t[s].count++; return; }
   }
-  atomicAdd(overflow, 1); // more distinct clusters than slots: this occurrence is not counted
+  atomicAdd(overflow, 1); // more distinct clusters than slots: this occurrence is not counted ...
+  over_flag[r] = 1;       // ... and the record is flagged: its estimate has to be redone from the history
 }
 // most frequent cluster of every record; ties go to the smaller fingerprint (the reference breaks
 // them by the lexicographic order of the member sets, which a fingerprint cannot reproduce: the

@@ -53,11 +53,16 @@ class Sampler:
         return ms.value, nl.value
 
     def run(self, n_samples: int, thin_interval: int = 1, burnin_interval: int = 0, *,
-            keep_links: bool = True, point_estimate=None) -> dict:
+            keep_links: bool = True, point_estimate=None, abort=None, progress=None) -> dict:
         """The sampling loop of ``sample()`` (src/sample.cpp:171-202) into fresh host arrays.
         ``point_estimate`` (an ``analysis.DevicePointEstimate``) receives every saved sample on the
         device; with ``keep_links=False`` the link vectors then never leave the GPU (``links`` of the
-        history is empty)."""
+        history is empty).
+
+        ``abort()`` is polled after every sweep and plays ``Progress::check_abort`` (sample.cpp:200):
+        when it returns true the loop stops and - like the reference, which breaks out of its loop and
+        returns what it has - the history comes back with ``n_saved`` rows filled (the others zero)
+        and ``aborted=True``.  ``progress(completed_sweeps)`` plays ``p.increment()`` (sample.cpp:201)."""
         N, FA, A = self.N, self.F * self.A, self.A
         self._check(self.lib.exb200_attach_point_estimate(self.h, point_estimate.h if point_estimate is not None else None))
         hist = dict(
@@ -75,8 +80,16 @@ class Sampler:
         ch.distort_dist_concs = hist["distort_dist_concs"].ctypes.data_as(c_f64p)
         ch.n_linked_ents = hist["n_linked_ents"].ctypes.data_as(c_i32p)
         ch.clust_params = hist["clust_params"].ctypes.data_as(c_f64p)
-        self._check(self.lib.exb200_run(self.h, n_samples, thin_interval, burnin_interval, C.byref(ch),
-                                        None, None, None))
+        abort_c = capi.ABORT_CB(lambda _ctx: 1 if abort() else 0) if abort is not None else None
+        progress_c = capi.PROGRESS_CB(lambda _ctx, done: progress(int(done))) if progress is not None else None
+        rc = self.lib.exb200_run(self.h, n_samples, thin_interval, burnin_interval, C.byref(ch),
+                                 C.cast(abort_c, C.c_void_p) if abort_c else None,
+                                 C.cast(progress_c, C.c_void_p) if progress_c else None, None)
+        self.last_n_saved = int(ch.n_saved)
+        if rc == capi.EXB200_ERR_ABORTED:   # partial history, as the reference returns after an interrupt
+            hist["aborted"], hist["n_saved"] = True, int(ch.n_saved)
+        else:
+            self._check(rc)
         # keep only the random cluster parameters, named as ClustParams::to_R_vec does
         # (src/clust_params.cpp:161-216)
         prior = self.model.clust_prior
@@ -212,7 +225,10 @@ def run_inference(x, n_samples: int, thin_interval: int = 1, burnin_interval: in
     with Sampler(x, seed=seed, device=device) as s:
         if point_estimate:
             from .analysis import DevicePointEstimate
-            with DevicePointEstimate(s.N, device=device) as pe:
+            # a record can be seen in at most n_samples distinct clusters: with that many slots (up to
+            # 32) the per-record tables cannot overflow; beyond that overflowed records are redone from
+            # the history, or reported by a RuntimeWarning when keep_links=False leaves none
+            with DevicePointEstimate(s.N, slots=int(min(max(n_samples, 8), 32)), device=device) as pe:
                 history = s.run(n_samples, thin_interval, burnin_interval, keep_links=keep_links, point_estimate=pe)
                 s._check(s.lib.exb200_attach_point_estimate(s.h, None))
                 pe_result = pe.finish(history["links"] if keep_links and n_samples else None) if n_samples else None

@@ -36,8 +36,9 @@ extern "C" {
 #endif
 
 /* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
-   estimates (exb200_pe_*) added */
-#define EXB200_ABI_VERSION 2
+   estimates (exb200_pe_*) added
+   3: exb200_pe_overflowed */
+#define EXB200_ABI_VERSION 3
 
 enum {
   EXB200_OK = 0,
@@ -293,6 +294,11 @@ int exb200_pe_add(exb200_pe* pe, const int32_t* links);
 int exb200_pe_add_chain(exb200_pe* pe, exb200_handle* h);
 int exb200_pe_finish(exb200_pe* pe, int32_t* smp_membership, double* mp_prob, int32_t* mp_sample,
                      int32_t* tied, int64_t* n_overflow);
+/* flags[r] = 1 for every record that was seen in more than `slots` distinct clusters: some of its
+   occurrences were not counted, so its estimate is unreliable and has to be redone from the link
+   history (analysis.DevicePointEstimate.finish does) or with more slots.  `slots` >= the number of
+   samples added can never overflow. */
+int exb200_pe_overflowed(exb200_pe* pe, uint8_t* flags);
 /* Record pairs ([n_pairs][2], 0-based) whose coreference is counted in every sample added from
    now on: counts[p] = samples in which both records had the same entity, the numerator of
    coreference_probs (R/coreference_probs.R:54-82); *n_samples = samples added since the pairs

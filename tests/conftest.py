@@ -18,3 +18,22 @@ def _built():
     """Build the native artefacts once per session (no-op when up to date)."""
     import __graft_entry__ as g
     g.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device: skipped (not failed) on a box without one.  The
+    refusal to run without a GPU is itself tested by the unmarked test_no_cpu_fallback."""
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items:
+        return
+    try:
+        import __graft_entry__ as g
+        g.build()
+        from exchanger_b200 import capi
+        have = capi.load_library().exb200_device_count() > 0
+    except Exception:
+        have = False
+    if not have:
+        skip = pytest.mark.skip(reason="no CUDA device visible (exb200_device_count() == 0)")
+        for it in gpu_items:
+            it.add_marker(skip)

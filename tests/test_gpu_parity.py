@@ -360,3 +360,128 @@ def test_run_inference_with_device_point_estimate_and_no_link_history():
     assert np.array_equal(lean.history["n_linked_ents"], fit.history["n_linked_ents"])
     if not fit.point_estimate["tied"].any():  # ties are settled from the history, which `lean` does not have
         assert np.array_equal(lean.point_estimate["membership"], fit.point_estimate["membership"])
+
+
+def test_abort_and_progress_callbacks_keep_the_partial_history():
+    """abort_cb / progress_cb of exb200_run play Progress::check_abort / p.increment
+    (src/sample.cpp:200-201): an abort after the 7th sweep stops the loop, the rows saved so far stay
+    (the reference breaks out of its loop and returns the partly filled matrices), the chain stands
+    at the aborted sweep and can go on."""
+    m, _ = readme_model("rldata500", n=200)
+    seen = []
+    with Sampler(m, seed=4) as g:
+        hist = g.run(10, thin_interval=2, burnin_interval=0, abort=lambda: len(seen) >= 6, progress=seen.append)
+        assert hist.get("aborted") and hist["n_saved"] == 3 and g.last_n_saved == 3   # sweeps 2, 4, 6 were saved
+        assert seen == list(range(1, 7))          # the abort is polled before the progress call, as in sample.cpp:200-201
+        assert g.state()["iteration"] == 7
+        o = OracleSampler(m, seed=4)
+        for s in range(3):
+            o.sweeps(2)
+            assert np.array_equal(hist["links"][s], o.state()["links"])
+        assert not hist["links"][3:].any()        # rows never reached stay as allocated
+        o.sweeps(1)
+        assert_same_state(g.state(), o.state(), "at the aborted sweep")
+        again = g.run(2, thin_interval=1)         # the handle is still usable
+        o.sweeps(2)
+        assert "aborted" not in again and np.array_equal(again["links"][1], o.state()["links"])
+
+
+def test_invalid_weights_are_reported_like_the_reference():
+    """A record without any valid link - entity-value pmf zero at its value, own singleton entity
+    removed - is the reference's "no valid links for record" (src/links.cpp:415-419, CHECK_WEIGHTS /
+    AliasSampler::check_weights src/alias_sampler.h:76-97): EXB200_ERR_WEIGHTS here, an error in the
+    oracle, and the handle refuses further work."""
+    cols, _ = load_rldata("rldata500", 120)
+    ap = readme_attr_params()
+    months = sorted({v for v in cols["bm"] if v is not None})
+    pmf = {v: 1.0 / (len(months) - 1) for v in months}
+    pmf[cols["bm"][0]] = 0.0                       # record 0 (and its like) can neither stay nor found an entity
+    ap["bm"].entity_dist_prior = pmf
+    m = exchanger(cols, ap, PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    with Sampler(m, seed=1) as g:
+        with pytest.raises(Exb200Error) as e:
+            g.sweeps(1)
+        assert e.value.status == -5 and "no valid outcome" in str(e.value)
+        with pytest.raises(Exb200Error):
+            g.sweeps(1)
+    o = OracleSampler(m, seed=1)
+    with pytest.raises(RuntimeError):
+        o.sweeps(1)
+
+
+def test_random_coupon_m_lockstep():
+    """GeneralizedCouponRP with a ShiftedNegBinomRV prior on m: the rnbinom draw of
+    GenCouponClustParams::update (src/clust_params.cpp:66-71) moves m every sweep."""
+    from exchanger_b200 import GeneralizedCouponRP, ShiftedNegBinomRV
+    cols, _ = load_rldata("rldata500", 300)
+    m = exchanger(cols, readme_attr_params(), GeneralizedCouponRP(ShiftedNegBinomRV(600, 0.5), GammaRV(1, 1)))
+    lockstep(m, 25)
+    with Sampler(m, seed=3) as g:
+        hist = g.run(12, 1, 0)
+    assert hist["clust_params_names"] == ["kappa", "m"]
+    ms = hist["clust_params"][:, 1]
+    assert len(set(ms.tolist())) > 3 and np.all(ms == np.round(ms)) and np.all(ms >= hist["n_linked_ents"][:, 0])
+
+
+def test_device_point_estimate_with_more_clusters_than_slots():
+    """A record seen in more distinct clusters than the device table has slots: the dropped
+    occurrences are counted, the record is flagged, and with the history at hand its estimate is
+    redone on the host, so the result still equals the restatement of src/point_estimate.cpp;
+    without the history a RuntimeWarning names the problem."""
+    from exchanger_b200.analysis import DevicePointEstimate, mp_clusters
+    rng = np.random.default_rng(3)
+    n, n_samples = 60, 24
+    hist = np.stack([rng.integers(0, 12, n) for _ in range(n_samples)]).astype(np.int32)  # every sample a fresh partition
+    best, prob = mp_clusters(hist)
+    want = clusters_to_membership(smp_clusters((best, prob)), n)
+    with DevicePointEstimate(n, slots=2) as pe:
+        for row in hist:
+            pe.add(row)
+        got = pe.finish(hist)
+        assert got["n_overflow"] > 0 and not got["overflowed"].any()
+        assert np.allclose(got["probabilities"], prob)
+        _, inv_w = np.unique(want, return_inverse=True)
+        firsts = {}
+        canon = np.array([firsts.setdefault(k, i) for i, k in enumerate(inv_w)])
+        assert np.array_equal(got["membership"], canon)
+        with pytest.warns(RuntimeWarning, match="distinct clusters"):
+            lean = pe.finish(None)
+        assert lean["overflowed"].any()
+    with DevicePointEstimate(n, slots=n_samples) as pe:   # slots >= samples can never overflow
+        for row in hist:
+            pe.add(row)
+        full = pe.finish(hist)
+        assert full["n_overflow"] == 0 and np.array_equal(full["membership"], canon)
+
+
+@pytest.mark.parametrize("include_self", [False, True])
+def test_neighbourhood_builder_matches_compute_close_values(include_self):
+    """k_neighbours (exb200_neighbours_*) against the restatement of compute_close_values
+    (R/AttributeIndex.R:117-137): the name domains of RLdata10000 and ~5 k synthetic names in two domains (with
+    typo variants, duplicates of length, isolated values and the empty string), threshold 3 and 1:
+    exact row_ptr / val_ids, probabilities and max_exp_factor to 1e-12."""
+    from exchanger_b200.capi import levenshtein_neighbours
+    from exchanger_b200.model import Levenshtein, compute_close_values, transform_dist_fn
+    from exchanger_b200.synthetic import synth_rldata
+    cols, _ = load_rldata("rldata10000")
+    domains = []
+    for name in ("fname_c1", "lname_c1"):
+        seen = []
+        for v in cols[name]:
+            if v is not None and v not in seen:
+                seen.append(v)
+        domains.append(seen)
+    _, doms, _, _ = synth_rldata(50_000)                        # D(fname) ~ 2 k, D(lname) ~ 5 k with typo variants
+    domains.append(doms[3] + ["", "X", "QQQQQQQQQQQQQQ", "ZZZZZZZZZZZZZZZZZZZZZZZZZZZZZZZ"])  # isolated values, 31 bytes
+    domains.append(doms[4][:3000])
+    for dom in domains:
+        for thr in (3, 1):
+            rp, ci, pr, mef = levenshtein_neighbours(dom, thr, include_self=include_self)
+            rp2, ci2, pr2, mef2 = compute_close_values(dom, transform_dist_fn(Levenshtein(), thr), include_self)
+            assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2), (len(dom), thr)
+            assert np.allclose(pr, pr2, rtol=1e-12, atol=0) and np.allclose(mef, mef2, rtol=1e-12, atol=0)
+            if not include_self:
+                iso = np.flatnonzero(np.diff(rp2) == 0)
+                assert np.all(mef[iso] == 0.0)                   # a value without a finite neighbour (AttributeIndex.R:135)
+    with pytest.raises(Exb200Error):
+        levenshtein_neighbours(["A" * 32], 3)
