@@ -163,7 +163,7 @@ typedef struct exo {
   /* statistics of the last sweep */
   long long n_cand; int n_changed, n_wide;
   /* scratch for the links update */
-  double *Lnew; int idx_attr; int *bptr, *bitem;
+  double *Lnew; int **bptr, **bitem; /* per attribute: items bucketed by their value */
   int *mhead, *mnext;             /* member lists (ascending record id) during the links update */
   int brute, has_dp;
   int wide_threshold;             /* scan order: records with more possible links go first */
@@ -372,7 +372,6 @@ exo *exo_create(const exb200_model *m) {
   s->mhead = (int *)malloc(sizeof(int) * 2 * N); s->mnext = (int *)malloc(sizeof(int) * N);
   s->corr = (int *)calloc(F * A, sizeof(int));
   s->wide_threshold = 4096;
-  s->bitem = (int *)malloc(sizeof(int) * 2 * N);
   s->at = (attr_t *)calloc(A, sizeof(attr_t));
   for (int i = 0; i < N * A; i++) {
     s->x[i] = m->rec_attrs[i] < 0 ? -1 : m->rec_attrs[i];
@@ -381,7 +380,6 @@ exo *exo_create(const exb200_model *m) {
   for (int r = 0; r < N; r++) s->fid[r] = m->file_ids[r];
   for (int f = 0; f < F; f++)
     for (int a = 0; a < A; a++) s->theta[f * A + a] = m->distort_probs[f + F * a];
-  int bestD = -1;
   for (int a = 0; a < A; a++) {
     const exb200_attr *in = &m->attrs[a];
     attr_t *t = &s->at[a];
@@ -429,9 +427,13 @@ exo *exo_create(const exb200_model *m) {
       free(cur);
     }
     if (alias_build(&t->Tpsi, t->psi, D) || attr_refresh(t)) set_err(s, a, "invalid pmf");
-    if (D > bestD) { bestD = D; s->idx_attr = a; }
   }
-  s->bptr = (int *)malloc(sizeof(int) * (bestD + 2));
+  s->bptr = (int **)malloc(sizeof(int *) * A);
+  s->bitem = (int **)malloc(sizeof(int *) * A);
+  for (int a = 0; a < A; a++) {
+    s->bptr[a] = (int *)malloc(sizeof(int) * (s->at[a].D + 2));
+    s->bitem[a] = (int *)malloc(sizeof(int) * 2 * N);
+  }
   /* labels -> smallest member record (entities without records are dropped) */
   {
     int maxlab = 0;
@@ -471,7 +473,9 @@ void exo_destroy(exo *s) {
     free(t->g); if (t->Tpsi.prob) alias_free(&t->Tpsi);
   }
   free(s->x); free(s->z); free(s->fid); free(s->lambda); free(s->ey); free(s->esize); free(s->theta);
-  free(s->ndist); free(s->corr); free(s->mhead); free(s->mnext); free(s->Lnew); free(s->bitem); free(s->bptr); free(s->at); free(s);
+  free(s->ndist); free(s->corr); free(s->mhead); free(s->mnext); free(s->Lnew);
+  for (int a = 0; s->bptr && a < s->A; a++) { free(s->bptr[a]); free(s->bitem[a]); }
+  free(s->bitem); free(s->bptr); free(s->at); free(s);
 }
 
 /* ------------------------------------------------------------------ 1. cluster prior */
@@ -583,16 +587,35 @@ static void links_prepare(exo *s) {
     }
     s->Lnew[r] = L;
   }
-  /* blocking buckets on the attribute with the largest domain: items (entity slots
-     0..2N-1) grouped by their value, ascending id inside a bucket */
-  int a0 = s->idx_attr, D = s->at[a0].D;
-  memset(s->bptr, 0, sizeof(int) * (D + 2));
-  for (int e = 0; e < 2 * N; e++) s->bptr[s->ey[(size_t)e * A + a0] + 1]++;
-  for (int v = 0; v < D; v++) s->bptr[v + 1] += s->bptr[v];
-  int *cur = (int *)malloc(sizeof(int) * (D + 1));
-  memcpy(cur, s->bptr, sizeof(int) * (D + 1));
-  for (int e = 0; e < 2 * N; e++) s->bitem[cur[s->ey[(size_t)e * A + a0]]++] = e;
-  free(cur);
+  /* blocking buckets, one index per attribute: items (entity slots 0..2N-1) grouped by their value
+     of the attribute, ascending id inside a bucket.  A record searches the shortest bucket among
+     its observed non-distorted attributes (pick_bucket) - the role of the set-size ordering of
+     getPossibleLinks (links.cpp:187-189); whichever bucket is used, the compatible items come out
+     in ascending id. */
+  for (int a0 = 0; a0 < A; a0++) {
+    int D = s->at[a0].D, *bp = s->bptr[a0], *bi = s->bitem[a0];
+    memset(bp, 0, sizeof(int) * (D + 2));
+    for (int e = 0; e < 2 * N; e++) bp[s->ey[(size_t)e * A + a0] + 1]++;
+    for (int v = 0; v < D; v++) bp[v + 1] += bp[v];
+    int *cur = (int *)malloc(sizeof(int) * (D + 1));
+    memcpy(cur, bp, sizeof(int) * (D + 1));
+    for (int e = 0; e < 2 * N; e++) bi[cur[s->ey[(size_t)e * A + a0]]++] = e;
+    free(cur);
+  }
+}
+
+/* the shortest bucket among the record's observed non-distorted attributes: items[lo..hi), or
+   every item (items = NULL) when there is none or in brute mode */
+static void pick_bucket(const exo *s, int r, const int **items, int *lo, int *hi) {
+  const int A = s->A;
+  *items = NULL; *lo = 0; *hi = 2 * s->N;
+  if (s->brute) return;
+  for (int a = 0; a < A; a++) {
+    int xv = s->x[r * A + a];
+    if (xv < 0 || s->z[r * A + a]) continue;
+    int b0 = s->bptr[a][xv], b1 = s->bptr[a][xv + 1];
+    if (b1 - b0 < *hi - *lo) { *items = s->bitem[a]; *lo = b0; *hi = b1; }
+  }
 }
 
 /* compatible(r, e): e agrees with r on every observed, non-distorted attribute of r - the
@@ -647,14 +670,12 @@ static int any_finite_conc(const exo *s) {
    live compatible entities in ascending id with log(prior) + log-likelihood.
    `removed` tells whether r's own singleton entity counts as removed (links.cpp:358-359). */
 static int link_candidates(const exo *s, int r, int **ids, double **lw, int *cap) {
-  const int N = s->N, A = s->A;
   int own = s->lambda[r], single = s->esize[own] == 1;
   int n = 0;
-  int a0 = s->idx_attr, xv0 = s->x[r * A + a0];
-  int use_bucket = !s->brute && xv0 >= 0 && !s->z[r * A + a0];
-  int lo = use_bucket ? s->bptr[xv0] : 0, hi = use_bucket ? s->bptr[xv0 + 1] : 2 * N;
+  const int *items; int lo, hi;
+  pick_bucket(s, r, &items, &lo, &hi);
   for (int q = lo; q < hi; q++) {
-    int e = use_bucket ? s->bitem[q] : q;
+    int e = items ? items[q] : q;
     int sz = s->esize[e];
     if (sz <= 0) continue;
     if (e == own) { if (single) continue; sz -= 1; } /* :359, :375 */
@@ -675,13 +696,12 @@ static int link_candidates(const exo *s, int r, int **ids, double **lw, int *cap
 /* number of possible links of record r: compatible items of non-zero likelihood among all 2N
    entity slots of the sweep (whatever their current size), its own potential entity excluded */
 static int count_possible_links(const exo *s, int r, int stop_after) {
-  const int N = s->N, A = s->A;
-  int a0 = s->idx_attr, xv0 = s->x[r * A + a0];
-  int use_bucket = !s->brute && xv0 >= 0 && !s->z[r * A + a0];
-  int lo = use_bucket ? s->bptr[xv0] : 0, hi = use_bucket ? s->bptr[xv0 + 1] : 2 * N;
+  const int N = s->N;
+  const int *items; int lo, hi;
+  pick_bucket(s, r, &items, &lo, &hi);
   int n = 0;
   for (int q = lo; q < hi && n <= stop_after; q++) {
-    int e = use_bucket ? s->bitem[q] : q;
+    int e = items ? items[q] : q;
     if (e == N + r) continue;
     if (e < N && s->esize[e] <= 0) continue; /* slots [0,N) without an entity at the start of the sweep */
     if (!compatible(s, r, e)) continue;

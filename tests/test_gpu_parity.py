@@ -38,10 +38,11 @@ def lockstep(model, n_sweeps, seed=11, every=1, wide_threshold=None, **options):
         gpu.set_option(k, v)
     stats = []
     for i in range(0, n_sweeps, every):
-        gpu.sweeps(every)
+        for _ in range(every):
+            gpu.sweeps(1)
+            stats.append(gpu.stats())
         oracle.sweeps(every)
         assert_same_state(gpu.state(), oracle.state(), f"after sweep {i + every}")
-        stats.append(gpu.stats())
     gpu.close()
     return stats
 
@@ -185,6 +186,23 @@ def test_synthetic_records_at_scale_lockstep():
     m, _ = synth_model(120_000, clust_prior("gen_coupon", 120_000), seed=DATA_SEED)
     stats = lockstep(m, 3)
     assert stats[-1]["n_entities"] < 120_000 and stats[-1]["n_tables"] >= 2
+
+
+@pytest.mark.parametrize("kind", ["gen_coupon", "pitman_yor"])
+def test_one_million_records_lockstep_from_the_first_sweep(kind):
+    """The benchmark's own generator at 1 M records (config C3, and C4's prior family), from the
+    all-singletons start through sweep 30 - the regime bench.py times: multi-bucket probes,
+    block-staged and tiled buckets, the serial path and a dozen dependency rounds are all live.
+    States are compared with the oracle every five sweeps (the oracle searches the shortest bucket
+    of the record's pinned attributes, so a sweep costs it about a second)."""
+    from bench import DATA_SEED, clust_prior
+    from exchanger_b200.synthetic import synth_model
+    n = 1_000_000
+    m, _ = synth_model(n, clust_prior(kind, n), seed=DATA_SEED)
+    stats = lockstep(m, 30, every=5, huge_min=2048)
+    tot = {k: sum(s[k] for s in stats) for k in ("n_probe", "n_long", "n_wide", "n_huge")}
+    assert all(v > 0 for v in tot.values()), tot
+    assert max(s["n_rounds"] for s in stats) >= 8 and stats[-1]["n_entities"] < 0.95 * n
 
 
 def test_sweep_in_slices_equals_the_sweep():
