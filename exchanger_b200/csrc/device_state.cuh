@@ -28,6 +28,7 @@ constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that m
 constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
 constexpr int CAND_INLINE = 4;      // candidate lists up to this length are stored at pool[CAND_INLINE * record]
+constexpr uint32_t CAND_OWN_ONLY = 0xFFFFFFFFu; // cand_off value: the list is {the record's own entity}, log-likelihood 0
 constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
 constexpr int HUGE_BATCH = 512;     // records with a huge bucket scanned per launch
 

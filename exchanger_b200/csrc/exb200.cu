@@ -18,6 +18,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "hostmath.hpp"
 #include "kernels.cuh"
 #include "neighbours.cuh"
@@ -99,6 +102,11 @@ struct exb200_handle {
   unsigned long long* d_gen_list = nullptr; // (entity << 8 | attribute) pairs that need the general scheme
   int* d_gen_count = nullptr;
   uint32_t round_ctr = 1;
+  int opt_tail = 1;            // rounds after the first in one persistent kernel (k_rounds_tail)
+  TailState tail{};            // its lists (allocated when first used)
+  void* d_select_tmp = nullptr; size_t select_tmp_bytes = 0;
+  int tail_grid = 0;           // co-resident blocks of k_rounds_tail for the current wide_threshold
+  int tail_grid_cap = -1;      // ... and the wide_threshold it was computed for
   int opt_check = 0;
   int trace = std::getenv("EXB200_TRACE") ? 1 : 0;
   int bucket_cap = 512, cand_cap = CAND_SMEM, long_cap = 4096, long_min = 32;
@@ -228,6 +236,11 @@ void refresh_clust_dev(exb200_handle* h) {
   for (int n = 0; n < LPE_MAX; n++) c.logpe[n] = std::log(prior_existing_host(h->cl, n));
   h->S.use_kbounds = !(h->cl.kind == EXB200_CLUST_PITMAN_YOR && h->cl.d == 0.0);
 }
+
+struct NotFinal { // records whose link is not final yet (selection of the tail's first list)
+  const uint8_t* fin;
+  __device__ __forceinline__ bool operator()(int r) const { return fin[r] != 1; }
+};
 
 int check_device_error(exb200_handle* h) {
   int e[2] = {0, 0};
@@ -807,10 +820,26 @@ int update_links(exb200_handle* h) {
   int n_act = N, n_actl = hc[C_NACTL_INIT];
   const int* act = nullptr; // round 1: every record (the short kernels skip the long ones)
   int rounds = 0;
+  // Round 1 runs over all records as separate launches; the rounds after it in ONE persistent
+  // cooperative kernel over the sorted list of the records still open (k_rounds_tail) - unless a
+  // record without a stored list has to take a serial turn inside the rounds (pool exhausted).
+  const bool use_tail = h->opt_tail && n_fence == 0;
+  if (use_tail && !h->tail.n) {
+    int rc = dalloc(h, &h->tail.list[0], (size_t)N); if (rc) return rc;
+    rc = dalloc(h, &h->tail.list[1], (size_t)N); if (rc) return rc;
+    rc = dalloc(h, &h->tail.flag, (size_t)N); if (rc) return rc;
+    rc = dalloc(h, &h->tail.blk_tot, (size_t)3 * 4096); if (rc) return rc;
+    rc = dalloc(h, &h->tail.n, 4); if (rc) return rc;
+    cub::DeviceSelect::If(nullptr, h->select_tmp_bytes, thrust::counting_iterator<int>(0), h->tail.list[0], h->tail.n, N,
+                          NotFinal{S.fin}, st);
+    char* tmp = nullptr;
+    rc = dalloc(h, &tmp, h->select_tmp_bytes); if (rc) return rc;
+    h->d_select_tmp = tmp;
+  }
   while (n_act + n_actl > 0) {
     rounds++;
     const uint32_t round = h->round_ctr++;
-    if (h->round_ctr == 0xFFFFFFF0u) { // reservation words would wrap: start over
+    if (h->round_ctr >= 0x7FFFFFF0u) { // reservation words would wrap: start over
       CK(cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, st));
       CK(cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), st));
       h->round_ctr = 1;
@@ -826,6 +855,41 @@ int update_links(exb200_handle* h) {
     }
     if (n_act > 0) KLAUNCH_DP(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
     if (n_actl > 0) KLAUNCH_DP(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
+    if (use_tail) {
+      // everything that is left, in ascending id; K bounds from the outcome of round 1
+      if (S.use_kbounds) {
+        int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
+        rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
+      }
+      CK(cudaMemsetAsync(h->tail.n, 0, sizeof(int) * 4, st));
+      CK(cub::DeviceSelect::If(h->d_select_tmp, h->select_tmp_bytes, thrust::counting_iterator<int>(0), h->tail.list[0],
+                               h->tail.n, N, NotFinal{S.fin}, st));
+      h->n_launches += 2;
+      const size_t smem = sizeof(double) * (size_t)std::max(h->long_cap, 1);
+      if (h->tail_grid_cap != h->long_cap) {
+        int per_sm = 0;
+        CK(S.has_dp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rounds_tail<true>, TAIL_TPB, smem)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rounds_tail<false>, TAIL_TPB, smem));
+        if (per_sm < 1) return fail(h, EXB200_ERR_CUDA, "k_rounds_tail does not fit a multiprocessor");
+        h->tail_grid = std::min(4096, per_sm * h->n_sm);
+        h->tail_grid_cap = h->long_cap;
+      }
+      uint32_t round0 = h->round_ctr;
+      int max_rounds = (int)std::min<long long>(4LL * N + 16, 0x30000000LL);
+      void* args[] = {(void*)&S, (void*)&h->tail, (void*)&round0, (void*)&max_rounds};
+      CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_rounds_tail<true> : (const void*)k_rounds_tail<false>,
+                                     dim3((unsigned)h->tail_grid), dim3(TAIL_TPB), args, smem, st));
+      h->n_launches++;
+      int tn[4];
+      CK(cudaMemcpyAsync(tn, h->tail.n, sizeof tn, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h->trace) std::fprintf(stderr, "[exb200] round 1: %d records, then %d open; %d more rounds in the persistent kernel (%d blocks)\n",
+                                 n_act, tn[0], tn[1], h->tail_grid);
+      h->round_ctr += (uint32_t)tn[1];
+      rounds += tn[1];
+      if (tn[2] || tn[3] > 0) return fail(h, EXB200_ERR_CUDA, "links update made no progress (internal error)");
+      break;
+    }
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h->trace) std::fprintf(stderr, "[exb200] round %d: short %d long %d -> %d %d%s\n", rounds, n_act, n_actl,
@@ -843,7 +907,7 @@ int update_links(exb200_handle* h) {
       const unsigned long long zero_base = 0;
       CK(cudaMemcpyAsync(S.wl_base, &zero_base, sizeof zero_base, cudaMemcpyHostToDevice, st));
       KLAUNCH(h, k_wide_fill_log, WIDE_BLOCKS, TPB, 0, S, 1);
-      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1);
+      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, 1); // pieces whose log overflowed
       wide_turn(h, w, 0, tot);
       const int zero = 0;
       CK(cudaMemcpyAsync(S.counters + C_NACT_OUT, &zero, sizeof zero, cudaMemcpyHostToDevice, st));
@@ -1293,7 +1357,9 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     TRY(upload(h, &h->d_tables, td.data(), td.size())); S.tables = h->d_tables;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(h, EXB200_ERR_CUDA, "upload failed"));
   }
-  if (cudaFuncSetAttribute(k_commit_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_rounds_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_rounds_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k_commit_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_commit_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_index_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(k_part_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
@@ -1326,6 +1392,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "est_threshold") h->est_threshold = (double)value;
   else if (n == "huge_min") h->huge_min = (int)std::max<int64_t>(0, value);
   else if (n == "index_partitioned") h->index_partitioned = value != 0;
+  else if (n == "rounds_tail") h->opt_tail = value != 0;
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);

@@ -1,10 +1,13 @@
 // sm_100a kernels of the Gibbs sweep.  Each kernel names the reference function it replaces.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "device_state.cuh"
 #include "rng.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace exb {
 
@@ -1044,6 +1047,25 @@ __device__ __forceinline__ unsigned long long resv_key(uint32_t round, int r) {
   return ((unsigned long long)(0xFFFFFFFFu - round) << 32) | (unsigned long long)(uint32_t)r;
 }
 
+// reservations of one record with a short list (thread) ...
+__device__ __forceinline__ void reserve_short(const DevState& S, int r, int cnt, unsigned long long key) {
+  atomicMin(&S.owner[S.lambda[r]], key);
+  atomicMin(&S.owner[S.N + r], key);
+  if (S.cand_off[r] == CAND_OWN_ONLY) return; // its only candidate is its own entity
+  const int* ids = S.cand_id + S.cand_off[r];
+  for (int j = 0; j < cnt; j++) atomicMin(&S.owner[ids[j]], key);
+}
+// ... and of one record with a long list (all threads of the block)
+__device__ __forceinline__ void reserve_long(const DevState& S, int r, unsigned long long key) {
+  const int cnt = S.cand_cnt[r];
+  const int* ids = S.cand_id + S.cand_off[r];
+  if (threadIdx.x == 0) {
+    atomicMin(&S.owner[S.lambda[r]], key);
+    atomicMin(&S.owner[S.N + r], key);
+  }
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) atomicMin(&S.owner[ids[j]], key);
+}
+
 __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   __shared__ int s_min;
   if (threadIdx.x == 0) s_min = 0x7FFFFFFF;
@@ -1056,14 +1078,8 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
     if (cnt <= S.long_min && S.fin[r] != 1) { // long records: k_reserve_w; wide records are final already
       mine = r;
       const unsigned long long key = resv_key(round, r);
-      if (cnt < 0) {
-        atomicMin(S.fence, key);
-      } else {
-        atomicMin(&S.owner[S.lambda[r]], key);
-        atomicMin(&S.owner[S.N + r], key);
-        const int* ids = S.cand_id + S.cand_off[r];
-        for (int j = 0; j < cnt; j++) atomicMin(&S.owner[ids[j]], key);
-      }
+      if (cnt < 0) atomicMin(S.fence, key);
+      else reserve_short(S, r, cnt, key);
     }
   }
 #pragma unroll
@@ -1075,15 +1091,8 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
 
 __global__ void __launch_bounds__(TPB) k_reserve_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   const int r = act[blockIdx.x]; // one block per record with a long list
-  const unsigned long long key = resv_key(round, r);
-  const int cnt = S.cand_cnt[r];
-  const int* ids = S.cand_id + S.cand_off[r];
-  if (threadIdx.x == 0) {
-    atomicMin(&S.owner[S.lambda[r]], key);
-    atomicMin(&S.owner[S.N + r], key);
-    atomicMin(&S.counters[C_MIN_ACTIVE], r);
-  }
-  for (int j = threadIdx.x; j < cnt; j += TPB) atomicMin(&S.owner[ids[j]], key);
+  reserve_long(S, r, resv_key(round, r));
+  if (threadIdx.x == 0) atomicMin(&S.counters[C_MIN_ACTIVE], r);
 }
 
 // move record r from entity `own` to `target`, keeping member lists sorted (the role of
@@ -1155,6 +1164,63 @@ __device__ __forceinline__ int live_size(const DevState& S, int e, int own, bool
   return e == own ? (single ? 0 : sz - 1) : sz; // links.cpp:359, :375
 }
 
+// Turn of one record with a short list, if it owns everything it reserved (thread per record).
+// Returns true if the record stays unfinalised.
+template <bool DP>
+__device__ __forceinline__ bool commit_short(const DevState& S, int r, int cnt, unsigned long long key) {
+  const int own = S.lambda[r];
+  const bool own_only = S.cand_off[r] == CAND_OWN_ONLY;
+  const int* ids = own_only ? &own : S.cand_id + S.cand_off[r];
+  bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
+  if (!own_only) for (int j = 0; j < cnt && mine; j++) mine = S.owner[ids[j]] == key;
+  if (!mine) return true;
+  const double zero_ll = 0.0;
+  const double* lls = own_only ? &zero_ll : S.cand_ll + S.cand_off[r];
+  const bool single = S.ent_size[own] == 1;
+  // weights of the live candidates (links.cpp:372-388)
+  double m1 = -CUDART_INF;
+  for (int j = 0; j < cnt; j++) {
+    const int sz = live_size(S, ids[j], own, single);
+    if (sz > 0) {
+      const double lw = cand_lw<DP>(S, r, ids[j], sz, lls[j]);
+      m1 = lw > m1 ? lw : m1;
+    }
+  }
+  double srel = 0.0;
+  if (m1 > -CUDART_INF)
+    for (int j = 0; j < cnt; j++) {
+      const int sz = live_size(S, ids[j], own, single);
+      if (sz > 0) srel += exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
+    }
+  const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+  const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
+  if (dec == 2) {
+    // entity-wise ready, only K is still uncertain: tighten this record's bounds
+    S.dlo[r] = single ? -1 : 0;
+    S.dhi[r] = single ? 0 : 1;
+    return true;
+  }
+  int target;
+  if (dec == 1) target = S.N + r;
+  else {
+    const double tt = u.b * srel;
+    double c = 0.0;
+    int pick = -1, lastpos = -1;
+    for (int j = 0; j < cnt; j++) {
+      const int sz = live_size(S, ids[j], own, single);
+      if (sz <= 0) continue;
+      const double w = exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
+      if (w > 0.0) lastpos = ids[j];
+      c += w;
+      if (tt < c) { pick = ids[j]; break; }
+    }
+    target = pick >= 0 ? pick : lastpos;
+    if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+  }
+  finalize_record(S, r, own, target, single);
+  return false;
+}
+
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1171,58 +1237,7 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
     } else if (cnt < 0) {
       // serial record: its turn comes when every earlier record is final
       if (S.counters[C_MIN_ACTIVE] == r) S.counters[C_WIDE_READY] = r;
-    } else if (!fenced) {
-      const int own = S.lambda[r];
-      const int* ids = S.cand_id + S.cand_off[r];
-      bool mine = S.owner[own] == key && S.owner[S.N + r] == key;
-      for (int j = 0; j < cnt && mine; j++) mine = S.owner[ids[j]] == key;
-      if (mine) {
-        const double* lls = S.cand_ll + S.cand_off[r];
-        const bool single = S.ent_size[own] == 1;
-        // weights of the live candidates (links.cpp:372-388)
-        double m1 = -CUDART_INF;
-        for (int j = 0; j < cnt; j++) {
-          const int sz = live_size(S, ids[j], own, single);
-          if (sz > 0) {
-            const double lw = cand_lw<DP>(S, r, ids[j], sz, lls[j]);
-            m1 = lw > m1 ? lw : m1;
-          }
-        }
-        double srel = 0.0;
-        if (m1 > -CUDART_INF)
-          for (int j = 0; j < cnt; j++) {
-            const int sz = live_size(S, ids[j], own, single);
-            if (sz > 0) srel += exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
-          }
-        const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-        const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
-        if (dec != 2) {
-          int target;
-          if (dec == 1) target = S.N + r;
-          else {
-            const double tt = u.b * srel;
-            double c = 0.0;
-            int pick = -1, lastpos = -1;
-            for (int j = 0; j < cnt; j++) {
-              const int sz = live_size(S, ids[j], own, single);
-              if (sz <= 0) continue;
-              const double w = exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
-              if (w > 0.0) lastpos = ids[j];
-              c += w;
-              if (tt < c) { pick = ids[j]; break; }
-            }
-            target = pick >= 0 ? pick : lastpos;
-            if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
-          }
-          finalize_record(S, r, own, target, single);
-          stay = false;
-        } else {
-          // entity-wise ready, only K is still uncertain: tighten this record's bounds
-          S.dlo[r] = single ? -1 : 0;
-          S.dhi[r] = single ? 0 : 1;
-        }
-      }
-    }
+    } else if (!fenced) stay = commit_short<DP>(S, r, cnt, key);
   }
   // append the records that stay to the next active list
   const unsigned m = __ballot_sync(FULL, stay);
@@ -1235,113 +1250,293 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
   }
 }
 
-// One BLOCK per record with a long candidate list.  All threads gather sizes and evaluate weights
-// into shared memory; one thread then accumulates them in candidate order, i.e. with exactly the
-// association of the sequential loop in k_commit and in the oracle.
+// Turn of one record with a long candidate list, taken by a whole BLOCK (any block size that is a
+// multiple of 32, up to 1024 threads).  All threads gather sizes and evaluate weights into shared
+// memory (s_w: one double per candidate); one thread then accumulates them in candidate order, i.e.
+// with exactly the association of the sequential loop in commit_short and in the oracle.
+// Returns true (to every thread) if the record stays unfinalised.
+struct CommitLongShared {
+  double red[32];
+  double m1, srel;
+  int dec, pick, last;
+};
+template <bool DP>
+__device__ bool commit_long(const DevState& S, int r, unsigned long long key, double* s_w, CommitLongShared& sh) {
+  const int cnt = S.cand_cnt[r];
+  const int own = S.lambda[r];
+  const int* ids = S.cand_id + S.cand_off[r];
+  const double* lls = S.cand_ll + S.cand_off[r];
+  const int nthr = blockDim.x;
+  // a record that owned all its items once owns them until its turn (earlier unfinalised records
+  // only disappear) and nothing it reads can change: its weights are summed once
+  const bool ready = S.fin[r] == 2;
+  int mine = 1;
+  if (!ready) {
+    mine = S.owner[own] == key && S.owner[S.N + r] == key;
+    for (int j = threadIdx.x; j < cnt && mine; j += nthr) mine = S.owner[ids[j]] == key;
+    mine = __syncthreads_and(mine);
+  }
+  if (!mine) return true;
+  const bool single = S.ent_size[own] == 1;
+  // s_w[j] = running sum (candidate order, summed by one thread: the association of the
+  // sequential loop in commit_short and in the oracle) of exp(lw_j - m1), 0 for candidates that are
+  // not live; sh.last = last candidate of positive weight; sh.srel = the total
+  auto fill_weights = [&](bool need_max) {
+    double m = -CUDART_INF;
+    for (int j = threadIdx.x; j < cnt; j += nthr) {
+      const int sz = live_size(S, ids[j], own, single);
+      const double lw = sz > 0 ? cand_lw<DP>(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
+      s_w[j] = lw;
+      m = lw > m ? lw : m;
+    }
+    if (threadIdx.x == 0) sh.last = -1;
+    if (need_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m, o); m = y > m ? y : m; }
+      if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double mm = -CUDART_INF;
+        for (int k = 0; k < nthr / 32; k++) mm = sh.red[k] > mm ? sh.red[k] : mm;
+        sh.m1 = mm;
+      }
+    }
+    __syncthreads();
+    const double m1 = sh.m1;
+    int last = -1;
+    for (int j = threadIdx.x; j < cnt; j += nthr) {
+      const double w = s_w[j] > -CUDART_INF ? exp(s_w[j] - m1) : 0.0;
+      s_w[j] = w;
+      if (w > 0.0) last = j;
+    }
+    if (last >= 0) atomicMax(&sh.last, last);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double c = 0.0;
+      if (m1 > -CUDART_INF) for (int j = 0; j < cnt; j++) { c += s_w[j]; s_w[j] = c; } // dead ones add 0
+      sh.srel = c;
+    }
+    __syncthreads();
+  };
+  if (ready) { if (threadIdx.x == 0) { sh.m1 = S.rdy_m1[r]; sh.srel = S.rdy_srel[r]; } __syncthreads(); }
+  else fill_weights(true);
+  const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
+  if (threadIdx.x == 0) sh.dec = decide_with_bounds(S, r, single, sh.m1, sh.srel, u.a);
+  __syncthreads();
+  const int dec = sh.dec;
+  if (dec == 2) {
+    if (threadIdx.x == 0) {
+      S.dlo[r] = single ? -1 : 0;
+      S.dhi[r] = single ? 0 : 1;
+      if (!ready) { S.fin[r] = 2; S.rdy_m1[r] = sh.m1; S.rdy_srel[r] = sh.srel; }
+    }
+    __syncthreads();
+    return true;
+  }
+  if (dec == 0) {
+    if (ready) { const double keep = sh.srel; fill_weights(false); if (threadIdx.x == 0) sh.srel = keep; __syncthreads(); } // the sums were not kept
+    // the first candidate whose running sum exceeds the threshold (it has a positive weight:
+    // a zero weight leaves the sum where it was); the running sums never decrease
+    if (threadIdx.x == 0) sh.pick = 0x7FFFFFFF;
+    __syncthreads();
+    const double tt = u.b * sh.srel;
+    for (int j = threadIdx.x; j < cnt; j += nthr)
+      if (tt < s_w[j] && (j == 0 || !(tt < s_w[j - 1]))) atomicMin(&sh.pick, j);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int target;
+    if (dec == 1) target = S.N + r;
+    else {
+      const int j = sh.pick != 0x7FFFFFFF ? sh.pick : sh.last;
+      target = j >= 0 ? ids[j] : -1;
+      if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
+    }
+    finalize_record(S, r, own, target, single);
+  }
+  __syncthreads();
+  return false;
+}
+
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restrict__ act, int n_act, uint32_t round) {
-  extern __shared__ double s_w[]; // [cnt] log-weights, then weights relative to the maximum, then their running sums
-  __shared__ double s_red[TPB / 32];
-  __shared__ double s_m1, s_srel;
-  __shared__ int s_dec, s_pick, s_last;
+  extern __shared__ double s_w[]; // [cnt]
+  __shared__ CommitLongShared sh;
   const int r = act[blockIdx.x];
-  const int cnt = S.cand_cnt[r];
   const unsigned long long key = resv_key(round, r);
   const unsigned long long fence = *S.fence;
   const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
   bool stay = true;
-  if (!fenced) {
-    const int own = S.lambda[r];
-    const int* ids = S.cand_id + S.cand_off[r];
-    const double* lls = S.cand_ll + S.cand_off[r];
-    // a record that owned all its items once owns them until its turn (earlier unfinalised records
-    // only disappear) and nothing it reads can change: its weights are summed once
-    const bool ready = S.fin[r] == 2;
-    int mine = 1;
-    if (!ready) {
-      mine = S.owner[own] == key && S.owner[S.N + r] == key;
-      for (int j = threadIdx.x; j < cnt && mine; j += TPB) mine = S.owner[ids[j]] == key;
-      mine = __syncthreads_and(mine);
-    }
-    if (mine) {
-      const bool single = S.ent_size[own] == 1;
-      // s_w[j] = running sum (candidate order, summed by one thread: the association of the
-      // sequential loop in k_commit and in the oracle) of exp(lw_j - m1), 0 for candidates that are
-      // not live; s_last = last candidate of positive weight; s_srel = the total
-      auto fill_weights = [&](bool need_max) {
-        double m = -CUDART_INF;
-        for (int j = threadIdx.x; j < cnt; j += TPB) {
-          const int sz = live_size(S, ids[j], own, single);
-          const double lw = sz > 0 ? cand_lw<DP>(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
-          s_w[j] = lw;
-          m = lw > m ? lw : m;
-        }
-        if (threadIdx.x == 0) s_last = -1;
-        if (need_max) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { const double y = __shfl_xor_sync(FULL, m, o); m = y > m ? y : m; }
-          if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
-          __syncthreads();
-          if (threadIdx.x == 0) {
-            double mm = -CUDART_INF;
-            for (int k = 0; k < TPB / 32; k++) mm = s_red[k] > mm ? s_red[k] : mm;
-            s_m1 = mm;
-          }
-        }
-        __syncthreads();
-        const double m1 = s_m1;
-        int last = -1;
-        for (int j = threadIdx.x; j < cnt; j += TPB) {
-          const double w = s_w[j] > -CUDART_INF ? exp(s_w[j] - m1) : 0.0;
-          s_w[j] = w;
-          if (w > 0.0) last = j;
-        }
-        if (last >= 0) atomicMax(&s_last, last);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double c = 0.0;
-          if (m1 > -CUDART_INF) for (int j = 0; j < cnt; j++) { c += s_w[j]; s_w[j] = c; } // dead ones add 0
-          s_srel = c;
-        }
-        __syncthreads();
-      };
-      if (ready) { if (threadIdx.x == 0) { s_m1 = S.rdy_m1[r]; s_srel = S.rdy_srel[r]; } __syncthreads(); }
-      else fill_weights(true);
-      const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-      if (threadIdx.x == 0) s_dec = decide_with_bounds(S, r, single, s_m1, s_srel, u.a);
-      __syncthreads();
-      const int dec = s_dec;
-      if (dec != 2) {
-        if (dec == 0) {
-          if (ready) { const double keep = s_srel; fill_weights(false); if (threadIdx.x == 0) s_srel = keep; __syncthreads(); } // the sums were not kept
-          // the first candidate whose running sum exceeds the threshold (it has a positive weight:
-          // a zero weight leaves the sum where it was); the running sums never decrease
-          if (threadIdx.x == 0) s_pick = 0x7FFFFFFF;
-          __syncthreads();
-          const double tt = u.b * s_srel;
-          for (int j = threadIdx.x; j < cnt; j += TPB)
-            if (tt < s_w[j] && (j == 0 || !(tt < s_w[j - 1]))) atomicMin(&s_pick, j);
-          __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-          int target;
-          if (dec == 1) target = S.N + r;
-          else {
-            const int j = s_pick != 0x7FFFFFFF ? s_pick : s_last;
-            target = j >= 0 ? ids[j] : -1;
-            if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
-          }
-          finalize_record(S, r, own, target, single);
-        }
-        stay = false;
-      } else if (threadIdx.x == 0) {
-        S.dlo[r] = single ? -1 : 0;
-        S.dhi[r] = single ? 0 : 1;
-        if (!ready) { S.fin[r] = 2; S.rdy_m1[r] = s_m1; S.rdy_srel[r] = s_srel; }
-      }
-    }
-  }
+  if (!fenced) stay = commit_long<DP>(S, r, key, s_w, sh);
   if (stay && threadIdx.x == 0) S.actl_out[atomicAdd(&S.counters[C_NACTL_OUT], 1)] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1d'  the dependency rounds after the first one, in ONE persistent cooperative kernel.
+// After round 1 a tenth of the records is left and every further round shrinks the set; launched
+// one by one, rounds 5+ cost a few microseconds of work and ~0.3 ms of launches, two N-wide scans
+// of the K bounds and a host synchronisation each.  Here the unfinalised records sit in a list
+// SORTED by record id (short and long lists together) and every round is three grid-wide steps:
+//   A  reservations (atomicMin of (round, id) on every item the record reads or may write)
+//   B  turns: records that own all they reserved decide and move (commit_short / commit_long);
+//      every position notes whether its record stays and by how much its K bounds moved
+//   C  one scan over the LIST of (stay, d dlo, d dhi): stable compaction into the next list, and
+//      plo / phi of the records that stay move by the prefix of the deltas before them - all the
+//      records whose bounds changed are in the list, and the list is sorted, so this is the
+//      exclusive prefix sum over all records that the per-round N-wide scans used to recompute.
+// Same arithmetic per record as k_commit / k_commit_w, so the chain is the same bit for bit.
+// ------------------------------------------------------------------------------------------
+struct TailState {
+  int* list[2];     // ping-pong lists of unfinalised records, ascending id
+  int* n;           // [0] length of the current list (in: from the selection after round 1), [1] rounds run,
+                    // [2] status (1: a round made no progress - internal error), [3] next list length
+  uint8_t* flag;    // [n] per position: stay | (d dlo + 2) << 1 | (d dhi + 2) << 4
+  int* blk_tot;     // [grid][3] per block: records that stay, sum of d dlo, sum of d dhi
+};
+constexpr int TAIL_TPB = 512;
+
+template <bool DP>
+__global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState T, uint32_t round0, int max_rounds) {
+  extern __shared__ double s_w[]; // [long_cap] weights of a long record
+  __shared__ CommitLongShared sh;
+  __shared__ int s_long[TAIL_TPB]; // positions (of the current tile) holding a long record
+  __shared__ int s_nlong;
+  __shared__ int s_red[3][TAIL_TPB / 32];
+  __shared__ int s_carry[3];
+  cg::grid_group grid = cg::this_grid();
+  const int nb = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  int cur = 0, rounds = 0;
+  int n = T.n[0];
+  while (n > 0 && rounds < max_rounds) {
+    const uint32_t round = round0 + (uint32_t)rounds;
+    const int* in = T.list[cur];
+    int* out = T.list[cur ^ 1];
+    const int per = (n + nb - 1) / nb;
+    const int i0 = min(n, b * per), i1 = min(n, i0 + per);
+    // ---- A: reservations
+    for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
+      const int i = t0 + threadIdx.x;
+      if (threadIdx.x == 0) s_nlong = 0;
+      __syncthreads();
+      if (i < i1) {
+        const int r = in[i];
+        const int cnt = S.cand_cnt[r];
+        if (cnt > S.long_min) s_long[atomicAdd(&s_nlong, 1)] = r;
+        else reserve_short(S, r, cnt, resv_key(round, r));
+      }
+      __syncthreads();
+      for (int k = 0; k < s_nlong; k++) reserve_long(S, s_long[k], resv_key(round, s_long[k]));
+      __syncthreads();
+    }
+    grid.sync();
+    // ---- B: turns
+    int my_stay = 0, my_dl = 0, my_dh = 0;
+    for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
+      const int i = t0 + threadIdx.x;
+      if (threadIdx.x == 0) s_nlong = 0;
+      __syncthreads();
+      if (i < i1) {
+        const int r = in[i];
+        const int cnt = S.cand_cnt[r];
+        if (cnt > S.long_min) s_long[atomicAdd(&s_nlong, 1)] = i;
+        else {
+          const int lo0 = S.dlo[r], hi0 = S.dhi[r];
+          const bool stay = commit_short<DP>(S, r, cnt, resv_key(round, r));
+          const int dl = (int)S.dlo[r] - lo0, dh = (int)S.dhi[r] - hi0;
+          T.flag[i] = (uint8_t)((stay ? 1 : 0) | ((dl + 2) << 1) | ((dh + 2) << 4));
+          my_stay += stay; my_dl += dl; my_dh += dh;
+        }
+      }
+      __syncthreads();
+      const int nl = s_nlong;
+      for (int k = 0; k < nl; k++) {
+        const int i2 = s_long[k], r = in[i2];
+        const int lo0 = S.dlo[r], hi0 = S.dhi[r];
+        const bool stay = commit_long<DP>(S, r, resv_key(round, r), s_w, sh); // ends with a barrier
+        if (threadIdx.x == 0) {
+          const int dl = (int)S.dlo[r] - lo0, dh = (int)S.dhi[r] - hi0;
+          T.flag[i2] = (uint8_t)((stay ? 1 : 0) | ((dl + 2) << 1) | ((dh + 2) << 4));
+          my_stay += stay; my_dl += dl; my_dh += dh;
+        }
+      }
+      __syncthreads();
+    }
+    // block totals
+    my_stay = warp_sum(my_stay); my_dl = warp_sum(my_dl); my_dh = warp_sum(my_dh);
+    if (lane == 0) { s_red[0][wp] = my_stay; s_red[1][wp] = my_dl; s_red[2][wp] = my_dh; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      int t = 0;
+      for (int k = 0; k < TAIL_TPB / 32; k++) t += s_red[threadIdx.x][k];
+      T.blk_tot[3 * b + threadIdx.x] = t;
+    }
+    grid.sync();
+    // ---- C: prefix over the blocks before this one, then a scan of the block's own positions
+    {
+      int a0 = 0, a1 = 0, a2 = 0, tot = 0;
+      for (int k = threadIdx.x; k < nb; k += TAIL_TPB) {
+        const int st = T.blk_tot[3 * k];
+        tot += st;
+        if (k < b) { a0 += st; a1 += T.blk_tot[3 * k + 1]; a2 += T.blk_tot[3 * k + 2]; }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); tot = warp_sum(tot);
+      __syncthreads(); // s_red is free again
+      if (lane == 0) { s_red[0][wp] = a0; s_red[1][wp] = a1; s_red[2][wp] = a2; }
+      if (wp == 0) { /* the total of `stay` over all blocks = next n, the same in every block */ }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        int t = 0;
+        for (int k = 0; k < TAIL_TPB / 32; k++) t += s_red[threadIdx.x][k];
+        s_carry[threadIdx.x] = t;
+      }
+      __syncthreads();
+      // next n: every block computes the same total
+      if (lane == 0) s_red[0][wp] = tot;
+      __syncthreads();
+      int n_next = 0;
+      for (int k = 0; k < TAIL_TPB / 32; k++) n_next += s_red[0][k];
+      // (tot was warp-reduced: lane 0 of every warp holds its warp's sum)
+      for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
+        const int i = t0 + threadIdx.x;
+        int st = 0, dl = 0, dh = 0, r = -1;
+        if (i < i1) {
+          const unsigned f = T.flag[i];
+          st = f & 1u; dl = (int)((f >> 1) & 7u) - 2; dh = (int)((f >> 4) & 7u) - 2;
+          r = in[i];
+        }
+        int x0 = st, x1 = dl, x2 = dh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y0 = __shfl_up_sync(FULL, x0, o), y1 = __shfl_up_sync(FULL, x1, o), y2 = __shfl_up_sync(FULL, x2, o);
+          if (lane >= o) { x0 += y0; x1 += y1; x2 += y2; }
+        }
+        __syncthreads(); // s_red reads of the previous step are done
+        if (lane == 31) { s_red[0][wp] = x0; s_red[1][wp] = x1; s_red[2][wp] = x2; }
+        __syncthreads();
+        int o0 = s_carry[0], o1 = s_carry[1], o2 = s_carry[2], t0s = 0, t1s = 0, t2s = 0;
+        for (int k = 0; k < TAIL_TPB / 32; k++) {
+          const int v0 = s_red[0][k], v1 = s_red[1][k], v2 = s_red[2][k];
+          if (k < wp) { o0 += v0; o1 += v1; o2 += v2; }
+          t0s += v0; t1s += v1; t2s += v2;
+        }
+        if (st) {
+          out[o0 + x0 - st] = r;
+          if (S.use_kbounds) { S.plo[r] += o1 + x1 - dl; S.phi_[r] += o2 + x2 - dh; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] += t0s; s_carry[1] += t1s; s_carry[2] += t2s; }
+        __syncthreads();
+      }
+      rounds++;
+      if (n_next >= n) { // no record took its turn: cannot happen (the smallest unfinalised record always can)
+        if (b == 0 && threadIdx.x == 0) T.n[2] = 1;
+        n = 0;
+      } else n = n_next;
+      cur ^= 1;
+    }
+    grid.sync();
+  }
+  if (b == 0 && threadIdx.x == 0) { T.n[1] = rounds; T.n[3] = n; }
 }
 
 // ------------------------------------------------------------------------------------------

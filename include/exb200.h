@@ -266,6 +266,8 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
      "table_min_usage" (default 16) a key mask wanted by at most this many records gets no table of
                  its own: another table serves them, or the batched scan over all items
      "index_partitioned" 0 builds every table with global atomics (debugging)
+     "rounds_tail" (default 1) the dependency rounds after the first run in one persistent
+                 cooperative kernel; 0 launches every round from the host
      "check"     recompute sizes / member lists / K from the links after every sweep and compare
      "trace"     print the phases of every sweep to stderr (also: environment EXB200_TRACE) */
 int exb200_set_option(exb200_handle* h, const char* name, int64_t value);

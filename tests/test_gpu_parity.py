@@ -148,12 +148,14 @@ def test_link_conditional_matches_oracle():
 
 
 def test_results_do_not_depend_on_batching_thresholds():
-    """Same seed, different wide-path thresholds -> identical chains (property test that holds at
-    any size: the sweep is sequentially consistent, batching is only scheduling)."""
+    """Same seed, different wide-path thresholds, rounds launched one by one (rounds_tail=0) or in
+    the persistent kernel -> identical chains (property test that holds at any size: the sweep is
+    sequentially consistent, batching is only scheduling)."""
     m, _ = readme_model("rldata10000", n=4000)
     states = []
     for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1), dict(bucket_cap=0, huge_min=0),
-                 dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0)):
+                 dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
+                 dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
@@ -192,15 +194,16 @@ def test_synthetic_records_at_scale_lockstep():
 def test_one_million_records_lockstep_from_the_first_sweep(kind):
     """The benchmark's own generator at 1 M records (config C3, and C4's prior family), from the
     all-singletons start through sweep 30 - the regime bench.py times: multi-bucket probes,
-    block-staged and tiled buckets, the serial path and a dozen dependency rounds are all live.
+    warp- and block-staged lists, the serial path and a dozen dependency rounds are all live.
     States are compared with the oracle every five sweeps (the oracle searches the shortest bucket
     of the record's pinned attributes, so a sweep costs it about a second)."""
     from bench import DATA_SEED, clust_prior
     from exchanger_b200.synthetic import synth_model
     n = 1_000_000
     m, _ = synth_model(n, clust_prior(kind, n), seed=DATA_SEED)
-    stats = lockstep(m, 30, every=5, huge_min=2048)
-    tot = {k: sum(s[k] for s in stats) for k in ("n_probe", "n_long", "n_wide", "n_huge")}
+    stats = lockstep(m, 30, every=5)
+    # (tiled buckets need more than 8192 items in one bucket: test_multi_bucket_probes_and_warp_scanned_buckets)
+    tot = {k: sum(s[k] for s in stats) for k in ("n_probe", "n_long", "n_wide")}
     assert all(v > 0 for v in tot.values()), tot
     assert max(s["n_rounds"] for s in stats) >= 8 and stats[-1]["n_entities"] < 0.95 * n
 
