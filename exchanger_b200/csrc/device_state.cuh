@@ -28,6 +28,7 @@ constexpr int KEY_ATTRS = 12;       // attributes (largest domains first) that m
 constexpr int N_TABLES = 1 << KEY_ATTRS;
 constexpr int WIDE_BLOCKS = 1024;   // partition of the item range in the wide path
 constexpr int CAND_INLINE = 4;      // candidate lists up to this length are stored at pool[CAND_INLINE * record]
+constexpr int FAST_CAND = 16;       // candidates the thread-per-record kernel keeps for one record
 constexpr uint32_t CAND_OWN_ONLY = 0xFFFFFFFFu; // cand_off value: the list is {the record's own entity}, log-likelihood 0
 constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
 constexpr int HUGE_BATCH = 512;     // records with a huge bucket scanned per launch
@@ -56,13 +57,28 @@ struct DevAttr {
 
 // One blocking table: items (entity slots) bucketed by their values on a set of key attributes
 // (bit k of `mask` = key attribute k).  CSR over buckets built per sweep by count / scan / fill.
+// A table comes in two forms.  CSR (count / scan / fill): contiguous buckets that many lanes can scan -
+// needed for the few key masks with long buckets.  CHAIN (key spaces about as large as the item
+// set): head[cell] -> item, node[item] = (packed attribute tuple, next item, flags) - one atomicExch
+// per item to build, no bucket bounds to fetch, and the tuple a probe has to compare sits in the
+// node it reads anyway (no gather of the entity table).
+struct ChainNode {
+  unsigned long long P; // packed attribute tuple of the item (pack_tuple)
+  int next;             // next item of the cell's chain (-1: end)
+  uint32_t flags;       // bit 0: the item is an entity slot whose potential entity is its twin
+};
 struct DevTable {
   uint32_t mask;
   int exact;         // 1: bucket = mixed-radix key; 0: bucket = mix(key) & (B - 1)
   uint32_t B;        // number of buckets
-  int pad;
+  int chain;         // 1: the chain form is built this sweep (probes walk head / node)
   int *ptr;          // [B]  after fill: END offset of bucket (start = ptr[b-1], 0 for b = 0)
   int *ids;          // [n_items]
+  unsigned long long kmask; // fields of the packed tuple that form the key
+  uint32_t cells;    // chain form: number of cells (power of two)
+  int csr;           // 1: the CSR form is built this sweep
+  int *head;         // [cells]
+  ChainNode *node;   // [2N]
 };
 
 struct ClustDev {
@@ -99,6 +115,11 @@ struct DevState {
   float *tab_est;               // [2^n_key] sum over the records wanting a full mask of the expected size
                                 //           of their pair bucket (what falling back to the pair would cost)
   const uint16_t *tab_remap;    // [2][2^n_key] wanted full mask / pair mask -> mask of a built table (0: none)
+  int pk_ok;                    // the attribute domains fit a 64-bit packed tuple (fast candidate path)
+  uint8_t pk_shift[MAX_ATTRS], pk_bits[MAX_ATTRS]; // field of attribute a in the packed tuple
+  int hop_cap;                  // chain items a thread walks for one record before the record is left to the CSR path
+  int *slow_list;               // [N] records the fast candidate kernel leaves to the bucket-scanning kernels
+  int *tab_over;                // [2^n_key] chain tables in which some record exceeded hop_cap / FAST_CAND
   int n_key;                    // number of key attributes
   int key_attr[KEY_ATTRS];      // key position -> attribute
   int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
@@ -167,7 +188,8 @@ enum CounterSlot {
   C_NHUGE = 13,     // size of huge_list
   C_NOLIST = 14,    // records without a stored list after candidate generation (diagnostic)
   C_NPROBE = 15,    // size of probe_list
-  C_NSLOTS = 16
+  C_NSLOW = 16,     // size of slow_list
+  C_NSLOTS = 17
 };
 
 } // namespace exb

@@ -829,12 +829,16 @@ int update_links(exb200_handle* h) {
     rc = dalloc(h, &h->tail.list[1], (size_t)N); if (rc) return rc;
     rc = dalloc(h, &h->tail.flag, (size_t)N); if (rc) return rc;
     rc = dalloc(h, &h->tail.blk_tot, (size_t)3 * 4096); if (rc) return rc;
-    rc = dalloc(h, &h->tail.n, 4); if (rc) return rc;
     cub::DeviceSelect::If(nullptr, h->select_tmp_bytes, thrust::counting_iterator<int>(0), h->tail.list[0], h->tail.n, N,
                           NotFinal{S.fin}, st);
     char* tmp = nullptr;
     rc = dalloc(h, &tmp, h->select_tmp_bytes); if (rc) return rc;
     h->d_select_tmp = tmp;
+    rc = dalloc(h, &h->tail.n, 8); if (rc) return rc;
+    rc = dalloc(h, &h->tail.long_pos, (size_t)N); if (rc) return rc;
+  }
+  if (use_tail && h->trace && !h->tail.dbg) {
+    int rc = dalloc(h, &h->tail.dbg, 257); if (rc) return rc;
   }
   while (n_act + n_actl > 0) {
     rounds++;
@@ -861,7 +865,7 @@ int update_links(exb200_handle* h) {
         int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
         rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
       }
-      CK(cudaMemsetAsync(h->tail.n, 0, sizeof(int) * 4, st));
+      CK(cudaMemsetAsync(h->tail.n, 0, sizeof(int) * 8, st));
       CK(cub::DeviceSelect::If(h->d_select_tmp, h->select_tmp_bytes, thrust::counting_iterator<int>(0), h->tail.list[0],
                                h->tail.n, N, NotFinal{S.fin}, st));
       h->n_launches += 2;
@@ -885,6 +889,16 @@ int update_links(exb200_handle* h) {
       CK(cudaStreamSynchronize(st));
       if (h->trace) std::fprintf(stderr, "[exb200] round 1: %d records, then %d open; %d more rounds in the persistent kernel (%d blocks)\n",
                                  n_act, tn[0], tn[1], h->tail_grid);
+      if (h->trace && h->tail.dbg) {
+        unsigned long long dbg[257];
+        CK(cudaMemcpy(dbg, h->tail.dbg, sizeof dbg, cudaMemcpyDeviceToHost));
+        unsigned long long prev = dbg[256];
+        for (int k = 0; k < std::min(tn[1], 64); k++) {
+          std::fprintf(stderr, "[exb200]   tail round %2d: %8llu records  reserve %7.1f us  turns %7.1f us  scan %7.1f us\n", k + 2, dbg[4 * k],
+                       (dbg[4 * k + 1] - prev) * 1e-3, (dbg[4 * k + 2] - dbg[4 * k + 1]) * 1e-3, (dbg[4 * k + 3] - dbg[4 * k + 2]) * 1e-3);
+          prev = dbg[4 * k + 3];
+        }
+      }
       h->round_ctr += (uint32_t)tn[1];
       rounds += tn[1];
       if (tn[2] || tn[3] > 0) return fail(h, EXB200_ERR_CUDA, "links update made no progress (internal error)");
@@ -938,6 +952,9 @@ int update_links(exb200_handle* h) {
   CK(cudaMemcpyAsync(c64, S.counters64, sizeof c64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[6], st));
   CK(cudaStreamSynchronize(st));
+  { // a record without a valid link (EXB200_ERR_WEIGHTS) also upsets the counts below: report it first
+    int rc = check_device_error(h); if (rc) return rc;
+  }
   if (hc[C_K] != h->K + dk_wide + hc[C_DK_TOTAL])
     return fail(h, EXB200_ERR_CUDA, "entity count mismatch after the links update: " + std::to_string(hc[C_K]) +
                                         " vs " + std::to_string(h->K + dk_wide + hc[C_DK_TOTAL]));

@@ -1164,6 +1164,7 @@ __device__ __forceinline__ int live_size(const DevState& S, int e, int own, bool
   return e == own ? (single ? 0 : sz - 1) : sz; // links.cpp:359, :375
 }
 
+constexpr int SHORT_MAX = 32; // log-weights a thread keeps for one record (the default long_min)
 // Turn of one record with a short list, if it owns everything it reserved (thread per record).
 // Returns true if the record stays unfinalised.
 template <bool DP>
@@ -1177,20 +1178,40 @@ __device__ __forceinline__ bool commit_short(const DevState& S, int r, int cnt, 
   const double zero_ll = 0.0;
   const double* lls = own_only ? &zero_ll : S.cand_ll + S.cand_off[r];
   const bool single = S.ent_size[own] == 1;
-  // weights of the live candidates (links.cpp:372-388)
+  // weights of the live candidates (links.cpp:372-388).  The sizes are gathered once (independent
+  // loads, four in flight) and the log-weights kept: the three passes of the sequential conditional
+  // (maximum, sum, inverse CDF) then run on the same values without touching memory again.
+  double lw[SHORT_MAX];
   double m1 = -CUDART_INF;
-  for (int j = 0; j < cnt; j++) {
-    const int sz = live_size(S, ids[j], own, single);
-    if (sz > 0) {
-      const double lw = cand_lw<DP>(S, r, ids[j], sz, lls[j]);
-      m1 = lw > m1 ? lw : m1;
+  if (cnt <= SHORT_MAX) {
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      int sz[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) sz[u] = j0 + u < cnt ? live_size(S, ids[j0 + u], own, single) : 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (j0 + u < cnt) {
+          const double v = sz[u] > 0 ? cand_lw<DP>(S, r, ids[j0 + u], sz[u], lls[j0 + u]) : -CUDART_INF;
+          lw[j0 + u] = v;
+          m1 = v > m1 ? v : m1;
+        }
+    }
+  } else { // (long_min raised above SHORT_MAX by an option: nothing is kept)
+    for (int j = 0; j < cnt; j++) {
+      const int sz = live_size(S, ids[j], own, single);
+      if (sz > 0) { const double v = cand_lw<DP>(S, r, ids[j], sz, lls[j]); m1 = v > m1 ? v : m1; }
     }
   }
+  auto lw_of = [&](int j) -> double {
+    if (cnt <= SHORT_MAX) return lw[j];
+    const int sz = live_size(S, ids[j], own, single);
+    return sz > 0 ? cand_lw<DP>(S, r, ids[j], sz, lls[j]) : -CUDART_INF;
+  };
   double srel = 0.0;
   if (m1 > -CUDART_INF)
     for (int j = 0; j < cnt; j++) {
-      const int sz = live_size(S, ids[j], own, single);
-      if (sz > 0) srel += exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
+      const double v = lw_of(j);
+      if (v != -CUDART_INF) srel += exp(v - m1); // (a candidate that is not live, or of zero weight, adds nothing)
     }
   const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
   const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
@@ -1207,9 +1228,9 @@ __device__ __forceinline__ bool commit_short(const DevState& S, int r, int cnt, 
     double c = 0.0;
     int pick = -1, lastpos = -1;
     for (int j = 0; j < cnt; j++) {
-      const int sz = live_size(S, ids[j], own, single);
-      if (sz <= 0) continue;
-      const double w = exp(cand_lw<DP>(S, r, ids[j], sz, lls[j]) - m1);
+      const double v = lw_of(j);
+      if (v == -CUDART_INF) continue; // not live
+      const double w = exp(v - m1);
       if (w > 0.0) lastpos = ids[j];
       c += w;
       if (tt < c) { pick = ids[j]; break; }
@@ -1389,90 +1410,129 @@ __global__ void __launch_bounds__(TPB) k_commit_w(DevState S, const int* __restr
 struct TailState {
   int* list[2];     // ping-pong lists of unfinalised records, ascending id
   int* n;           // [0] length of the current list (in: from the selection after round 1), [1] rounds run,
-                    // [2] status (1: a round made no progress - internal error), [3] next list length
+                    // [2] status (1: a round made no progress - internal error), [3] list length at exit,
+                    // [4] next tile of 32 positions to hand out, [5] long records of the round, [6] next of them
   uint8_t* flag;    // [n] per position: stay | (d dlo + 2) << 1 | (d dhi + 2) << 4
-  int* blk_tot;     // [grid][3] per block: records that stay, sum of d dlo, sum of d dhi
+  int* blk_tot;     // [grid][3] per chunk of positions: records that stay, sum of d dlo, sum of d dhi
+  int* long_pos;    // [n] positions holding a record with a long list (this round)
+  unsigned long long* dbg; // trace: [round][4] = (records, ns after A, after B, after C) of the first 64 rounds (may be null)
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 constexpr int TAIL_TPB = 512;
 
+// Steps A and B hand out tiles of 32 positions to warps from a shared cursor and have no block
+// barrier: the cost of a record's turn varies by orders of magnitude (a chain of dependent loads per
+// candidate), and a barrier per tile made every tile as slow as its slowest record.  Records with
+// long lists are reserved by their warp (lanes strided over the list) and listed; their turns are
+// taken by whole blocks, again handed out one at a time, while other blocks still work on tiles -
+// turns of one round touch disjoint items, so the order does not matter.
 template <bool DP>
 __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState T, uint32_t round0, int max_rounds) {
   extern __shared__ double s_w[]; // [long_cap] weights of a long record
   __shared__ CommitLongShared sh;
-  __shared__ int s_long[TAIL_TPB]; // positions (of the current tile) holding a long record
-  __shared__ int s_nlong;
   __shared__ int s_red[3][TAIL_TPB / 32];
   __shared__ int s_carry[3];
+  __shared__ int s_next;
   cg::grid_group grid = cg::this_grid();
   const int nb = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int gw = b * (TAIL_TPB / 32) + wp, n_warps = nb * (TAIL_TPB / 32);
   int cur = 0, rounds = 0;
   int n = T.n[0];
+  if (T.dbg && b == 0 && threadIdx.x == 0) T.dbg[256] = global_ns();
   while (n > 0 && rounds < max_rounds) {
     const uint32_t round = round0 + (uint32_t)rounds;
     const int* in = T.list[cur];
     int* out = T.list[cur ^ 1];
-    const int per = (n + nb - 1) / nb;
-    const int i0 = min(n, b * per), i1 = min(n, i0 + per);
-    // ---- A: reservations
-    for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
-      const int i = t0 + threadIdx.x;
-      if (threadIdx.x == 0) s_nlong = 0;
-      __syncthreads();
-      if (i < i1) {
-        const int r = in[i];
-        const int cnt = S.cand_cnt[r];
-        if (cnt > S.long_min) s_long[atomicAdd(&s_nlong, 1)] = r;
-        else reserve_short(S, r, cnt, resv_key(round, r));
+    // chunks of positions (a multiple of 32) whose totals step C scans: chunk c = positions [c per, (c+1) per)
+    const int per = ((n + nb - 1) / nb + 31) & ~31;
+    // ---- A: reservations (tiles assigned round-robin: the work per record is a few atomics)
+    if (threadIdx.x < 3) T.blk_tot[3 * b + threadIdx.x] = 0;
+    for (int t0 = gw * 32; t0 < n; t0 += n_warps * 32) {
+      const int i = t0 + lane;
+      int r = -1, cnt = 0;
+      if (i < n) { r = in[i]; cnt = S.cand_cnt[r]; }
+      const bool is_long = r >= 0 && cnt > S.long_min;
+      if (r >= 0 && !is_long) reserve_short(S, r, cnt, resv_key(round, r));
+      unsigned lm = __ballot_sync(FULL, is_long);
+      if (lm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&T.n[5], __popc(lm));
+        base = __shfl_sync(FULL, base, 0);
+        if (is_long) T.long_pos[base + __popc(lm & ((1u << lane) - 1u))] = i;
+        for (; lm; lm &= lm - 1) { // the warp reserves the items of each long record
+          const int src = __ffs(lm) - 1;
+          const int r2 = __shfl_sync(FULL, r, src), c2 = __shfl_sync(FULL, cnt, src);
+          const unsigned long long key = resv_key(round, r2);
+          const int* ids = S.cand_id + S.cand_off[r2];
+          if (lane == 0) { atomicMin(&S.owner[S.lambda[r2]], key); atomicMin(&S.owner[S.N + r2], key); }
+          for (int j = lane; j < c2; j += 128) { // four independent loads in flight per lane
+            int id[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) id[u] = j + 32 * u < c2 ? ids[j + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (id[u] >= 0) atomicMin(&S.owner[id[u]], key);
+          }
+        }
       }
-      __syncthreads();
-      for (int k = 0; k < s_nlong; k++) reserve_long(S, s_long[k], resv_key(round, s_long[k]));
-      __syncthreads();
     }
     grid.sync();
-    // ---- B: turns
-    int my_stay = 0, my_dl = 0, my_dh = 0;
-    for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
-      const int i = t0 + threadIdx.x;
-      if (threadIdx.x == 0) s_nlong = 0;
-      __syncthreads();
-      if (i < i1) {
+    if (T.dbg && b == 0 && threadIdx.x == 0 && rounds < 64) { T.dbg[4 * rounds] = (unsigned long long)n; T.dbg[4 * rounds + 1] = global_ns(); }
+    // ---- B: turns.  Short lists: warps take tiles from the cursor ...
+    for (;;) {
+      int t0 = 0;
+      if (lane == 0) t0 = atomicAdd(&T.n[4], 32);
+      t0 = __shfl_sync(FULL, t0, 0);
+      if (t0 >= n) break;
+      const int i = t0 + lane;
+      int stay = 0, dl = 0, dh = 0;
+      if (i < n) {
         const int r = in[i];
         const int cnt = S.cand_cnt[r];
-        if (cnt > S.long_min) s_long[atomicAdd(&s_nlong, 1)] = i;
-        else {
+        if (cnt <= S.long_min) {
           const int lo0 = S.dlo[r], hi0 = S.dhi[r];
-          const bool stay = commit_short<DP>(S, r, cnt, resv_key(round, r));
-          const int dl = (int)S.dlo[r] - lo0, dh = (int)S.dhi[r] - hi0;
-          T.flag[i] = (uint8_t)((stay ? 1 : 0) | ((dl + 2) << 1) | ((dh + 2) << 4));
-          my_stay += stay; my_dl += dl; my_dh += dh;
+          stay = commit_short<DP>(S, r, cnt, resv_key(round, r)) ? 1 : 0;
+          dl = (int)S.dlo[r] - lo0; dh = (int)S.dhi[r] - hi0;
+          T.flag[i] = (uint8_t)(stay | ((dl + 2) << 1) | ((dh + 2) << 4));
         }
       }
-      __syncthreads();
-      const int nl = s_nlong;
-      for (int k = 0; k < nl; k++) {
-        const int i2 = s_long[k], r = in[i2];
-        const int lo0 = S.dlo[r], hi0 = S.dhi[r];
-        const bool stay = commit_long<DP>(S, r, resv_key(round, r), s_w, sh); // ends with a barrier
-        if (threadIdx.x == 0) {
-          const int dl = (int)S.dlo[r] - lo0, dh = (int)S.dhi[r] - hi0;
-          T.flag[i2] = (uint8_t)((stay ? 1 : 0) | ((dl + 2) << 1) | ((dh + 2) << 4));
-          my_stay += stay; my_dl += dl; my_dh += dh;
-        }
+      stay = warp_sum(stay); dl = warp_sum(dl); dh = warp_sum(dh);
+      if (lane == 0) { // a tile lies inside one chunk
+        int* tot = T.blk_tot + 3 * (t0 / per);
+        if (stay) atomicAdd(&tot[0], stay);
+        if (dl) atomicAdd(&tot[1], dl);
+        if (dh) atomicAdd(&tot[2], dh);
       }
-      __syncthreads();
     }
-    // block totals
-    my_stay = warp_sum(my_stay); my_dl = warp_sum(my_dl); my_dh = warp_sum(my_dh);
-    if (lane == 0) { s_red[0][wp] = my_stay; s_red[1][wp] = my_dl; s_red[2][wp] = my_dh; }
     __syncthreads();
-    if (threadIdx.x < 3) {
-      int t = 0;
-      for (int k = 0; k < TAIL_TPB / 32; k++) t += s_red[threadIdx.x][k];
-      T.blk_tot[3 * b + threadIdx.x] = t;
+    // ... long lists: blocks take them one at a time
+    const int n_long = T.n[5];
+    for (;;) {
+      if (threadIdx.x == 0) s_next = atomicAdd(&T.n[6], 1);
+      __syncthreads();
+      const int k = s_next;
+      if (k >= n_long) break;
+      const int i2 = T.long_pos[k], r = in[i2];
+      const int lo0 = S.dlo[r], hi0 = S.dhi[r];
+      const bool stay = commit_long<DP>(S, r, resv_key(round, r), s_w, sh); // ends with a barrier
+      if (threadIdx.x == 0) {
+        const int dl = (int)S.dlo[r] - lo0, dh = (int)S.dhi[r] - hi0;
+        T.flag[i2] = (uint8_t)((stay ? 1 : 0) | ((dl + 2) << 1) | ((dh + 2) << 4));
+        int* tot = T.blk_tot + 3 * (i2 / per);
+        if (stay) atomicAdd(&tot[0], 1);
+        if (dl) atomicAdd(&tot[1], dl);
+        if (dh) atomicAdd(&tot[2], dh);
+      }
     }
     grid.sync();
-    // ---- C: prefix over the blocks before this one, then a scan of the block's own positions
+    if (T.dbg && b == 0 && threadIdx.x == 0 && rounds < 64) T.dbg[4 * rounds + 2] = global_ns();
+    // ---- C: prefix over the chunks before this block's, then a scan of the chunk's own positions
     {
+      if (b == 0 && threadIdx.x == 0) { T.n[4] = 0; T.n[5] = 0; T.n[6] = 0; } // cursors of the next round
+      const int i0 = min(n, b * per), i1 = min(n, i0 + per);
       int a0 = 0, a1 = 0, a2 = 0, tot = 0;
       for (int k = threadIdx.x; k < nb; k += TAIL_TPB) {
         const int st = T.blk_tot[3 * k];
@@ -1480,9 +1540,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
         if (k < b) { a0 += st; a1 += T.blk_tot[3 * k + 1]; a2 += T.blk_tot[3 * k + 2]; }
       }
       a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); tot = warp_sum(tot);
-      __syncthreads(); // s_red is free again
       if (lane == 0) { s_red[0][wp] = a0; s_red[1][wp] = a1; s_red[2][wp] = a2; }
-      if (wp == 0) { /* the total of `stay` over all blocks = next n, the same in every block */ }
       __syncthreads();
       if (threadIdx.x < 3) {
         int t = 0;
@@ -1490,12 +1548,10 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
         s_carry[threadIdx.x] = t;
       }
       __syncthreads();
-      // next n: every block computes the same total
-      if (lane == 0) s_red[0][wp] = tot;
+      if (lane == 0) s_red[0][wp] = tot; // every block computes the same total: the next n
       __syncthreads();
       int n_next = 0;
       for (int k = 0; k < TAIL_TPB / 32; k++) n_next += s_red[0][k];
-      // (tot was warp-reduced: lane 0 of every warp holds its warp's sum)
       for (int t0 = i0; t0 < i1; t0 += TAIL_TPB) {
         const int i = t0 + threadIdx.x;
         int st = 0, dl = 0, dh = 0, r = -1;
@@ -1527,6 +1583,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
         if (threadIdx.x == 0) { s_carry[0] += t0s; s_carry[1] += t1s; s_carry[2] += t2s; }
         __syncthreads();
       }
+      if (T.dbg && b == 0 && threadIdx.x == 0 && rounds < 64) T.dbg[4 * rounds + 3] = global_ns();
       rounds++;
       if (n_next >= n) { // no record took its turn: cannot happen (the smallest unfinalised record always can)
         if (b == 0 && threadIdx.x == 0) T.n[2] = 1;
