@@ -94,6 +94,9 @@ struct exb200_handle {
   uint16_t* d_remap = nullptr;
   PartBuild pb{};              // partitioned build of the large tables
   int* d_part_tabs = nullptr;
+  int* d_chain_tabs = nullptr;
+  int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
+  int hop_cap = 64;
   int pb_tables_cap = 0;
   int huge_cap_alloc = -1;     // wide_threshold the huge-bucket scratch lists were sized for
   int* d_bsum = nullptr; size_t bsum_cap = 0;
@@ -522,6 +525,60 @@ int ensure_table(exb200_handle* h, int tab) {
   return EXB200_OK;
 }
 
+// CSR form of the given blocking tables (count / scan / fill)
+int build_csr_tables(exb200_handle* h, const std::vector<int>& tabs) {
+  DevState& S = h->S;
+  const int N = h->N;
+  cudaStream_t st = h->stream;
+  if (tabs.empty()) return EXB200_OK;
+  for (int t : tabs) { int rc = ensure_table(h, t); if (rc) return rc; }
+  // tables with many buckets are built by partitioning (k_part_a / k_part_b); the few small ones
+  // (their bucket arrays stay in the L2) by global atomics (k_index_count / k_index_fill)
+  std::vector<int> large, small, tiny;
+  for (int t : tabs) {
+    const uint32_t B = h->tables[t].d.B;
+    const bool part = h->index_partitioned && B >= 16u * PART_SIZE && B <= (uint32_t)MAX_PARTS * PART_SIZE && (int)large.size() < PA_MAX_TABS;
+    if (part) large.push_back(t);
+    else if (h->index_partitioned && B <= (uint32_t)SMALL_B_MAX) { tiny.push_back(t); small.push_back(t); }
+    else small.push_back(t);
+  }
+  // `small` keeps the tiny tables for the memset / scan; they are removed from the atomic kernels' list
+  std::vector<int> atomic_tabs;
+  for (int t : small) if (std::find(tiny.begin(), tiny.end(), t) == tiny.end()) atomic_tabs.push_back(t);
+  for (int t : small) CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
+  if (!large.empty()) {
+    const long long cap = 2LL * N;
+    if ((int)large.size() > h->pb_tables_cap) {
+      const int want = std::min(PA_MAX_TABS, ((int)large.size() + 7) / 8 * 8);
+      int rc = dalloc(h, &h->pb.pairs, (size_t)want * cap); if (rc) return rc;
+      h->pb_tables_cap = want;
+    }
+    PartBuild& P = h->pb;
+    P.n_tab = (int)large.size(); P.tabs = h->d_part_tabs; P.cap = cap;
+    CK(cudaMemcpyAsync(h->d_part_tabs, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(P.part_cnt, 0, sizeof(int) * (size_t)P.n_tab * MAX_PARTS, st));
+  }
+  CK(cudaMemcpyAsync(h->d_active, atomic_tabs.data(), sizeof(int) * atomic_tabs.size(), cudaMemcpyHostToDevice, st));
+  if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
+  for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 0);
+  if (!large.empty()) {
+    KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
+    KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
+  }
+  for (int t : small) {
+    int rc = scan_exclusive<int>(h, h->tables[t].d.ptr, h->tables[t].d.ptr, (int)h->tables[t].d.B);
+    if (rc) return rc;
+  }
+  if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
+  for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 1);
+  if (!large.empty()) {
+    KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
+    k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
+    h->n_launches++;
+  }
+  return EXB200_OK;
+}
+
 // serial path: possible links of up to WIDE_NB records among all the items (counting pass)
 int wide_count(exb200_handle* h, const int* recs, int nb, int* totals) {
   DevState& S = h->S;
@@ -557,7 +614,7 @@ int update_links(exb200_handle* h) {
   CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * 2 * N_TABLES, st));
   CK(cudaMemsetAsync(S.tab_est, 0, sizeof(float) * N_TABLES, st));
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
-  CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 2, st));
+  CK(cudaMemsetAsync(S.counters64, 0, sizeof(long long) * 66, st));
   {
     const unsigned long long shared_from = (unsigned long long)CAND_INLINE * (unsigned long long)N; // after the per-record slots
     CK(cudaMemcpyAsync(S.pool_cursor, &shared_from, sizeof shared_from, cudaMemcpyHostToDevice, st));
@@ -620,9 +677,6 @@ int update_links(exb200_handle* h) {
       remap[N_TABLES + t] = (uint16_t)best;
     }
   }
-  for (int t : active) {
-    int rc = ensure_table(h, t); if (rc) return rc;
-  }
   if (h->trace) {
     for (int t = 1; t < NT; t++)
       if (usage[t] > 0 || usage[N_TABLES + t] > 0)
@@ -632,60 +686,71 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * remap.size(), cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
-  if (!active.empty()) {
-    // tables with many buckets are built by partitioning (k_part_a / k_part_b); the few small ones
-    // (their bucket arrays stay in the L2) by global atomics (k_index_count / k_index_fill)
-    std::vector<int> large, small, tiny;
+  // Form of every table of this sweep: the chain form for key spaces about as large as the item set
+  // (one atomicExch per item, probes walk a short chain of nodes holding packed tuples), the CSR
+  // form for the few masks with long buckets (scanned by many lanes).
+  std::vector<int> csr_tabs, chain_tabs;
+  {
+    const double items = 1.2 * (double)N;
     for (int t : active) {
-      const uint32_t B = h->tables[t].d.B;
-      const bool part = h->index_partitioned && B >= 16u * PART_SIZE && B <= (uint32_t)MAX_PARTS * PART_SIZE && (int)large.size() < PA_MAX_TABS;
-      if (part) large.push_back(t);
-      else if (h->index_partitioned && B <= (uint32_t)SMALL_B_MAX) { tiny.push_back(t); small.push_back(t); }
-      else small.push_back(t);
-    }
-    // `small` keeps the tiny tables for the memset / scan; they are removed from the atomic kernels' list
-    std::vector<int> atomic_tabs;
-    for (int t : small) if (std::find(tiny.begin(), tiny.end(), t) == tiny.end()) atomic_tabs.push_back(t);
-    for (int t : small) CK(cudaMemsetAsync(h->tables[t].d.ptr, 0, sizeof(int) * ((size_t)h->tables[t].d.B + 1), st));
-    if (!large.empty()) {
-      const long long cap = 2LL * N;
-      if ((int)large.size() > h->pb_tables_cap) {
-        const int want = std::min(PA_MAX_TABS, ((int)large.size() + 7) / 8 * 8);
-        int rc = dalloc(h, &h->pb.pairs, (size_t)want * cap); if (rc) return rc;
-        h->pb_tables_cap = want;
+      TableHost& T = h->tables[t];
+      const bool chain = S.pk_ok && h->opt_fast && T.d.B > (uint32_t)SMALL_B_MAX && 4.0 * (double)T.keys >= items;
+      if (chain) {
+        if (!T.d.head) {
+          uint32_t cells = 1024;
+          while ((double)cells < std::min(1.2 * (double)N, (double)T.keys)) cells <<= 1;
+          T.d.cells = cells;
+          unsigned long long km = 0;
+          for (int k = 0; k < S.n_key; k++)
+            if (t >> k & 1) km |= ((1ull << S.pk_bits[S.key_attr[k]]) - 1ull) << S.pk_shift[S.key_attr[k]];
+          T.d.kmask = km;
+          int rc = dalloc(h, &T.d.head, (size_t)cells); if (rc) return rc;
+          rc = dalloc(h, &T.d.node, (size_t)2 * N); if (rc) return rc;
+        }
+        chain_tabs.push_back(t);
+      } else csr_tabs.push_back(t);
+      if (T.d.chain != (chain ? 1 : 0) || T.d.csr != (chain ? 0 : 1)) {
+        T.d.chain = chain ? 1 : 0; T.d.csr = chain ? 0 : 1;
+        CK(cudaMemcpyAsync(h->d_tables + t, &T.d, sizeof(DevTable), cudaMemcpyHostToDevice, st));
       }
-      PartBuild& P = h->pb;
-      P.n_tab = (int)large.size(); P.tabs = h->d_part_tabs; P.cap = cap;
-      CK(cudaMemcpyAsync(h->d_part_tabs, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice, st));
-      CK(cudaMemsetAsync(P.part_cnt, 0, sizeof(int) * (size_t)P.n_tab * MAX_PARTS, st));
     }
-    CK(cudaMemcpyAsync(h->d_active, atomic_tabs.data(), sizeof(int) * atomic_tabs.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(h->ev[12], st));
-    if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-    for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 0);
-    if (!large.empty()) {
-      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
-      KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
-    }
-    CK(cudaEventRecord(h->ev[13], st));
-    for (int t : small) {
-      int rc = scan_exclusive<int>(h, h->tables[t].d.ptr, h->tables[t].d.ptr, (int)h->tables[t].d.B);
-      if (rc) return rc;
-    }
-    CK(cudaEventRecord(h->ev[14], st));
-    if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-    for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 1);
-    if (!large.empty()) {
-      KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
-      k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
-      h->n_launches++;
-    }
-    h->has_index_events = true;
-  } else h->has_index_events = false;
+  }
+  CK(cudaEventRecord(h->ev[12], st));
+  h->has_index_events = !active.empty();
+  { int rc = build_csr_tables(h, csr_tabs); if (rc) return rc; }
+  CK(cudaEventRecord(h->ev[14], st));
+  if (!chain_tabs.empty()) {
+    for (int t : chain_tabs) CK(cudaMemsetAsync(h->tables[t].d.head, 0xFF, sizeof(int) * (size_t)h->tables[t].d.cells, st));
+    CK(cudaMemsetAsync(S.tab_over, 0, sizeof(int) * N_TABLES, st));
+    CK(cudaMemcpyAsync(h->d_chain_tabs, chain_tabs.data(), sizeof(int) * chain_tabs.size(), cudaMemcpyHostToDevice, st));
+    KLAUNCH(h, k_chain_build, nblk(2LL * N), TPB, 0, S, h->d_chain_tabs, (int)chain_tabs.size());
+  }
   CK(cudaEventRecord(h->ev[3], st));
-  KLAUNCH(h, (k_cand<8, 64>), nblk((long long)N, 64 / 8), 64, 0, S, (const int*)nullptr, N);
-  CK(cudaEventRecord(h->ev[10], st));
   int hc[C_NSLOTS];
+  if (chain_tabs.empty()) KLAUNCH(h, (k_cand<8, 64>), nblk((long long)N, 64 / 8), 64, 0, S, (const int*)nullptr, N);
+  else {
+    // thread per record over the chain tables; what it cannot finish is listed for the bucket kernels
+    KLAUNCH(h, k_cand_fast, nblk(N), TPB, 0, S);
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hc[C_NSLOW] > 0) {
+      // chains longer than hop_cap / more than FAST_CAND candidates: those tables get their CSR form too
+      std::vector<int> over(N_TABLES), lazy;
+      CK(cudaMemcpy(over.data(), S.tab_over, sizeof(int) * N_TABLES, cudaMemcpyDeviceToHost));
+      for (int t : chain_tabs)
+        if (over[t]) {
+          lazy.push_back(t);
+          h->tables[t].d.csr = 1;
+          int rc = ensure_table(h, t); if (rc) return rc;
+          CK(cudaMemcpyAsync(h->d_tables + t, &h->tables[t].d, sizeof(DevTable), cudaMemcpyHostToDevice, st));
+        }
+      int rc = build_csr_tables(h, lazy); if (rc) return rc;
+      if (h->trace) std::fprintf(stderr, "[exb200] fast path left %d records to the bucket kernels (%d chain tables also built as CSR)\n",
+                                 hc[C_NSLOW], (int)lazy.size());
+      KLAUNCH(h, (k_cand<8, 64>), nblk((long long)hc[C_NSLOW], 64 / 8), 64, 0, S, (const int*)S.slow_list, hc[C_NSLOW]);
+    }
+  }
+  CK(cudaEventRecord(h->ev[10], st));
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   auto t_tr = std::chrono::steady_clock::now();
@@ -948,7 +1013,7 @@ int update_links(exb200_handle* h) {
   std::swap(S.ent_size, S.ent_size_nx);
   std::swap(S.ent_head, S.ent_head_nx);
   CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
-  long long c64[2];
+  long long c64[66];
   CK(cudaMemcpyAsync(c64, S.counters64, sizeof c64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(h->ev[6], st));
   CK(cudaStreamSynchronize(st));
@@ -961,6 +1026,7 @@ int update_links(exb200_handle* h) {
   h->K = hc[C_K];
   h->stats.n_entities = h->K;
   h->stats.n_links_changed = hc[C_CHANGED];
+  for (int k = 0; k < 32; k++) { c64[0] += c64[2 + 2 * k]; c64[1] += c64[3 + 2 * k]; } // k_cand_fast spreads its counts
   h->stats.n_candidates = c64[0];
   h->stats.n_bucket_items = c64[1];
   return EXB200_OK;
@@ -1056,8 +1122,8 @@ int sweep_finish(exb200_handle* h) {
   CK(cudaStreamSynchronize(st));
   auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
   h->stats.ms_clust = ms(0, 1); h->stats.ms_prep = ms(1, 2); h->stats.ms_index = ms(2, 3);
-  h->stats.ms_index_count = h->has_index_events ? ms(12, 13) : 0.f;
-  h->stats.ms_index_fill = h->has_index_events ? ms(14, 3) : 0.f;
+  h->stats.ms_index_count = h->has_index_events ? ms(12, 14) : 0.f; // CSR tables
+  h->stats.ms_index_fill = h->has_index_events ? ms(14, 3) : 0.f;   // chain tables
   h->stats.ms_cand = ms(3, 10); h->stats.ms_cand_long = ms(10, 4); h->stats.ms_wide = ms(4, 11); h->stats.ms_rounds = ms(11, 5); h->stats.ms_canon = ms(5, 6);
   h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
   if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
@@ -1317,7 +1383,10 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &S.unk_list, (size_t)N));
   TRY(dalloc(h, &S.wide_part, (size_t)3 * WIDE_PIECES));
   TRY(dalloc(h, &S.counters, (size_t)C_NSLOTS));
-  TRY(dalloc(h, &S.counters64, 2));
+  TRY(dalloc(h, &S.counters64, 66));
+  TRY(dalloc(h, &S.slow_list, (size_t)N));
+  TRY(dalloc(h, &S.tab_over, (size_t)N_TABLES));
+  TRY(dalloc(h, &h->d_chain_tabs, (size_t)N_TABLES));
   TRY(dalloc(h, &S.dev_err, 2));
   TRY(dalloc(h, &S.lwbuf, (size_t)16 * N));
   S.wl_cap = 10ull * N; // 10N doubles + 10N ints inside the 16N doubles of lwbuf
@@ -1354,6 +1423,18 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     for (int k = 0; k < S.n_key; k++) { S.key_attr[k] = keys[k]; S.key_pos[keys[k]] = (int8_t)k; }
     h->n_tab = 1 << S.n_key;
   }
+  { // packed attribute tuples: one field per attribute, if they fit 64 bits (and a record is one 32-byte row)
+    int shift = 0;
+    S.pk_ok = h->RS == 8 && h->ES == 8;
+    for (int a = 0; a < A; a++) {
+      int bits = 1;
+      while ((1ll << bits) < (long long)m->attrs[a].domain_size) bits++;
+      if (shift + bits > 64) { S.pk_ok = 0; break; }
+      S.pk_shift[a] = (uint8_t)shift; S.pk_bits[a] = (uint8_t)bits;
+      shift += bits;
+    }
+    S.hop_cap = h->hop_cap;
+  }
   h->tables.resize((size_t)h->n_tab);
   uint32_t Bhash = 1024; // about one bucket per indexed item (twins are not indexed)
   while ((double)Bhash < 1.2 * (double)N) Bhash <<= 1;
@@ -1366,7 +1447,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
     h->tables[t].keys = keys;
     d.exact = keys <= (unsigned long long)Bhash;
     d.B = d.exact ? (uint32_t)keys : Bhash;
-    d.ptr = nullptr; d.ids = nullptr;
+    d.ptr = nullptr; d.ids = nullptr; d.chain = 0; d.csr = 1; d.kmask = 0; d.cells = 0; d.head = nullptr; d.node = nullptr;
   }
   {
     std::vector<DevTable> td((size_t)h->n_tab);
@@ -1410,11 +1491,14 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "huge_min") h->huge_min = (int)std::max<int64_t>(0, value);
   else if (n == "index_partitioned") h->index_partitioned = value != 0;
   else if (n == "rounds_tail") h->opt_tail = value != 0;
+  else if (n == "fast_path") h->opt_fast = value != 0;
+  else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }
   else return fail(h, EXB200_ERR_INVALID, "unknown option " + n);
   h->S.bucket_cap = h->bucket_cap; h->S.cand_cap = h->cand_cap; h->S.long_cap = h->long_cap;
   h->S.long_min = h->long_min; h->S.est_threshold = h->est_threshold; h->S.huge_min = h->huge_min;
+  h->S.hop_cap = h->hop_cap;
   return EXB200_OK;
 }
 

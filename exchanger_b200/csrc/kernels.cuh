@@ -97,6 +97,48 @@ __device__ __forceinline__ Probe make_probe(const DevState& S, uint32_t mask, co
   return p;
 }
 
+// ---- packed attribute tuples (fast candidate path; S.pk_ok: the domains fit 64 bits and A <= 8)
+__device__ __forceinline__ unsigned long long pk_field(const DevState& S, int a) {
+  return ((1ull << S.pk_bits[a]) - 1ull) << S.pk_shift[a];
+}
+__device__ __forceinline__ unsigned long long pack_tuple(const DevState& S, const int* y) {
+  unsigned long long P = 0;
+  for (int a = 0; a < S.A; a++) P |= (unsigned long long)(uint32_t)y[a] << S.pk_shift[a];
+  return P;
+}
+__device__ __forceinline__ int unpack_attr(const DevState& S, unsigned long long P, int a) {
+  return (int)((P >> S.pk_shift[a]) & ((1ull << S.pk_bits[a]) - 1ull));
+}
+// fields (M) and values (V) of the attributes a record pins: an item with packed tuple P agrees with
+// the record on every observed non-distorted attribute (links.cpp:122-131) iff ((P ^ V) & M) == 0
+__device__ __forceinline__ void record_fields(const DevState& S, const int* x, uint32_t zm, unsigned long long& M,
+                                              unsigned long long& V) {
+  M = 0; V = 0;
+  for (int a = 0; a < S.A; a++)
+    if (x[a] >= 0 && !((zm >> a) & 1u)) { M |= pk_field(S, a); V |= (unsigned long long)(uint32_t)x[a] << S.pk_shift[a]; }
+}
+// cell of a chain table for key fields K (the packed tuple restricted to the table's key attributes)
+__device__ __forceinline__ uint32_t chain_cell(const DevTable& t, unsigned long long K) {
+  return (uint32_t)(mix64(K & t.kmask) & (unsigned long long)(t.cells - 1u));
+}
+// ... for a record x whose unpinned key attributes ea / eb take the probed values ev / fv
+__device__ __forceinline__ uint32_t chain_cell_probe(const DevState& S, const DevTable& t, const int* x, int ea, int ev,
+                                                     int eb, int fv) {
+  unsigned long long K = 0;
+  for (uint32_t m = t.mask; m; m &= m - 1) {
+    const int a = S.key_attr[__ffs(m) - 1];
+    K |= (unsigned long long)(uint32_t)(a == ea ? ev : (a == eb ? fv : x[a])) << S.pk_shift[a];
+  }
+  return chain_cell(t, K);
+}
+__device__ __forceinline__ ChainNode load_node(const ChainNode* p) {
+  const int4 v = *reinterpret_cast<const int4*>(p);
+  ChainNode n;
+  n.P = ((unsigned long long)(uint32_t)v.y << 32) | (unsigned long long)(uint32_t)v.x;
+  n.next = v.z; n.flags = (uint32_t)v.w;
+  return n;
+}
+
 // log p(w | v) = log get_distortion_prob(v, w)   (src/attribute_index.cpp:36-47, 77-92)
 __device__ __forceinline__ double log_distortion_prob(const DevAttr& t, int v, int w) {
   if (t.is_const) {
@@ -726,27 +768,41 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
         deferred = true;
       }
     } else if (!wide && pr.n_un > 0) {
-      // lanes take the probed values round-robin and walk their own (short) buckets
+      // lanes take the probed values round-robin and walk their own (short) buckets - or, for a
+      // table in chain form, the chains of their cells (the node holds the item's packed tuple)
       const DevTable& t = S.tables[tab];
-      int j_next = gl, v_cur = 0, w_cur = 0, q = 0, q_end = 0, visited = 0;
+      const bool chain = t.chain != 0;
+      int j_next = gl, v_cur = 0, w_cur = 0, q = 0, q_end = 0, visited = 0, c_item = -1;
       for (;;) {
-        while (q >= q_end && j_next < pr.count) {
+        while ((chain ? c_item < 0 : q >= q_end) && j_next < pr.count) {
           pr.values(j_next, v_cur, w_cur);
-          const uint32_t b = pr.bucket(S, t, x, v_cur, w_cur);
-          q = b ? t.ptr[b - 1] : 0;
-          q_end = t.ptr[b];
+          if (chain) c_item = t.head[chain_cell_probe(S, t, x, pr.a1, v_cur, pr.n_un == 2 ? pr.a2 : -1, w_cur)];
+          else {
+            const uint32_t b = pr.bucket(S, t, x, v_cur, w_cur);
+            q = b ? t.ptr[b - 1] : 0;
+            q_end = t.ptr[b];
+          }
           j_next += GL;
         }
-        const bool active = q < q_end;
+        const bool active = chain ? c_item >= 0 : q < q_end;
         if (spill || !__any_sync(gmask, active)) break;
         int item = -1;
         bool ok = false;
         double ll = 0.0;
         if (active) {
-          item = t.ids[q++];
+          int yv[8];
+          const int* y = yv;
+          if (chain) {
+            item = c_item;
+            const ChainNode nd = load_node(&t.node[item]);
+            c_item = nd.next;
+            for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
+          } else {
+            item = t.ids[q++];
+            y = S.ent_y + (size_t)item * S.ES;
+          }
           visited++;
           if (item != S.N + r) {
-            const int* y = S.ent_y + (size_t)item * S.ES;
             // hashed buckets: an item counts in the probe of its own value only
             ok = pr.own_probe(y, v_cur, w_cur) && item_compatible(S, x, zm, y);
             if (ok) {
@@ -827,6 +883,127 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1b''  chain form of the large blocking tables (key spaces about as large as the item set):
+// every indexed item is pushed on the chain of its cell with ONE atomicExch per table; its node
+// (packed tuple, next, twin flag) is written at the item's own index - coalesced.  Replaces the
+// partition / count / scan / fill passes of the CSR form for these tables.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_chain_build(DevState S, const int* __restrict__ tabs, int n_tabs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * S.N || !item_indexed(S, i)) return;
+  const unsigned long long P = pack_tuple(S, S.ent_y + (size_t)i * S.ES);
+  const int fl = (i < S.N && S.twin[i]) ? 1 : 0;
+  for (int k = 0; k < n_tabs; k++) {
+    const DevTable& t = S.tables[tabs[k]];
+    const int prev = atomicExch(&t.head[chain_cell(t, P)], i);
+    *reinterpret_cast<int4*>(&t.node[i]) = make_int4((int)(uint32_t)P, (int)(uint32_t)(P >> 32), prev, fl);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c'  candidate generation, ONE THREAD per record, for records whose table is in chain form and
+// whose key attributes are all pinned (19 of 20 records at 10 M): the thread walks the chain of its
+// cell, compares packed tuples (the node it has to read anyway holds the item's attributes: no
+// gather of the entity table, no bucket bounds), keeps up to FAST_CAND candidates sorted by id in
+// local memory and stores them.  A list that is just the record's own entity with log-likelihood 0
+// (7 of 8 records) is not stored at all (CAND_OWN_ONLY).  Everything else is handed on:
+//   * records that probe several cells (an unpinned key attribute)    -> probe_list (warp / record)
+//   * records of tables in CSR form, records without a table, chains longer than hop_cap or more
+//     than FAST_CAND candidates                                         -> slow_list (k_cand<8>)
+// Same candidate sets, same order, same log-likelihoods as k_cand.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
+  __shared__ unsigned s_stat[2];
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned n_cand = 0, n_hops = 0;
+  if (r < S.N) {
+    int x[8];
+    {
+      const int4* xp = reinterpret_cast<const int4*>(S.rec_x + (size_t)r * 8); // RS == 8 on this path
+      const int4 x0 = xp[0], x1 = xp[1];
+      x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+    }
+    const uint32_t zm = S.rec_z[r];
+    int tab = S.tab_remap[S.rec_tab[r]];
+    if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+    bool slow = tab == 0;
+    if (!slow) {
+      const DevTable& t = S.tables[tab];
+      unsigned long long M, V;
+      record_fields(S, x, zm, M, V);
+      if (!t.chain) slow = true;
+      else if ((M & t.kmask) != t.kmask) {
+        // an unpinned key attribute: the cells of its possible values are probed
+        const Probe pr = make_probe(S, t.mask, x, zm);
+        if (pr.n_un == 3) slow = true;                 // not served by this table after all (k_cand marks it)
+        else if (pr.count > 512) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r; // a block, one thread per probe
+        else S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r;
+      } else {
+        const int own = S.lambda[r];
+        const uint32_t zs = zm & ~S.dp_mask;
+        int ids[FAST_CAND];
+        double lls[FAST_CAND];
+        int cnt = 0, hops = 0;
+        bool over = false;
+        auto insert = [&](int id, double ll) {
+          if (cnt == FAST_CAND) { over = true; return; }
+          int j = cnt++;
+          while (j > 0 && ids[j - 1] > id) { ids[j] = ids[j - 1]; lls[j] = lls[j - 1]; j--; }
+          ids[j] = id; lls[j] = ll;
+        };
+        int item = t.head[chain_cell(t, V)];
+        while (item >= 0 && !over) {
+          if (++hops > S.hop_cap) { over = true; break; }
+          const ChainNode nd = load_node(&t.node[item]);
+          if (item != S.N + r && ((nd.P ^ V) & M) == 0) {
+            double ll = 0.0; // item_loglik on the packed tuple
+            for (int a = 0; a < S.A; a++)
+              if (x[a] >= 0 && ((zs >> a) & 1u)) ll += log_distortion_prob(S.attrs[a], unpack_attr(S, nd.P, a), x[a]);
+            if (ll > -CUDART_INF) {
+              insert(item, ll);
+              if ((nd.flags & 1u) && item != r) insert(S.N + item, ll); // the twin potential entity of that slot
+            }
+          }
+          item = nd.next;
+        }
+        n_hops = (unsigned)hops;
+        if (over) { S.tab_over[tab] = 1; slow = true; }
+        else {
+          uint32_t off = 0;
+          int code = cnt;
+          bool other = false;
+          for (int j = 0; j < cnt; j++) other |= ids[j] != own;
+          if (cnt == 1 && !other && lls[0] == 0.0 && S.long_min >= 1) off = CAND_OWN_ONLY;
+          else if (cnt > 0) {
+            unsigned long long o = (unsigned long long)CAND_INLINE * (unsigned long long)r;
+            if (cnt > CAND_INLINE) o = atomicAdd(S.pool_cursor, (unsigned long long)cnt);
+            if (o + (unsigned long long)cnt > S.pool_cap) { code = -2; other = true; }
+            else {
+              off = (uint32_t)o;
+              for (int j = 0; j < cnt; j++) {
+                S.cand_id[o + j] = ids[j]; S.cand_ll[o + j] = lls[j];
+                if (ids[j] != own) S.referenced[ids[j]] = 1;
+              }
+            }
+          }
+          finish_candidates(S, r, off, code, other);
+          if (code >= 0) n_cand = (unsigned)cnt;
+        }
+      }
+    }
+    if (slow) S.slow_list[atomicAdd(&S.counters[C_NSLOW], 1)] = r;
+  }
+  // statistics: per block, spread over 32 slots (one hot address would serialise 40 k blocks)
+  n_cand = (unsigned)warp_sum((int)n_cand); n_hops = (unsigned)warp_sum((int)n_hops);
+  if ((threadIdx.x & 31) == 0) { if (n_cand) atomicAdd(&s_stat[0], n_cand); if (n_hops) atomicAdd(&s_stat[1], n_hops); }
+  __syncthreads();
+  if (threadIdx.x < 2 && s_stat[threadIdx.x])
+    atomicAdd((unsigned long long*)&S.counters64[2 + 2 * (blockIdx.x & 31) + threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+}
+
 __host__ __device__ __forceinline__ int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // Block-wide tail of candidate staging: sort `cnt` staged (id, ll) pairs by id, append them to the
@@ -905,9 +1082,9 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
         continue;
       }
     }
-    auto visit = [&](int item, int v, int w2) {
+    auto visit = [&](int item, int v, int w2, const int* y) {
       if (item == S.N + r) return;
-      const int* y = S.ent_y + (size_t)item * S.ES;
+      if (!y) y = S.ent_y + (size_t)item * S.ES;
       if (pr.n_un > 0 && !pr.own_probe(y, v, w2)) return;
       if (!item_compatible(S, x, zm, y)) return;
       const double ll = item_loglik(S, x, zm, y);
@@ -922,9 +1099,19 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       for (int j = threadIdx.x; j < pr.count; j += blockDim.x) {
         int v, w2;
         pr.values(j, v, w2);
+        if (t.chain) { // chain form: the node holds the item's packed tuple
+          for (int item = t.head[chain_cell_probe(S, t, x, pr.a1, v, pr.n_un == 2 ? pr.a2 : -1, w2)]; item >= 0 && s_cnt <= cap;) {
+            const ChainNode nd = load_node(&t.node[item]);
+            int yv[8];
+            for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
+            visit(item, v, w2, yv);
+            item = nd.next;
+          }
+          continue;
+        }
         const uint32_t b = pr.bucket(S, t, x, v, w2);
         const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
-        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, w2);
+        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, w2, nullptr);
       }
     } else {
       const uint32_t b = S.rec_bkt[r];
@@ -932,7 +1119,7 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
         if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
         const int q = q0 + threadIdx.x;
-        if (q < hi) visit(t.ids[q], 0, 0);
+        if (q < hi) visit(t.ids[q], 0, 0, nullptr);
       }
     }
     __syncthreads();

@@ -266,6 +266,10 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
      "table_min_usage" (default 16) a key mask wanted by at most this many records gets no table of
                  its own: another table serves them, or the batched scan over all items
      "index_partitioned" 0 builds every table with global atomics (debugging)
+     "fast_path" (default 1) candidate lists by one thread per record over tables in chain form
+                 (needs attribute domains that pack into 64 bits); 0: bucket-scanning kernels only
+     "hop_cap"   (default 64) chain items a thread walks for one record before the record is left
+                 to the bucket-scanning kernels (whose CSR form of that table is then built too)
      "rounds_tail" (default 1) the dependency rounds after the first run in one persistent
                  cooperative kernel; 0 launches every round from the host
      "check"     recompute sizes / member lists / K from the links after every sweep and compare

@@ -149,13 +149,15 @@ def test_link_conditional_matches_oracle():
 
 def test_results_do_not_depend_on_batching_thresholds():
     """Same seed, different wide-path thresholds, rounds launched one by one (rounds_tail=0) or in
-    the persistent kernel -> identical chains (property test that holds at any size: the sweep is
+    the persistent kernel, candidates from the thread-per-record kernel over chain tables or (fast_path=0,
+    or chains cut short by hop_cap) from the bucket-scanning kernels -> identical chains (property test that holds at any size: the sweep is
     sequentially consistent, batching is only scheduling)."""
     m, _ = readme_model("rldata10000", n=4000)
     states = []
     for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1), dict(bucket_cap=0, huge_min=0),
                  dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
-                 dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0)):
+                 dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0),
+                 dict(fast_path=0), dict(hop_cap=1), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
