@@ -95,8 +95,9 @@ struct exb200_handle {
   PartBuild pb{};              // partitioned build of the large tables
   int* d_part_tabs = nullptr;
   int* d_chain_tabs = nullptr;
+  unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
-  int hop_cap = 64;
+  int hop_cap = 1024;
   int pb_tables_cap = 0;
   int huge_cap_alloc = -1;     // wide_threshold the huge-bucket scratch lists were sized for
   int* d_bsum = nullptr; size_t bsum_cap = 0;
@@ -698,7 +699,7 @@ int update_links(exb200_handle* h) {
       if (chain) {
         if (!T.d.head) {
           uint32_t cells = 1024;
-          while ((double)cells < std::min(1.2 * (double)N, (double)T.keys)) cells <<= 1;
+          while ((double)cells < std::min(0.6 * (double)N, (double)T.keys)) cells <<= 1; // <= 32 MB at 10 M records: L2 resident
           T.d.cells = cells;
           unsigned long long km = 0;
           for (int k = 0; k < S.n_key; k++)
@@ -722,17 +723,24 @@ int update_links(exb200_handle* h) {
   if (!chain_tabs.empty()) {
     for (int t : chain_tabs) CK(cudaMemsetAsync(h->tables[t].d.head, 0xFF, sizeof(int) * (size_t)h->tables[t].d.cells, st));
     CK(cudaMemsetAsync(S.tab_over, 0, sizeof(int) * N_TABLES, st));
-    CK(cudaMemcpyAsync(h->d_chain_tabs, chain_tabs.data(), sizeof(int) * chain_tabs.size(), cudaMemcpyHostToDevice, st));
-    KLAUNCH(h, k_chain_build, nblk(2LL * N), TPB, 0, S, h->d_chain_tabs, (int)chain_tabs.size());
+    if (!h->d_pk) {
+      int rc = dalloc(h, &h->d_pk, (size_t)2 * N); if (rc) return rc;
+      rc = dalloc(h, &h->d_pkfl, (size_t)2 * N); if (rc) return rc;
+    }
+    KLAUNCH(h, k_chain_pack, nblk(2LL * N), TPB, 0, S, h->d_pk, h->d_pkfl);
+    for (int t : chain_tabs) KLAUNCH(h, k_chain_build, nblk(2LL * N), TPB, 0, S, t, h->d_pk, h->d_pkfl);
   }
   CK(cudaEventRecord(h->ev[3], st));
   int hc[C_NSLOTS];
   if (chain_tabs.empty()) KLAUNCH(h, (k_cand<8, 64>), nblk((long long)N, 64 / 8), 64, 0, S, (const int*)nullptr, N);
   else {
     // thread per record over the chain tables; what it cannot finish is listed for the bucket kernels
+    const auto t_f = std::chrono::steady_clock::now();
     KLAUNCH(h, k_cand_fast, nblk(N), TPB, 0, S);
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (h->trace) std::fprintf(stderr, "[exb200] index + thread-per-record candidates (host lap) %8.2f ms; %d records for warps, %d for blocks, %d for the bucket kernels\n",
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f).count(), hc[C_NPROBE], hc[C_NLONG_TODO], hc[C_NSLOW]);
     if (hc[C_NSLOW] > 0) {
       // chains longer than hop_cap / more than FAST_CAND candidates: those tables get their CSR form too
       std::vector<int> over(N_TABLES), lazy;

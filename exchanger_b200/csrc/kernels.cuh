@@ -64,6 +64,7 @@ __device__ __forceinline__ ProbeValues probe_values(const DevState& S, int ea, c
 // their possible values (n_un = 3: more than two, or too many combinations - the table cannot
 // serve the record and its possible links are listed by the batched scan over all the items).
 constexpr int MAX_PROBES = 16384;
+constexpr int FAST_PROBES = 128; // probes one thread of the fast candidate kernel makes for a record
 struct Probe {
   int n_un, a1, a2, count;
   ProbeValues p1, p2;
@@ -889,16 +890,30 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
 // (packed tuple, next, twin flag) is written at the item's own index - coalesced.  Replaces the
 // partition / count / scan / fill passes of the CSR form for these tables.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_chain_build(DevState S, const int* __restrict__ tabs, int n_tabs) {
+// pass 1: packed tuple of every indexed item (~0: not indexed), bit 63 of the word below it: twin flag
+__global__ void __launch_bounds__(TPB) k_chain_pack(DevState S, unsigned long long* __restrict__ P, uint8_t* __restrict__ fl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * S.N || !item_indexed(S, i)) return;
-  const unsigned long long P = pack_tuple(S, S.ent_y + (size_t)i * S.ES);
-  const int fl = (i < S.N && S.twin[i]) ? 1 : 0;
-  for (int k = 0; k < n_tabs; k++) {
-    const DevTable& t = S.tables[tabs[k]];
-    const int prev = atomicExch(&t.head[chain_cell(t, P)], i);
-    *reinterpret_cast<int4*>(&t.node[i]) = make_int4((int)(uint32_t)P, (int)(uint32_t)(P >> 32), prev, fl);
+  if (i >= 2 * S.N) return;
+  const bool idx = item_indexed(S, i);
+  fl[i] = (uint8_t)(idx ? ((i < S.N && S.twin[i]) ? 3 : 1) : 0); // bit 0: indexed, bit 1: twin
+  if (idx) {
+    const int4* yp = reinterpret_cast<const int4*>(S.ent_y + (size_t)i * 8); // ES == 8 on this path
+    const int4 y0 = yp[0], y1 = yp[1];
+    const int y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    P[i] = pack_tuple(S, y);
   }
+}
+// pass 2, once per table (its head array stays in the L2 during the pass)
+__global__ void __launch_bounds__(TPB) k_chain_build(DevState S, int tab, const unsigned long long* __restrict__ P,
+                                                     const uint8_t* __restrict__ fl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * S.N) return;
+  const uint8_t f = fl[i];
+  if (!(f & 1)) return;
+  const DevTable& t = S.tables[tab];
+  const unsigned long long p = P[i];
+  const int prev = atomicExch(&t.head[chain_cell(t, p)], i);
+  *reinterpret_cast<int4*>(&t.node[i]) = make_int4((int)(uint32_t)p, (int)(uint32_t)(p >> 32), prev, (int)(f >> 1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -934,14 +949,18 @@ __global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
       const DevTable& t = S.tables[tab];
       unsigned long long M, V;
       record_fields(S, x, zm, M, V);
+      Probe pr;
+      pr.n_un = 0; pr.count = 1; pr.a1 = pr.a2 = -1;
       if (!t.chain) slow = true;
       else if ((M & t.kmask) != t.kmask) {
-        // an unpinned key attribute: the cells of its possible values are probed
-        const Probe pr = make_probe(S, t.mask, x, zm);
+        // an unpinned key attribute: the cells of its possible values are probed - by this thread if
+        // they are few (a distorted name: its neighbourhood row), else by a warp or a block
+        pr = make_probe(S, t.mask, x, zm);
         if (pr.n_un == 3) slow = true;                 // not served by this table after all (k_cand marks it)
-        else if (pr.count > 512) S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r; // a block, one thread per probe
-        else S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r;
-      } else {
+        else if (pr.count > 512) { S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r; pr.n_un = -1; } // a block, one thread per probe
+        else if (pr.count > FAST_PROBES) { S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; pr.n_un = -1; }
+      }
+      if (!slow && pr.n_un >= 0) {
         const int own = S.lambda[r];
         const uint32_t zs = zm & ~S.dp_mask;
         int ids[FAST_CAND];
@@ -954,23 +973,34 @@ __global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
           while (j > 0 && ids[j - 1] > id) { ids[j] = ids[j - 1]; lls[j] = lls[j - 1]; j--; }
           ids[j] = id; lls[j] = ll;
         };
-        int item = t.head[chain_cell(t, V)];
-        while (item >= 0 && !over) {
-          if (++hops > S.hop_cap) { over = true; break; }
-          const ChainNode nd = load_node(&t.node[item]);
-          if (item != S.N + r && ((nd.P ^ V) & M) == 0) {
-            double ll = 0.0; // item_loglik on the packed tuple
-            for (int a = 0; a < S.A; a++)
-              if (x[a] >= 0 && ((zs >> a) & 1u)) ll += log_distortion_prob(S.attrs[a], unpack_attr(S, nd.P, a), x[a]);
-            if (ll > -CUDART_INF) {
-              insert(item, ll);
-              if ((nd.flags & 1u) && item != r) insert(S.N + item, ll); // the twin potential entity of that slot
-            }
+        for (int pj = 0; pj < pr.count && !over; pj++) {
+          // fields / values the items of this probe must match: the pinned attributes, and the probed
+          // values of the unpinned key attributes (an item sits in the cell of its own key only)
+          unsigned long long Mp = M, Vp = V;
+          if (pr.n_un > 0) {
+            int v1, v2;
+            pr.values(pj, v1, v2);
+            Mp |= pk_field(S, pr.a1); Vp |= (unsigned long long)(uint32_t)v1 << S.pk_shift[pr.a1];
+            if (pr.n_un == 2) { Mp |= pk_field(S, pr.a2); Vp |= (unsigned long long)(uint32_t)v2 << S.pk_shift[pr.a2]; }
           }
-          item = nd.next;
+          int item = t.head[chain_cell(t, Vp)];
+          while (item >= 0 && !over) {
+            if (++hops > S.hop_cap) { over = true; break; }
+            const ChainNode nd = load_node(&t.node[item]);
+            if (item != S.N + r && ((nd.P ^ Vp) & Mp) == 0) {
+              double ll = 0.0; // item_loglik on the packed tuple
+              for (int a = 0; a < S.A; a++)
+                if (x[a] >= 0 && ((zs >> a) & 1u)) ll += log_distortion_prob(S.attrs[a], unpack_attr(S, nd.P, a), x[a]);
+              if (ll > -CUDART_INF) {
+                insert(item, ll);
+                if ((nd.flags & 1u) && item != r) insert(S.N + item, ll); // the twin potential entity of that slot
+              }
+            }
+            item = nd.next;
+          }
         }
         n_hops = (unsigned)hops;
-        if (over) { S.tab_over[tab] = 1; slow = true; }
+        if (over) { if (pr.n_un == 0) S.tab_over[tab] = 1; slow = true; } // (probing records need no CSR form: k_cand<32> walks chains)
         else {
           uint32_t off = 0;
           int code = cnt;
@@ -2305,13 +2335,20 @@ __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, i
   return lw;
 }
 
-__device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
+// `xs`: the record row of a singleton entity, already in registers (its only member); nullptr: the
+// members are read from the sorted member list starting at `head`
+__device__ __forceinline__ int draw_entity_value(const DevState& S, int e, int a, int head, const int* xs = nullptr) {
+  // fn(row) for every member row in ascending record id
+  auto each = [&](auto&& fn) {
+    if (xs) fn(xs);
+    else for (int r = head; r >= 0; r = S.rec_next[r]) fn(S.rec_x + (size_t)r * S.RS);
+  };
   const DevAttr& t = S.attrs[a];
   int nobs = 0, first = -1;
-  for (int r = head; r >= 0; r = S.rec_next[r]) {
-    const int xv = S.rec_x[(size_t)r * S.RS + a];
+  each([&](const int* x) {
+    const int xv = x[a];
     if (xv >= 0) { if (first < 0) first = xv; nobs++; }
-  }
+  });
   const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
   if (nobs == 0) return alias_draw(t.aprob, t.aalias, t.D, u0.a); // entities.cpp:387-389
 
@@ -2322,27 +2359,25 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
     double w[NMAX_FAST];
     int nv = 0;
     double Cc = 1.0;
-    for (int r = head; r >= 0; r = S.rec_next[r]) {
-      const int* x = S.rec_x + (size_t)r * S.RS;
+    each([&](const int* x) {
       const int xv = x[a];
-      if (xv < 0) continue;
+      if (xv < 0) return;
       Cc *= S.theta[x[S.RS - 1] * S.A + a] * t.psi[xv];
       bool seen = false;
       for (int j = 0; j < nv; j++) seen |= vals[j] == xv;
       if (!seen) vals[nv++] = xv;
-    }
+    });
     const double* g = t.g + (size_t)nobs * t.D;
     double sumw = 0.0, rest = t.G[nobs];
     for (int j = 0; j < nv; j++) {
       const int v = vals[j];
       double ww = t.phi[v];
-      for (int r = head; r >= 0; r = S.rec_next[r]) {
-        const int* x = S.rec_x + (size_t)r * S.RS;
+      each([&](const int* x) {
         const int xv = x[a];
-        if (xv < 0) continue;
+        if (xv < 0) return;
         const double th = S.theta[x[S.RS - 1] * S.A + a];
         ww *= xv == v ? 1.0 - th : th * t.psi[xv] / t.om[v];
-      }
+      });
       w[j] = ww;
       sumw += ww;
       rest -= g[v];
@@ -2370,24 +2405,23 @@ __device__ int draw_entity_value(const DevState& S, int e, int a, int head) {
 
   bool same = true; // every observed member value equals the first one
   if (nobs == 2)
-    for (int r = head; r >= 0; r = S.rec_next[r]) {
-      const int xv = S.rec_x[(size_t)r * S.RS + a];
+    each([&](const int* x) {
+      const int xv = x[a];
       same &= xv < 0 || xv == first;
-    }
+    });
   if (!t.is_const && t.exclude && (nobs == 1 || (nobs == 2 && same && !((S.dp_mask >> a) & 1u)))) {
     // one observed member value x, held by one member (singletons above all) or by two: every
     // v != x has weight (prod_m theta_m) phi(v) (mef(v) p(x|v))^nobs whose row sums are static, so
     // drawEntityValueIndex (entities.cpp:351-431) reduces to "keep x" versus a search in the
     // row's prefix sums
     double th = 1.0, wx = t.phi[first];
-    for (int r = head; r >= 0; r = S.rec_next[r]) {
-      const int* x = S.rec_x + (size_t)r * S.RS;
+    each([&](const int* x) {
       if (x[a] >= 0) {
         const double thm = S.theta[x[S.RS - 1] * S.A + a];
         th *= thm;
         wx *= 1.0 - thm * t.mef[first];
       }
-    }
+    });
     const double* cs = nobs == 1 ? t.cs : t.cs2;
     const int lo = t.row[first], hi = t.row[first + 1];
     const double rsum = hi > lo ? cs[hi - 1] : 0.0;
@@ -2532,7 +2566,30 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long
   __shared__ int s_base;
   const int e = e_lo + blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t need = 0;
-  if (e < e_hi && S.ent_size[e] > 0) {
+  const int sz = e < e_hi ? S.ent_size[e] : 0;
+  if (sz == 1 && S.RS == 8 && S.ES == 8) {
+    // a singleton: its only member is record e (entities are named after their smallest member), whose
+    // row is read once - coalesced - and whose new attribute row is written once
+    int x[8], yn[8];
+    {
+      const int4* xp = reinterpret_cast<const int4*>(S.rec_x + (size_t)e * 8);
+      const int4 x0 = xp[0], x1 = xp[1];
+      x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+    }
+#pragma unroll
+    for (int a = 0; a < 8; a++) yn[a] = 0;
+    for (int a = 0; a < S.A; a++) {
+      const int v = draw_entity_value(S, e, a, e, x);
+      if (v >= 0) yn[a] = v; else need |= 1u << a;
+    }
+    int* y = S.ent_y + (size_t)e * 8;
+    if (need) { for (int a = 0; a < S.A; a++) if (!((need >> a) & 1u)) y[a] = yn[a]; }
+    else {
+      int4* yp = reinterpret_cast<int4*>(y);
+      yp[0] = make_int4(yn[0], yn[1], yn[2], yn[3]);
+      yp[1] = make_int4(yn[4], yn[5], yn[6], yn[7]);
+    }
+  } else if (sz > 0) {
     const int head = S.ent_head[e];
     int* y = S.ent_y + (size_t)e * S.ES;
     for (int a = 0; a < S.A; a++) {

@@ -268,7 +268,7 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
      "index_partitioned" 0 builds every table with global atomics (debugging)
      "fast_path" (default 1) candidate lists by one thread per record over tables in chain form
                  (needs attribute domains that pack into 64 bits); 0: bucket-scanning kernels only
-     "hop_cap"   (default 64) chain items a thread walks for one record before the record is left
+     "hop_cap"   (default 1024) chain items a thread walks for one record before the record is left
                  to the bucket-scanning kernels (whose CSR form of that table is then built too)
      "rounds_tail" (default 1) the dependency rounds after the first run in one persistent
                  cooperative kernel; 0 launches every round from the host
