@@ -33,7 +33,24 @@ WORKLOADS = {
 }
 A = 5
 DATA_SEED = 20260101
-CPU_SAMPLE_RECORDS = 20_000
+# The reference's sweep costs 40-60 us per record on one host core, growing with the record count
+# (its containers are hash maps; measured on the B200 box's host: profiles/README.md, "reference
+# scaling"), so a whole 10 M sweep is about ten minutes per core.  Its arm therefore times a SAMPLE of
+# the same generator, as large as the wall budget allows, started from a burnt-in state.
+REF_US_PER_RECORD = 50.0          # planning figure for the sample size only
+REF_BUDGET_S = 150.0              # timed + warm-up sweeps of the reference arm
+CPU_BASELINE_BUDGET_S = 20.0      # the one-core baseline inside the normal bench line
+REF_BURNIN = 20                   # sweeps (by the oracle) before the reference is timed: SURVEY.md 8d window
+
+
+def distort_prior(name: str):
+    from exchanger_b200 import BetaRV
+    return BetaRV(1, 1) if name == "beta11" else BetaRV(1, 50)
+
+
+def ref_sample_records(n_workload: int, sweeps: int, budget_s: float) -> int:
+    n = int(budget_s / (max(sweeps, 1) * REF_US_PER_RECORD * 1e-6))
+    return int(max(20_000, min(n_workload, 1_000_000, (n // 10_000) * 10_000)))
 
 
 def clust_prior(kind: str, n: int):
@@ -90,66 +107,108 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- reference arm
 def _ref_worker(args):
-    """One chain of the reference's own State::update() (oracle/_ref) on the bounded sample."""
-    n_rec, kind, seed, burn, warm, steps = args
-    from checkers import RefSampler
-    from exchanger_b200.model import Levenshtein, compute_close_values, transform_dist_fn
+    """One chain of the reference's own State::update() (oracle/_ref) on the bounded sample: the model
+    is prepared on the host (neighbourhoods by oracle/exnbr.c), brought to the window SURVEY.md 8d
+    prescribes by REF_BURNIN sweeps of the oracle (whose chain has the reference's law and costs a
+    fraction of its time), handed to the reference as its initial state, then timed."""
+    n_rec, kind, seed, warm, steps, prior, threads = args
+    from checkers import OracleSampler, RefSampler, cpu_neighbours
+    from exchanger_b200.model import model_with_state
     from exchanger_b200.synthetic import synth_model
 
-    def pyn(dom, thr):
-        return compute_close_values(dom, transform_dist_fn(Levenshtein(), thr), False)
+    def nbr(dom, thr):
+        return cpu_neighbours(dom, thr, False, threads)
 
-    model, _ = synth_model(n_rec, clust_prior(kind, n_rec), seed=DATA_SEED, neighbour_fn=pyn)
-    ref = RefSampler(model, seed=seed)
-    ref.update(burn + warm)
+    model, _ = synth_model(n_rec, clust_prior(kind, n_rec), seed=DATA_SEED, neighbour_fn=nbr,
+                           distort_prior=distort_prior(prior))
+    o = OracleSampler(model, seed=seed)
+    o.sweeps(REF_BURNIN)
+    ref = RefSampler(model_with_state(model, o.state()), seed=seed)
+    del o
+    ref.update(warm)
     t0 = time.perf_counter()
     ref.update(steps)
     return time.perf_counter() - t0
 
 
-def reference_throughput(kind: str, n_workload: int, steps: int, warmup: int, procs: int, burn: int = 12):
+def reference_throughput(kind: str, n_workload: int, steps: int, warmup: int, procs: int, budget_s: float,
+                         prior: str = "beta150"):
     """sweeps/s of the reference CPU sampler, expressed at the workload size: the sample's
     link-updates/s divided by the workload's record count (optimistic for the reference, whose
-    per-record cost grows with N)."""
+    per-record cost grows with N).  Returns (sweeps/s, link-updates/s, seconds, sample records)."""
     import multiprocessing as mp
-    jobs = [(CPU_SAMPLE_RECORDS, kind, 100 + i, burn, warmup, steps) for i in range(procs)]
+    n_sample = ref_sample_records(n_workload, steps + warmup, budget_s)
+    threads = max(1, (os.cpu_count() or 1) // procs)
+    jobs = [(n_sample, kind, 100 + i, warmup, steps, prior, threads) for i in range(procs)]
     if procs == 1:
         secs = [_ref_worker(jobs[0])]
     else:
         with mp.get_context("spawn").Pool(procs) as pool:
             secs = pool.map(_ref_worker, jobs)
     t = max(secs)
-    updates_per_s = procs * steps * CPU_SAMPLE_RECORDS / t
-    return updates_per_s / n_workload, updates_per_s, t
+    updates_per_s = procs * steps * n_sample / t
+    return updates_per_s / n_workload, updates_per_s, t, n_sample
 
 
-def sample_text(procs: int, steps: int, burn: int) -> str:
-    return (f"{procs} independent chain(s) of the reference's own State::update() (oracle/_ref) on a "
-            f"{CPU_SAMPLE_RECORDS}-record sample of the same synthetic generator, {burn} burn-in sweeps, "
-            f"{steps} timed sweeps each; sweeps/s = link-updates/s / workload records")
+def sample_text(procs: int, steps: int, n_sample: int) -> str:
+    return (f"{procs} independent chain(s) of the reference's own State::update() (oracle/_ref), one per host core, each on a "
+            f"{n_sample}-record sample of the same synthetic generator, started from the state after {REF_BURNIN} sweeps, "
+            f"{steps} timed sweeps each; sweeps/s = link-updates/s / workload records (the reference is single-threaded "
+            "and its per-record cost grows with the record count, so this flatters it)")
 
 
 def run_reference(opt, n_records, kind, desc):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import __graft_entry__ as entry
+    entry.build()   # builds the checkers (oracle/) only where they are stale; the CUDA library is not used here
     procs = max(1, min(os.cpu_count() or 1, 32))
-    burn = 12
-    v, ups, t = reference_throughput(kind, n_records, opt.steps, opt.warmup, procs, burn)
+    v, ups, t, n_sample = reference_throughput(kind, n_records, opt.steps, opt.warmup, procs, REF_BUDGET_S, opt.distort_prior)
     line = {
         "impl": "reference", "metric": "gibbs_sweeps_per_s", "value": v, "unit": "sweeps/s",
-        "link_updates_per_s": ups, "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup,
+        "link_updates_per_s": ups, "one_core_link_updates_per_s": ups / procs,
+        "n_gpus": opt.gpus, "steps": opt.steps, "warmup": opt.warmup,
         "ms_per_step": 1e3 * t / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind},
+        "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind,
+                   "distort_prior": "Beta(1,1)" if opt.distort_prior == "beta11" else "Beta(1,50)",
+                   "sample_records_per_chain": n_sample},
         "cpu_baseline": {"value": v, "unit": "sweeps/s", "cores": procs, "kind": "reference",
-                         "sample": sample_text(procs, opt.steps, burn)},
+                         "sample": sample_text(procs, opt.steps, n_sample)},
         "e2e": {"value": v, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------- this repo's arm
+def shared_model(n_records, kind, prior, rank, world, local, barrier):
+    """The synthetic model, built ONCE per node: rank 0 generates the records and computes the value
+    neighbourhoods on ITS OWN GPU, the other ranks load the pickled model from /dev/shm."""
+    import pickle
+    from exchanger_b200.capi import levenshtein_neighbours
+    from exchanger_b200.synthetic import synth_model
+    path = f"/dev/shm/exb200_model_{n_records}_{kind}_{prior}_{DATA_SEED}_{os.environ.get('MASTER_PORT', '0')}.pkl"
+    t0 = time.perf_counter()
+    model = None
+    if rank == 0:
+        model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED, distort_prior=distort_prior(prior),
+                               neighbour_fn=lambda dom, thr: levenshtein_neighbours(dom, thr, device=local))
+        if world > 1:
+            with open(path + ".tmp", "wb") as f:
+                pickle.dump(model, f, protocol=pickle.HIGHEST_PROTOCOL)
+            os.replace(path + ".tmp", path)
+    if world > 1:
+        barrier()
+        if rank != 0:
+            with open(path, "rb") as f:
+                model = pickle.load(f)
+        barrier()
+        if rank == 0:
+            os.unlink(path)
+    return model, time.perf_counter() - t0
+
+
 def run_ours(opt, n_records, kind, desc):
     import torch
     import torch.distributed as dist
@@ -169,7 +228,6 @@ def run_ours(opt, n_records, kind, desc):
         dist.barrier()
     from exchanger_b200.model import model_with_state
     from exchanger_b200.sampler import Sampler
-    from exchanger_b200.synthetic import synth_model
 
     def barrier():
         torch.cuda.synchronize()
@@ -177,31 +235,33 @@ def run_ours(opt, n_records, kind, desc):
             dist.barrier()
             torch.cuda.synchronize()
 
-    t_build = time.perf_counter()
-    model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED)
-    t_build = time.perf_counter() - t_build
+    model, t_build = shared_model(n_records, kind, opt.distort_prior, rank, world, local, barrier)
     gpu = Sampler(model, seed=1000 + rank, device=local)
-    gpu.sweeps(opt.burnin)          # untimed: reach the steady-state regime
-    gpu.sweeps(opt.warmup)          # W warm-up steps
+    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_index_count", "ms_index_fill", "ms_cand", "ms_cand_fast", "ms_cand_long",
+                  "ms_wide", "ms_rounds", "ms_canon", "ms_entities", "ms_distort", "ms_total")
+
+    def timed(n, acc=None):
+        """n sweeps one by one: (device ms, launches), per-phase sums into acc"""
+        ms_sum, nl_sum = 0.0, 0
+        for _ in range(n):
+            ms, nl = gpu.sweeps_timed(1)
+            ms_sum += ms
+            nl_sum += nl
+            if acc is not None:
+                st = gpu.stats()
+                for k in phase_keys:
+                    acc[k] += st[k]
+                for k in ("n_candidates", "n_rounds", "n_wide", "n_tables", "n_slow", "n_probe", "n_long"):
+                    acc[k] = acc.get(k, 0) + st[k]
+        return ms_sum, nl_sum
+
+    gpu.sweeps(opt.burnin)          # untimed: reach the window SURVEY.md 8d prescribes (sweeps 21-120)
+    ms_warm, _ = timed(opt.warmup)  # W warm-up steps (sweeps 21 .. 20+W; they count for the long window below)
     barrier()
     clocks = ClockSampler(local)
-    phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_index_count", "ms_index_fill", "ms_cand", "ms_cand_long",
-                  "ms_wide", "ms_rounds", "ms_canon", "ms_entities", "ms_distort", "ms_total")
     acc = {k: 0.0 for k in phase_keys}
-    cand = rounds = wide = launches = tables = 0
-    dev_ms = 0.0
     t0 = time.perf_counter()
-    for _ in range(opt.steps):      # EXACTLY K steps
-        ms, nl = gpu.sweeps_timed(1)
-        dev_ms += ms
-        launches += nl
-        st = gpu.stats()
-        for k in phase_keys:
-            acc[k] += st[k]
-        cand += st["n_candidates"]
-        rounds += st["n_rounds"]
-        wide += st["n_wide"]
-        tables += st["n_tables"]
+    dev_ms, launches = timed(opt.steps, acc)      # EXACTLY K steps
     barrier()
     wall = time.perf_counter() - t0
     clk = clocks.stop()
@@ -211,6 +271,19 @@ def run_ours(opt, n_records, kind, desc):
         dist.all_reduce(secs, op=dist.ReduceOp.MAX)
     t_max = float(secs.item())
     value = world * opt.steps / t_max
+
+    # ---- the rest of the chain, device-timed on rank 0's clock: the whole window of SURVEY.md 8d
+    # (sweeps 21-120) and a late figure (sweeps 201-220: the sweep gets slower as more records carry
+    # distorted names)
+    windows = None
+    if opt.long_window and opt.burnin == 20 and opt.warmup + opt.steps <= 100:
+        ms_rest, _ = timed(100 - opt.warmup - opt.steps)
+        ms_21_120 = ms_warm + dev_ms + ms_rest
+        gpu.sweeps(80)
+        ms_late, _ = timed(20)
+        windows = {"sweeps_21_120": {"value": 100.0 / (ms_21_120 * 1e-3), "unit": "sweeps/s", "ms_per_sweep": ms_21_120 / 100.0},
+                   "sweeps_201_220": {"value": 20.0 / (ms_late * 1e-3), "unit": "sweeps/s", "ms_per_sweep": ms_late / 20.0},
+                   "what": "one chain per GPU, device time of this rank's chain (CUDA events on the library's stream)"}
 
     # ---- end to end through the public API with host buffers (create -> run -> state -> destroy);
     # three repetitions, the median is reported (host-side page faults and frees make single shots noisy)
@@ -239,11 +312,13 @@ def run_ours(opt, n_records, kind, desc):
 
     if rank == 0:
         # ---- roofline of the dominant single kernel (algorithmic bytes: DESIGN.md section 5)
-        n, cbar, rho = n_records, cand / opt.steps / n_records, k_ent / n_records
-        tbar = tables / opt.steps  # blocking tables built per sweep
+        n, cbar, rho = n_records, acc["n_candidates"] / opt.steps / n_records, k_ent / n_records
+        tbar = acc["n_tables"] / opt.steps  # blocking tables built per sweep
+        fast = acc["ms_cand_fast"] > 0
         # single kernels only (the index build, the rounds and the serial path are multi-kernel phases)
         kernels = {
-            "k_cand (links: candidate generation)": (acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
+            ("k_cand_fast (links: candidate generation)" if fast else "k_cand (links: candidate generation)"):
+                (acc["ms_cand_fast"] if fast else acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
             "k_entities (entity attributes)": (acc["ms_entities"], n * (4 + 4 * A + 4 * A * rho)),
             "k_distort (distortion indicators)": (acc["ms_distort"], n * (9 * A + 4)),
             "k_prep (links: new-entity attributes)": (acc["ms_prep"], n * (5 * A + 4 + 4 * A + 8)),
@@ -260,9 +335,9 @@ def run_ours(opt, n_records, kind, desc):
         cpu = None
         if world == 1 and not opt.no_cpu_baseline:
             try:
-                v, ups, _ = reference_throughput(kind, n_records, 6, 1, 1, burn=12)
+                v, ups, _, n_sample = reference_throughput(kind, n_records, 2, 1, 1, CPU_BASELINE_BUDGET_S, opt.distort_prior)
                 cpu = {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "reference",
-                       "link_updates_per_s": ups, "sample": sample_text(1, 6, 12)}
+                       "link_updates_per_s": ups, "sample": sample_text(1, 2, n_sample)}
             except Exception as e:  # the checker is missing: say so, do not fake a number
                 cpu = {"value": None, "unit": "sweeps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         line = {
@@ -271,8 +346,10 @@ def run_ours(opt, n_records, kind, desc):
             "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup, "ms_per_step": 1e3 * t_max / opt.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "records": n_records, "attributes": A, "clust_prior": kind,
-                       "distort_prior": "Beta(1,50)", "name_frequencies": "Zipf exponent 0.5 (synthetic.py)", "parallelism": f"{world} independent chain(s)",
-                       "burnin_sweeps": opt.burnin, "model_build_s": round(t_build, 1),
+                       "distort_prior": "Beta(1,1) (README model)" if opt.distort_prior == "beta11" else "Beta(1,50)",
+                       "name_frequencies": "Zipf exponent 0.5 (synthetic.py)", "parallelism": f"{world} independent chain(s)",
+                       "burnin_sweeps": opt.burnin, "timed_sweeps": f"{opt.burnin + opt.warmup + 1}-{opt.burnin + opt.warmup + opt.steps}",
+                       "model_build_s": round(t_build, 1),
                        "l2": f"inputs larger than L2: resident state {n_records * 150 / 1e6:.0f} MB streamed every sweep"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d / opt.steps),
@@ -285,10 +362,12 @@ def run_ours(opt, n_records, kind, desc):
                                    "achieved": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9,
                                    "frac": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu,
+            "windows": windows,
             "phases_ms": {k[3:]: acc[k] / opt.steps for k in phase_keys},
             "sweep_stats": {"candidates_per_record": cbar, "entities_per_record": rho,
-                            "rounds_per_sweep": rounds / opt.steps, "wide_records_per_sweep": wide / opt.steps,
-                            "tables_per_sweep": tbar},
+                            "rounds_per_sweep": acc["n_rounds"] / opt.steps, "wide_records_per_sweep": acc["n_wide"] / opt.steps,
+                            "tables_per_sweep": tbar, "records_left_to_bucket_kernels": acc["n_slow"] / opt.steps,
+                            "launches_per_sweep": launches / opt.steps},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -308,9 +387,11 @@ def run_sharded(opt, n_records, kind, desc):
     if rank == 0:
         entry.build()
     dist.barrier()
+    from exchanger_b200.capi import levenshtein_neighbours
     from exchanger_b200.sharded import ShardedSampler
     from exchanger_b200.synthetic import synth_model
-    model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED)
+    model, _ = synth_model(n_records, clust_prior(kind, n_records), seed=DATA_SEED, distort_prior=distort_prior(opt.distort_prior),
+                           neighbour_fn=lambda dom, thr: levenshtein_neighbours(dom, thr, device=local))
     g = ShardedSampler(model, seed=1000, device=local)
     g.sweeps(opt.burnin + opt.warmup)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -347,6 +428,10 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the record count (debugging)")
     ap.add_argument("--burnin", type=int, default=20, help="untimed sweeps before the warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distort-prior", default="beta150", choices=["beta150", "beta11"],
+                    help="prior of the distortion probabilities: Beta(1,50) (default) or the README model's Beta(1,1)")
+    ap.add_argument("--no-long-window", dest="long_window", action="store_false",
+                    help="skip the extra sweeps 21-120 / 201-220 figures")
     ap.add_argument("--mode", default="chains", choices=["chains", "shard"],
                     help="N > 1: independent chains (default, weak scaling) or one chain sharded over the GPUs")
     opt = ap.parse_args()

@@ -121,10 +121,11 @@ struct exb200_handle {
   int table_min_usage = 16;     // a key mask wanted by at most this many records never gets a table of its own
   int n_tab = 0; // 2^n_key
   exb200_stats stats{};
-  cudaEvent_t ev[16]{};
+  cudaEvent_t ev[20]{};
   std::string err;
   bool poisoned = false;
   bool has_index_events = false;
+  bool fast_ran = false;       // k_cand_fast ran this sweep (events 3 / 13 bracket it)
   long long n_launches = 0; // kernels launched by this handle
   struct exb200_pe* pe = nullptr; // point estimate fed by exb200_run (not owned)
   // saved samples leave the device behind the next sweep: snapshot (D2D) -> pinned buffer on the
@@ -639,25 +640,36 @@ int update_links(exb200_handle* h) {
   {
     const double items = 1.2 * (double)N;
     std::vector<char> built(NT, 0);
+    auto keys_of = [&](int t) { return (double)h->tables[t].keys; };
+    // a table whose key space is much larger than the item set is built in chain form (one atomicExch
+    // per item, tiny chains): cheap to build, and its probes cost one node per item
+    auto chainable = [&](int t) { return S.pk_ok && h->opt_fast && h->tables[t].d.B > (uint32_t)SMALL_B_MAX && keys_of(t) >= 16.0 * items; };
     for (int t = 1; t < NT; t++)
-      if (usage[t] > 0 && (double)est[t] >= h->table_full_cost * items) { built[t] = 1; active.push_back(t); remap[t] = (uint16_t)t; }
+      if (usage[t] > 0 && (double)est[t] >= (chainable(t) ? 0.05 : 1.0) * h->table_full_cost * items) { built[t] = 1; active.push_back(t); remap[t] = (uint16_t)t; }
     std::vector<int> wanted;
     for (int t = 1; t < NT; t++) if (usage[N_TABLES + t] > 0) wanted.push_back(t);
     std::sort(wanted.begin(), wanted.end(), [&](int a, int b) { return usage[N_TABLES + a] > usage[N_TABLES + b]; });
-    auto keys_of = [&](int t) { return (double)h->tables[t].keys; };
-    // a built table b serves the pair mask t directly if b is a subset of t, or by probing every
-    // value of ONE extra key attribute e with a small domain (b = subset of t + e).  Expected
-    // bucket visits per record: D_e probes of at least one visit each.
+    // A built table b serves the pair mask t directly if b is a subset of t.  It also serves it if it
+    // has extra key attributes: a record that cannot pin one of them probes the bucket of every
+    // possible value (make_probe).  CSR form: ONE extra attribute with a small domain, short buckets.
+    // Chain form: up to two extra attributes (a record rarely lacks them: most probes are single).
+    // Returns the expected bucket visits per record (-1: not served).
     auto visits_via = [&](int b, int t) -> double {
       const int extra = b & ~t;
       const double per_bucket = std::max(1.0, items / keys_of(b));
       if (extra == 0) return per_bucket;
-      if ((extra & (extra - 1)) || (b & t) == 0) return -1.0; // not served
-      int pos = 0;
-      while (!((extra >> pos) & 1)) pos++;
-      const int D = h->attrs[S.key_attr[pos]].D;
+      if ((b & t) == 0) return -1.0; // shares no pinned attribute with the pair
+      double probes = 1.0, expected = 1.0;
+      int n_extra = 0;
+      for (int pos = 0; pos < S.n_key; pos++)
+        if ((extra >> pos) & 1) {
+          const double D = (double)h->attrs[S.key_attr[pos]].D;
+          probes *= D; n_extra++;
+          expected *= 1.0 + 0.05 * D; // a record lacks an extra attribute now and then (missing or distorted)
+        }
+      if (chainable(b)) return n_extra <= 2 && probes <= 4096.0 ? per_bucket * expected : -1.0; // (make_probe: at most two, MAX_PROBES)
       // (one thread walks each probed bucket: short buckets only)
-      return D <= 256 && per_bucket <= 32.0 ? (double)D * per_bucket : -1.0;
+      return n_extra == 1 && probes <= 256.0 && per_bucket <= 32.0 ? probes * per_bucket : -1.0;
     };
     for (int t : wanted) {
       int best = 0;
@@ -667,7 +679,7 @@ int update_links(exb200_handle* h) {
         if (v > 0.0 && (best == 0 || v < best_visits)) { best_visits = v; best = b; }
       }
       // expected bucket visits through the substitute versus the cost of a table of its own
-      const bool too_slow = !best || (double)usage[N_TABLES + t] * best_visits > h->table_pair_cost * items;
+      const bool too_slow = !best || (double)usage[N_TABLES + t] * best_visits > (chainable(t) ? 0.2 : 1.0) * h->table_pair_cost * items;
       if (too_slow && usage[N_TABLES + t] <= h->table_min_usage && !built[t]) {
         // a handful of records: no table for them (remap 0 if nothing serves them: their possible
         // links are then listed by the batched scan over all the items)
@@ -695,7 +707,7 @@ int update_links(exb200_handle* h) {
     const double items = 1.2 * (double)N;
     for (int t : active) {
       TableHost& T = h->tables[t];
-      const bool chain = S.pk_ok && h->opt_fast && T.d.B > (uint32_t)SMALL_B_MAX && 4.0 * (double)T.keys >= items;
+      const bool chain = S.pk_ok && h->opt_fast && T.d.B > (uint32_t)SMALL_B_MAX && (double)T.keys >= 16.0 * items;
       if (chain) {
         if (!T.d.head) {
           uint32_t cells = 1024;
@@ -732,11 +744,13 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaEventRecord(h->ev[3], st));
   int hc[C_NSLOTS];
+  h->fast_ran = !chain_tabs.empty();
   if (chain_tabs.empty()) KLAUNCH(h, (k_cand<8, 64>), nblk((long long)N, 64 / 8), 64, 0, S, (const int*)nullptr, N);
   else {
     // thread per record over the chain tables; what it cannot finish is listed for the bucket kernels
     const auto t_f = std::chrono::steady_clock::now();
     KLAUNCH(h, k_cand_fast, nblk(N), TPB, 0, S);
+    CK(cudaEventRecord(h->ev[13], st));
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h->trace) std::fprintf(stderr, "[exb200] index + thread-per-record candidates (host lap) %8.2f ms; %d records for warps, %d for blocks, %d for the bucket kernels\n",
@@ -769,6 +783,7 @@ int update_links(exb200_handle* h) {
     t_tr = now;
   };
   h->stats.n_probe = hc[C_NPROBE];
+  h->stats.n_slow = h->fast_ran ? hc[C_NSLOW] : 0;
   h->stats.n_huge = 0;
   if (hc[C_NPROBE] > 0) { // records that probe several buckets: a warp each
     KLAUNCH(h, (k_cand<32, 128>), nblk((long long)hc[C_NPROBE], 128 / 32), 128, 0, S, (const int*)S.probe_list, hc[C_NPROBE]);
@@ -1133,6 +1148,7 @@ int sweep_finish(exb200_handle* h) {
   h->stats.ms_index_count = h->has_index_events ? ms(12, 14) : 0.f; // CSR tables
   h->stats.ms_index_fill = h->has_index_events ? ms(14, 3) : 0.f;   // chain tables
   h->stats.ms_cand = ms(3, 10); h->stats.ms_cand_long = ms(10, 4); h->stats.ms_wide = ms(4, 11); h->stats.ms_rounds = ms(11, 5); h->stats.ms_canon = ms(5, 6);
+  h->stats.ms_cand_fast = h->fast_ran ? ms(3, 13) : 0.f;
   h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
   if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
   return EXB200_OK;

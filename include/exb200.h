@@ -37,7 +37,7 @@ extern "C" {
 
 /* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
    estimates (exb200_pe_*) added
-   3: exb200_pe_overflowed */
+   3: exb200_pe_overflowed; exb200_stats grew (ms_cand_fast, n_slow) */
 #define EXB200_ABI_VERSION 3
 
 enum {
@@ -173,6 +173,8 @@ typedef struct exb200_stats {
   int32_t n_probe;        /* records taken by a whole warp in the second candidate launch (several
                              buckets to probe, or one bucket of 513..8192 items)                  */
   int32_t n_huge;         /* records whose bucket was cut into tiles (longer than huge_min)       */
+  float ms_cand_fast;     /* the thread-per-record candidate kernel alone (part of ms_cand)       */
+  int32_t n_slow;         /* records that kernel left to the bucket-scanning kernels              */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;

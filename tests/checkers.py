@@ -14,6 +14,43 @@ from exchanger_b200.capi import CModel, CState, FlatModel, c_f64p, c_i32p
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libexref.so")
 ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libexoracle.so")
+NBR_SO = os.path.join(ROOT, "oracle", "_build", "libexnbr.so")
+
+
+def cpu_neighbours(domain, threshold: int, include_self: bool = False, n_threads: int | None = None):
+    """Thresholded-Levenshtein neighbourhoods on the host cores (oracle/exnbr.c): same result as
+    ``model.compute_close_values`` / the GPU builder, for the CPU legs of bench.py.
+    Returns ``(row_ptr, val_ids, probs, max_exp_factor)``."""
+    if not os.path.exists(NBR_SO):
+        build_checkers()
+    lib = C.CDLL(NBR_SO)
+    lib.exnbr_create.restype = C.c_void_p
+    lib.exnbr_create.argtypes = [C.c_void_p, c_i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.exnbr_nnz.restype = C.c_int64
+    lib.exnbr_nnz.argtypes = [C.c_void_p]
+    lib.exnbr_get.argtypes = [C.c_void_p, C.POINTER(C.c_int64), c_i32p, c_f64p, c_f64p]
+    lib.exnbr_destroy.argtypes = [C.c_void_p]
+    n = len(domain)
+    chars = np.zeros((n, 32), np.uint8)
+    lens = np.zeros(n, np.int32)
+    for i, s in enumerate(domain):
+        b = s.encode("latin-1", errors="replace")
+        if len(b) > 31:
+            raise ValueError("strings longer than 31 bytes are not supported")
+        lens[i] = len(b)
+        chars[i, :len(b)] = np.frombuffer(b, np.uint8)
+    h = lib.exnbr_create(chars.ctypes.data_as(C.c_void_p), lens.ctypes.data_as(c_i32p), n, int(threshold),
+                         int(include_self), int(n_threads or os.cpu_count() or 1))
+    if not h:
+        raise ValueError("exnbr_create: bad arguments")
+    try:
+        nnz = lib.exnbr_nnz(h)
+        row_ptr, cols, probs, mef = np.zeros(n + 1, np.int64), np.zeros(nnz, np.int32), np.zeros(nnz), np.zeros(n)
+        lib.exnbr_get(h, row_ptr.ctypes.data_as(C.POINTER(C.c_int64)), cols.ctypes.data_as(c_i32p),
+                      probs.ctypes.data_as(c_f64p), mef.ctypes.data_as(c_f64p))
+    finally:
+        lib.exnbr_destroy(h)
+    return row_ptr, cols, probs, mef
 
 
 def build_checkers():
