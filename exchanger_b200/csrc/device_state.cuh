@@ -189,7 +189,8 @@ enum CounterSlot {
   C_NOLIST = 14,    // records without a stored list after candidate generation (diagnostic)
   C_NPROBE = 15,    // size of probe_list
   C_NSLOW = 16,     // size of slow_list
-  C_NSLOTS = 17
+  C_NMULTI = 17,    // records the first pass of k_cand_fast left to its second pass
+  C_NSLOTS = 18
 };
 
 } // namespace exb

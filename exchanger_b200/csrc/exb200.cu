@@ -711,7 +711,7 @@ int update_links(exb200_handle* h) {
       if (chain) {
         if (!T.d.head) {
           uint32_t cells = 1024;
-          while ((double)cells < std::min(0.6 * (double)N, (double)T.keys)) cells <<= 1; // <= 32 MB at 10 M records: L2 resident
+          while ((double)cells < std::min(1.2 * (double)N, (double)T.keys)) cells <<= 1; // about one cell per indexed item
           T.d.cells = cells;
           unsigned long long km = 0;
           for (int k = 0; k < S.n_key; k++)
@@ -749,12 +749,17 @@ int update_links(exb200_handle* h) {
   else {
     // thread per record over the chain tables; what it cannot finish is listed for the bucket kernels
     const auto t_f = std::chrono::steady_clock::now();
-    KLAUNCH(h, k_cand_fast, nblk(N), TPB, 0, S);
+    KLAUNCH(h, k_cand_fast, nblk(N, FAST_TPB), FAST_TPB, 0, S, (const int*)nullptr, N, S.huge_list); // (huge_list is free until k_cand_long)
     CK(cudaEventRecord(h->ev[13], st));
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (h->trace) std::fprintf(stderr, "[exb200] index + thread-per-record candidates (host lap) %8.2f ms; %d records for warps, %d for blocks, %d for the bucket kernels\n",
-                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f).count(), hc[C_NPROBE], hc[C_NLONG_TODO], hc[C_NSLOW]);
+    if (hc[C_NMULTI] > 0) { // second pass: the records that probe several cells, one thread each
+      KLAUNCH(h, k_cand_fast, nblk(hc[C_NMULTI], FAST_TPB), FAST_TPB, 0, S, (const int*)S.huge_list, hc[C_NMULTI], (int*)nullptr);
+      CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    if (h->trace) std::fprintf(stderr, "[exb200] index + thread-per-record candidates (host lap) %8.2f ms; %d records for warps, %d for blocks, %d for the bucket kernels, %d in the second pass\n",
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f).count(), hc[C_NPROBE], hc[C_NLONG_TODO], hc[C_NSLOW], hc[C_NMULTI]);
     if (hc[C_NSLOW] > 0) {
       // chains longer than hop_cap / more than FAST_CAND candidates: those tables get their CSR form too
       std::vector<int> over(N_TABLES), lazy;

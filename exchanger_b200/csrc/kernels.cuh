@@ -928,11 +928,13 @@ __global__ void __launch_bounds__(TPB) k_chain_build(DevState S, int tab, const 
 //     than FAST_CAND candidates                                         -> slow_list (k_cand<8>)
 // Same candidate sets, same order, same log-likelihoods as k_cand.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
-  __shared__ unsigned s_stat[2];
-  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
-  __syncthreads();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// Two passes: the first over all records does the single-cell ones and lists the records that probe
+// several cells (`multi_list`); the second runs over that list, so that a warp is not held up by
+// the one lane in thirty that makes a hundred probes.  No block barrier: warps retire on their own.
+constexpr int FAST_TPB = 128;
+__global__ void __launch_bounds__(FAST_TPB) k_cand_fast(DevState S, const int* __restrict__ list, int n_rec, int* __restrict__ multi_list) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gi < n_rec ? (list ? list[gi] : gi) : S.N;
   unsigned n_cand = 0, n_hops = 0;
   if (r < S.N) {
     int x[8];
@@ -959,6 +961,7 @@ __global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
         if (pr.n_un == 3) slow = true;                 // not served by this table after all (k_cand marks it)
         else if (pr.count > 512) { S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r; pr.n_un = -1; } // a block, one thread per probe
         else if (pr.count > FAST_PROBES) { S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; pr.n_un = -1; }
+        else if (multi_list) { multi_list[atomicAdd(&S.counters[C_NMULTI], 1)] = r; pr.n_un = -1; } // second pass
       }
       if (!slow && pr.n_un >= 0) {
         const int own = S.lambda[r];
@@ -1026,12 +1029,13 @@ __global__ void __launch_bounds__(TPB) k_cand_fast(DevState S) {
     }
     if (slow) S.slow_list[atomicAdd(&S.counters[C_NSLOW], 1)] = r;
   }
-  // statistics: per block, spread over 32 slots (one hot address would serialise 40 k blocks)
+  // statistics: per warp, spread over 32 slots (one hot address would serialise 300 k warps)
   n_cand = (unsigned)warp_sum((int)n_cand); n_hops = (unsigned)warp_sum((int)n_hops);
-  if ((threadIdx.x & 31) == 0) { if (n_cand) atomicAdd(&s_stat[0], n_cand); if (n_hops) atomicAdd(&s_stat[1], n_hops); }
-  __syncthreads();
-  if (threadIdx.x < 2 && s_stat[threadIdx.x])
-    atomicAdd((unsigned long long*)&S.counters64[2 + 2 * (blockIdx.x & 31) + threadIdx.x], (unsigned long long)s_stat[threadIdx.x]);
+  if ((threadIdx.x & 31) == 0) {
+    long long* slot = S.counters64 + 2 + 2 * ((gi >> 5) & 31);
+    if (n_cand) atomicAdd((unsigned long long*)&slot[0], (unsigned long long)n_cand);
+    if (n_hops) atomicAdd((unsigned long long*)&slot[1], (unsigned long long)n_hops);
+  }
 }
 
 __host__ __device__ __forceinline__ int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }

@@ -158,8 +158,14 @@ public:
   typename std::vector<T>::iterator end() { return payload().end(); }
   typename std::vector<T>::const_iterator begin() const { return payload().begin(); }
   typename std::vector<T>::const_iterator end() const { return payload().end(); }
-  AttrProxy attr(const std::string &name);
+  AttrProxy attr(const std::string &name) const;
   Vector<std::string, STRSXP> names() const;
+  template <class... Args> static Vector create(Args... args) {
+    Vector v;
+    const T vals[] = {T(args)...};
+    v.payload().assign(vals, vals + sizeof...(Args));
+    return v;
+  }
 };
 template <> inline std::vector<int> &Vector<int, INTSXP>::payload() const { return node->ints; }
 template <> inline std::vector<double> &Vector<double, REALSXP>::payload() const { return node->reals; }
@@ -172,18 +178,48 @@ template <class T, int TYPE> Vector<std::string, STRSXP> Vector<T, TYPE>::names(
   return it == node->attrs.end() ? CharacterVector() : CharacterVector(it->second);
 }
 
-class IntegerMatrix : public IntegerVector {
+// matrices: column-major payload, dimensions in the node (dimnames live in the attributes
+// "rownames" / "colnames": see rownames() / colnames() below)
+template <class Base, class T> class MatrixT : public Base {
 public:
+  MatrixT() {}
+  MatrixT(const SEXP &n) : Base(n) {}
+  MatrixT(const RObject &o) : Base(o.node) {}
+  MatrixT(int nrow, int ncol) : Base(nrow * ncol) { this->node->nrow = nrow; this->node->ncol = ncol; }
+  int nrow() const { return this->node->nrow; }
+  int ncol() const { return this->node->ncol; }
+  T &operator()(int i, int j) { return (*this)[(size_t)i + (size_t)j * this->node->nrow]; }
+  const T &operator()(int i, int j) const { return (*this)[(size_t)i + (size_t)j * this->node->nrow]; }
+  struct RowProxy {
+    MatrixT *m; int i;
+    template <class V> RowProxy &operator=(const V &v) {
+      for (int j = 0; j < m->ncol(); j++) (*m)(i, j) = (T)v[j];
+      return *this;
+    }
+  };
+  RowProxy row(int i) { return RowProxy{this, i}; }
+};
+class IntegerMatrix : public MatrixT<IntegerVector, int> {
+public:
+  using MatrixT<IntegerVector, int>::MatrixT;
   IntegerMatrix() {}
-  IntegerMatrix(const SEXP &n) : IntegerVector(n) {}
-  IntegerMatrix(const RObject &o) : IntegerVector(o.node) {}
+  IntegerMatrix operator-(int s) const { // NA stays NA, as in R
+    IntegerMatrix r(nrow(), ncol());
+    for (int k = 0; k < size(); k++) r[k] = (*this)[k] == NA_INTEGER ? NA_INTEGER : (*this)[k] - s;
+    r.node->attrs = node->attrs;
+    return r;
+  }
 };
-class NumericMatrix : public NumericVector {
+class NumericMatrix : public MatrixT<NumericVector, double> {
 public:
+  using MatrixT<NumericVector, double>::MatrixT;
   NumericMatrix() {}
-  NumericMatrix(const SEXP &n) : NumericVector(n) {}
-  NumericMatrix(const RObject &o) : NumericVector(o.node) {}
 };
+inline IntegerVector operator-(const IntegerVector &v, int s) {
+  IntegerVector r(v.size());
+  for (int k = 0; k < v.size(); k++) r[k] = v[k] == NA_INTEGER ? NA_INTEGER : v[k] - s;
+  return r;
+}
 
 class S4;
 class List;
@@ -213,12 +249,21 @@ public:
   operator List() const;
   operator arma::vec() const { return arma::vec(NumericVector(get()).node->reals); }
   operator arma::ivec() const { return arma::ivec(get()->ints); }
+  operator arma::imat() const {
+    SEXP n = get(); arma::imat m(n->nrow, n->ncol); m.d = n->ints; return m;
+  }
+  operator arma::mat() const {
+    SEXP n = NumericVector(get()).node; arma::mat m(get()->nrow, get()->ncol); m.d = n->reals; return m;
+  }
+  operator std::string() const { return get()->strs.at(0); }
+  AttrProxy &operator=(const AttrProxy &v) { owner->attrs[name] = v.get(); return *this; } // slot <- slot
   AttrProxy &operator=(const SEXP &v) { owner->attrs[name] = v; return *this; }
   AttrProxy &operator=(const RObject &v) { owner->attrs[name] = v.node; return *this; }
   AttrProxy &operator=(double v) { owner->attrs[name] = make_real({v}); return *this; }
   AttrProxy &operator=(int v) { owner->attrs[name] = make_int({v}); return *this; }
+  AttrProxy &operator=(bool v) { owner->attrs[name] = make_lgl(v); return *this; }
 };
-template <class T, int TYPE> AttrProxy Vector<T, TYPE>::attr(const std::string &name) {
+template <class T, int TYPE> AttrProxy Vector<T, TYPE>::attr(const std::string &name) const {
   return AttrProxy(node, name);
 }
 
@@ -242,12 +287,28 @@ public:
   int size() const { return node ? (int)node->items.size() : 0; }
   int length() const { return size(); }
   AttrProxy operator[](int i) const { return AttrProxy(node->items.at(i)); }
-  AttrProxy operator[](const std::string &key) const {
-    for (size_t i = 0; i < node->names.size(); i++)
-      if (node->names[i] == key) return AttrProxy(node->items[i]);
-    throw std::runtime_error("shim: no list element '" + key + "'");
-  }
-  AttrProxy operator[](const char *key) const { return (*this)[std::string(key)]; }
+  // element by name: readable like an AttrProxy, assignable (appends when the name is new)
+  struct NameProxy {
+    SEXP list; std::string key;
+    int find() const {
+      for (size_t i = 0; i < list->names.size(); i++) if (list->names[i] == key) return (int)i;
+      return -1;
+    }
+    AttrProxy read() const {
+      const int i = find();
+      if (i < 0) throw std::runtime_error("shim: no list element '" + key + "'");
+      return AttrProxy(list->items[i]);
+    }
+    template <class T> operator T() const { return (T)read(); }
+    NameProxy &operator=(const RObject &v) {
+      const int i = find();
+      if (i >= 0) list->items[i] = v.node; else { list->items.push_back(v.node); list->names.push_back(key); }
+      return *this;
+    }
+  };
+  NameProxy operator[](const std::string &key) const { return NameProxy{node, key}; }
+  NameProxy operator[](const char *key) const { return NameProxy{node, std::string(key)}; }
+  CharacterVector names() const { return CharacterVector(make_str(node->names)); }
   struct iterator {
     const List *l; int i;
     AttrProxy operator*() const { return (*l)[i]; }
@@ -263,8 +324,41 @@ public:
 inline AttrProxy::operator S4() const { return S4(get()); }
 inline AttrProxy::operator List() const { return List(get()); }
 
-template <class T> T as(const SEXP &x) { return T(x); }
-template <class T> T as(const RObject &x) { return T(x.node); }
+template <class T> struct as_impl { static T from(const SEXP &x) { return T(x); } };
+template <> struct as_impl<double> { static double from(const SEXP &x) { return node_as_double(x); } };
+template <> struct as_impl<int> { static int from(const SEXP &x) { return (int)node_as_double(x); } };
+template <> struct as_impl<bool> { static bool from(const SEXP &x) { return node_as_double(x) != 0; } };
+template <> struct as_impl<std::string> { static std::string from(const SEXP &x) { return x->strs.at(0); } };
+template <> struct as_impl<arma::ivec> { static arma::ivec from(const SEXP &x) { return arma::ivec(x->ints); } };
+template <> struct as_impl<arma::imat> {
+  static arma::imat from(const SEXP &x) { arma::imat m(x->nrow, x->ncol); m.d = x->ints; return m; }
+};
+template <class T> T as(const SEXP &x) { return as_impl<T>::from(x); }
+template <class T> T as(const RObject &x) { return as_impl<T>::from(x.node); }
+template <class T> T as(const AttrProxy &x) { return as_impl<T>::from(x.get()); }
+template <class T> T as(const std::string &x) { return T(x); }
+
+// table() of a factor-coded integer vector: counts of the codes 1..max
+inline IntegerVector table(const IntegerVector &codes) {
+  int mx = 0;
+  for (int v : codes) mx = std::max(mx, v);
+  IntegerVector t(mx);
+  for (int v : codes) if (v >= 1) t[v - 1] += 1;
+  return t;
+}
+
+// rownames(x) / colnames(x): readable as a CharacterVector, assignable
+struct DimNamesProxy {
+  SEXP node; const char *which;
+  operator CharacterVector() const {
+    auto it = node->attrs.find(which);
+    return it == node->attrs.end() ? CharacterVector() : CharacterVector(it->second);
+  }
+  DimNamesProxy &operator=(const CharacterVector &v) { node->attrs[which] = v.node; return *this; }
+  DimNamesProxy &operator=(const DimNamesProxy &v) { node->attrs[which] = CharacterVector(v).node; return *this; }
+};
+inline DimNamesProxy rownames(const RObject &x) { return DimNamesProxy{x.node, "rownames"}; }
+inline DimNamesProxy colnames(const RObject &x) { return DimNamesProxy{x.node, "colnames"}; }
 
 inline RObject wrap(const std::vector<int> &v) { return RObject(make_int(v)); }
 inline RObject wrap(const arma::ivec &v) { return RObject(make_int(v.d)); }
