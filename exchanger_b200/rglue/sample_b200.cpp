@@ -301,7 +301,7 @@ Rcpp::S4 final_state_to_R(const Rcpp::S4 &init_state, const FlatModel &fm, exb20
     final_state.slot("clust_params") = cp;
   } else {
     Rcpp::S4 cp("GeneralizedCouponRP");
-    cp.slot("m") = st.clust.m;
+    cp.slot("m") = (int)st.clust.m;                                   // m_ is an int in the reference (clust_params.cpp:138,146)
     cp.slot("kappa") = st.clust.kind == EXB200_CLUST_COUPON ? R_PosInf : st.clust.kappa;
     final_state.slot("clust_params") = cp;
   }

@@ -257,7 +257,10 @@ public:
   }
   operator std::string() const { return get()->strs.at(0); }
   AttrProxy &operator=(const AttrProxy &v) { owner->attrs[name] = v.get(); return *this; } // slot <- slot
-  AttrProxy &operator=(const SEXP &v) { owner->attrs[name] = v; return *this; }
+  AttrProxy &operator=(const SEXP &v) { // (an attribute set to NULL is removed, as in R)
+    if (v || owner->type == S4SXP) owner->attrs[name] = v; else owner->attrs.erase(name);
+    return *this;
+  }
   AttrProxy &operator=(const RObject &v) { owner->attrs[name] = v.node; return *this; }
   AttrProxy &operator=(double v) { owner->attrs[name] = make_real({v}); return *this; }
   AttrProxy &operator=(int v) { owner->attrs[name] = make_int({v}); return *this; }

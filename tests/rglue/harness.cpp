@@ -11,10 +11,14 @@
 #include <progress.hpp>
 
 #include <cstdint>
-#include <sstream>
+#include <cstdio>
 #include <string>
 
 #include "exb200.h"
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void segv_handler(int) { void* bt[40]; int n = backtrace(bt, 40); backtrace_symbols_fd(bt, n, 2); _exit(3); }
 
 using namespace Rcpp;
 
@@ -128,48 +132,51 @@ static S4 make_model(const exb200_model* m) {
   return model;
 }
 
-// ---- JSON dump of an R object tree
-static void dump_strs(std::ostringstream& o, const std::vector<std::string>& v) {
-  o << "[";
-  for (size_t i = 0; i < v.size(); i++) o << (i ? "," : "") << "\"" << v[i] << "\"";
-  o << "]";
+// ---- JSON dump of an R object tree (plain string building: no iostreams across library boundaries)
+typedef std::string Out;
+static void put(Out& o, long long v) { char b[32]; snprintf(b, sizeof b, "%lld", v); o += b; }
+static void put(Out& o, double v) { char b[40]; snprintf(b, sizeof b, "%.17g", v); o += b; }
+static void dump_strs(Out& o, const std::vector<std::string>& v, size_t n) {
+  o += "[";
+  for (size_t i = 0; i < n; i++) { o += i ? ",\"" : "\""; o += v[i]; o += "\""; }
+  o += "]";
 }
-static void dump(std::ostringstream& o, const SEXP& n, int max_values) {
-  if (!n) { o << "null"; return; }
-  static const char* tn[] = {"NULL", "", "", "", "", "", "", "", "", "", "logical", "", "", "integer", "double", "", "character", "", "", "list"};
-  o << "{\"type\":\"" << (n->type == S4SXP ? "S4" : tn[n->type]) << "\"";
-  if (n->type == S4SXP) o << ",\"class\":\"" << n->klass << "\"";
+static void dump(Out& o, const SEXP& n, int max_values) {
+  if (!n) { o += "null"; return; }
+  const char* tname = n->type == S4SXP ? "S4" : n->type == LGLSXP ? "logical" : n->type == INTSXP ? "integer"
+                      : n->type == REALSXP ? "double" : n->type == STRSXP ? "character" : n->type == VECSXP ? "list" : "NULL";
+  o += "{\"type\":\""; o += tname; o += "\"";
+  if (n->type == S4SXP) { o += ",\"class\":\""; o += n->klass; o += "\""; }
   const size_t len = n->type == INTSXP || n->type == LGLSXP ? n->ints.size() : n->type == REALSXP ? n->reals.size()
                      : n->type == STRSXP ? n->strs.size() : n->items.size();
-  if (n->type != S4SXP) o << ",\"len\":" << len;
-  if (n->nrow || n->ncol) o << ",\"dim\":[" << n->nrow << "," << n->ncol << "]";
+  if (n->type != S4SXP) { o += ",\"len\":"; put(o, (long long)len); }
+  if (n->nrow || n->ncol) { o += ",\"dim\":["; put(o, (long long)n->nrow); o += ","; put(o, (long long)n->ncol); o += "]"; }
   if (n->type == VECSXP) {
-    o << ",\"names\":"; dump_strs(o, n->names);
-    o << ",\"items\":[";
-    for (size_t i = 0; i < n->items.size(); i++) { if (i) o << ","; dump(o, n->items[i], max_values); }
-    o << "]";
+    o += ",\"names\":"; dump_strs(o, n->names, n->names.size());
+    o += ",\"items\":[";
+    for (size_t i = 0; i < n->items.size(); i++) { if (i) o += ","; dump(o, n->items[i], max_values); }
+    o += "]";
   }
-  const bool all = (long long)len <= max_values;
+  const size_t shown = (long long)len <= max_values ? len : (size_t)max_values;
   if (n->type == INTSXP || n->type == LGLSXP) {
-    o << ",\"values\":[";
-    for (size_t i = 0; i < (all ? len : (size_t)max_values); i++) { if (i) o << ","; if (n->ints[i] == NA_INTEGER) o << "null"; else o << n->ints[i]; }
-    o << "]";
+    o += ",\"values\":[";
+    for (size_t i = 0; i < shown; i++) { if (i) o += ","; if (n->ints[i] == NA_INTEGER) o += "null"; else put(o, (long long)n->ints[i]); }
+    o += "]";
   } else if (n->type == REALSXP) {
-    o.precision(17);
-    o << ",\"values\":[";
-    for (size_t i = 0; i < (all ? len : (size_t)max_values); i++) {
-      if (i) o << ",";
-      if (std::isfinite(n->reals[i])) o << n->reals[i]; else o << (n->reals[i] > 0 ? "\"Inf\"" : "\"-Inf\"");
+    o += ",\"values\":[";
+    for (size_t i = 0; i < shown; i++) {
+      if (i) o += ",";
+      if (std::isfinite(n->reals[i])) put(o, n->reals[i]); else o += n->reals[i] > 0 ? "\"Inf\"" : "\"-Inf\"";
     }
-    o << "]";
-  } else if (n->type == STRSXP) { o << ",\"values\":"; dump_strs(o, std::vector<std::string>(n->strs.begin(), n->strs.begin() + (all ? len : (size_t)max_values))); }
+    o += "]";
+  } else if (n->type == STRSXP) { o += ",\"values\":"; dump_strs(o, n->strs, shown); }
   if (!n->attrs.empty()) {
-    o << ",\"" << (n->type == S4SXP ? "slots" : "attrs") << "\":{";
+    o += n->type == S4SXP ? ",\"slots\":{" : ",\"attrs\":{";
     bool first = true;
-    for (auto& kv : n->attrs) { o << (first ? "" : ",") << "\"" << kv.first << "\":"; dump(o, kv.second, max_values); first = false; }
-    o << "}";
+    for (auto& kv : n->attrs) { o += first ? "\"" : ",\""; o += kv.first; o += "\":"; dump(o, kv.second, max_values); first = false; }
+    o += "}";
   }
-  o << "}";
+  o += "}";
 }
 
 static std::string g_out;
@@ -180,22 +187,22 @@ extern "C" {
 // true at its (abort_after + 1)-th call.  Returns the ExchangERFit as JSON, or {"error": ...}.
 const char* rglue_run(const exb200_model* m, int n_samples, int thin, int burnin, int which, int abort_after,
                       uint64_t seed, int max_values) {
-  std::ostringstream o;
+  Out o;
+  signal(SIGSEGV, segv_handler);
   try {
     exref_seed(seed);
     Progress::abort_after() = abort_after;
     Progress::increments() = 0;
     S4 model = make_model(m);
     S4 fit = which == 0 ? reference_sample(model, n_samples, thin, burnin) : sample(model, n_samples, thin, burnin);
-    o << "{\"increments\":" << Progress::increments() << ",\"fit\":";
+    o += "{\"increments\":"; put(o, (long long)Progress::increments()); o += ",\"fit\":";
     dump(o, fit.node, max_values);
-    o << "}";
+    o += "}";
   } catch (std::exception& e) {
-    o.str("");
-    o << "{\"error\":\"" << e.what() << "\"}";
+    o = "{\"error\":\""; o += e.what(); o += "\"}";
   }
   Progress::abort_after() = -1;
-  g_out = o.str();
+  g_out = o;
   return g_out.c_str();
 }
 

@@ -508,3 +508,37 @@ def test_neighbourhood_builder_matches_compute_close_values(include_self):
                 assert np.all(mef[iso] == 0.0)                   # a value without a finite neighbour (AttributeIndex.R:135)
     with pytest.raises(Exb200Error):
         levenshtein_neighbours(["A" * 32], 3)
+
+
+def test_r_glue_end_to_end_on_the_gpu():
+    """exchanger_b200/rglue/sample_b200.cpp (the replacement of src/sample.cpp, compiled against the
+    stand-in Rcpp headers) linked with the REAL libexb200.so: `.sample()` on an ExchangERModel S4 object
+    returns the chain that the Python binding returns for the same Philox key - history, final state,
+    1-based labels, R's column-major matrices."""
+    import os
+    import test_rglue as tg
+    gpu_so = os.path.join(tg.ROOT, "oracle", "_build", "librglue_gpu.so")
+    if not os.path.exists(gpu_so):
+        pytest.skip("glue harness not built")
+    lib = tg.harness(gpu_so)
+    m, _ = readme_model("rldata500", n=200)
+    out = tg.run(lib, m, 5, 2, 4, which=1, seed=77)
+    fit = run_inference(m, n_samples=5, thin_interval=2, burnin_interval=4, seed=int(lib.rglue_seed_for(77)))
+    N, A = m.n_records, m.n_attrs
+    slots = out["fit"]["slots"]
+    hist = dict(zip(slots["history"]["names"], slots["history"]["items"]))
+    assert list(hist) == ["links", "distort_probs", "distort_counts", "distort_dist_concs", "n_linked_ents", "clust_params"]
+    links = np.array(hist["links"]["values"]).reshape(N, 5).T
+    assert np.array_equal(links, fit.history["links"] + 1)
+    assert hist["n_linked_ents"]["values"] == fit.history["n_linked_ents"][:, 0].tolist()
+    assert np.array_equal(np.array(hist["distort_probs"]["values"]).reshape(A, 5).T, fit.history["distort_probs"])
+    assert np.array_equal(np.array(hist["distort_counts"]["values"]).reshape(A, 5).T, fit.history["distort_counts"])
+    assert np.array_equal(np.array(hist["clust_params"]["values"]).reshape(2, 5).T, fit.history["clust_params"])
+    assert hist["clust_params"]["attrs"]["colnames"]["values"] == ["alpha", "d"]
+    st = slots["state"]["slots"]
+    assert st["iteration"]["values"] == [fit.state.iteration] == [12]
+    assert np.array_equal(np.array(st["links"]["values"]), fit.state.links + 1)
+    K = len(fit.state.ent_ids)
+    assert np.array_equal(np.array(st["ent_attrs"]["values"]).reshape(K, A).T, fit.state.ent_attrs + 1)
+    assert np.array_equal(np.array(st["rec_distortions"]["values"]).reshape(N, A).T, fit.state.rec_distortions)
+    assert out["increments"] == 12
