@@ -1106,7 +1106,7 @@ int sweep_links(exb200_handle* h) {
 int sweep_entities(exb200_handle* h, int lo, int hi) {
   DevState& S = h->S;
   CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), h->stream));
-  if (hi > lo) KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
+  if (hi > lo) KLAUNCH(h, k_entities, nblk((long long)(hi - lo) * ENT_GL, TPB), TPB, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
   KLAUNCH_DP(h, k_entities_general, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
   return EXB200_OK;
 }

@@ -2564,50 +2564,44 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
 }
 
 // (entity slots [e_lo, e_hi): the whole range on one GPU, a slice under within-chain sharding)
-__global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count,
+// One LANE per (entity, attribute), eight lanes per entity: the draw of one attribute is a chain of
+// a dozen dependent table reads (tables in the L2) and a thread that did all attributes of an entity
+// one after the other left the kernel latency-bound at half occupancy.  The lanes of an entity read
+// the same member rows (broadcast) and write neighbouring words of the entity's attribute row.
+constexpr int ENT_GL = 8;
+__global__ void __launch_bounds__(TPB, 4) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count,
                                                   int e_lo, int e_hi) {
   __shared__ int s_warp[TPB / 32]; // (launched with blocks of up to TPB threads)
   __shared__ int s_base;
-  const int e = e_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t need = 0;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = e_lo + gi / ENT_GL, gl = gi & (ENT_GL - 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  bool needs = false; // this lane's (entity, attribute) pair is left to the general scheme
+  int a_need = 0;
   const int sz = e < e_hi ? S.ent_size[e] : 0;
-  if (sz == 1 && S.RS == 8 && S.ES == 8) {
-    // a singleton: its only member is record e (entities are named after their smallest member), whose
-    // row is read once - coalesced - and whose new attribute row is written once
-    int x[8], yn[8];
-    {
+  if (sz > 0) {
+    // a singleton's only member is record e itself (entities are named after their smallest member):
+    // its row is read once, coalesced
+    const bool single = sz == 1 && S.RS == 8;
+    int x[8];
+    if (single) {
       const int4* xp = reinterpret_cast<const int4*>(S.rec_x + (size_t)e * 8);
       const int4 x0 = xp[0], x1 = xp[1];
       x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
     }
-#pragma unroll
-    for (int a = 0; a < 8; a++) yn[a] = 0;
-    for (int a = 0; a < S.A; a++) {
-      const int v = draw_entity_value(S, e, a, e, x);
-      if (v >= 0) yn[a] = v; else need |= 1u << a;
-    }
-    int* y = S.ent_y + (size_t)e * 8;
-    if (need) { for (int a = 0; a < S.A; a++) if (!((need >> a) & 1u)) y[a] = yn[a]; }
-    else {
-      int4* yp = reinterpret_cast<int4*>(y);
-      yp[0] = make_int4(yn[0], yn[1], yn[2], yn[3]);
-      yp[1] = make_int4(yn[4], yn[5], yn[6], yn[7]);
-    }
-  } else if (sz > 0) {
-    const int head = S.ent_head[e];
+    const int head = single ? e : S.ent_head[e];
     int* y = S.ent_y + (size_t)e * S.ES;
-    for (int a = 0; a < S.A; a++) {
-      const int v = draw_entity_value(S, e, a, head);
-      if (v >= 0) y[a] = v; else need |= 1u << a;
+    for (int a = gl; a < S.A; a += ENT_GL) { // (more than eight attributes: a lane takes several; at most one can be listed per pass below)
+      const int v = draw_entity_value(S, e, a, head, single ? x : nullptr);
+      if (v >= 0) y[a] = v;
+      else if (!needs) { needs = true; a_need = a; }
+      else gen_list[atomicAdd(gen_count, 1)] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)a; // (rare: A > 8)
     }
   }
   // the (entity, attribute) pairs left to the general scheme are listed (one atomic per block)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int mine = __popc(need);
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
-  if (lane == 31) s_warp[w] = incl;
+  const unsigned m = __ballot_sync(FULL, needs);
+  const int mine = __popc(m);
+  if (lane == 0) s_warp[w] = mine;
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
@@ -2615,9 +2609,7 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long
     s_base = t ? atomicAdd(gen_count, t) : 0;
   }
   __syncthreads();
-  int pos = s_base + s_warp[w] + incl - mine;
-  for (uint32_t m = need; m; m &= m - 1)
-    gen_list[pos++] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)(__ffs(m) - 1);
+  if (needs) gen_list[s_base + s_warp[w] + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)a_need;
 }
 
 // one warp per listed (entity, attribute) pair, whatever the launch shape

@@ -506,8 +506,10 @@ def test_neighbourhood_builder_matches_compute_close_values(include_self):
             if not include_self:
                 iso = np.flatnonzero(np.diff(rp2) == 0)
                 assert np.all(mef[iso] == 0.0)                   # a value without a finite neighbour (AttributeIndex.R:135)
-    with pytest.raises(Exb200Error):
+    with pytest.raises(ValueError):        # 31 bytes is the limit of the packed layout
         levenshtein_neighbours(["A" * 32], 3)
+    with pytest.raises(Exb200Error):       # ... and 8 of the threshold
+        levenshtein_neighbours(["AB", "AC"], 9)
 
 
 def test_r_glue_end_to_end_on_the_gpu():
