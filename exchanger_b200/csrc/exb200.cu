@@ -623,7 +623,9 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaMemsetAsync(S.referenced, 0, (size_t)2 * N, st));
   CK(cudaEventRecord(h->ev[1], st));
-  KLAUNCH(h, k_prep, nblk(N), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
+  if (h->A <= PREP_GL && h->opt_fast)
+    KLAUNCH(h, k_prep_lanes, std::min(nblk((long long)N * PREP_GL), h->n_sm * 32), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
+  else KLAUNCH(h, k_prep, nblk(N), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
   std::vector<int> usage(2 * (size_t)N_TABLES);
   std::vector<float> est(N_TABLES);
   CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * usage.size(), cudaMemcpyDeviceToHost, st));
@@ -1106,7 +1108,7 @@ int sweep_links(exb200_handle* h) {
 int sweep_entities(exb200_handle* h, int lo, int hi) {
   DevState& S = h->S;
   CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), h->stream));
-  if (hi > lo) KLAUNCH(h, k_entities, nblk((long long)(hi - lo) * ENT_GL, TPB), TPB, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
+  if (hi > lo) KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
   KLAUNCH_DP(h, k_entities_general, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
   return EXB200_OK;
 }
