@@ -623,9 +623,7 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaMemsetAsync(S.referenced, 0, (size_t)2 * N, st));
   CK(cudaEventRecord(h->ev[1], st));
-  if (h->A <= PREP_GL && h->opt_fast)
-    KLAUNCH(h, k_prep_lanes, std::min(nblk((long long)N * PREP_GL), h->n_sm * 32), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
-  else KLAUNCH(h, k_prep, nblk(N), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
+  KLAUNCH(h, k_prep, nblk(N), TPB, sizeof(int) * 3 * ((size_t)1 << S.n_key), S);
   std::vector<int> usage(2 * (size_t)N_TABLES);
   std::vector<float> est(N_TABLES);
   CK(cudaMemcpyAsync(usage.data(), S.tab_usage, sizeof(int) * usage.size(), cudaMemcpyDeviceToHost, st));

@@ -322,128 +322,6 @@ __global__ void __launch_bounds__(TPB, 4) k_prep(DevState S) {
   }
 }
 
-// The same, one LANE per (record, attribute), eight lanes per record (A <= 8): the draw of one
-// attribute is a chain of dependent table reads, and five of them one after the other per thread kept
-// the kernel latency-bound at a third of the occupancy.  Sums and the choice of the blocking key are
-// accumulated over the attributes in ascending order from the lanes' values, so every number is the
-// one the thread-per-record kernel computes.
-constexpr int PREP_GL = 8;
-__global__ void __launch_bounds__(TPB) k_prep_lanes(DevState S) {
-  extern __shared__ int s_prep[]; // [2][2^n_key] usage counts, [2^n_key] expected visits (float)
-  const int AA = 1 << S.n_key;
-  int* s_usage = s_prep;
-  float* s_est = reinterpret_cast<float*>(s_prep + 2 * AA);
-  for (int i = threadIdx.x; i < AA; i += blockDim.x) { s_usage[i] = 0; s_usage[AA + i] = 0; s_est[i] = 0.f; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, gl = lane & (PREP_GL - 1), gbase = lane & ~(PREP_GL - 1);
-  const unsigned gmask = 0xFFu << gbase;
-  const int a = gl;
-  for (long long r0 = (long long)blockIdx.x * (TPB / PREP_GL); r0 < S.N; r0 += (long long)gridDim.x * (TPB / PREP_GL)) {
-    const int r = (int)r0 + (int)(threadIdx.x / PREP_GL);
-    if (r >= S.N) continue; // (the whole group: its lanes share r)
-    const uint32_t zm = S.rec_z[r];
-    int yv = 0, flags = 0, my_kp = 0, my_softlen = 0; // flags: 1 observed, 2 pinned key attribute, 4 string, 8 distorted string key attribute
-    double l = 0.0, my_sel = 2.0;
-    if (a < S.A) {
-      const DevAttr& t = S.attrs[a];
-      const int xv = S.rec_x[(size_t)r * S.RS + a];
-      const bool zz = (zm >> a) & 1u;
-      if (xv < 0) { // unobserved: prior draw (links.cpp:434-437)
-        const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
-        yv = alias_draw(t.aprob, t.aalias, t.D, u.a);
-      } else {
-        flags |= 1;
-        l = zz ? t.logE[xv] : t.logphi[xv];
-        if (!zz) { // links.cpp:440-442
-          yv = xv;
-          if (S.key_pos[a] >= 0) { flags |= 2 | (t.is_const ? 0 : 4); my_kp = S.key_pos[a]; my_sel = t.psi[xv]; }
-        } else if (t.is_const) {
-          if (t.exclude) { // law of rejectionSampleConstant (links.cpp:290-314): phi/(1-psi), v != x
-            yv = xv;
-            for (int k = 0; k < REJECT_CAP; k++) {
-              const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, k);
-              yv = alias_draw(t.aprob + t.D, t.aalias + t.D, t.D, u.a);
-              if (yv != xv) break;
-            }
-            if (yv == xv) dev_fail(S, EXB200_ERR_WEIGHTS, r);
-          } else { // links.cpp:449-452
-            const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
-            yv = alias_draw(t.pprob, t.palias, t.D, u.a);
-          }
-        } else { // links.cpp:454-461: phi(v) p(x | v) over the neighbourhood of x (static prefix sums)
-          const int lo = t.row[xv], hi = t.row[xv + 1];
-          if (S.key_pos[a] >= 0 && !((S.dp_mask >> a) & 1u)) { flags |= 8; my_kp = S.key_pos[a]; my_softlen = hi - lo; }
-          const double tot = hi > lo ? t.csn[hi - 1] : 0.0;
-          yv = xv;
-          if (tot > 0.0) {
-            const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_NEWATTR, a, 0);
-            const double tt = u.a * tot;
-            int a0 = lo, b0 = hi; // first j with tt < csn[j]
-            while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (tt < t.csn[mid]) b0 = mid; else a0 = mid + 1; }
-            if (a0 == hi) { // rounding: the last entry of positive weight
-              a0 = lo; b0 = hi - 1;
-              while (a0 < b0) { const int mid = (a0 + b0) >> 1; if (t.csn[mid] >= tot) b0 = mid; else a0 = mid + 1; }
-            }
-            yv = t.col[a0];
-          }
-        }
-      }
-      S.ent_y[(size_t)(S.N + r) * S.ES + a] = yv;
-    }
-    // twin: r alone in entity slot r and its potential entity would have the same attributes
-    const bool same = a >= S.A || S.ent_y[(size_t)r * S.ES + a] == yv;
-    const bool all_same = ((__ballot_sync(gmask, same) >> gbase) & 0xFFu) == 0xFFu;
-    // the attributes in ascending order, as the thread-per-record loop sees them
-    double L = 0.0, s1 = 2.0, s2 = 2.0;
-    int b1 = -1, b2 = -1, soft = -1, soft_len = 0;
-    uint32_t nd_mask = 0;
-    bool pinned_string = false;
-    for (int k = 0; k < S.A; k++) {
-      const int src = gbase + k;
-      const double lk = __shfl_sync(gmask, l, src), sel = __shfl_sync(gmask, my_sel, src);
-      const int fl = __shfl_sync(gmask, flags, src), kp = __shfl_sync(gmask, my_kp, src), sl = __shfl_sync(gmask, my_softlen, src);
-      if (fl & 1) L += lk;
-      if (fl & 2) {
-        pinned_string |= (fl & 4) != 0;
-        nd_mask |= 1u << kp;
-        if (sel < s1) { s2 = s1; b2 = b1; s1 = sel; b1 = kp; }
-        else if (sel < s2) { s2 = sel; b2 = kp; }
-      }
-      if ((fl & 8) && (soft < 0 || sl < soft_len)) { soft = kp; soft_len = sl; }
-    }
-    if (gl == 0) {
-      S.Lnew[r] = L;
-      const int sz_r = S.ent_size[r];
-      S.ent_size[S.N + r] = 0;
-      S.ent_head[S.N + r] = -1;
-      S.fin[r] = 0;
-      // blocking table (see k_prep)
-      uint32_t tab = 0, pair = 0;
-      if (b1 >= 0 && !pinned_string && soft >= 0 && soft_len <= 1024) {
-        pair = (1u << b1) | (1u << soft);
-        tab = pair;
-        atomicAdd(&s_usage[AA + pair], 1);
-      } else if (b1 >= 0) {
-        pair = (1u << b1) | (b2 >= 0 ? 1u << b2 : 0u);
-        const double est = 2.0 * (double)S.N * s1 * (b2 >= 0 ? s2 : 1.0);
-        tab = est > S.est_threshold ? nd_mask : pair;
-        atomicAdd(&s_usage[AA + pair], 1);
-        if (tab != pair) { atomicAdd(&s_usage[tab], 1); atomicAdd(&s_est[tab], (float)est); }
-      }
-      S.rec_tab[r] = (uint16_t)tab;
-      S.rec_alt[r] = (uint16_t)pair;
-      S.twin[r] = S.lambda[r] == r && sz_r == 1 && all_same;
-      S.live0[r] = sz_r > 0;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < AA; i += blockDim.x) {
-    if (s_usage[i]) atomicAdd(&S.tab_usage[i], s_usage[i]);
-    if (s_usage[AA + i]) atomicAdd(&S.tab_usage[N_TABLES + i], s_usage[AA + i]);
-    if (s_est[i] != 0.f) atomicAdd(&S.tab_est[i], s_est[i]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // K1b  blocking index over the items (entity slots) of the sweep: live entities [0,N) and the
 // N potential entities [N,2N).  Replaces Entities::inverse_index_ (src/entities.h:51): instead
