@@ -150,6 +150,7 @@ struct DevState {
   int *wl_tot;                  // [WIDE_NB] possible links per record
   unsigned long long *wl_base;  // [WIDE_NB] start of the record's list in wl_id / wl_ll (~0: not listed)
   int *wl_id; double *wl_ll;    // [wl_cap] lists of the current batch (carved out of lwbuf)
+  int *wlb_id; double *wlb_ll;  // lists of the wide records that have a bucket, sorted by (record, item) (k_wide_emit / sort / k_wide_split)
   uint8_t *wl_log_k; int *wl_log_item; double *wl_log_ll; // [WIDE_PIECES][wl_logcap] hits of the counting pass, per piece
   int *wl_logn;                 // [WIDE_PIECES] entries logged (-1: the piece's log overflowed)
   int wl_logcap;

@@ -95,6 +95,11 @@ struct exb200_handle {
   PartBuild pb{};              // partitioned build of the large tables
   int* d_part_tabs = nullptr;
   int* d_chain_tabs = nullptr;
+  // scratch of wide_bucket_lists
+  unsigned long long* we_keys[2] = {nullptr, nullptr}; double* we_vals[2] = {nullptr, nullptr};
+  unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
+  int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
+  int opt_wide_buckets = 1;
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
   int hop_cap = 1024;
@@ -601,10 +606,65 @@ int wide_count(exb200_handle* h, const int* recs, int nb, int* totals) {
   return EXB200_OK;
 }
 // ... and the turn of one listed record
-void wide_turn(exb200_handle* h, int r, unsigned long long base, int len) {
+void wide_turn(exb200_handle* h, int r, unsigned long long base, int len, int src = 0) {
   const int n_blocks = std::max(1, std::min(WIDE_BLOCKS, (len + 2047) / 2048));
-  KLAUNCH_DP(h, k_wide_reduce, n_blocks, TPB, 0, h->S, r, base, len);
-  KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, h->S, r, base, len, n_blocks);
+  KLAUNCH_DP(h, k_wide_reduce, n_blocks, TPB, 0, h->S, r, base, len, src);
+  KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, h->S, r, base, len, n_blocks, src);
+}
+
+// Possible links of the wide records that have a bucket, listed from the bucket itself (k_wide_emit),
+// sorted by (record, item) and cut into one list per record.  `recs` ascending; on return
+// base[i] / len[i] locate record i's list in wlb_id / wlb_ll.  Returns EXB200_OK with *ok = false
+// when the lists do not fit the scratch (the caller then scans all items for these records too).
+constexpr int WIDE_BUCKET_MAX = 65536;
+int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vector<int>& base, std::vector<int>& len, bool* ok) {
+  DevState& S = h->S;
+  cudaStream_t st = h->stream;
+  const int n = (int)recs.size();
+  *ok = false;
+  if (n > WIDE_BUCKET_MAX) return EXB200_OK;
+  if (!h->we_keys[0]) {
+    h->we_cap = std::min<unsigned long long>(8ull * h->N + (1ull << 20), 48ull << 20);
+    int rc = 0;
+    for (int k = 0; k < 2 && !rc; k++) { rc = dalloc(h, &h->we_keys[k], (size_t)h->we_cap); if (!rc) rc = dalloc(h, &h->we_vals[k], (size_t)h->we_cap); }
+    if (!rc) rc = dalloc(h, &S.wlb_id, (size_t)h->we_cap);
+    if (!rc) rc = dalloc(h, &S.wlb_ll, (size_t)h->we_cap);
+    if (!rc) rc = dalloc(h, &h->we_cursor, 1);
+    if (!rc) rc = dalloc(h, &h->we_recs, (size_t)WIDE_BUCKET_MAX);
+    if (!rc) rc = dalloc(h, &h->we_seg, (size_t)2 * WIDE_BUCKET_MAX);
+    if (rc) return rc;
+    cub::DeviceRadixSort::SortPairs(nullptr, h->we_tmp_bytes, h->we_keys[0], h->we_keys[1],
+                                    reinterpret_cast<unsigned long long*>(h->we_vals[0]), reinterpret_cast<unsigned long long*>(h->we_vals[1]),
+                                    (long long)h->we_cap, 0, 64, st);
+    char* tmp = nullptr;
+    rc = dalloc(h, &tmp, h->we_tmp_bytes); if (rc) return rc;
+    h->we_tmp = tmp;
+  }
+  CK(cudaMemcpyAsync(h->we_recs, recs.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->we_cursor, 0, sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(h->we_seg, 0, sizeof(int) * 2 * (size_t)n, st));
+  KLAUNCH(h, k_wide_emit, n * WE_BLOCKS, TPB, 0, S, h->we_recs, n, h->we_keys[0], h->we_vals[0], h->we_cursor, h->we_cap);
+  unsigned long long n_emit = 0;
+  CK(cudaMemcpyAsync(&n_emit, h->we_cursor, sizeof n_emit, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_emit > h->we_cap) return EXB200_OK; // does not fit: the batched scan takes these records
+  base.assign(n, 0); len.assign(n, 0);
+  if (n_emit > 0) {
+    int top = 32; // key bits that matter: the item and the batch position
+    while ((1ll << (top - 32)) < (long long)n && top < 64) top++;
+    size_t bytes = h->we_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(h->we_tmp, bytes, h->we_keys[0], h->we_keys[1],
+                                       reinterpret_cast<unsigned long long*>(h->we_vals[0]), reinterpret_cast<unsigned long long*>(h->we_vals[1]),
+                                       (long long)n_emit, 0, top, st));
+    h->n_launches += 4;
+    KLAUNCH(h, k_wide_split, nblk((long long)n_emit), TPB, 0, S, h->we_keys[1], h->we_vals[1], (long long)n_emit, h->we_seg, h->we_seg + n);
+    std::vector<int> seg(2 * (size_t)n);
+    CK(cudaMemcpyAsync(seg.data(), h->we_seg, sizeof(int) * seg.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) { base[i] = seg[i]; len[i] = seg[n + i] > 0 ? seg[n + i] - seg[i] : 0; }
+  }
+  *ok = true;
+  return EXB200_OK;
 }
 
 // ---- 2. links: Links::update (links.cpp:477-489)
@@ -837,30 +897,60 @@ int update_links(exb200_handle* h) {
     CK(cudaStreamSynchronize(st));
     for (int r : unk) serial.push_back((r << 1) | 1);
   }
+  std::vector<int> known; // wide records found by the candidate scan of their own bucket
   if (hc[C_NWIDE] > 0) {
-    std::vector<int> w(hc[C_NWIDE]);
-    CK(cudaMemcpyAsync(w.data(), S.wide_list, sizeof(int) * w.size(), cudaMemcpyDeviceToHost, st));
+    known.resize(hc[C_NWIDE]);
+    CK(cudaMemcpyAsync(known.data(), S.wide_list, sizeof(int) * known.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int r : w) serial.push_back(r << 1);
+    std::sort(known.begin(), known.end());
+    for (int r : known) serial.push_back(r << 1);
   }
   std::sort(serial.begin(), serial.end());
   CK(cudaEventRecord(h->ev[4], st));
-  std::vector<int> wide; // the records that took their turn first
-  int dk_wide = 0;
-  for (size_t g = 0; g < serial.size(); g += WIDE_NB) {
-    const int nb = (int)std::min<size_t>(WIDE_NB, serial.size() - g);
-    int recs[WIDE_NB], tot[WIDE_NB];
-    for (int q = 0; q < nb; q++) recs[q] = serial[g + q] >> 1;
+  // their possible links, listed from the buckets they were found in (instead of one more scan of all items)
+  std::vector<int> kb_base, kb_len;
+  bool from_buckets = false;
+  if (!known.empty() && h->opt_wide_buckets) {
     const auto t_a = std::chrono::steady_clock::now();
-    int rc = wide_count(h, recs, nb, tot); if (rc) return rc;
+    int rc = wide_bucket_lists(h, known, kb_base, kb_len, &from_buckets); if (rc) return rc;
     if (h->trace) {
       long long sum = 0;
-      for (int q = 0; q < nb; q++) sum += tot[q];
-      std::fprintf(stderr, "[exb200] serial batch of %d: count pass %.2f ms, %lld possible links\n", nb,
-                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum);
+      for (int v : kb_len) sum += v;
+      std::fprintf(stderr, "[exb200] %d wide records listed from their buckets: %.2f ms, %lld possible links%s\n", (int)known.size(),
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum, from_buckets ? "" : " (did not fit: batched scan)");
     }
-    int b = 0;
-    while (b < nb) { // groups whose lists fit the scratch together
+  }
+  std::vector<int> wide; // the records that took their turn first
+  int dk_wide = 0;
+  // The serial list is taken in ascending id, in stretches that hold at most WIDE_NB records whose
+  // possible links have to be listed by the batched scan over all items; the turns of a stretch are
+  // then taken in order, whichever way a record's list was made (lists are static, sizes are not).
+  size_t g = 0;
+  while (g < serial.size()) {
+    int recs[WIDE_NB], tot[WIDE_NB], nb = 0;
+    size_t g_end = g, entry_of_slot[WIDE_NB];
+    std::vector<int> slot; // per entry of the stretch: its scan slot, or -1 - (position in `known`)
+    for (; g_end < serial.size(); g_end++) {
+      const int r = serial[g_end] >> 1;
+      const bool scan = (serial[g_end] & 1) || !from_buckets;
+      if (scan && nb == WIDE_NB) break;
+      if (scan) { recs[nb] = r; entry_of_slot[nb] = g_end; slot.push_back(nb++); }
+      else slot.push_back(-1 - (int)(std::lower_bound(known.begin(), known.end(), r) - known.begin()));
+    }
+    if (nb > 0) {
+      const auto t_a = std::chrono::steady_clock::now();
+      int rc = wide_count(h, recs, nb, tot); if (rc) return rc;
+      if (h->trace) {
+        long long sum = 0;
+        for (int q = 0; q < nb; q++) sum += tot[q];
+        std::fprintf(stderr, "[exb200] serial batch of %d: count pass %.2f ms, %lld possible links\n", nb,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum);
+      }
+    }
+    size_t e = 0; // entries of the stretch handled so far
+    int b = 0;    // scan slots whose lists have been filled
+    while (e < slot.size()) {
+      // the next group of scan slots whose lists fit the scratch together
       unsigned long long bases[WIDE_NB], used = 0;
       int sel[WIDE_NB], n_sel = 0;
       for (int q = 0; q < nb; q++) bases[q] = ~0ull;
@@ -868,27 +958,39 @@ int update_links(exb200_handle* h) {
       for (; b < nb; b++) {
         if (used + (unsigned long long)tot[b] > S.wl_cap) break;
         bases[b] = used; used += (unsigned long long)tot[b];
-        if ((serial[g + b] & 1) && tot[b] <= h->long_cap) sel[n_sel++] = b; // keeps its list
+        if (tot[b] <= h->long_cap && (serial[entry_of_slot[b]] & 1)) sel[n_sel++] = b; // keeps its list
       }
-      if (b == b0) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
-      CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
-      KLAUNCH(h, k_wide_fill_log, WIDE_BLOCKS, TPB, 0, S, nb);
-      KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb); // pieces whose log overflowed
-      if (n_sel > 0) {
-        CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
-        KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
-      }
-      for (int q = b0; q < b; q++) {
-        if ((serial[g + q] & 1) && tot[q] <= h->long_cap) continue;
-        if (serial[g + q] & 1) { // no bucket and more than wide_threshold possible links
-          static const int code_wide = -1;
-          CK(cudaMemcpyAsync(S.cand_cnt + recs[q], &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
+      if (b == b0 && b < nb) return fail(h, EXB200_ERR_CUDA, "serial path: list larger than its scratch (internal error)");
+      if (b > b0) {
+        CK(cudaMemcpyAsync(S.wl_base, bases, sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, st));
+        KLAUNCH(h, k_wide_fill_log, WIDE_BLOCKS, TPB, 0, S, nb);
+        KLAUNCH(h, k_wide_scan<true>, WIDE_BLOCKS, TPB, 0, S, S.batch_list, nb); // pieces whose log overflowed
+        if (n_sel > 0) {
+          CK(cudaMemcpyAsync(S.wl_sel, sel, sizeof(int) * n_sel, cudaMemcpyHostToDevice, st));
+          KLAUNCH(h, k_wide_store, n_sel, TPB, 0, S, S.batch_list, S.wl_sel, h->long_cap);
         }
-        wide_turn(h, recs[q], bases[q], tot[q]);
-        wide.push_back(recs[q]);
+      }
+      // turns, in order, up to the first entry whose list is not filled yet
+      for (; e < slot.size(); e++) {
+        const int sl = slot[e], entry = serial[g + e], r = entry >> 1;
+        if (sl >= b) break;
+        if (sl < 0) { // listed from its bucket
+          const int k = -1 - sl;
+          wide_turn(h, r, (unsigned long long)kb_base[k], kb_len[k], 1);
+          wide.push_back(r);
+          continue;
+        }
+        if ((entry & 1) && tot[sl] <= h->long_cap) continue; // keeps its list and waits for the rounds
+        if (entry & 1) { // no bucket and more than wide_threshold possible links
+          static const int code_wide = -1;
+          CK(cudaMemcpyAsync(S.cand_cnt + r, &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        wide_turn(h, r, bases[sl], tot[sl]);
+        wide.push_back(r);
       }
       CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
     }
+    g = g_end;
   }
   if (!serial.empty()) {
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved
@@ -1521,6 +1623,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "index_partitioned") h->index_partitioned = value != 0;
   else if (n == "rounds_tail") h->opt_tail = value != 0;
   else if (n == "fast_path") h->opt_fast = value != 0;
+  else if (n == "wide_buckets") h->opt_wide_buckets = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }

@@ -1,6 +1,7 @@
 // sm_100a kernels of the Gibbs sweep.  Each kernel names the reference function it replaces.
 #pragma once
 #include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -2095,10 +2096,11 @@ __global__ void __launch_bounds__(TPB) k_wide_store(DevState S, const int* __res
 
 // Turn of record r, listed at wl_base = `base` with `len` entries: every warp of the grid reduces a
 // contiguous piece (lanes strided: coalesced) to (max, sum of exp(lw - max)) in wide_part[2p], [2p+1].
+// (src = 1: the list is in wlb_id / wlb_ll - possible links listed from the record's own bucket)
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len) {
-  const int* ids = S.wl_id + base;
-  const double* ll = S.wl_ll + base;
+__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len, int src) {
+  const int* ids = (src ? S.wlb_id : S.wl_id) + base;
+  const double* ll = (src ? S.wlb_ll : S.wl_ll) + base;
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
   const int lane = threadIdx.x & 31, p = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
@@ -2138,13 +2140,13 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned
 // scale the piece sums to the global max in parallel, walk block sums and piece sums in order,
 // then one warp scans the chosen piece in order
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks) {
+__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks, int src) {
   __shared__ double s_bsum[WIDE_BLOCKS];
   __shared__ double s_red[TPB];
   __shared__ double s_m1, s_tt, s_c;
   __shared__ int s_piece, s_target, s_tail;
-  const int* ids = S.wl_id + base;
-  const double* ll = S.wl_ll + base;
+  const int* ids = (src ? S.wlb_id : S.wl_id) + base;
+  const double* ll = (src ? S.wlb_ll : S.wl_ll) + base;
   const int n_pieces = n_blocks * (TPB / 32);
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
@@ -2249,6 +2251,88 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned
     if (target < 0) { dev_fail(S, EXB200_ERR_WEIGHTS, r); target = own; }
     finalize_record(S, r, own, target, single);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Possible links of the wide records that HAVE a bucket (their candidate scan found more than
+// wide_threshold possible links): instead of scanning all 2N items for them once more
+// (k_wide_scan), their own bucket / cells are enumerated again and every possible link is emitted as
+// (key = batch position << 32 | item, log-likelihood), in any order; one radix sort by key then
+// leaves every record's list contiguous and in ascending item order (k_wide_split cuts it up).
+// WE_BLOCKS blocks per record share its tiles of bucket items (or its probes).
+// ------------------------------------------------------------------------------------------
+constexpr int WE_BLOCKS = 8;
+constexpr int WE_TILE = 2048;
+__global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __restrict__ recs, int n, unsigned long long* __restrict__ keys,
+                                                   double* __restrict__ vals, unsigned long long* __restrict__ cursor,
+                                                   unsigned long long cap) {
+  const int i = blockIdx.x / WE_BLOCKS, jb = blockIdx.x % WE_BLOCKS;
+  if (i >= n) return;
+  const int r = recs[i];
+  const int* x = S.rec_x + (size_t)r * S.RS;
+  const uint32_t zm = S.rec_z[r];
+  int tab = S.tab_remap[S.rec_tab[r]];
+  if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+  const DevTable& t = S.tables[tab];
+  const Probe pr = make_probe(S, t.mask, x, zm);
+  // one possible link (and its twin) of record i; the threads that get here together share one atomic
+  auto emit = [&](int item, double ll, bool twin) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    const int mine = twin ? 2 : 1;
+    const int before = cg::exclusive_scan(g, mine);
+    unsigned long long base = 0;
+    if (g.thread_rank() == g.size() - 1) base = atomicAdd(cursor, (unsigned long long)(before + mine));
+    base = g.shfl(base, g.size() - 1) + (unsigned long long)before;
+    if (base + (unsigned long long)mine <= cap) {
+      keys[base] = ((unsigned long long)(uint32_t)i << 32) | (unsigned long long)(uint32_t)item; vals[base] = ll;
+      if (twin) { keys[base + 1] = ((unsigned long long)(uint32_t)i << 32) | (unsigned long long)(uint32_t)(S.N + item); vals[base + 1] = ll; }
+    }
+  };
+  auto visit = [&](int item, int v, int w2, const int* y) {
+    if (item == S.N + r) return;
+    if (!y) y = S.ent_y + (size_t)item * S.ES;
+    if (pr.n_un > 0 && !pr.own_probe(y, v, w2)) return;
+    if (!item_compatible(S, x, zm, y)) return;
+    const double ll = item_loglik(S, x, zm, y);
+    if (!(ll > -CUDART_INF)) return;
+    emit(item, ll, item < S.N && item != r && S.twin[item]);
+  };
+  if (pr.n_un == 0) {
+    const uint32_t b = S.rec_bkt[r];
+    const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+    for (int q0 = lo + jb * WE_TILE; q0 < hi; q0 += WE_BLOCKS * WE_TILE)
+      for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], 0, 0, nullptr);
+  } else if (pr.n_un <= 2) {
+    for (int j = jb * TPB + threadIdx.x; j < pr.count; j += WE_BLOCKS * TPB) {
+      int v, w2;
+      pr.values(j, v, w2);
+      if (t.chain) {
+        for (int item = t.head[chain_cell_probe(S, t, x, pr.a1, v, pr.n_un == 2 ? pr.a2 : -1, w2)]; item >= 0;) {
+          const ChainNode nd = load_node(&t.node[item]);
+          int yv[8];
+          for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
+          visit(item, v, w2, yv);
+          item = nd.next;
+        }
+      } else {
+        const uint32_t b = pr.bucket(S, t, x, v, w2);
+        const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+        for (int q = lo; q < hi; q++) visit(t.ids[q], v, w2, nullptr);
+      }
+    }
+  }
+}
+// keys sorted by (batch position, item): lists into wlb_id / wlb_ll, start and length of every record's list
+__global__ void __launch_bounds__(TPB) k_wide_split(DevState S, const unsigned long long* __restrict__ keys, const double* __restrict__ vals,
+                                                    long long n, int* __restrict__ seg_base, int* __restrict__ seg_len) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const int pos = (int)(k >> 32);
+  S.wlb_id[i] = (int)(uint32_t)k;
+  S.wlb_ll[i] = vals[i];
+  if (i == 0 || (int)(keys[i - 1] >> 32) != pos) seg_base[pos] = (int)i;
+  if (i == n - 1 || (int)(keys[i + 1] >> 32) != pos) seg_len[pos] = (int)i + 1; // end for now: the host subtracts the start
 }
 
 // Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares

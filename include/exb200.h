@@ -272,6 +272,8 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
                  (needs attribute domains that pack into 64 bits); 0: bucket-scanning kernels only
      "hop_cap"   (default 1024) chain items a thread walks for one record before the record is left
                  to the bucket-scanning kernels (whose CSR form of that table is then built too)
+     "wide_buckets" (default 1) the possible links of a wide record are listed from the bucket its
+                 candidate scan found too long, and sorted; 0: by one more scan over all items
      "rounds_tail" (default 1) the dependency rounds after the first run in one persistent
                  cooperative kernel; 0 launches every round from the host
      "check"     recompute sizes / member lists / K from the links after every sweep and compare

@@ -55,13 +55,15 @@ def test_rldata500_lockstep_every_prior(prior):
     assert max(s["n_rounds"] for s in stats) >= 2  # the dependency rounds were exercised
 
 
+@pytest.mark.parametrize("wide_buckets", [1, 0])
 @pytest.mark.parametrize("threshold", [0, 2, 5])
-def test_wide_records_take_their_turn_first(threshold):
+def test_wide_records_take_their_turn_first(threshold, wide_buckets):
     """Scan order of the specification: records with more than `wide_threshold` possible links go
     first (serial path against every item), the rest follows in ascending id.  Small thresholds
-    push many records of RLdata500 through that path."""
+    push many records of RLdata500 through that path - their lists made from the bucket the candidate
+    scan found too long and sorted (wide_buckets=1), or by one more scan over all items."""
     m, _ = readme_model("rldata500", n=250)
-    stats = lockstep(m, 8, wide_threshold=threshold)
+    stats = lockstep(m, 8, wide_threshold=threshold, wide_buckets=wide_buckets)
     assert sum(s["n_wide"] for s in stats) > (50 if threshold == 0 else 0)
 
 
@@ -157,7 +159,7 @@ def test_results_do_not_depend_on_batching_thresholds():
     for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1), dict(bucket_cap=0, huge_min=0),
                  dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
                  dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0),
-                 dict(fast_path=0), dict(hop_cap=1), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0)):
+                 dict(fast_path=0), dict(hop_cap=1), dict(wide_buckets=0), dict(wide_buckets=0, fast_path=0, rounds_tail=0), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
