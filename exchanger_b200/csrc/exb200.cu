@@ -565,9 +565,20 @@ int build_csr_tables(exb200_handle* h, const std::vector<int>& tabs) {
     CK(cudaMemcpyAsync(h->d_part_tabs, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(P.part_cnt, 0, sizeof(int) * (size_t)P.n_tab * MAX_PARTS, st));
   }
+  // the tiny tables in groups that share one pass over the items (their counters fit shared memory together)
+  std::vector<SmallTabs> tiny_groups;
+  for (int t : tiny) {
+    const int B = (int)h->tables[t].d.B;
+    if (tiny_groups.empty() || tiny_groups.back().n == SMALL_TABS_MAX || tiny_groups.back().off[tiny_groups.back().n] + B > SMALL_SMEM_INTS) {
+      SmallTabs g{}; g.n = 0; g.off[0] = 0;
+      tiny_groups.push_back(g);
+    }
+    SmallTabs& g = tiny_groups.back();
+    g.tab[g.n] = t; g.off[g.n + 1] = g.off[g.n] + B; g.n++;
+  }
   CK(cudaMemcpyAsync(h->d_active, atomic_tabs.data(), sizeof(int) * atomic_tabs.size(), cudaMemcpyHostToDevice, st));
   if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-  for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 0);
+  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * g.off[g.n], S, g, 0);
   if (!large.empty()) {
     KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
     KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
@@ -577,7 +588,7 @@ int build_csr_tables(exb200_handle* h, const std::vector<int>& tabs) {
     if (rc) return rc;
   }
   if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-  for (int t : tiny) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * h->tables[t].d.B, S, t, 1);
+  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * g.off[g.n], S, g, 1);
   if (!large.empty()) {
     KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
     k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
@@ -740,7 +751,10 @@ int update_links(exb200_handle* h) {
       }
       // expected bucket visits through the substitute versus the cost of a table of its own
       const bool too_slow = !best || (double)usage[N_TABLES + t] * best_visits > (chainable(t) ? 0.2 : 1.0) * h->table_pair_cost * items;
-      if (too_slow && usage[N_TABLES + t] <= h->table_min_usage && !built[t]) {
+      // (a table with few buckets is cheap - two passes with shared-memory histograms - and always
+      // cheaper than listing its records' possible links by a scan over all items)
+      const bool tiny = h->index_partitioned && h->tables[t].d.B <= (uint32_t)SMALL_B_MAX && h->table_min_usage > 0;
+      if (too_slow && usage[N_TABLES + t] <= h->table_min_usage && !built[t] && !tiny) {
         // a handful of records: no table for them (remap 0 if nothing serves them: their possible
         // links are then listed by the batched scan over all the items)
         remap[N_TABLES + t] = (uint16_t)(best && best_visits <= 65536.0 ? best : 0);

@@ -64,7 +64,7 @@ __device__ __forceinline__ ProbeValues probe_values(const DevState& S, int ea, c
 // The probes of one record in one table: up to two unpinned key attributes, every combination of
 // their possible values (n_un = 3: more than two, or too many combinations - the table cannot
 // serve the record and its possible links are listed by the batched scan over all the items).
-constexpr int MAX_PROBES = 16384;
+constexpr int MAX_PROBES = 131072;
 constexpr int FAST_PROBES = 128; // probes one thread of the fast candidate kernel makes for a record
 struct Probe {
   int n_un, a1, a2, count;
@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(TPB, 4) k_prep(DevState S) {
 // of one hash set per (attribute, value) kept up to date by every change, CSR buckets over
 // attribute pairs are rebuilt once per sweep and stay fixed during the links update.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool item_indexed(const DevState& S, int i) {
+  return i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N];
+}
 __global__ void __launch_bounds__(TPB) k_index_count(DevState S, const int* __restrict__ active, int n_active) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * S.N) return;
@@ -356,26 +359,41 @@ __global__ void __launch_bounds__(TPB) k_index_fill(DevState S, const int* __res
 // block histogram to ptr[]; after the exclusive scan, phase 1 reserves one slice per (block, bucket)
 // with a single atomicAdd on ptr[b] (which thereby ends as the bucket's END offset) and places the ids.
 constexpr int SMALL_B_MAX = 8192;
-__global__ void __launch_bounds__(TPB) k_index_small(DevState S, int tab, int phase) {
-  extern __shared__ int s_dyn[]; // [B]
-  const DevTable& t = S.tables[tab];
-  const int B = (int)t.B;
+constexpr int SMALL_TABS_MAX = 16;      // tables per launch ...
+constexpr int SMALL_SMEM_INTS = 49152;  // ... and their buckets together (192 KB of shared memory)
+struct SmallTabs { int n; int tab[SMALL_TABS_MAX]; int off[SMALL_TABS_MAX + 1]; }; // off: start of each table's counters
+// All the given tables in one pass over the item tuples (every item is read once per phase, whatever
+// the number of tables).
+__global__ void __launch_bounds__(TPB) k_index_small(DevState S, SmallTabs T, int phase) {
+  extern __shared__ int s_dyn[]; // [off[n]]
+  const int total = T.off[T.n];
   const int n = 2 * S.N;
   const int per = (n + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(n, i0 + per);
-  for (int b = threadIdx.x; b < B; b += TPB) s_dyn[b] = 0;
+  for (int b = threadIdx.x; b < total; b += TPB) s_dyn[b] = 0;
   __syncthreads();
   for (int i = i0 + threadIdx.x; i < i1; i += TPB)
-    if (i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N])
-      atomicAdd(&s_dyn[bucket_of(S, t, S.ent_y + (size_t)i * S.ES)], 1);
+    if (item_indexed(S, i)) {
+      const int* y = S.ent_y + (size_t)i * S.ES;
+      for (int k = 0; k < T.n; k++) atomicAdd(&s_dyn[T.off[k] + bucket_of(S, S.tables[T.tab[k]], y)], 1);
+    }
   __syncthreads();
-  for (int b = threadIdx.x; b < B; b += TPB)
-    if (s_dyn[b]) s_dyn[b] = atomicAdd(&t.ptr[b], s_dyn[b]); // phase 0: value unused; phase 1: slice base
+  for (int q = threadIdx.x; q < total; q += TPB)
+    if (s_dyn[q]) {
+      int k = 0;
+      while (q >= T.off[k + 1]) k++;
+      s_dyn[q] = atomicAdd(&S.tables[T.tab[k]].ptr[q - T.off[k]], s_dyn[q]); // phase 0: value unused; phase 1: slice base
+    }
   if (phase == 0) return;
   __syncthreads();
   for (int i = i0 + threadIdx.x; i < i1; i += TPB)
-    if (i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N])
-      t.ids[atomicAdd(&s_dyn[bucket_of(S, t, S.ent_y + (size_t)i * S.ES)], 1)] = i;
+    if (item_indexed(S, i)) {
+      const int* y = S.ent_y + (size_t)i * S.ES;
+      for (int k = 0; k < T.n; k++) {
+        const DevTable& t = S.tables[T.tab[k]];
+        t.ids[atomicAdd(&s_dyn[T.off[k] + bucket_of(S, t, y)], 1)] = i;
+      }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -404,9 +422,6 @@ struct PartBuild {
   long long cap;             // pairs per table
 };
 
-__device__ __forceinline__ bool item_indexed(const DevState& S, int i) {
-  return i < S.N ? S.ent_size[i] > 0 : !S.twin[i - S.N];
-}
 
 // phase 0: partition histogram; phase 1: scatter of the pairs.  Every item tuple is read once per
 // phase for all tables; shared memory holds one histogram (and one slice base) per table.
@@ -1370,6 +1385,19 @@ __device__ __forceinline__ int decide_with_bounds(const DevState& S, int r, bool
   return new_lo ? 1 : 0;
 }
 
+// A record without any live candidate founds an entity whatever the uniform says (u1 wa < wa with
+// wb = 0), provided its new-entity weight is valid at both ends of the K interval: seven records in
+// eight, for which the logarithms, exponentials and the Philox call of the general decision are
+// skipped.  Returns true if that shortcut applies (the general path handles everything else,
+// including the errors).
+__device__ __forceinline__ bool founds_for_sure(const DevState& S, int r, bool single) {
+  const int klo = max(0, S.K0 + (S.use_kbounds ? S.plo[r] : 0) - (single ? 1 : 0));
+  const int khi = min(S.N - 1, S.K0 + (S.use_kbounds ? S.phi_[r] : 0) - (single ? 1 : 0));
+  const bool kink = S.cl.kind != EXB200_CLUST_PITMAN_YOR && (double)klo < S.cl.m && S.cl.m < (double)khi;
+  const double Ln = S.Lnew[r], p_lo = prior_new(S.cl, klo), p_hi = prior_new(S.cl, khi);
+  return !kink && Ln > -CUDART_INF && Ln < CUDART_INF && p_lo > 0.0 && p_lo < CUDART_INF && p_hi > 0.0 && p_hi < CUDART_INF;
+}
+
 __device__ __forceinline__ void finalize_record(const DevState& S, int r, int own, int target, bool single) {
   const bool is_new = target == S.N + r;
   const int dk = (is_new ? 1 : 0) - (single ? 1 : 0);
@@ -1435,6 +1463,10 @@ __device__ __forceinline__ bool commit_short(const DevState& S, int r, int cnt, 
       const double v = lw_of(j);
       if (v != -CUDART_INF) srel += exp(v - m1); // (a candidate that is not live, or of zero weight, adds nothing)
     }
+  if (!(m1 > -CUDART_INF) && founds_for_sure(S, r, single)) {
+    finalize_record(S, r, own, S.N + r, single);
+    return false;
+  }
   const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
   const int dec = decide_with_bounds(S, r, single, m1, srel, u.a);
   if (dec == 2) {
