@@ -100,6 +100,7 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
+  WideTurn* d_turns = nullptr; size_t turns_cap = 0; int turns_grid = 0;
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
   int hop_cap = 1024;
@@ -623,6 +624,31 @@ void wide_turn(exb200_handle* h, int r, unsigned long long base, int len, int sr
   KLAUNCH_DP(h, k_wide_commit, 1, TPB, 0, h->S, r, base, len, n_blocks, src);
 }
 
+// ... and the turns of several listed records, in the order given, in one persistent kernel
+int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
+  if (turns.empty()) return EXB200_OK;
+  DevState& S = h->S;
+  cudaStream_t st = h->stream;
+  if (turns.size() > h->turns_cap) {
+    h->turns_cap = std::max<size_t>(1024, 2 * turns.size());
+    int rc = dalloc(h, &h->d_turns, h->turns_cap); if (rc) return rc;
+  }
+  if (!h->turns_grid) {
+    int per_sm = 0;
+    CK(S.has_dp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_turns<true>, TPB, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wide_turns<false>, TPB, 0));
+    h->turns_grid = std::max(1, std::min(WIDE_BLOCKS, per_sm * h->n_sm));
+  }
+  CK(cudaMemcpyAsync(h->d_turns, turns.data(), sizeof(WideTurn) * turns.size(), cudaMemcpyHostToDevice, st));
+  int n = (int)turns.size();
+  void* args[] = {(void*)&S, (void*)&h->d_turns, (void*)&n};
+  CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_wide_turns<true> : (const void*)k_wide_turns<false>,
+                                 dim3((unsigned)h->turns_grid), dim3(TPB), args, 0, st));
+  h->n_launches++;
+  CK(cudaStreamSynchronize(st)); // `turns` and `n` live on the caller's stack
+  return EXB200_OK;
+}
+
 // Possible links of the wide records that have a bucket, listed from the bucket itself (k_wide_emit),
 // sorted by (record, item) and cut into one list per record.  `recs` ascending; on return
 // base[i] / len[i] locate record i's list in wlb_id / wlb_ll.  Returns EXB200_OK with *ok = false
@@ -985,12 +1011,13 @@ int update_links(exb200_handle* h) {
         }
       }
       // turns, in order, up to the first entry whose list is not filled yet
+      std::vector<WideTurn> turns;
       for (; e < slot.size(); e++) {
         const int sl = slot[e], entry = serial[g + e], r = entry >> 1;
         if (sl >= b) break;
         if (sl < 0) { // listed from its bucket
           const int k = -1 - sl;
-          wide_turn(h, r, (unsigned long long)kb_base[k], kb_len[k], 1);
+          turns.push_back(WideTurn{r, kb_len[k], 1, 0, (unsigned long long)kb_base[k]});
           wide.push_back(r);
           continue;
         }
@@ -999,9 +1026,10 @@ int update_links(exb200_handle* h) {
           static const int code_wide = -1;
           CK(cudaMemcpyAsync(S.cand_cnt + r, &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
         }
-        wide_turn(h, r, bases[sl], tot[sl]);
+        turns.push_back(WideTurn{r, tot[sl], 0, 0, bases[sl]});
         wide.push_back(r);
       }
+      { int rc = wide_turns(h, turns); if (rc) return rc; }
       CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
     }
     g = g_end;

@@ -66,35 +66,49 @@ __device__ __forceinline__ ProbeValues probe_values(const DevState& S, int ea, c
 // serve the record and its possible links are listed by the batched scan over all the items).
 constexpr int MAX_PROBES = 131072;
 constexpr int FAST_PROBES = 128; // probes one thread of the fast candidate kernel makes for a record
+constexpr int PROBE_NOT_SERVED = 4; // Probe::n_un: more than three unpinned key attributes, or too many combinations
+struct Pv { int v1, v2, v3; };      // the probed values of the (up to three) unpinned key attributes
 struct Probe {
-  int n_un, a1, a2, count;
-  ProbeValues p1, p2;
-  __device__ __forceinline__ void values(int j, int& v1, int& v2) const {
-    v1 = p1.value(j % p1.n);
-    v2 = n_un == 2 ? p2.value(j / p1.n) : 0;
+  int n_un, a1, a2, a3, count;
+  ProbeValues p1, p2, p3;
+  __device__ __forceinline__ Pv values(int j) const {
+    Pv v;
+    v.v1 = p1.value(j % p1.n);
+    v.v2 = n_un >= 2 ? p2.value((j / p1.n) % p2.n) : 0;
+    v.v3 = n_un >= 3 ? p3.value(j / (p1.n * p2.n)) : 0;
+    return v;
   }
-  __device__ __forceinline__ uint32_t bucket(const DevState& S, const DevTable& t, const int* x, int v1, int v2) const {
-    return bucket_of(S, t, x, a1, v1, n_un == 2 ? a2 : -1, v2);
+  __device__ __forceinline__ int value_of(int a, const int* x, const Pv& v) const { // x with the probed values put in
+    return a == a1 ? v.v1 : (n_un >= 2 && a == a2 ? v.v2 : (n_un >= 3 && a == a3 ? v.v3 : x[a]));
   }
-  __device__ __forceinline__ bool own_probe(const int* y, int v1, int v2) const { // hashed buckets: an item counts in the probe of its own values only
-    return y[a1] == v1 && (n_un < 2 || y[a2] == v2);
+  __device__ __forceinline__ uint32_t bucket(const DevState& S, const DevTable& t, const int* x, const Pv& v) const {
+    uint64_t key = 0;
+    for (uint32_t m = t.mask; m; m &= m - 1) {
+      const int a = S.key_attr[__ffs(m) - 1];
+      key = key * (uint64_t)S.attrs[a].D + (uint64_t)value_of(a, x, v);
+    }
+    return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
+  }
+  __device__ __forceinline__ bool own_probe(const int* y, const Pv& v) const { // hashed buckets: an item counts in the probe of its own values only
+    return y[a1] == v.v1 && (n_un < 2 || y[a2] == v.v2) && (n_un < 3 || y[a3] == v.v3);
   }
 };
 __device__ __forceinline__ Probe make_probe(const DevState& S, uint32_t mask, const int* x, uint32_t zm) {
   Probe p;
-  p.n_un = 0; p.a1 = p.a2 = -1; p.count = 1;
-  p.p1.col = p.p2.col = nullptr; p.p1.n = p.p2.n = 1;
+  p.n_un = 0; p.a1 = p.a2 = p.a3 = -1; p.count = 1;
+  p.p1.col = p.p2.col = p.p3.col = nullptr; p.p1.n = p.p2.n = p.p3.n = 1;
   for (uint32_t m = mask; m; m &= m - 1) {
     const int a = S.key_attr[__ffs(m) - 1];
     if (x[a] >= 0 && !((zm >> a) & 1u)) continue;
     if (p.n_un == 0) { p.a1 = a; p.p1 = probe_values(S, a, x, zm); }
     else if (p.n_un == 1) { p.a2 = a; p.p2 = probe_values(S, a, x, zm); }
+    else if (p.n_un == 2) { p.a3 = a; p.p3 = probe_values(S, a, x, zm); }
     p.n_un++;
   }
-  if (p.n_un > 2) p.n_un = 3;
+  if (p.n_un > 3) p.n_un = PROBE_NOT_SERVED;
   else if (p.n_un >= 1) {
-    const long long c = (long long)p.p1.n * (long long)(p.n_un == 2 ? p.p2.n : 1);
-    if (c > MAX_PROBES) p.n_un = 3; else p.count = (int)c;
+    const long long c = (long long)p.p1.n * (long long)p.p2.n * (long long)p.p3.n;
+    if (c > MAX_PROBES) p.n_un = PROBE_NOT_SERVED; else p.count = (int)c;
   }
   return p;
 }
@@ -123,13 +137,12 @@ __device__ __forceinline__ void record_fields(const DevState& S, const int* x, u
 __device__ __forceinline__ uint32_t chain_cell(const DevTable& t, unsigned long long K) {
   return (uint32_t)(mix64(K & t.kmask) & (unsigned long long)(t.cells - 1u));
 }
-// ... for a record x whose unpinned key attributes ea / eb take the probed values ev / fv
-__device__ __forceinline__ uint32_t chain_cell_probe(const DevState& S, const DevTable& t, const int* x, int ea, int ev,
-                                                     int eb, int fv) {
+// ... for a record x whose unpinned key attributes take the probed values v
+__device__ __forceinline__ uint32_t chain_cell_probe(const DevState& S, const DevTable& t, const int* x, const Probe& pr, const Pv& v) {
   unsigned long long K = 0;
   for (uint32_t m = t.mask; m; m &= m - 1) {
     const int a = S.key_attr[__ffs(m) - 1];
-    K |= (unsigned long long)(uint32_t)(a == ea ? ev : (a == eb ? fv : x[a])) << S.pk_shift[a];
+    K |= (unsigned long long)(uint32_t)pr.value_of(a, x, v) << S.pk_shift[a];
   }
   return chain_cell(t, K);
 }
@@ -725,7 +738,7 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
     if (!wide) {
       const DevTable& t = S.tables[tab];
       pr = make_probe(S, t.mask, x, zm); // n_un >= 1: the buckets of the unpinned attributes' possible values are probed
-      if (pr.n_un == 3) { wide = true; pr.n_un = 0; } // not served by this table after all: batched scan over all items
+      if (pr.n_un == PROBE_NOT_SERVED) { wide = true; pr.n_un = 0; } // not served by this table after all: batched scan over all items
       else if (pr.n_un == 0) {
         const uint32_t b = bucket_of(S, t, x);
         if (gl == 0) S.rec_bkt[r] = b;
@@ -789,13 +802,14 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
       // table in chain form, the chains of their cells (the node holds the item's packed tuple)
       const DevTable& t = S.tables[tab];
       const bool chain = t.chain != 0;
-      int j_next = gl, v_cur = 0, w_cur = 0, q = 0, q_end = 0, visited = 0, c_item = -1;
+      int j_next = gl, q = 0, q_end = 0, visited = 0, c_item = -1;
+      Pv v_cur = {0, 0, 0};
       for (;;) {
         while ((chain ? c_item < 0 : q >= q_end) && j_next < pr.count) {
-          pr.values(j_next, v_cur, w_cur);
-          if (chain) c_item = t.head[chain_cell_probe(S, t, x, pr.a1, v_cur, pr.n_un == 2 ? pr.a2 : -1, w_cur)];
+          v_cur = pr.values(j_next);
+          if (chain) c_item = t.head[chain_cell_probe(S, t, x, pr, v_cur)];
           else {
-            const uint32_t b = pr.bucket(S, t, x, v_cur, w_cur);
+            const uint32_t b = pr.bucket(S, t, x, v_cur);
             q = b ? t.ptr[b - 1] : 0;
             q_end = t.ptr[b];
           }
@@ -821,7 +835,7 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
           visited++;
           if (item != S.N + r) {
             // hashed buckets: an item counts in the probe of its own value only
-            ok = pr.own_probe(y, v_cur, w_cur) && item_compatible(S, x, zm, y);
+            ok = pr.own_probe(y, v_cur) && item_compatible(S, x, zm, y);
             if (ok) {
               ll = item_loglik(S, x, zm, y);
               ok = ll > -CUDART_INF;
@@ -968,13 +982,13 @@ __global__ void __launch_bounds__(FAST_TPB) k_cand_fast(DevState S, const int* _
       unsigned long long M, V;
       record_fields(S, x, zm, M, V);
       Probe pr;
-      pr.n_un = 0; pr.count = 1; pr.a1 = pr.a2 = -1;
+      pr.n_un = 0; pr.count = 1; pr.a1 = pr.a2 = pr.a3 = -1;
       if (!t.chain) slow = true;
       else if ((M & t.kmask) != t.kmask) {
         // an unpinned key attribute: the cells of its possible values are probed - by this thread if
         // they are few (a distorted name: its neighbourhood row), else by a warp or a block
         pr = make_probe(S, t.mask, x, zm);
-        if (pr.n_un == 3) slow = true;                 // not served by this table after all (k_cand marks it)
+        if (pr.n_un == PROBE_NOT_SERVED) slow = true;  // not served by this table after all (k_cand marks it)
         else if (pr.count > 512) { S.long_todo[atomicAdd(&S.counters[C_NLONG_TODO], 1)] = r; pr.n_un = -1; } // a block, one thread per probe
         else if (pr.count > FAST_PROBES) { S.probe_list[atomicAdd(&S.counters[C_NPROBE], 1)] = r; pr.n_un = -1; }
         else if (multi_list) { multi_list[atomicAdd(&S.counters[C_NMULTI], 1)] = r; pr.n_un = -1; } // second pass
@@ -997,10 +1011,10 @@ __global__ void __launch_bounds__(FAST_TPB) k_cand_fast(DevState S, const int* _
           // values of the unpinned key attributes (an item sits in the cell of its own key only)
           unsigned long long Mp = M, Vp = V;
           if (pr.n_un > 0) {
-            int v1, v2;
-            pr.values(pj, v1, v2);
-            Mp |= pk_field(S, pr.a1); Vp |= (unsigned long long)(uint32_t)v1 << S.pk_shift[pr.a1];
-            if (pr.n_un == 2) { Mp |= pk_field(S, pr.a2); Vp |= (unsigned long long)(uint32_t)v2 << S.pk_shift[pr.a2]; }
+            const Pv v = pr.values(pj);
+            Mp |= pk_field(S, pr.a1); Vp |= (unsigned long long)(uint32_t)v.v1 << S.pk_shift[pr.a1];
+            if (pr.n_un >= 2) { Mp |= pk_field(S, pr.a2); Vp |= (unsigned long long)(uint32_t)v.v2 << S.pk_shift[pr.a2]; }
+            if (pr.n_un >= 3) { Mp |= pk_field(S, pr.a3); Vp |= (unsigned long long)(uint32_t)v.v3 << S.pk_shift[pr.a3]; }
           }
           int item = t.head[chain_cell(t, Vp)];
           while (item >= 0 && !over) {
@@ -1132,10 +1146,10 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
         continue;
       }
     }
-    auto visit = [&](int item, int v, int w2, const int* y) {
+    auto visit = [&](int item, const Pv& v, const int* y) {
       if (item == S.N + r) return;
       if (!y) y = S.ent_y + (size_t)item * S.ES;
-      if (pr.n_un > 0 && !pr.own_probe(y, v, w2)) return;
+      if (pr.n_un > 0 && !pr.own_probe(y, v)) return;
       if (!item_compatible(S, x, zm, y)) return;
       const double ll = item_loglik(S, x, zm, y);
       if (!(ll > -CUDART_INF)) return;
@@ -1147,21 +1161,20 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
     if (pr.n_un > 0) {
       // one thread per probe: the buckets are short, the probes independent
       for (int j = threadIdx.x; j < pr.count; j += blockDim.x) {
-        int v, w2;
-        pr.values(j, v, w2);
+        const Pv v = pr.values(j);
         if (t.chain) { // chain form: the node holds the item's packed tuple
-          for (int item = t.head[chain_cell_probe(S, t, x, pr.a1, v, pr.n_un == 2 ? pr.a2 : -1, w2)]; item >= 0 && s_cnt <= cap;) {
+          for (int item = t.head[chain_cell_probe(S, t, x, pr, v)]; item >= 0 && s_cnt <= cap;) {
             const ChainNode nd = load_node(&t.node[item]);
             int yv[8];
             for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
-            visit(item, v, w2, yv);
+            visit(item, v, yv);
             item = nd.next;
           }
           continue;
         }
-        const uint32_t b = pr.bucket(S, t, x, v, w2);
+        const uint32_t b = pr.bucket(S, t, x, v);
         const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
-        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, w2, nullptr);
+        for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, nullptr);
       }
     } else {
       const uint32_t b = S.rec_bkt[r];
@@ -1169,7 +1182,7 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       for (int q0 = lo; q0 < hi; q0 += blockDim.x) {
         if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
         const int q = q0 + threadIdx.x;
-        if (q < hi) visit(t.ids[q], 0, 0, nullptr);
+        if (q < hi) visit(t.ids[q], Pv{0, 0, 0}, nullptr);
       }
     }
     __syncthreads();
@@ -2129,15 +2142,17 @@ __global__ void __launch_bounds__(TPB) k_wide_store(DevState S, const int* __res
 // Turn of record r, listed at wl_base = `base` with `len` entries: every warp of the grid reduces a
 // contiguous piece (lanes strided: coalesced) to (max, sum of exp(lw - max)) in wide_part[2p], [2p+1].
 // (src = 1: the list is in wlb_id / wlb_ll - possible links listed from the record's own bucket)
+// `vblock` of `n_vblocks`: the block's place in the grid of the stand-alone kernel (the persistent
+// kernel k_wide_turns gives every block several)
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len, int src) {
+__device__ __forceinline__ void wide_reduce_block(const DevState& S, int r, unsigned long long base, int len, int src, int vblock, int n_vblocks) {
   const int* ids = (src ? S.wlb_id : S.wl_id) + base;
   const double* ll = (src ? S.wlb_ll : S.wl_ll) + base;
   const int own = S.lambda[r];
   const bool single = S.ent_size[own] == 1;
-  const int lane = threadIdx.x & 31, p = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, p = vblock * (TPB / 32) + (threadIdx.x >> 5);
   long long lo, hi;
-  wide_piece(len, gridDim.x * (TPB / 32), p, lo, hi);
+  wide_piece(len, n_vblocks * (TPB / 32), p, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
   for (long long i0 = lo; i0 < hi; i0 += 256) { // 8 entries per lane in flight (a piece has at most 256 unless the grid is capped)
     int id[8], sz[8];
@@ -2168,11 +2183,16 @@ __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned
   if (lane == 0) { S.wide_part[2 * p] = m; S.wide_part[2 * p + 1] = sum; }
 }
 
+template <bool DP>
+__global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len, int src) {
+  wide_reduce_block<DP>(S, r, base, len, src, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // decision and commit of record r (one block; n_blocks = grid of the k_wide_reduce before it):
 // scale the piece sums to the global max in parallel, walk block sums and piece sums in order,
 // then one warp scans the chosen piece in order
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks, int src) {
+__device__ void wide_commit_block(const DevState& S, int r, unsigned long long base, int len, int n_blocks, int src) {
   __shared__ double s_bsum[WIDE_BLOCKS];
   __shared__ double s_red[TPB];
   __shared__ double s_m1, s_tt, s_c;
@@ -2284,6 +2304,26 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned
     finalize_record(S, r, own, target, single);
   }
 }
+template <bool DP>
+__global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks, int src) {
+  wide_commit_block<DP>(S, r, base, len, n_blocks, src);
+}
+
+// The turns of many wide records, one after the other, in ONE persistent cooperative kernel (two
+// grid-wide barriers per record instead of two launches): same pieces, same sums as the two kernels.
+struct WideTurn { int r, len, src, pad; unsigned long long base; };
+template <bool DP>
+__global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* turns, int n) {
+  cg::grid_group grid = cg::this_grid();
+  for (int t = 0; t < n; t++) {
+    const WideTurn w = turns[t];
+    const int n_blocks = max(1, min(WIDE_BLOCKS, (w.len + 2047) / 2048));
+    for (int vb = blockIdx.x; vb < n_blocks; vb += gridDim.x) wide_reduce_block<DP>(S, w.r, w.base, w.len, w.src, vb, n_blocks);
+    grid.sync();
+    if (blockIdx.x == 0) wide_commit_block<DP>(S, w.r, w.base, w.len, n_blocks, w.src);
+    grid.sync();
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Possible links of the wide records that HAVE a bucket (their candidate scan found more than
@@ -2320,10 +2360,10 @@ __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __rest
       if (twin) { keys[base + 1] = ((unsigned long long)(uint32_t)i << 32) | (unsigned long long)(uint32_t)(S.N + item); vals[base + 1] = ll; }
     }
   };
-  auto visit = [&](int item, int v, int w2, const int* y) {
+  auto visit = [&](int item, const Pv& v, const int* y) {
     if (item == S.N + r) return;
     if (!y) y = S.ent_y + (size_t)item * S.ES;
-    if (pr.n_un > 0 && !pr.own_probe(y, v, w2)) return;
+    if (pr.n_un > 0 && !pr.own_probe(y, v)) return;
     if (!item_compatible(S, x, zm, y)) return;
     const double ll = item_loglik(S, x, zm, y);
     if (!(ll > -CUDART_INF)) return;
@@ -2333,23 +2373,22 @@ __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __rest
     const uint32_t b = S.rec_bkt[r];
     const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
     for (int q0 = lo + jb * WE_TILE; q0 < hi; q0 += WE_BLOCKS * WE_TILE)
-      for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], 0, 0, nullptr);
-  } else if (pr.n_un <= 2) {
+      for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], Pv{0, 0, 0}, nullptr);
+  } else if (pr.n_un < PROBE_NOT_SERVED) {
     for (int j = jb * TPB + threadIdx.x; j < pr.count; j += WE_BLOCKS * TPB) {
-      int v, w2;
-      pr.values(j, v, w2);
+      const Pv v = pr.values(j);
       if (t.chain) {
-        for (int item = t.head[chain_cell_probe(S, t, x, pr.a1, v, pr.n_un == 2 ? pr.a2 : -1, w2)]; item >= 0;) {
+        for (int item = t.head[chain_cell_probe(S, t, x, pr, v)]; item >= 0;) {
           const ChainNode nd = load_node(&t.node[item]);
           int yv[8];
           for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
-          visit(item, v, w2, yv);
+          visit(item, v, yv);
           item = nd.next;
         }
       } else {
-        const uint32_t b = pr.bucket(S, t, x, v, w2);
+        const uint32_t b = pr.bucket(S, t, x, v);
         const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
-        for (int q = lo; q < hi; q++) visit(t.ids[q], v, w2, nullptr);
+        for (int q = lo; q < hi; q++) visit(t.ids[q], v, nullptr);
       }
     }
   }
