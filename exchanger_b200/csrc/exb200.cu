@@ -100,6 +100,7 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
+  int opt_tiny_always = 0;     // build every wanted table with few buckets, however few records want it (measured: slower)
   WideTurn* d_turns = nullptr; size_t turns_cap = 0; int turns_grid = 0;
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
@@ -779,7 +780,7 @@ int update_links(exb200_handle* h) {
       const bool too_slow = !best || (double)usage[N_TABLES + t] * best_visits > (chainable(t) ? 0.2 : 1.0) * h->table_pair_cost * items;
       // (a table with few buckets is cheap - two passes with shared-memory histograms - and always
       // cheaper than listing its records' possible links by a scan over all items)
-      const bool tiny = h->index_partitioned && h->tables[t].d.B <= (uint32_t)SMALL_B_MAX && h->table_min_usage > 0;
+      const bool tiny = h->opt_tiny_always && h->index_partitioned && h->tables[t].d.B <= (uint32_t)SMALL_B_MAX;
       if (too_slow && usage[N_TABLES + t] <= h->table_min_usage && !built[t] && !tiny) {
         // a handful of records: no table for them (remap 0 if nothing serves them: their possible
         // links are then listed by the batched scan over all the items)
@@ -1666,6 +1667,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "rounds_tail") h->opt_tail = value != 0;
   else if (n == "fast_path") h->opt_fast = value != 0;
   else if (n == "wide_buckets") h->opt_wide_buckets = value != 0;
+  else if (n == "tiny_tables_always") h->opt_tiny_always = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);
   else if (n == "table_cost_permille") { h->table_full_cost = (double)value * 1e-3; h->table_pair_cost = 0.25 * (double)value * 1e-3; }

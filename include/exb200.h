@@ -274,6 +274,8 @@ int exb200_link_conditional(exb200_handle* h, int32_t rid, int32_t cap, int32_t*
                  to the bucket-scanning kernels (whose CSR form of that table is then built too)
      "wide_buckets" (default 1) the possible links of a wide record are listed from the bucket its
                  candidate scan found too long, and sorted; 0: by one more scan over all items
+     "tiny_tables_always" (default 0) build a wanted table with at most 8192 buckets however few
+                 records want it (otherwise "table_min_usage" decides)
      "rounds_tail" (default 1) the dependency rounds after the first run in one persistent
                  cooperative kernel; 0 launches every round from the host
      "check"     recompute sizes / member lists / K from the links after every sweep and compare
