@@ -642,9 +642,13 @@ int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
   }
   CK(cudaMemcpyAsync(h->d_turns, turns.data(), sizeof(WideTurn) * turns.size(), cudaMemcpyHostToDevice, st));
   int n = (int)turns.size();
+  // as many blocks as the longest list has pieces of 2048 entries (a grid-wide barrier costs more with more blocks)
+  int want = 1;
+  for (const WideTurn& w : turns) want = std::max(want, (w.len + 2047) / 2048);
+  const int grid = std::min(h->turns_grid, want);
   void* args[] = {(void*)&S, (void*)&h->d_turns, (void*)&n};
   CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_wide_turns<true> : (const void*)k_wide_turns<false>,
-                                 dim3((unsigned)h->turns_grid), dim3(TPB), args, 0, st));
+                                 dim3((unsigned)grid), dim3(TPB), args, 0, st));
   h->n_launches++;
   CK(cudaStreamSynchronize(st)); // `turns` and `n` live on the caller's stack
   return EXB200_OK;
