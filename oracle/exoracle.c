@@ -1198,3 +1198,8 @@ void exo_test_draws(uint64_t seed, int kind, double p1, double p2, int n, double
     }
   }
 }
+/* entity-value pmf of attribute a (moves with a Dirichlet prior, entities.cpp:133-156) */
+void exo_get_phi(exo *s, int a, double *out) { memcpy(out, s->at[a].phi, sizeof(double) * s->at[a].D); }
+/* Entities::update_distributions only */
+void exo_update_distributions(exo *s) { phase_entity_dists(s); }
+

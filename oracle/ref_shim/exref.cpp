@@ -273,3 +273,25 @@ extern "C" void exref_get_concs(void *p, double *out) {
   ExRef *h = (ExRef *)p;
   for (int a = 0; a < h->A; a++) out[a] = h->state->distort_dist_concs_.get(a);
 }
+// ---- single phases of State::update, for the tests of the draws' laws
+// Links::update only (src/links.cpp:477-489)
+extern "C" int exref_update_links(void *p) {
+  ExRef *h = (ExRef *)p; State &s = *h->state;
+  try { s.links_.update(s.ents_, s.recs_, s.distort_dist_concs_, s.clust_params_, s.cache_.attr_indices_); }
+  catch (std::exception &e) { std::cerr << "exref_update_links: " << e.what() << std::endl; return -1; }
+  return 0;
+}
+// Entities::update_distributions only (src/entities.cpp:133-156)
+extern "C" int exref_update_distributions(void *p) {
+  ExRef *h = (ExRef *)p;
+  try { h->state->ents_.update_distributions(); }
+  catch (std::exception &e) { std::cerr << "exref_update_distributions: " << e.what() << std::endl; return -1; }
+  return 0;
+}
+// entity-value pmf of attribute aid
+extern "C" void exref_get_phi(void *p, int aid, int D, double *out) {
+  ExRef *h = (ExRef *)p;
+  IndexNonUniformDiscreteDist *d = h->state->ents_.get_distribution(aid);
+  for (int v = 0; v < D; v++) out[v] = d->get_probability(v);
+}
+

@@ -83,6 +83,9 @@ class RefSampler:
         lib.exref_prior_existing.argtypes = [C.c_void_p, C.c_int]
         lib.exref_prior_new.argtypes = [C.c_void_p, C.c_int]
         lib.exref_cluster_size.argtypes = [C.c_void_p, C.c_int]
+        lib.exref_update_links.argtypes = [C.c_void_p]
+        lib.exref_update_distributions.argtypes = [C.c_void_p]
+        lib.exref_get_phi.argtypes = [C.c_void_p, C.c_int, C.c_int, c_f64p]
         lib.exref_log_weight_entity_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.exref_distortion_prob.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         lib.exref_exp_distortion_prob.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -161,6 +164,8 @@ class OracleSampler:
         lib.exo_link_conditional.argtypes = [C.c_void_p, C.c_int, C.c_int, c_i32p, c_f64p, c_f64p]
         lib.exo_log_weight_entity_value.restype = C.c_double
         lib.exo_log_weight_entity_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.exo_get_phi.argtypes = [C.c_void_p, C.c_int, c_f64p]
+        lib.exo_update_distributions.argtypes = [C.c_void_p]
         self.lib = lib
         self.model = model
         self.flat = FlatModel(model, seed)

@@ -8,9 +8,11 @@ import numpy as np
 import pytest
 
 from checkers import ORACLE_SO, REF_SO, OracleSampler, RefSampler
+from exchanger_b200 import BetaRV, GammaRV, PitmanYorRP, exchanger
+from exchanger_b200.capi import c_f64p
 from exchanger_b200.analysis import clusters_to_membership, pairwise_measures, smp_clusters
 from exchanger_b200.model import model_with_state
-from fixtures import PRIORS, load_rldata, model_with_files, readme_model
+from fixtures import PRIORS, load_rldata, model_with_files, readme_attr_params, readme_model
 
 needs_ref = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (reference sources absent)")
 
@@ -352,3 +354,152 @@ def test_closed_form_entity_value_schemes_draw_from_the_reference_law():
         if keep.sum() > 1:
             worst_p = min(worst_p, chisquare(obs[keep], exp[keep]).pvalue)
     assert worst_p > 1e-5   # thirty tests: a false alarm once in a few thousand runs (the seeds are fixed anyway)
+
+
+def _new_entity_law(model, a, x, distorted, phi=None):
+    """Law of the attribute a new entity gets from its founding record (src/links.cpp:424-468), from
+    the model's tables: NA -> phi; not distorted -> the record's value; distorted categorical ->
+    phi(v)/(1-psi(v)), v != x (target of rejectionSampleConstant, :290-314) or, with
+    exclude_entity_value = FALSE, the EMPIRICAL pmf psi (:449-452); distorted string ->
+    phi(v) p(x | v) over the values v that have x in their neighbourhood (:454-461)."""
+    idx, spec = model.attr_indices[a], model.attr_params[a]
+    psi = np.asarray(idx.probs)
+    phi = psi if phi is None else phi
+    D = len(psi)
+    if x < 0:
+        return phi / phi.sum()
+    if not distorted:
+        return np.eye(D)[x]
+    if idx.is_constant:
+        if not spec.exclude_entity_value:
+            return psi
+        w = phi / (1.0 - psi)
+        w[x] = 0.0
+        return w / w.sum()
+    w = np.zeros(D)
+    for v in range(D):
+        row = slice(idx.close_row_ptr[v], idx.close_row_ptr[v + 1])
+        hit = np.flatnonzero(idx.close_val_ids[row] == x)
+        if hit.size:
+            w[v] = phi[v] * idx.close_probs[row][hit[0]]
+    return w / w.sum()
+
+
+@needs_ref
+@pytest.mark.parametrize("exclude", [True, False])
+def test_new_entity_attribute_draws_follow_the_reference_law(exclude):
+    """The attributes of a newly founded entity (src/links.cpp:424-468) - prior draw for a missing
+    value, copy for an undistorted one, rejection sampler / empirical pmf / neighbourhood pmf for a
+    distorted one - drawn by the REFERENCE's own Links::update and by the restatement (alias draws,
+    rejection, inverse CDF over the neighbourhood row), both against the law computed from the model's
+    tables: 800 independent sweeps each from the same state, chi-square per attribute.  The founding
+    record is the last one, so nobody can join its entity after the draw."""
+    from scipy.stats import chisquare
+    months = [str(k) for k in range(1, 13)]
+
+    def build(n):
+        cols, _ = load_rldata("rldata500", n)
+        ap = readme_attr_params(exclude=exclude)
+        ap["bm"].entity_dist_prior = {v: (k + 1.0) / 78.0 for k, v in enumerate(months)}   # phi != psi for one attribute
+        return exchanger(cols, ap, PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+
+    # the founding record must be able to found an entity when all its values are distorted: both its
+    # names need some entity value they could be a distortion of (a neighbour)
+    probe = build(200)
+    def has_neighbour(a, x):
+        idx = probe.attr_indices[a]
+        return bool((idx.close_val_ids == x).any())
+    n = next(k + 1 for k in range(199, 100, -1) if has_neighbour(3, probe.rec_attrs[3, k]) and has_neighbour(4, probe.rec_attrs[4, k]))
+    base = build(n)
+    N, A = base.n_records, base.n_attrs
+    last = N - 1
+    phi_bm = np.array([base.attr_params[1].entity_dist_prior[v] for v in base.attr_indices[1].domain])
+    assert base.attr_names[1] == "bm"
+    configs = {"all distorted": (np.ones(A, np.int32), None), "missing first name": (np.zeros(A, np.int32), 3)}
+    n_draws, worst = 800, 1.0
+    for name, (z, na_attr) in configs.items():
+        m = model_with_state(base, dict(iteration=0, links=base.links, ent_ids=base.ent_ids, ent_attrs=base.ent_attrs,
+                                        rec_distortions=base.rec_distortions.copy(), distort_probs=base.distort_probs,
+                                        distort_dist_concs=base.distort_dist_concs,
+                                        clust=dict(alpha=base.clust_params.alpha, d=base.clust_params.d, m=0, kappa=0)))
+        m.rec_distortions[:, last] = z
+        if na_attr is not None:
+            m.rec_attrs = m.rec_attrs.copy()
+            m.rec_attrs[na_attr, last] = -2147483648
+        x = m.rec_attrs[:, last]
+        for who in ("reference", "oracle"):
+            counts = [np.zeros(len(idx.probs)) for idx in m.attr_indices]
+            got = 0
+            for seed in range(n_draws):
+                if who == "reference":
+                    s = RefSampler(m, seed=500 + seed)
+                    assert s.lib.exref_update_links(s.h) == 0
+                else:
+                    s = OracleSampler(m, seed=500 + seed)
+                    s.phases(2)
+                st = s.state()
+                e = st["links"][last]
+                if (st["links"] == e).sum() != 1:
+                    continue            # it joined an existing entity this time
+                col = int(np.flatnonzero(st["ent_ids"] == e)[0])
+                got += 1
+                for a in range(A):
+                    counts[a][st["ent_attrs"][a, col]] += 1
+            assert got > 150, (name, who, got)   # (a record with nothing pinned often joins an existing entity instead)
+            for a in range(A):
+                law = _new_entity_law(m, a, int(x[a]) if x[a] >= 0 else -1, bool(z[a]), phi_bm if a == 1 else None)
+                assert counts[a][law == 0].sum() == 0, (name, who, a)      # never a value outside the support
+                big = law * got >= 5
+                if big.sum() < 2:
+                    assert counts[a][big].sum() == got or big.sum() == 0
+                    continue
+                obs = np.append(counts[a][big], counts[a][~big].sum())
+                exp = np.append(law[big], law[~big].sum()) * got
+                keep = exp > 0
+                worst = min(worst, chisquare(obs[keep], exp[keep]).pvalue)
+    assert worst > 1e-5   # twenty tests; the seeds are fixed
+
+
+@needs_ref
+def test_dirichlet_update_of_the_entity_distribution_follows_the_reference_law():
+    """Entities::update_distributions (src/entities.cpp:133-156, rdirichlet src/dirichlet.h:12-34):
+    phi_a ~ Dirichlet(count_a(v) + alpha).  The reference's own draws (at construction,
+    entities.cpp:233, and by update_distributions) and the restatement's against the Beta marginals
+    of that Dirichlet: Kolmogorov-Smirnov on three values of two attributes, 300 draws each."""
+    from scipy.stats import beta, kstest
+    from exchanger_b200 import DirichletRV
+    cols, _ = load_rldata("rldata500", 300)
+    ap = readme_attr_params()
+    for k in ("bm", "fname_c1"):
+        ap[k].entity_dist_prior = DirichletRV(0.5)
+    m = exchanger(cols, ap, PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    attrs = [m.attr_names.index("bm"), m.attr_names.index("fname_c1")]
+    n_draws, worst = 300, 1.0
+    draws = {(who, a): [] for who in ("reference", "reference update", "oracle", "oracle update") for a in attrs}
+    for seed in range(n_draws):
+        r, o = RefSampler(m, seed=900 + seed), OracleSampler(m, seed=900 + seed)
+        for a in attrs:
+            D = len(m.attr_indices[a].probs)
+            buf = np.zeros(D)
+            r.lib.exref_get_phi(r.h, a, D, buf.ctypes.data_as(c_f64p))
+            draws[("reference", a)].append(buf.copy())
+            o.lib.exo_get_phi(o.h, a, buf.ctypes.data_as(c_f64p))
+            draws[("oracle", a)].append(buf.copy())
+        assert r.lib.exref_update_distributions(r.h) == 0
+        o.lib.exo_update_distributions(o.h)
+        for a in attrs:
+            D = len(m.attr_indices[a].probs)
+            buf = np.zeros(D)
+            r.lib.exref_get_phi(r.h, a, D, buf.ctypes.data_as(c_f64p))
+            draws[("reference update", a)].append(buf.copy())
+            o.lib.exo_get_phi(o.h, a, buf.ctypes.data_as(c_f64p))
+            draws[("oracle update", a)].append(buf.copy())
+    for (who, a), rows in draws.items():
+        phi = np.array(rows)
+        assert np.allclose(phi.sum(axis=1), 1.0)
+        D = phi.shape[1]
+        cnt = np.bincount(m.ent_attrs[a], minlength=D) + 0.5
+        for v in np.argsort(-cnt)[[0, D // 2, D - 1]]:      # a frequent, a middling and a rare value
+            p = kstest(phi[:, v], beta(cnt[v], cnt.sum() - cnt[v]).cdf).pvalue
+            worst = min(worst, p)
+    assert worst > 1e-4   # 24 tests; the seeds are fixed
