@@ -296,11 +296,16 @@ def run_ours(opt, n_records, kind, desc):
         barrier()
         te = time.perf_counter()
         with Sampler(host_model, seed=2000 + rank, device=local) as g2:
+            t_create = time.perf_counter() - te
             h2d = g2.flat.nbytes()
             hist = g2.run(opt.steps, 1, 0)     # every sweep saved: links row copied back each step
+            t_run = time.perf_counter() - te - t_create
             fin = g2.state()
+            t_state = time.perf_counter() - te - t_create - t_run
         barrier()
         te = time.perf_counter() - te
+        e2e_stages = {"create": round(t_create, 3), "run": round(t_run, 3), "get_state": round(t_state, 3),
+                      "destroy": round(te - t_create - t_run - t_state, 3)}
         d2h = sum(v.nbytes for v in hist.values() if hasattr(v, "nbytes")) + \
             sum(v.nbytes for v in fin.values() if hasattr(v, "nbytes"))
         del hist, fin
@@ -353,7 +358,7 @@ def run_ours(opt, n_records, kind, desc):
                        "l2": f"inputs larger than L2: resident state {n_records * 150 / 1e6:.0f} MB streamed every sweep"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d / opt.steps),
-                    "d2h_bytes_per_step": int(d2h / opt.steps), "runs": e2e_runs,
+                    "d2h_bytes_per_step": int(d2h / opt.steps), "runs": e2e_runs, "stages_s_last_run": e2e_stages,
                     "what": "exb200_create + exb200_run(steps saved sweeps) + exb200_get_state + exb200_destroy, host buffers; median of 3"},
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
