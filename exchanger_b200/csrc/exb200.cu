@@ -731,7 +731,7 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
   *ok = false;
   if (n > WIDE_BUCKET_MAX) return EXB200_OK;
   if (!h->we_keys[0]) {
-    h->we_cap = std::min<unsigned long long>(8ull * h->N + (1ull << 20), 48ull << 20);
+    h->we_cap = std::min<unsigned long long>(2ull * h->N + (1ull << 20), 48ull << 20); // (10.4 M entries at 10 M records, sweep 200)
     int rc = 0;
     for (int k = 0; k < 2 && !rc; k++) { rc = dalloc(h, &h->we_keys[k], (size_t)h->we_cap); if (!rc) rc = dalloc(h, &h->we_vals[k], (size_t)h->we_cap); }
     if (!rc) rc = dalloc(h, &S.wlb_id, (size_t)h->we_cap);
