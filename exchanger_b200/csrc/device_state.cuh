@@ -31,6 +31,7 @@ constexpr int CAND_INLINE = 4;      // candidate lists up to this length are sto
 constexpr int FAST_CAND = 16;       // candidates the thread-per-record kernel keeps for one record
 constexpr uint32_t CAND_OWN_ONLY = 0xFFFFFFFFu; // cand_off value: the list is {the record's own entity}, log-likelihood 0
 constexpr int WIDE_NB = 128;        // records whose possible links are listed in one pass over the items
+constexpr int ACT_TABS_MAX = 48;    // built tables a record without a serving table chooses from
 constexpr int HUGE_BATCH = 512;     // records with a huge bucket scanned per launch
 
 // Per-attribute tables: the device form of ConstantAttributeIndex / NonConstantAttributeIndex
@@ -121,6 +122,9 @@ struct DevState {
   int *slow_list;               // [N] records the fast candidate kernel leaves to the bucket-scanning kernels
   int *tab_over;                // [2^n_key] chain tables in which some record exceeded hop_cap / FAST_CAND
   int n_key;                    // number of key attributes
+  int n_act_tabs;               // blocking tables built this sweep ...
+  uint16_t act_tabs[ACT_TABS_MAX]; // ... and their key masks (a record no table serves picks the cheapest of them, k_wide_emit)
+  double emit_cost_cap;         // ... unless even that one costs more cell / item reads than this (then: scan over all items)
   int key_attr[KEY_ATTRS];      // key position -> attribute
   int8_t key_pos[MAX_ATTRS];    // attribute -> key position (-1: not a key attribute)
   uint32_t *cand_off;           // [N]

@@ -100,6 +100,7 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
+  double emit_cost_cap = 4194304.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
   int opt_tiny_always = 0;     // build every wanted table with few buckets, however few records want it (measured: slower)
   WideTurn* d_turns = nullptr; size_t turns_cap = 0; int turns_grid = 0;
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
@@ -724,7 +725,7 @@ int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
 // base[i] / len[i] locate record i's list in wlb_id / wlb_ll.  Returns EXB200_OK with *ok = false
 // when the lists do not fit the scratch (the caller then scans all items for these records too).
 constexpr int WIDE_BUCKET_MAX = 65536;
-int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vector<int>& base, std::vector<int>& len, bool* ok) {
+int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vector<int>& base, std::vector<int>& len, std::vector<int>& served, bool* ok) {
   DevState& S = h->S;
   cudaStream_t st = h->stream;
   const int n = (int)recs.size();
@@ -738,7 +739,7 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
     if (!rc) rc = dalloc(h, &S.wlb_ll, (size_t)h->we_cap);
     if (!rc) rc = dalloc(h, &h->we_cursor, 1);
     if (!rc) rc = dalloc(h, &h->we_recs, (size_t)WIDE_BUCKET_MAX);
-    if (!rc) rc = dalloc(h, &h->we_seg, (size_t)2 * WIDE_BUCKET_MAX);
+    if (!rc) rc = dalloc(h, &h->we_seg, (size_t)4 * WIDE_BUCKET_MAX); // start, end, served, selection
     if (rc) return rc;
     cub::DeviceRadixSort::SortPairs(nullptr, h->we_tmp_bytes, h->we_keys[0], h->we_keys[1],
                                     reinterpret_cast<unsigned long long*>(h->we_vals[0]), reinterpret_cast<unsigned long long*>(h->we_vals[1]),
@@ -749,14 +750,17 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
   }
   CK(cudaMemcpyAsync(h->we_recs, recs.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h->we_cursor, 0, sizeof(unsigned long long), st));
-  CK(cudaMemsetAsync(h->we_seg, 0, sizeof(int) * 2 * (size_t)n, st));
-  KLAUNCH(h, k_wide_emit, n * WE_BLOCKS, TPB, 0, S, h->we_recs, n, h->we_keys[0], h->we_vals[0], h->we_cursor, h->we_cap);
+  CK(cudaMemsetAsync(h->we_seg, 0, sizeof(int) * 3 * (size_t)n, st));
+  KLAUNCH(h, k_wide_emit, n * WE_BLOCKS, TPB, 0, S, h->we_recs, n, h->we_keys[0], h->we_vals[0], h->we_cursor, h->we_cap, h->we_seg + 2 * n);
   unsigned long long n_emit = 0;
   CK(cudaMemcpyAsync(&n_emit, h->we_cursor, sizeof n_emit, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (n_emit > h->we_cap) return EXB200_OK; // does not fit: the batched scan takes these records
-  base.assign(n, 0); len.assign(n, 0);
-  if (n_emit > 0) {
+  base.assign(n, 0); len.assign(n, 0); served.assign(n, 0);
+  if (n_emit == 0) {
+    CK(cudaMemcpyAsync(served.data(), h->we_seg + 2 * n, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  } else {
     int top = 32; // key bits that matter: the item and the batch position
     while ((1ll << (top - 32)) < (long long)n && top < 64) top++;
     size_t bytes = h->we_tmp_bytes;
@@ -765,10 +769,10 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
                                        (long long)n_emit, 0, top, st));
     h->n_launches += 4;
     KLAUNCH(h, k_wide_split, nblk((long long)n_emit), TPB, 0, S, h->we_keys[1], h->we_vals[1], (long long)n_emit, h->we_seg, h->we_seg + n);
-    std::vector<int> seg(2 * (size_t)n);
+    std::vector<int> seg(3 * (size_t)n);
     CK(cudaMemcpyAsync(seg.data(), h->we_seg, sizeof(int) * seg.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < n; i++) { base[i] = seg[i]; len[i] = seg[n + i] > 0 ? seg[n + i] - seg[i] : 0; }
+    for (int i = 0; i < n; i++) { base[i] = seg[i]; len[i] = seg[n + i] > 0 ? seg[n + i] - seg[i] : 0; served[i] = seg[2 * n + i]; }
   }
   *ok = true;
   return EXB200_OK;
@@ -869,6 +873,9 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaMemcpyAsync(h->d_remap, remap.data(), sizeof(uint16_t) * remap.size(), cudaMemcpyHostToDevice, st));
   h->stats.n_tables = (int)active.size();
+  S.n_act_tabs = (int)std::min<size_t>(active.size(), ACT_TABS_MAX);
+  for (int k = 0; k < S.n_act_tabs; k++) S.act_tabs[k] = (uint16_t)active[k];
+  S.emit_cost_cap = h->emit_cost_cap;
   // Form of every table of this sweep: the chain form for key spaces about as large as the item set
   // (one atomicExch per item, probes walk a short chain of nodes holding packed tuples), the CSR
   // form for the few masks with long buckets (scanned by many lanes).
@@ -1000,34 +1007,64 @@ int update_links(exb200_handle* h) {
   // items are listed in batches (k_wide_scan).  Scan order: those with more than
   // wide_threshold take their turn first, in ascending id, one at a time; the others keep their list
   // like everybody else and wait for the rounds.
-  std::vector<int> serial; // (record << 1) | needs classification
+  std::vector<int> unk; // no stored list and no count of their possible links yet
   if (hc[C_NUNK] > 0) {
-    std::vector<int> unk(hc[C_NUNK]);
+    unk.resize(hc[C_NUNK]);
     CK(cudaMemcpyAsync(unk.data(), S.unk_list, sizeof(int) * unk.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int r : unk) serial.push_back((r << 1) | 1);
   }
   std::vector<int> known; // wide records found by the candidate scan of their own bucket
   if (hc[C_NWIDE] > 0) {
     known.resize(hc[C_NWIDE]);
     CK(cudaMemcpyAsync(known.data(), S.wide_list, sizeof(int) * known.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    std::sort(known.begin(), known.end());
-    for (int r : known) serial.push_back(r << 1);
   }
-  std::sort(serial.begin(), serial.end());
+  if (!unk.empty() || !known.empty()) CK(cudaStreamSynchronize(st));
+  std::sort(unk.begin(), unk.end());
+  std::sort(known.begin(), known.end());
   CK(cudaEventRecord(h->ev[4], st));
-  // their possible links, listed from the buckets they were found in (instead of one more scan of all items)
-  std::vector<int> kb_base, kb_len;
+  // Their possible links are listed from the blocking tables (k_wide_emit): the wide records from the
+  // bucket they were found in, the others through the cheapest table built this sweep - instead of a
+  // scan over all the items, which is left to the records no table can serve.
+  std::vector<int> listed(known.size() + unk.size()); // both kinds, ascending
+  std::merge(known.begin(), known.end(), unk.begin(), unk.end(), listed.begin());
+  auto is_unk = [&](int r) { return std::binary_search(unk.begin(), unk.end(), r); };
+  std::vector<int> kb_base, kb_len, kb_served;
   bool from_buckets = false;
-  if (!known.empty() && h->opt_wide_buckets) {
+  if (!listed.empty() && h->opt_wide_buckets) {
     const auto t_a = std::chrono::steady_clock::now();
-    int rc = wide_bucket_lists(h, known, kb_base, kb_len, &from_buckets); if (rc) return rc;
+    int rc = wide_bucket_lists(h, listed, kb_base, kb_len, kb_served, &from_buckets); if (rc) return rc;
     if (h->trace) {
       long long sum = 0;
-      for (int v : kb_len) sum += v;
-      std::fprintf(stderr, "[exb200] %d wide records listed from their buckets: %.2f ms, %lld possible links%s\n", (int)known.size(),
-                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum, from_buckets ? "" : " (did not fit: batched scan)");
+      int n_served = 0;
+      for (size_t i = 0; i < kb_len.size(); i++) { sum += kb_len[i]; n_served += kb_served[i]; }
+      std::fprintf(stderr, "[exb200] %d wide records and %d without a serving table listed from the tables: %.2f ms, %lld possible links, %d left to the scan%s\n",
+                   (int)known.size(), (int)unk.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum,
+                   from_buckets ? (int)listed.size() - n_served : (int)unk.size(), from_buckets ? "" : " (did not fit: batched scan)");
+    }
+  }
+  std::vector<int> serial; // (record << 1) | no count of its possible links yet (listed by the batched scan, then classified)
+  std::vector<char> listed_wide_unk(listed.size(), 0); // listed, and found to have more than wide_threshold possible links
+  {
+    std::vector<int> keep; // positions in `listed`: at most wide_threshold possible links - they keep their list and wait for the rounds
+    for (size_t i = 0; i < listed.size(); i++) {
+      const int r = listed[i];
+      const bool u = is_unk(r);
+      if (!from_buckets) serial.push_back((r << 1) | (u ? 1 : 0)); // everything by the batched scan
+      else if (!u) serial.push_back(r << 1);
+      else if (!kb_served[i]) serial.push_back((r << 1) | 1);
+      else if (kb_len[i] > h->long_cap) { listed_wide_unk[i] = 1; serial.push_back(r << 1); }
+      else keep.push_back((int)i);
+    }
+    h->stats.n_listed = 0; h->stats.n_scanned = 0;
+    for (size_t i = 0; i < listed.size(); i++) {
+      const bool u = is_unk(listed[i]);
+      if (from_buckets && u && kb_served[i]) h->stats.n_listed++;
+      else if (!from_buckets || u) h->stats.n_scanned++;
+    }
+    if (!keep.empty()) {
+      const int n = (int)listed.size();
+      CK(cudaMemcpyAsync(h->we_seg + 3 * n, keep.data(), sizeof(int) * keep.size(), cudaMemcpyHostToDevice, st));
+      KLAUNCH(h, k_wide_store_b, (int)keep.size(), TPB, 0, S, h->we_recs, h->we_seg + 3 * n, h->we_seg, h->we_seg + n);
+      CK(cudaStreamSynchronize(st)); // `keep` is on the stack
     }
   }
   std::vector<int> wide; // the records that took their turn first
@@ -1045,7 +1082,7 @@ int update_links(exb200_handle* h) {
       const bool scan = (serial[g_end] & 1) || !from_buckets;
       if (scan && nb == WIDE_NB) break;
       if (scan) { recs[nb] = r; entry_of_slot[nb] = g_end; slot.push_back(nb++); }
-      else slot.push_back(-1 - (int)(std::lower_bound(known.begin(), known.end(), r) - known.begin()));
+      else slot.push_back(-1 - (int)(std::lower_bound(listed.begin(), listed.end(), r) - listed.begin()));
     }
     if (nb > 0) {
       const auto t_a = std::chrono::steady_clock::now();
@@ -1085,8 +1122,12 @@ int update_links(exb200_handle* h) {
       for (; e < slot.size(); e++) {
         const int sl = slot[e], entry = serial[g + e], r = entry >> 1;
         if (sl >= b) break;
-        if (sl < 0) { // listed from its bucket
+        if (sl < 0) { // listed from the tables
           const int k = -1 - sl;
+          if (listed_wide_unk[k]) { // more than wide_threshold possible links, as it turned out
+            static const int code_wide = -1;
+            CK(cudaMemcpyAsync(S.cand_cnt + r, &code_wide, sizeof(int), cudaMemcpyHostToDevice, st));
+          }
           turns.push_back(WideTurn{r, kb_len[k], 1, 0, (unsigned long long)kb_base[k]});
           wide.push_back(r);
           continue;
@@ -1736,6 +1777,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "rounds_tail") h->opt_tail = value != 0;
   else if (n == "fast_path") h->opt_fast = value != 0;
   else if (n == "wide_buckets") h->opt_wide_buckets = value != 0;
+  else if (n == "emit_cost_cap") h->emit_cost_cap = (double)value;
   else if (n == "tiny_tables_always") h->opt_tiny_always = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);

@@ -113,6 +113,68 @@ __device__ __forceinline__ Probe make_probe(const DevState& S, uint32_t mask, co
   return p;
 }
 
+// The same for the listing kernel of the serial path (k_wide_emit), which spreads the probes of one
+// record over several blocks and can therefore afford many more of them: up to four unpinned key
+// attributes (every key attribute of the largest tables), the count in 64 bits.
+constexpr int BIG_UNPINNED = 4;
+struct BigProbe {
+  int n_un;           // unpinned key attributes (BIG_UNPINNED + 1: not served)
+  int a[BIG_UNPINNED];
+  ProbeValues p[BIG_UNPINNED];
+  long long count;
+  __device__ __forceinline__ void values(long long j, int* v) const {
+    for (int k = 0; k < n_un; k++) { v[k] = p[k].value((int)(j % p[k].n)); j /= p[k].n; }
+  }
+  __device__ __forceinline__ int value_of(int attr, const int* x, const int* v) const {
+    for (int k = 0; k < n_un; k++) if (a[k] == attr) return v[k];
+    return x[attr];
+  }
+  __device__ __forceinline__ uint32_t bucket(const DevState& S, const DevTable& t, const int* x, const int* v) const {
+    uint64_t key = 0;
+    for (uint32_t m = t.mask; m; m &= m - 1) {
+      const int at = S.key_attr[__ffs(m) - 1];
+      key = key * (uint64_t)S.attrs[at].D + (uint64_t)value_of(at, x, v);
+    }
+    return t.exact ? (uint32_t)key : (uint32_t)(mix64(key) & (uint64_t)(t.B - 1));
+  }
+  __device__ __forceinline__ uint32_t cell(const DevState& S, const DevTable& t, const int* x, const int* v) const {
+    unsigned long long K = 0;
+    for (uint32_t m = t.mask; m; m &= m - 1) {
+      const int at = S.key_attr[__ffs(m) - 1];
+      K |= (unsigned long long)(uint32_t)value_of(at, x, v) << S.pk_shift[at];
+    }
+    return (uint32_t)(mix64(K & t.kmask) & (unsigned long long)(t.cells - 1u));
+  }
+  __device__ __forceinline__ bool own_probe(const int* y, const int* v) const { // an item counts in the probe of its own values only
+    bool ok = true;
+    for (int k = 0; k < n_un; k++) ok &= y[a[k]] == v[k];
+    return ok;
+  }
+};
+__device__ __forceinline__ BigProbe make_big_probe(const DevState& S, uint32_t mask, const int* x, uint32_t zm) {
+  BigProbe p;
+  p.n_un = 0; p.count = 1;
+  for (int k = 0; k < BIG_UNPINNED; k++) { p.a[k] = -1; p.p[k].col = nullptr; p.p[k].n = 1; }
+  for (uint32_t m = mask; m; m &= m - 1) {
+    const int a = S.key_attr[__ffs(m) - 1];
+    if (x[a] >= 0 && !((zm >> a) & 1u)) continue;
+    if (p.n_un < BIG_UNPINNED) {
+      p.a[p.n_un] = a; p.p[p.n_un] = probe_values(S, a, x, zm);
+      p.count = p.count > (1ll << 40) ? p.count : p.count * (long long)p.p[p.n_un].n;
+    }
+    p.n_un++;
+  }
+  return p;
+}
+// What listing the possible links of record x through table t would cost (about one unit per cell or
+// bucket item read), for the choice of a table for a record that its own table does not serve.
+__device__ __forceinline__ double big_probe_cost(const DevState& S, const DevTable& t, const int* x, uint32_t zm) {
+  const BigProbe p = make_big_probe(S, t.mask, x, zm);
+  if (p.n_un > BIG_UNPINNED) return CUDART_INF;
+  if (t.chain) return 2.0 * (double)p.count;
+  return (double)p.count * (1.0 + 1.2 * (double)S.N / (double)t.B);
+}
+
 // ---- packed attribute tuples (fast candidate path; S.pk_ok: the domains fit 64 bits and A <= 8)
 __device__ __forceinline__ unsigned long long pk_field(const DevState& S, int a) {
   return ((1ull << S.pk_bits[a]) - 1ull) << S.pk_shift[a];
@@ -2335,18 +2397,35 @@ __global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* 
 // ------------------------------------------------------------------------------------------
 constexpr int WE_BLOCKS = 8;
 constexpr int WE_TILE = 2048;
+// A record that its own table does not serve (cand_cnt = -3: no table for its key mask, or too many
+// probe combinations for the candidate kernels) is listed through the cheapest of the tables built
+// this sweep - chain tables are probed with up to four unpinned key attributes - and `served[i]`
+// says whether there was one within emit_cost_cap (else: batched scan over all the items).
 __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __restrict__ recs, int n, unsigned long long* __restrict__ keys,
                                                    double* __restrict__ vals, unsigned long long* __restrict__ cursor,
-                                                   unsigned long long cap) {
+                                                   unsigned long long cap, int* __restrict__ served) {
   const int i = blockIdx.x / WE_BLOCKS, jb = blockIdx.x % WE_BLOCKS;
   if (i >= n) return;
   const int r = recs[i];
   const int* x = S.rec_x + (size_t)r * S.RS;
   const uint32_t zm = S.rec_z[r];
-  int tab = S.tab_remap[S.rec_tab[r]];
-  if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+  const bool unserved = S.cand_cnt[r] == -3;
+  int tab = 0;
+  if (!unserved) {
+    tab = S.tab_remap[S.rec_tab[r]];
+    if (!tab) tab = S.tab_remap[N_TABLES + S.rec_alt[r]];
+  } else {
+    double best = S.emit_cost_cap;
+    for (int k = 0; k < S.n_act_tabs; k++) {
+      const double c = big_probe_cost(S, S.tables[S.act_tabs[k]], x, zm);
+      if (c < best) { best = c; tab = S.act_tabs[k]; }
+    }
+  }
+  if (jb == 0 && threadIdx.x == 0) served[i] = tab != 0;
+  if (!tab) return;
   const DevTable& t = S.tables[tab];
-  const Probe pr = make_probe(S, t.mask, x, zm);
+  const BigProbe pr = make_big_probe(S, t.mask, x, zm);
+  if (pr.n_un > BIG_UNPINNED) { if (jb == 0 && threadIdx.x == 0) served[i] = 0; return; } // (cannot happen for a record with a stored bucket)
   // one possible link (and its twin) of record i; the threads that get here together share one atomic
   auto emit = [&](int item, double ll, bool twin) {
     cg::coalesced_group g = cg::coalesced_threads();
@@ -2360,7 +2439,7 @@ __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __rest
       if (twin) { keys[base + 1] = ((unsigned long long)(uint32_t)i << 32) | (unsigned long long)(uint32_t)(S.N + item); vals[base + 1] = ll; }
     }
   };
-  auto visit = [&](int item, const Pv& v, const int* y) {
+  auto visit = [&](int item, const int* v, const int* y) {
     if (item == S.N + r) return;
     if (!y) y = S.ent_y + (size_t)item * S.ES;
     if (pr.n_un > 0 && !pr.own_probe(y, v)) return;
@@ -2369,19 +2448,22 @@ __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __rest
     if (!(ll > -CUDART_INF)) return;
     emit(item, ll, item < S.N && item != r && S.twin[item]);
   };
-  if (pr.n_un == 0) {
-    const uint32_t b = S.rec_bkt[r];
+  if (pr.n_un == 0 && t.csr) {
+    const uint32_t b = unserved ? bucket_of(S, t, x) : S.rec_bkt[r];
     const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+    const int none[1] = {0};
     for (int q0 = lo + jb * WE_TILE; q0 < hi; q0 += WE_BLOCKS * WE_TILE)
-      for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], Pv{0, 0, 0}, nullptr);
-  } else if (pr.n_un < PROBE_NOT_SERVED) {
-    for (int j = jb * TPB + threadIdx.x; j < pr.count; j += WE_BLOCKS * TPB) {
-      const Pv v = pr.values(j);
+      for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], none, nullptr);
+  } else {
+    for (long long j = (long long)jb * TPB + threadIdx.x; j < pr.count; j += WE_BLOCKS * TPB) {
+      int v[BIG_UNPINNED];
+      pr.values(j, v);
       if (t.chain) {
-        for (int item = t.head[chain_cell_probe(S, t, x, pr, v)]; item >= 0;) {
+        for (int item = t.head[pr.cell(S, t, x, v)]; item >= 0;) {
           const ChainNode nd = load_node(&t.node[item]);
           int yv[8];
           for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
+          // (n_un = 0: the cell may hold items of other keys too - the pinned attributes are compared in visit)
           visit(item, v, yv);
           item = nd.next;
         }
@@ -2404,6 +2486,38 @@ __global__ void __launch_bounds__(TPB) k_wide_split(DevState S, const unsigned l
   S.wlb_ll[i] = vals[i];
   if (i == 0 || (int)(keys[i - 1] >> 32) != pos) seg_base[pos] = (int)i;
   if (i == n - 1 || (int)(keys[i + 1] >> 32) != pos) seg_len[pos] = (int)i + 1; // end for now: the host subtracts the start
+}
+
+// records listed by k_wide_emit that turned out to have at most wide_threshold possible links keep their
+// list like everybody else (the counterpart of k_wide_store; one block per record, list sorted already)
+__global__ void __launch_bounds__(TPB) k_wide_store_b(DevState S, const int* __restrict__ recs, const int* __restrict__ sel,
+                                                      const int* __restrict__ seg_base, const int* __restrict__ seg_end) {
+  __shared__ unsigned long long s_off;
+  const int i = sel[blockIdx.x], r = recs[i];
+  const int base = seg_base[i];
+  const int cnt = seg_end[i] > 0 ? seg_end[i] - base : 0;
+  const int own = S.lambda[r];
+  if (threadIdx.x == 0) s_off = cnt > 0 ? atomicAdd(S.pool_cursor, (unsigned long long)cnt) : 0ull;
+  __syncthreads();
+  const unsigned long long o = s_off;
+  const bool overflow = o + (unsigned long long)cnt > S.pool_cap;
+  if (!overflow) for (int k = threadIdx.x; k < cnt; k += TPB) {
+    const int id = S.wlb_id[base + k];
+    S.cand_id[o + k] = id; S.cand_ll[o + k] = S.wlb_ll[base + k];
+    if (id != own) S.referenced[id] = 1;
+  }
+  if (threadIdx.x == 0) {
+    const bool other = overflow || cnt > 1 || (cnt == 1 && S.wlb_id[base] != own);
+    S.cand_off[r] = overflow ? 0u : (uint32_t)o;
+    S.cand_cnt[r] = overflow ? -2 : cnt;
+    S.dlo[r] = other ? -1 : 0;
+    S.dhi[r] = 1;
+    if (overflow) atomicAdd(&S.counters[C_NFENCE], 1);
+    else {
+      atomicAdd((unsigned long long*)&S.counters64[0], (unsigned long long)cnt);
+      if (cnt > S.long_min) S.actl_in[atomicAdd(&S.counters[C_NACTL_INIT], 1)] = r;
+    }
+  }
 }
 
 // Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares

@@ -37,8 +37,9 @@ extern "C" {
 
 /* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
    estimates (exb200_pe_*) added
-   3: exb200_pe_overflowed; exb200_stats grew (ms_cand_fast, n_slow) */
-#define EXB200_ABI_VERSION 3
+   3: exb200_pe_overflowed; exb200_stats grew (ms_cand_fast, n_slow)
+   4: exb200_stats grew (n_listed, n_scanned) */
+#define EXB200_ABI_VERSION 4
 
 enum {
   EXB200_OK = 0,
@@ -175,6 +176,9 @@ typedef struct exb200_stats {
   int32_t n_huge;         /* records whose bucket was cut into tiles (longer than huge_min)       */
   float ms_cand_fast;     /* the thread-per-record candidate kernel alone (part of ms_cand)       */
   int32_t n_slow;         /* records that kernel left to the bucket-scanning kernels              */
+  int32_t n_listed;       /* records no table served directly whose possible links were listed through
+                             the cheapest table built this sweep (k_wide_emit)                    */
+  int32_t n_scanned;      /* records whose possible links were listed by the scan over all items  */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;

@@ -159,7 +159,8 @@ def test_results_do_not_depend_on_batching_thresholds():
     for opts in (dict(), dict(cand_cap=4, long_min=2), dict(cand_cap=32, bucket_cap=0, est_threshold=1), dict(bucket_cap=0, huge_min=0),
                  dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
                  dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0),
-                 dict(fast_path=0), dict(hop_cap=1), dict(wide_buckets=0), dict(wide_buckets=0, fast_path=0, rounds_tail=0), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0)):
+                 dict(fast_path=0), dict(hop_cap=1), dict(wide_buckets=0), dict(wide_buckets=0, fast_path=0, rounds_tail=0), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0),
+                 dict(table_min_usage=1000000), dict(table_min_usage=1000000, emit_cost_cap=0), dict(table_min_usage=1000000, emit_cost_cap=64)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
@@ -182,6 +183,24 @@ def test_multi_bucket_probes_and_warp_scanned_buckets():
     assert sum(s["n_probe"] for s in stats) > 100
     stats = lockstep(m, 4, bucket_cap=0, huge_min=4)  # block-staged lists and tiled buckets
     assert sum(s["n_huge"] for s in stats) > 10
+
+
+def test_records_no_table_serves_are_listed_through_the_cheapest_table():
+    """Rare key masks get no table of their own (table_min_usage high): their records' possible
+    links are listed through the cheapest table that IS built - a chain table probed with up to four
+    unpinned key attributes, or the bucket of a CSR table - instead of a scan over all the items
+    (emit_cost_cap=0 forces that scan).  Same chain as the oracle either way."""
+    cols, _ = load_rldata("rldata10000", 4000)
+    rng = np.random.default_rng(7)
+    for k in ("fname_c1", "lname_c1", "by", "bd"):  # missing values make rare key masks
+        cols[k] = [None if rng.random() < 0.15 else v for v in cols[k]]
+    m = exchanger(cols, readme_attr_params(), PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
+    stats = lockstep(m, 6, table_min_usage=1000000)
+    assert sum(s["n_listed"] for s in stats) > 100, [(s["n_listed"], s["n_scanned"], s["n_tables"]) for s in stats]
+    stats = lockstep(m, 4, table_min_usage=1000000, wide_threshold=20)  # ... some of them wide after all
+    assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
+    stats = lockstep(m, 4, table_min_usage=1000000, emit_cost_cap=0)
+    assert sum(s["n_scanned"] for s in stats) > 100 and sum(s["n_listed"] for s in stats) == 0
 
 
 def test_synthetic_records_at_scale_lockstep():

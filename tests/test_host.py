@@ -102,7 +102,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(capi.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.exb200_abi_version() == 3
+    assert lib.exb200_abi_version() == 4
 
 
 def test_struct_layouts_match_the_header():
