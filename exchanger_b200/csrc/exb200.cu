@@ -100,9 +100,11 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
-  double emit_cost_cap = 4194304.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
+  int opt_round0 = 1; // records that found an entity whatever happens are final before round 1 (k_bounds_init)
+  double emit_cost_cap = 262144.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
   int opt_tiny_always = 0;     // build every wanted table with few buckets, however few records want it (measured: slower)
   WideTurn* d_turns = nullptr; size_t turns_cap = 0; int turns_grid = 0;
+  unsigned* d_turn_sync = nullptr; // [2 * turns_cap] arrivals / commit flags of k_wide_turns
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
   int hop_cap = 1024;
@@ -699,6 +701,7 @@ int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
   if (turns.size() > h->turns_cap) {
     h->turns_cap = std::max<size_t>(1024, 2 * turns.size());
     int rc = dalloc(h, &h->d_turns, h->turns_cap); if (rc) return rc;
+    rc = dalloc(h, &h->d_turn_sync, 2 * h->turns_cap); if (rc) return rc;
   }
   if (!h->turns_grid) {
     int per_sm = 0;
@@ -712,11 +715,28 @@ int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
   int want = 1;
   for (const WideTurn& w : turns) want = std::max(want, (w.len + 2047) / 2048);
   const int grid = std::min(h->turns_grid, want);
-  void* args[] = {(void*)&S, (void*)&h->d_turns, (void*)&n};
+  CK(cudaMemsetAsync(h->d_turn_sync, 0, sizeof(unsigned) * 2 * (size_t)n, st));
+  unsigned long long* dbg = nullptr;
+  if (h->trace) { int rc = dalloc(h, &dbg, 4 * (size_t)n); if (rc) return rc; } // (trace only: not freed before destroy)
+  void* args[] = {(void*)&S, (void*)&h->d_turns, (void*)&n, (void*)&h->d_turn_sync, (void*)&dbg};
   CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_wide_turns<true> : (const void*)k_wide_turns<false>,
                                  dim3((unsigned)grid), dim3(TPB), args, 0, st));
   h->n_launches++;
   CK(cudaStreamSynchronize(st)); // `turns` and `n` live on the caller's stack
+  if (dbg) {
+    std::vector<unsigned long long> d(4 * (size_t)n);
+    CK(cudaMemcpy(d.data(), dbg, sizeof(unsigned long long) * d.size(), cudaMemcpyDeviceToHost));
+    double red = 0, wait = 0, com = 0, gap = 0;
+    for (int t = 0; t < n; t++) {
+      red += (double)(d[4 * t + 1] - d[4 * t]); wait += (double)(d[4 * t + 2] - d[4 * t + 1]); com += (double)(d[4 * t + 3] - d[4 * t + 2]);
+      if (t) gap += (double)(d[4 * t] - d[4 * t - 1]);
+    }
+    std::fprintf(stderr, "[exb200]   per turn (block 0, us): reduce %.2f, wait for the others %.2f, commit %.2f, to the next turn %.2f; kernel %.1f us for %d turns on %d blocks\n",
+                 red / n * 1e-3, wait / n * 1e-3, com / n * 1e-3, gap / std::max(1, n - 1) * 1e-3, (double)(d[4 * (size_t)n - 1] - d[0]) * 1e-3, n, grid);
+    for (int t = 0; t < std::min(n, 12); t++)
+      std::fprintf(stderr, "[exb200]     turn %d len %d: reduce %.2f wait %.2f commit %.2f\n", t, turns[t].len, (double)(d[4 * t + 1] - d[4 * t]) * 1e-3,
+                   (double)(d[4 * t + 2] - d[4 * t + 1]) * 1e-3, (double)(d[4 * t + 3] - d[4 * t + 2]) * 1e-3);
+  }
   return EXB200_OK;
 }
 
@@ -731,6 +751,7 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
   const int n = (int)recs.size();
   *ok = false;
   if (n > WIDE_BUCKET_MAX) return EXB200_OK;
+  const auto t_0 = std::chrono::steady_clock::now();
   if (!h->we_keys[0]) {
     h->we_cap = std::min<unsigned long long>(2ull * h->N + (1ull << 20), 48ull << 20); // (10.4 M entries at 10 M records, sweep 200)
     int rc = 0;
@@ -755,6 +776,8 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
   unsigned long long n_emit = 0;
   CK(cudaMemcpyAsync(&n_emit, h->we_cursor, sizeof n_emit, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (h->trace) std::fprintf(stderr, "[exb200]   k_wide_emit: %.2f ms, %llu entries\n",
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_0).count(), n_emit);
   if (n_emit > h->we_cap) return EXB200_OK; // does not fit: the batched scan takes these records
   base.assign(n, 0); len.assign(n, 0); served.assign(n, 0);
   if (n_emit == 0) {
@@ -1140,13 +1163,17 @@ int update_links(exb200_handle* h) {
         turns.push_back(WideTurn{r, tot[sl], 0, 0, bases[sl]});
         wide.push_back(r);
       }
+      const auto t_t = std::chrono::steady_clock::now();
       { int rc = wide_turns(h, turns); if (rc) return rc; }
       CK(cudaStreamSynchronize(st)); // bases / sel are on the stack
+      if (h->trace && !turns.empty())
+        std::fprintf(stderr, "[exb200] %d serial turns: %.2f ms\n", (int)turns.size(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_t).count());
     }
     g = g_end;
   }
-  if (!serial.empty()) {
-    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved
+  if (!listed.empty()) {
+    CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved (k_wide_store, k_wide_store_b)
     CK(cudaStreamSynchronize(st));
   }
   const int n_fence = hc[C_NFENCE]; // candidate pool exhausted: these take their turn serially inside the rounds
@@ -1161,7 +1188,15 @@ int update_links(exb200_handle* h) {
     S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
   }
   // records whose list did not fit the candidate pool (n_fence) are pending too
-  if (S.use_kbounds) KLAUNCH(h, k_bounds_init, nblk(N), TPB, 0, S, n_fence > 0 ? 1 : 0);
+  {
+    // round 0 needs prior_weight_new(K) positive and finite whatever K is when the record's turn comes
+    // (clust_params.cpp:9-31: alpha + d K; kappa |m - K|, |m - K| - zero only at K = m)
+    const exb200_clust& c = h->cl;
+    bool sure = h->opt_round0 != 0;
+    if (c.kind == EXB200_CLUST_PITMAN_YOR) sure = sure && c.alpha > 0.0 && c.d >= 0.0 && std::isfinite(c.alpha + c.d * (double)N);
+    else sure = sure && c.m > (double)(N - 1) && std::isfinite(c.m) /* K without the record is at most N - 1 */ && (c.kind != EXB200_CLUST_GEN_COUPON || (c.kappa > 0.0 && std::isfinite(c.kappa * c.m)));
+    if (S.use_kbounds || sure) KLAUNCH(h, k_bounds_init, nblk(N), TPB, 0, S, n_fence > 0 ? 1 : 0, sure ? 1 : 0);
+  }
   CK(cudaEventRecord(h->ev[11], st));
 
   // dependency rounds
@@ -1777,6 +1812,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "rounds_tail") h->opt_tail = value != 0;
   else if (n == "fast_path") h->opt_fast = value != 0;
   else if (n == "wide_buckets") h->opt_wide_buckets = value != 0;
+  else if (n == "round0") h->opt_round0 = value != 0;
   else if (n == "emit_cost_cap") h->emit_cost_cap = (double)value;
   else if (n == "tiny_tables_always") h->opt_tiny_always = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);

@@ -1386,8 +1386,8 @@ __global__ void __launch_bounds__(TPB) k_reserve(DevState S, const int* __restri
   int mine = 0x7FFFFFFF;
   if (i < n_act) {
     const int r = act ? act[i] : i;
-    const int cnt = S.cand_cnt[r];
-    if (cnt <= S.long_min && S.fin[r] != 1) { // long records: k_reserve_w; wide records are final already
+    const int cnt = S.fin[r] == 1 ? 0x7FFFFFFF : S.cand_cnt[r]; // (final already: wide records, round 0)
+    if (cnt <= S.long_min) { // long records: k_reserve_w
       mine = r;
       const unsigned long long key = resv_key(round, r);
       if (cnt < 0) atomicMin(S.fence, key);
@@ -1578,8 +1578,8 @@ __global__ void __launch_bounds__(TPB) k_commit(DevState S, const int* __restric
   int r = -1;
   if (i < n_act) {
     r = act ? act[i] : i;
-    const int cnt = S.cand_cnt[r];
-    stay = cnt <= S.long_min && S.fin[r] != 1; // long records live in the other list; wide ones are final
+    const int cnt = S.fin[r] == 1 ? 0x7FFFFFFF : S.cand_cnt[r]; // (final already: wide records, round 0)
+    stay = cnt <= S.long_min; // long records live in the other list
     const unsigned long long key = resv_key(round, r);
     const unsigned long long fence = *S.fence;
     const bool fenced = (fence >> 32) == (key >> 32) && (uint32_t)fence < (uint32_t)r;
@@ -2292,7 +2292,8 @@ __device__ void wide_commit_block(const DevState& S, int r, unsigned long long b
     double srel = 0.0;
     for (int b = 0; b < n_blocks; b++) srel += s_bsum[b];
     const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
-    const int k = S.K0 + S.counters[C_DK_TOTAL] - (single ? 1 : 0); // every earlier record is final
+    // (read past the L1: the counter is moved by atomics, which a cached copy of this very block would not see)
+    const int k = S.K0 + __ldcg(&S.counters[C_DK_TOTAL]) - (single ? 1 : 0); // every earlier record is final
     bool invalid = false;
     const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
     if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
@@ -2371,19 +2372,56 @@ __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned
   wide_commit_block<DP>(S, r, base, len, n_blocks, src);
 }
 
-// The turns of many wide records, one after the other, in ONE persistent cooperative kernel (two
-// grid-wide barriers per record instead of two launches): same pieces, same sums as the two kernels.
+// The turns of many wide records, one after the other, in ONE persistent kernel: same pieces, same
+// sums as the two kernels.  Only the blocks that hold pieces of a record's list take part in its
+// turn, and they synchronise among themselves through two words per turn (arrivals after the
+// reduction, a flag once block 0 has committed) instead of two barriers over the whole grid: a turn
+// over a list of a few thousand entries costs a few microseconds whatever the longest list of the
+// stretch is.  Launched cooperatively, so that every block is resident while others spin on it.
 struct WideTurn { int r, len, src, pad; unsigned long long base; };
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 template <bool DP>
-__global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* turns, int n) {
-  cg::grid_group grid = cg::this_grid();
+__global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* turns, int n, unsigned* __restrict__ sync,
+                                                    unsigned long long* __restrict__ dbg) { // dbg (trace, may be null): [n][4] ns of block 0
+  unsigned* arrived = sync;      // [n] blocks that have reduced their pieces of turn t
+  unsigned* committed = sync + n; // [n] 1: turn t is committed
+  int waited = -1;                // last turn this block knows to be committed
   for (int t = 0; t < n; t++) {
     const WideTurn w = turns[t];
     const int n_blocks = max(1, min(WIDE_BLOCKS, (w.len + 2047) / 2048));
+    const int taking_part = min(n_blocks, (int)gridDim.x);
+    if ((int)blockIdx.x >= taking_part) continue;
+    if (t > 0 && waited < t - 1) { // sizes and member lists as the previous turn left them
+      if (threadIdx.x == 0) while (ld_acquire_u32(&committed[t - 1]) == 0u) {}
+      __syncthreads();
+      waited = t - 1;
+    }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t] = global_ns();
     for (int vb = blockIdx.x; vb < n_blocks; vb += gridDim.x) wide_reduce_block<DP>(S, w.r, w.base, w.len, w.src, vb, n_blocks);
-    grid.sync();
-    if (blockIdx.x == 0) wide_commit_block<DP>(S, w.r, w.base, w.len, n_blocks, w.src);
-    grid.sync();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 1] = global_ns();
+    if (taking_part > 1) {
+      __syncthreads();
+      if (threadIdx.x == 0) red_release_add_u32(&arrived[t], 1u);
+    }
+    if (blockIdx.x == 0) {
+      if (taking_part > 1) {
+        if (threadIdx.x == 0) while (ld_acquire_u32(&arrived[t]) < (unsigned)taking_part) {}
+      }
+      __syncthreads();
+      if (dbg && threadIdx.x == 0) dbg[4 * t + 2] = global_ns();
+      wide_commit_block<DP>(S, w.r, w.base, w.len, n_blocks, w.src);
+      __syncthreads();
+      if (threadIdx.x == 0) red_release_add_u32(&committed[t], 1u);
+      if (dbg && threadIdx.x == 0) dbg[4 * t + 3] = global_ns();
+      waited = t;
+    }
   }
 }
 
@@ -2454,6 +2492,15 @@ __global__ void __launch_bounds__(TPB) k_wide_emit(DevState S, const int* __rest
     const int none[1] = {0};
     for (int q0 = lo + jb * WE_TILE; q0 < hi; q0 += WE_BLOCKS * WE_TILE)
       for (int q = q0 + threadIdx.x; q < min(hi, q0 + WE_TILE); q += TPB) visit(t.ids[q], none, nullptr);
+  } else if (!t.chain && 1.2 * (double)S.N >= 64.0 * (double)t.B) {
+    // CSR table with long buckets: the blocks take the probes in turn, all threads stride over the bucket
+    for (long long j = jb; j < pr.count; j += WE_BLOCKS) {
+      int v[BIG_UNPINNED];
+      pr.values(j, v);
+      const uint32_t b = pr.bucket(S, t, x, v);
+      const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+      for (int q = lo + threadIdx.x; q < hi; q += TPB) visit(t.ids[q], v, nullptr);
+    }
   } else {
     for (long long j = (long long)jb * TPB + threadIdx.x; j < pr.count; j += WE_BLOCKS * TPB) {
       int v[BIG_UNPINNED];
@@ -2523,11 +2570,22 @@ __global__ void __launch_bounds__(TPB) k_wide_store_b(DevState S, const int* __r
 // Upper bound of an unfinalised record's change of K: it can only add an entity (+1) if it shares
 // its entity at its turn, i.e. if the entity has other members now or some other record may join
 // it first (the entity is on somebody's candidate list, or a record without a list is pending).
-__global__ void __launch_bounds__(TPB) k_bounds_init(DevState S, int any_nolist) {
+// "Round 0" (sure_ok: prior_weight_new is positive and finite for every possible K): a record that
+// is alone in its entity, has no candidate but that entity, and whose entity and potential entity
+// are on nobody's stored list founds its entity whatever happens before its turn - nothing it reads
+// can change and nothing it writes is read by anybody else - so it is final here and now, without
+// reservations (seven records in eight at 10 M).  Same outcome as its turn in round 1.
+__global__ void __launch_bounds__(TPB) k_bounds_init(DevState S, int any_nolist, int sure_ok) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= S.N || S.fin[r] == 1) return;
   const int own = S.lambda[r];
-  S.dhi[r] = (any_nolist || S.ent_size[own] > 1 || S.referenced[own]) ? 1 : 0;
+  const int sz = S.ent_size[own];
+  const bool shared = any_nolist || sz > 1 || S.referenced[own];
+  if (S.use_kbounds) S.dhi[r] = shared ? 1 : 0;
+  if (sure_ok && !shared && sz == 1 && S.cand_off[r] == CAND_OWN_ONLY && S.cand_cnt[r] == 1 && !S.referenced[S.N + r]) {
+    const double Ln = S.Lnew[r];
+    if (Ln > -CUDART_INF && Ln < CUDART_INF) finalize_record(S, r, own, S.N + r, true);
+  }
 }
 
 // wide records are final before the rounds start and their change of K is folded into K0

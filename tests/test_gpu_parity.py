@@ -160,7 +160,7 @@ def test_results_do_not_depend_on_batching_thresholds():
                  dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
                  dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0),
                  dict(fast_path=0), dict(hop_cap=1), dict(wide_buckets=0), dict(wide_buckets=0, fast_path=0, rounds_tail=0), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0),
-                 dict(table_min_usage=1000000), dict(table_min_usage=1000000, emit_cost_cap=0), dict(table_min_usage=1000000, emit_cost_cap=64)):
+                 dict(round0=0), dict(round0=0, rounds_tail=0), dict(table_min_usage=150), dict(table_min_usage=150, emit_cost_cap=0), dict(table_min_usage=150, emit_cost_cap=64)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
@@ -195,11 +195,11 @@ def test_records_no_table_serves_are_listed_through_the_cheapest_table():
     for k in ("fname_c1", "lname_c1", "by", "bd"):  # missing values make rare key masks
         cols[k] = [None if rng.random() < 0.15 else v for v in cols[k]]
     m = exchanger(cols, readme_attr_params(), PitmanYorRP(GammaRV(1, 1), BetaRV(1, 1)))
-    stats = lockstep(m, 6, table_min_usage=1000000)
+    stats = lockstep(m, 6, table_min_usage=150)
     assert sum(s["n_listed"] for s in stats) > 100, [(s["n_listed"], s["n_scanned"], s["n_tables"]) for s in stats]
-    stats = lockstep(m, 4, table_min_usage=1000000, wide_threshold=20)  # ... some of them wide after all
+    stats = lockstep(m, 4, table_min_usage=150, wide_threshold=20)  # ... some of them wide after all
     assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
-    stats = lockstep(m, 4, table_min_usage=1000000, emit_cost_cap=0)
+    stats = lockstep(m, 4, table_min_usage=150, emit_cost_cap=0)
     assert sum(s["n_scanned"] for s in stats) > 100 and sum(s["n_listed"] for s in stats) == 0
 
 
