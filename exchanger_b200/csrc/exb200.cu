@@ -1188,6 +1188,7 @@ int update_links(exb200_handle* h) {
     S.K0 = h->K + dk_wide; // what the remaining records see as the starting number of entities
   }
   // records whose list did not fit the candidate pool (n_fence) are pending too
+  bool round0_ran = false;
   {
     // round 0 needs prior_weight_new(K) positive and finite whatever K is when the record's turn comes
     // (clust_params.cpp:9-31: alpha + d K; kappa |m - K|, |m - K| - zero only at K = m)
@@ -1196,6 +1197,7 @@ int update_links(exb200_handle* h) {
     if (c.kind == EXB200_CLUST_PITMAN_YOR) sure = sure && c.alpha > 0.0 && c.d >= 0.0 && std::isfinite(c.alpha + c.d * (double)N);
     else sure = sure && c.m > (double)(N - 1) && std::isfinite(c.m) /* K without the record is at most N - 1 */ && (c.kind != EXB200_CLUST_GEN_COUPON || (c.kappa > 0.0 && std::isfinite(c.kappa * c.m)));
     if (S.use_kbounds || sure) KLAUNCH(h, k_bounds_init, nblk(N), TPB, 0, S, n_fence > 0 ? 1 : 0, sure ? 1 : 0);
+    round0_ran = sure && n_fence == 0;
   }
   CK(cudaEventRecord(h->ev[11], st));
 
@@ -1223,8 +1225,12 @@ int update_links(exb200_handle* h) {
   if (use_tail && h->trace && !h->tail.dbg) {
     int rc = dalloc(h, &h->tail.dbg, 257); if (rc) return rc;
   }
+  // After round 0 one record in eight is left: no separate launches for round 1 either - the
+  // persistent kernel starts from the compacted list of the open records (a thread per record over all
+  // N would keep nearly every warp busy with its one or two open records).
+  const bool skip_round1 = use_tail && round0_ran;
   while (n_act + n_actl > 0) {
-    rounds++;
+    if (!skip_round1) rounds++;
     const uint32_t round = h->round_ctr++;
     if (h->round_ctr >= 0x7FFFFFF0u) { // reservation words would wrap: start over
       CK(cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, st));
@@ -1234,14 +1240,16 @@ int update_links(exb200_handle* h) {
     const int init[3] = {0, 0x7FFFFFFF, -1}; // C_NACT_OUT, C_MIN_ACTIVE, C_WIDE_READY
     CK(cudaMemcpyAsync(S.counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(S.counters + C_NACTL_OUT, 0, sizeof(int), st));
-    if (n_act > 0) KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
-    if (n_actl > 0) KLAUNCH(h, k_reserve_w, n_actl, TPB, 0, S, S.actl_in, n_actl, round);
-    if (S.use_kbounds) {
-      int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
-      rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
+    if (!skip_round1) {
+      if (n_act > 0) KLAUNCH(h, k_reserve, nblk(n_act), TPB, 0, S, act, n_act, round);
+      if (n_actl > 0) KLAUNCH(h, k_reserve_w, n_actl, TPB, 0, S, S.actl_in, n_actl, round);
+      if (S.use_kbounds) {
+        int rc = scan_exclusive<int8_t>(h, S.dlo, S.plo, N); if (rc) return rc;
+        rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
+      }
+      if (n_act > 0) KLAUNCH_DP(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
+      if (n_actl > 0) KLAUNCH_DP(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
     }
-    if (n_act > 0) KLAUNCH_DP(h, k_commit, nblk(n_act), TPB, 0, S, act, n_act, round);
-    if (n_actl > 0) KLAUNCH_DP(h, k_commit_w, n_actl, TPB, sizeof(double) * (size_t)std::max(h->long_cap, 1), S, S.actl_in, n_actl, round);
     if (use_tail) {
       // everything that is left, in ascending id; K bounds from the outcome of round 1
       if (S.use_kbounds) {
