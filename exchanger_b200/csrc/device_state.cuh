@@ -54,6 +54,8 @@ struct DevAttr {
   double G[NMAX_FAST + 1];                 // sum_v g_n(v)
   double *lt_diff, *lt_same;               // per sweep, [F][D]: log(theta mef(v)); log(1 - theta mef(v))
                                            // or log(1 - eff + eff p(v|v)) when the value is not excluded
+  double *sg;                              // per sweep, [F][D][2], exclude_entity_value only: for an entity whose ONE observed
+                                           // member (file f) has value x, the weight of keeping x and of all other values
 };
 
 // One blocking table: items (entity slots) bucketed by their values on a set of key attributes

@@ -487,6 +487,7 @@ int build_attr(exb200_handle* h, const exb200_attr& in, int a) {
 #undef NEWD
   rc = dalloc(h, &da.lt_diff, (size_t)h->F * D); if (rc) return rc;
   rc = dalloc(h, &da.lt_same, (size_t)h->F * D); if (rc) return rc;
+  rc = dalloc(h, &da.sg, (size_t)2 * h->F * D); if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream)); // the host vectors go out of scope
   return refresh_phi(h, a);
 }
@@ -1403,9 +1404,15 @@ int sweep_links(exb200_handle* h) {
 }
 int sweep_entities(exb200_handle* h, int lo, int hi) {
   DevState& S = h->S;
-  CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int), h->stream));
-  if (hi > lo) KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, lo, hi);   // ents_.update_attributes(...)
-  KLAUNCH_DP(h, k_entities_general, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count);
+  CK(cudaMemsetAsync(h->d_gen_count, 0, sizeof(int) * 3, h->stream));
+  const long long gen_cap = (long long)h->N * h->A;
+  if (hi > lo) { // ents_.update_attributes(...)
+    int* multi = S.act_in; // [N] (free outside the links update)
+    KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, gen_cap, lo, hi, multi);
+    KLAUNCH(h, k_entities_slow, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count, gen_cap);
+    KLAUNCH(h, k_entities_multi, h->n_sm * 16, 128, 0, S, (const int*)multi, h->d_gen_list, h->d_gen_count);
+  }
+  KLAUNCH_DP(h, k_entities_general, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count, gen_cap);
   return EXB200_OK;
 }
 int sweep_distort(exb200_handle* h, int lo, int hi) {
@@ -1733,7 +1740,7 @@ int exb200_create(const exb200_model* m, int device, exb200_handle** out) {
   TRY(dalloc(h, &h->pb.part_start, (size_t)PA_MAX_TABS * (MAX_PARTS + 1)));
   TRY(dalloc(h, &h->d_cl_counts, 2));
   TRY(dalloc(h, &h->d_gen_list, (size_t)N * (size_t)A)); // worst case (include mode): every entity, every attribute
-  TRY(dalloc(h, &h->d_gen_count, 1));
+  TRY(dalloc(h, &h->d_gen_count, 3));
   cudaMemsetAsync(S.owner, 0xFF, sizeof(unsigned long long) * 2 * N, h->stream);
   cudaMemsetAsync(S.fence, 0xFF, sizeof(unsigned long long), h->stream);
   cudaMemsetAsync(S.dev_err, 0, sizeof(int) * 2, h->stream);

@@ -278,6 +278,29 @@ __global__ void k_theta_tables(DevState S, int a) {
     const double eff = S.theta[f * S.A + a] * t.mef[v];
     t.lt_diff[i] = log(eff);
     t.lt_same[i] = t.exclude ? log(1.0 - eff) : log(1.0 - eff + eff * (t.is_const ? t.psi[v] : 1.0));
+    if (t.exclude) {
+      // An entity with one observed member value x (a singleton above all): the two weights its draw
+      // compares - the very expressions of draw_entity_value for nobs = 1, so that k_entities can take
+      // "keep x" from this table and leave everything else to that function.
+      const double th = S.theta[f * S.A + a];
+      double keep, other;
+      if (t.is_const) {
+        double Cc = 1.0, ww = t.phi[v], rest = t.G[1];
+        Cc *= th * t.psi[v];
+        ww *= 1.0 - th;
+        rest -= t.g[(size_t)t.D + v];
+        if (rest < 0.0) rest = 0.0;
+        keep = ww; other = Cc * rest;
+      } else {
+        double thp = 1.0, wx = t.phi[v];
+        thp *= th;
+        wx *= 1.0 - th * t.mef[v];
+        const int lo = t.row[v], hi = t.row[v + 1];
+        const double rsum = hi > lo ? t.cs[hi - 1] : 0.0;
+        keep = wx; other = thp * rsum;
+      }
+      t.sg[2 * (size_t)i] = keep; t.sg[2 * (size_t)i + 1] = other;
+    }
   }
 }
 
@@ -2666,12 +2689,13 @@ __device__ double log_weight_entity_value(const DevState& S, const DevAttr& t, i
   return lw;
 }
 
-// `xs`: the record row of a singleton entity, already in registers (its only member); nullptr: the
-// members are read from the sorted member list starting at `head`
-__device__ __forceinline__ int draw_entity_value(const DevState& S, int e, int a, int head, const int* xs = nullptr) {
+// `xs`: the record rows (8 ints each) of the entity's `n_xs` members in ascending id, read already (a
+// singleton's only row, the few rows of a small cluster); nullptr: the members are read from the
+// sorted member list starting at `head`
+__device__ __forceinline__ int draw_entity_value(const DevState& S, int e, int a, int head, const int* xs = nullptr, int n_xs = 1) {
   // fn(row) for every member row in ascending record id
   auto each = [&](auto&& fn) {
-    if (xs) fn(xs);
+    if (xs) for (int k = 0; k < n_xs; k++) fn(xs + 8 * k);
     else for (int r = head; r >= 0; r = S.rec_next[r]) fn(S.rec_x + (size_t)r * S.RS);
   };
   const DevAttr& t = S.attrs[a];
@@ -2891,12 +2915,16 @@ __device__ int draw_entity_value_warp(const DevState& S, int e, int a, int head)
 }
 
 // (entity slots [e_lo, e_hi): the whole range on one GPU, a slice under within-chain sharding)
+// gen_list holds two lists of (entity << 8 | attribute) pairs: from the front (gen_count[0]) the pairs
+// left to the general scheme (k_entities_general), from the back (gen_count[1], last entry at
+// gen_cap - 1) the draws of singletons that did not keep their member's value (k_entities_slow).
 __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count,
-                                                  int e_lo, int e_hi) {
+                                                  long long gen_cap, int e_lo, int e_hi, int* __restrict__ multi_list) {
   __shared__ int s_warp[TPB / 32]; // (launched with blocks of up to TPB threads)
   __shared__ int s_base;
   const int e = e_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t need = 0;
+  uint32_t need = 0, slow = 0;
+  bool deferred = false;
   const int sz = e < e_hi ? S.ent_size[e] : 0;
   if (sz == 1 && S.RS == 8 && S.ES == 8) {
     // a singleton: its only member is record e (entities are named after their smallest member), whose
@@ -2910,16 +2938,34 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long
 #pragma unroll
     for (int a = 0; a < 8; a++) yn[a] = 0;
     for (int a = 0; a < S.A; a++) {
-      const int v = draw_entity_value(S, e, a, e, x);
-      if (v >= 0) yn[a] = v; else need |= 1u << a;
+      // "keep the member's value" straight from the per-sweep table (nineteen draws in twenty).  The
+      // others are listed for k_entities_slow - one thread per draw through the general function,
+      // which recomputes the same weights from the same uniform - instead of being made here by one
+      // lane or two while the rest of the warp waits.
+      const DevAttr& t = S.attrs[a];
+      const int xv = x[a];
+      int v = -2;
+      if (xv >= 0 && t.exclude) {
+        const double2 kw = *reinterpret_cast<const double2*>(t.sg + 2 * ((size_t)x[7] * t.D + xv));
+        const double total = kw.x + kw.y;
+        if (total > 0.0 && isfinite(total)) {
+          const U2 u0 = uniforms(S.seed, e, S.iter, PH_ENT_ATTR, a, 0);
+          if (u0.a * total < kw.x) v = xv;
+        }
+      }
+      if (v >= 0) yn[a] = v; else slow |= 1u << a;
     }
     int* y = S.ent_y + (size_t)e * 8;
-    if (need) { for (int a = 0; a < S.A; a++) if (!((need >> a) & 1u)) y[a] = yn[a]; }
+    if (slow) { for (int a = 0; a < S.A; a++) if (!((slow >> a) & 1u)) y[a] = yn[a]; }
     else {
       int4* yp = reinterpret_cast<int4*>(y);
       yp[0] = make_int4(yn[0], yn[1], yn[2], yn[3]);
       yp[1] = make_int4(yn[4], yn[5], yn[6], yn[7]);
     }
+  } else if (sz > 0 && multi_list) {
+    // more than one member: listed for k_entities_multi, so that a warp of singletons does not wait
+    // for the lane that walks a member list
+    deferred = true;
   } else if (sz > 0) {
     const int head = S.ent_head[e];
     int* y = S.ent_y + (size_t)e * S.ES;
@@ -2928,34 +2974,100 @@ __global__ void __launch_bounds__(TPB) k_entities(DevState S, unsigned long long
       if (v >= 0) y[a] = v; else need |= 1u << a;
     }
   }
-  // the (entity, attribute) pairs left to the general scheme are listed (one atomic per block)
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int mine = __popc(need);
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
-  if (lane == 31) s_warp[w] = incl;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int k = 0; k < (int)blockDim.x / 32; k++) { const int c = s_warp[k]; s_warp[k] = t; t += c; }
-    s_base = t ? atomicAdd(gen_count, t) : 0;
+  {
+    const unsigned dm = __ballot_sync(FULL, deferred);
+    if (dm) {
+      const int ln = threadIdx.x & 31;
+      int base = 0;
+      if (ln == __ffs(dm) - 1) base = atomicAdd(gen_count + 2, __popc(dm));
+      base = __shfl_sync(FULL, base, __ffs(dm) - 1);
+      if (deferred) multi_list[base + __popc(dm & ((1u << ln) - 1u))] = e;
+    }
   }
-  __syncthreads();
-  int pos = s_base + s_warp[w] + incl - mine;
-  for (uint32_t m = need; m; m &= m - 1)
-    gen_list[pos++] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)(__ffs(m) - 1);
+  // both kinds of pairs are listed with one atomic per block and list
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int which = 0; which < 2; which++) {
+    const uint32_t mask = which ? slow : need;
+    const int mine = __popc(mask);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+    __syncthreads(); // (s_warp / s_base of the first list have been read)
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < (int)blockDim.x / 32; k++) { const int c = s_warp[k]; s_warp[k] = t; t += c; }
+      s_base = t ? atomicAdd(gen_count + which, t) : 0;
+    }
+    __syncthreads();
+    long long pos = (long long)s_base + s_warp[w] + incl - mine;
+    for (uint32_t m = mask; m; m &= m - 1) {
+      const unsigned long long pr = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)(__ffs(m) - 1);
+      gen_list[which ? gen_cap - 1 - pos : pos] = pr;
+      pos++;
+    }
+  }
+}
+
+// the entities with several members that k_entities listed (gen_count[2] of them): one thread per
+// entity; the rows of up to ENT_ROWS members are read once and kept for all the attributes
+constexpr int ENT_ROWS = 4;
+__global__ void __launch_bounds__(128) k_entities_multi(DevState S, const int* __restrict__ multi_list, unsigned long long* __restrict__ gen_list,
+                                                        int* __restrict__ gen_count) {
+  const int n = gen_count[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int e = multi_list[i];
+    const int head = S.ent_head[e], sz = S.ent_size[e];
+    int xm[ENT_ROWS * 8];
+    const bool rows = sz <= ENT_ROWS && S.RS == 8;
+    if (rows) {
+      int k = 0;
+      for (int r = head; r >= 0 && k < ENT_ROWS; r = S.rec_next[r], k++) {
+        const int4* xp = reinterpret_cast<const int4*>(S.rec_x + (size_t)r * 8);
+        const int4 x0 = xp[0], x1 = xp[1];
+        int* x = xm + 8 * k;
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+      }
+    }
+    int* y = S.ent_y + (size_t)e * S.ES;
+    for (int a = 0; a < S.A; a++) {
+      const int v = rows ? draw_entity_value(S, e, a, head, xm, sz) : draw_entity_value(S, e, a, head);
+      if (v >= 0) y[a] = v;
+      else gen_list[atomicAdd(gen_count, 1)] = ((unsigned long long)(uint32_t)e << 8) | (unsigned long long)a;
+    }
+  }
+}
+
+// the singleton draws k_entities listed: one thread per (entity, attribute) pair
+__global__ void __launch_bounds__(TPB) k_entities_slow(DevState S, unsigned long long* __restrict__ gen_list, int* __restrict__ gen_count,
+                                                       long long gen_cap) {
+  const int n = gen_count[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long p = gen_list[gen_cap - 1 - i];
+    const int e = (int)(p >> 8), a = (int)(p & 0xFFu);
+    int x[8];
+    {
+      const int4* xp = reinterpret_cast<const int4*>(S.rec_x + (size_t)e * 8);
+      const int4 x0 = xp[0], x1 = xp[1];
+      x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+    }
+    const int v = draw_entity_value(S, e, a, e, x);
+    if (v >= 0) S.ent_y[(size_t)e * 8 + a] = v;
+    else gen_list[gen_cap - 1 - i] = p | (1ull << 63); // the general scheme after all: flagged where it stands
+  }
 }
 
 // one warp per listed (entity, attribute) pair, whatever the launch shape
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_entities_general(DevState S, const unsigned long long* __restrict__ gen_list,
-                                                          const int* __restrict__ gen_count) {
+                                                          const int* __restrict__ gen_count, long long gen_cap) {
   const int lane = threadIdx.x & 31;
-  const int n = *gen_count;
+  const int n = gen_count[0], n_back = gen_count[1]; // the front list, and the flagged entries of the back list
   const int n_warps = gridDim.x * (TPB / 32);
-  for (int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); i < n; i += n_warps) {
-    const unsigned long long p = gen_list[i];
+  for (int i = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); i < n + n_back; i += n_warps) {
+    unsigned long long p = i < n ? gen_list[i] : gen_list[gen_cap - 1 - (i - n)];
+    if (i >= n) { if (!(p >> 63)) continue; p &= ~(1ull << 63); }
     const int e = (int)(p >> 8), a = (int)(p & 0xFFu);
     const int v = draw_entity_value_warp<DP>(S, e, a, S.ent_head[e]);
     if (lane == 0) S.ent_y[(size_t)e * S.ES + a] = v;
