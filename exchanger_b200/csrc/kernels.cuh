@@ -1998,7 +1998,7 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
   __shared__ int s_r[WIDE_NB], s_b[WIDE_NB];
   __shared__ uint8_t s_more[WIDE_NB];        // the record pins an attribute beyond the eighth
   __shared__ int s_run[TPB / 32][WIDE_NB];
-  __shared__ uint16_t s_q[TPB / 32][WIDE_Q]; // per-warp queue of (record << 5 | lane) pairs waiting for their likelihood
+  __shared__ uint32_t s_q[TPB / 32][WIDE_Q]; // per-warp queue of (record << 24 | item - first item of the piece) pairs waiting for their likelihood
   __shared__ int s_n;
   if (threadIdx.x == 0) {
     int n = 0;
@@ -2053,8 +2053,8 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
     for (int a = 0; a < 8; a++) if (a * W < 64) P |= hash_w(y[a], W) << (W * a);
     // Pairs that pass the pinned attributes are queued per warp and their likelihoods evaluated 32
     // at a time, one pair per lane: the evaluation is a chain of dependent loads (neighbourhood
-    // search), far too slow to run with a lane or two active.  The queue is filled in (record,
-    // item) order and emptied before the next 32 items, so every record sees its items in order.
+    // search), far too slow to run with a lane or two active.  The queue is filled in (step,
+    // record, item) order and emptied in that order, so every record sees its items in ascending order.
     auto drain = [&](int cnt) {
       int k = -1 - lane, rank = 0; // inactive lanes: distinct keys that match nobody
       long long it = 0;
@@ -2062,8 +2062,8 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
       bool hit = false;
       if (lane < cnt) {
         const unsigned e = s_q[wp][(qh + lane) & (WIDE_Q - 1)];
-        k = (int)(e >> 5);
-        it = base + (long long)(e & 31u);
+        k = (int)(e >> 24);
+        it = lo + (long long)(e & 0xFFFFFFu);
         const int r = k < n_act ? s_r[k] : 0;
         hit = k < n_act && it != (long long)S.N + r;
         if (hit) {
@@ -2114,17 +2114,20 @@ __global__ void __launch_bounds__(TPB) k_wide_scan(DevState S, const int* __rest
       const bool h2 = ((P ^ mv2.y) & mv2.x) == 0, h3 = ((P ^ mv3.y) & mv3.x) == 0;
       if (!__any_sync(FULL, live && (h0 | h1 | h2 | h3))) continue;
       const unsigned lt = (1u << lane) - 1u;
+      const uint32_t off = (uint32_t)(i - lo); // (a piece holds far fewer than 2^24 items)
       const unsigned m0 = __ballot_sync(FULL, live && h0), m1 = __ballot_sync(FULL, live && h1);
       const unsigned m2 = __ballot_sync(FULL, live && h2), m3 = __ballot_sync(FULL, live && h3);
       // (the padding records of the last group match next to nothing and are dropped in drain)
-      if (m0) { if (live && h0) s_q[wp][(qh + qn + __popc(m0 & lt)) & (WIDE_Q - 1)] = (uint16_t)((k4 << 5) | lane); qn += __popc(m0); }
-      if (m1) { if (live && h1) s_q[wp][(qh + qn + __popc(m1 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 1) << 5) | lane); qn += __popc(m1); }
-      if (m2) { if (live && h2) s_q[wp][(qh + qn + __popc(m2 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 2) << 5) | lane); qn += __popc(m2); }
-      if (m3) { if (live && h3) s_q[wp][(qh + qn + __popc(m3 & lt)) & (WIDE_Q - 1)] = (uint16_t)(((k4 + 3) << 5) | lane); qn += __popc(m3); }
+      if (m0) { if (live && h0) s_q[wp][(qh + qn + __popc(m0 & lt)) & (WIDE_Q - 1)] = ((uint32_t)k4 << 24) | off; qn += __popc(m0); }
+      if (m1) { if (live && h1) s_q[wp][(qh + qn + __popc(m1 & lt)) & (WIDE_Q - 1)] = ((uint32_t)(k4 + 1) << 24) | off; qn += __popc(m1); }
+      if (m2) { if (live && h2) s_q[wp][(qh + qn + __popc(m2 & lt)) & (WIDE_Q - 1)] = ((uint32_t)(k4 + 2) << 24) | off; qn += __popc(m2); }
+      if (m3) { if (live && h3) s_q[wp][(qh + qn + __popc(m3 & lt)) & (WIDE_Q - 1)] = ((uint32_t)(k4 + 3) << 24) | off; qn += __popc(m3); }
       __syncwarp();
       while (qn >= 32) drain(32);
     }
-    if (qn) drain(qn);
+    // (what is left waits for the pairs of the next 32 items: a drain costs a chain of dependent loads
+    // whatever the number of lanes that take part in it)
+    if (qn && base + 32 >= hi) drain(qn);
   }
   if (!FILL) {
     __syncwarp();
@@ -2226,99 +2229,129 @@ __global__ void __launch_bounds__(TPB) k_wide_store(DevState S, const int* __res
 
 // Turn of record r, listed at wl_base = `base` with `len` entries: every warp of the grid reduces a
 // contiguous piece (lanes strided: coalesced) to (max, sum of exp(lw - max)) in wide_part[2p], [2p+1].
-// (src = 1: the list is in wlb_id / wlb_ll - possible links listed from the record's own bucket)
+// (src = 1: the list is in wlb_id / wlb_ll - possible links listed from the tables)
 // `vblock` of `n_vblocks`: the block's place in the grid of the stand-alone kernel (the persistent
-// kernel k_wide_turns gives every block several)
+// kernel k_wide_turns gives every block several).
+// A turn is a chain of dependent memory accesses, so what does not depend on the turns before it
+// (the list entries - WideTile; the record's own entity) is read before the wait for the previous
+// turn, and the sums take two passes (maximum, then independent exponentials) instead of a running
+// rescaled sum whose every step waits for the last one.
+struct WideTile { int id[8]; double l[8]; };
+__device__ __forceinline__ void wide_piece_of(int len, int n_vblocks, int vblock, long long& lo, long long& hi) {
+  wide_piece(len, n_vblocks * (TPB / 32), vblock * (TPB / 32) + (threadIdx.x >> 5), lo, hi);
+}
+__device__ __forceinline__ void wide_load_tile(const int* ids, const double* ll, long long i0, long long hi, WideTile& t) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const long long i = i0 + j * 32 + lane;
+    t.id[j] = i < hi ? ids[i] : -1;
+    t.l[j] = i < hi ? ll[i] : 0.0;
+  }
+}
+// sizes are read past the L1 (they change between the turns of one kernel)
+__device__ __forceinline__ int live_size_cg(const DevState& S, int e, int own, bool single) {
+  const int sz = __ldcg(&S.ent_size[e]);
+  return e == own ? (single ? 0 : sz - 1) : sz;
+}
 template <bool DP>
-__device__ __forceinline__ void wide_reduce_block(const DevState& S, int r, unsigned long long base, int len, int src, int vblock, int n_vblocks) {
+__device__ __forceinline__ void wide_reduce_block(const DevState& S, int r, unsigned long long base, int len, int src, int vblock,
+                                                  int n_vblocks, int own, bool single, const WideTile* first) {
   const int* ids = (src ? S.wlb_id : S.wl_id) + base;
   const double* ll = (src ? S.wlb_ll : S.wl_ll) + base;
-  const int own = S.lambda[r];
-  const bool single = S.ent_size[own] == 1;
   const int lane = threadIdx.x & 31, p = vblock * (TPB / 32) + (threadIdx.x >> 5);
   long long lo, hi;
-  wide_piece(len, n_vblocks * (TPB / 32), p, lo, hi);
+  wide_piece_of(len, n_vblocks, vblock, lo, hi);
   double m = -CUDART_INF, sum = 0.0;
   for (long long i0 = lo; i0 < hi; i0 += 256) { // 8 entries per lane in flight (a piece has at most 256 unless the grid is capped)
-    int id[8], sz[8];
-    double l[8];
+    WideTile t;
+    if (first && i0 == lo) t = *first; else wide_load_tile(ids, ll, i0, hi, t);
+    int sz[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) sz[j] = t.id[j] >= 0 ? live_size_cg(S, t.id[j], own, single) : 0;
+    double v[8], mt = -CUDART_INF;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const long long i = i0 + j * 32 + lane;
-      id[j] = i < hi ? ids[i] : -1;
-      l[j] = i < hi ? ll[i] : 0.0;
+      v[j] = sz[j] > 0 ? cand_lw<DP>(S, r, t.id[j], sz[j], t.l[j]) : -CUDART_INF;
+      mt = v[j] > mt ? v[j] : mt;
     }
+    if (!(mt > -CUDART_INF)) continue;
+    const double mn = mt > m ? mt : m;
+    double st = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) sz[j] = id[j] >= 0 ? live_size(S, id[j], own, single) : 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      if (sz[j] <= 0) continue;
-      const double v = cand_lw<DP>(S, r, id[j], sz[j], l[j]);
-      if (!(v > -CUDART_INF)) continue;
-      if (v > m) { sum = sum * exp(m - v) + 1.0; m = v; } else sum += exp(v - m);
-    }
+    for (int j = 0; j < 8; j++) if (v[j] > -CUDART_INF) st += exp(v[j] - mn);
+    sum = (m > -CUDART_INF ? sum * exp(m - mn) : 0.0) + st;
+    m = mn;
   }
+  // the warp's maximum first, then one rescaling per lane and a plain sum
+  double mw = m;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double m2 = __shfl_xor_sync(FULL, m, o), s2 = __shfl_xor_sync(FULL, sum, o);
-    const double mm = m2 > m ? m2 : m;
-    if (mm > -CUDART_INF) sum = (m > -CUDART_INF ? sum * exp(m - mm) : 0.0) + (m2 > -CUDART_INF ? s2 * exp(m2 - mm) : 0.0);
-    m = mm;
-  }
-  if (lane == 0) { S.wide_part[2 * p] = m; S.wide_part[2 * p + 1] = sum; }
+  for (int o = 16; o > 0; o >>= 1) { const double m2 = __shfl_xor_sync(FULL, mw, o); mw = m2 > mw ? m2 : mw; }
+  double sw = m > -CUDART_INF ? sum * exp(m - mw) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(FULL, sw, o);
+  if (lane == 0) { S.wide_part[2 * p] = mw; S.wide_part[2 * p + 1] = sw; }
 }
 
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_wide_reduce(DevState S, int r, unsigned long long base, int len, int src) {
-  wide_reduce_block<DP>(S, r, base, len, src, (int)blockIdx.x, (int)gridDim.x);
+  const int own = S.lambda[r];
+  wide_reduce_block<DP>(S, r, base, len, src, (int)blockIdx.x, (int)gridDim.x, own, S.ent_size[own] == 1, nullptr);
+}
+
+// decision "found a new entity" with the record's new-entity log-likelihood at hand (decide_new reads it)
+__device__ __forceinline__ bool decide_new_l(const DevState& S, double lnew, int k, double m1, double srel, double u1, bool& invalid) {
+  const double lwn = log(prior_new(S.cl, k)) + lnew;
+  const double m2 = m1 > lwn ? m1 : lwn;
+  invalid = !(m2 > -CUDART_INF);
+  const double wa = exp(lwn - m2);
+  const double wb = m1 > -CUDART_INF ? srel * exp(m1 - m2) : 0.0;
+  return u1 * (wa + wb) < wa;
 }
 
 // decision and commit of record r (one block; n_blocks = grid of the k_wide_reduce before it):
 // scale the piece sums to the global max in parallel, walk block sums and piece sums in order,
-// then one warp scans the chosen piece in order
+// then one warp scans the chosen piece in order.  `u`, `lnew`: the record's uniforms and new-entity
+// log-likelihood (static: the caller has them before the sums are ready).
 template <bool DP>
-__device__ void wide_commit_block(const DevState& S, int r, unsigned long long base, int len, int n_blocks, int src) {
+__device__ void wide_commit_block(const DevState& S, int r, unsigned long long base, int len, int n_blocks, int src, int own, bool single,
+                                  U2 u, double lnew) {
   __shared__ double s_bsum[WIDE_BLOCKS];
-  __shared__ double s_red[TPB];
-  __shared__ double s_m1, s_tt, s_c;
+  __shared__ double s_red[TPB / 32];
+  __shared__ double s_tt, s_c;
   __shared__ int s_piece, s_target, s_tail;
   const int* ids = (src ? S.wlb_id : S.wl_id) + base;
   const double* ll = (src ? S.wlb_ll : S.wl_ll) + base;
   const int n_pieces = n_blocks * (TPB / 32);
-  const int own = S.lambda[r];
-  const bool single = S.ent_size[own] == 1;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   double* scaled = S.wide_part + 2 * WIDE_PIECES;
   double m = -CUDART_INF;
-  for (int p = threadIdx.x; p < n_pieces; p += TPB) m = S.wide_part[2 * p] > m ? S.wide_part[2 * p] : m;
-  s_red[threadIdx.x] = m;
+  for (int p = threadIdx.x; p < n_pieces; p += TPB) { const double mp = __ldcg(&S.wide_part[2 * p]); m = mp > m ? mp : m; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const double m2 = __shfl_xor_sync(FULL, m, o); m = m2 > m ? m2 : m; }
+  if (lane == 0) s_red[wp] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double mm = -CUDART_INF;
-    for (int k = 0; k < TPB; k++) mm = s_red[k] > mm ? s_red[k] : mm;
-    s_m1 = mm;
+  double m1 = s_red[0];
+#pragma unroll
+  for (int k = 1; k < TPB / 32; k++) m1 = s_red[k] > m1 ? s_red[k] : m1;
+  for (int p = threadIdx.x; p < n_pieces; p += TPB) {
+    const double mp = __ldcg(&S.wide_part[2 * p]);
+    scaled[p] = mp > -CUDART_INF ? __ldcg(&S.wide_part[2 * p + 1]) * exp(mp - m1) : 0.0;
   }
   __syncthreads();
-  const double m1 = s_m1;
   for (int b = threadIdx.x; b < n_blocks; b += TPB) {
     double t = 0.0;
-    for (int w = 0; w < TPB / 32; w++) {
-      const int p = b * (TPB / 32) + w;
-      const double mp = S.wide_part[2 * p];
-      const double sc = mp > -CUDART_INF ? S.wide_part[2 * p + 1] * exp(mp - m1) : 0.0;
-      scaled[p] = sc;
-      t += sc;
-    }
+    for (int w = 0; w < TPB / 32; w++) t += scaled[b * (TPB / 32) + w];
     s_bsum[b] = t;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double srel = 0.0;
     for (int b = 0; b < n_blocks; b++) srel += s_bsum[b];
-    const U2 u = uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0);
     // (read past the L1: the counter is moved by atomics, which a cached copy of this very block would not see)
     const int k = S.K0 + __ldcg(&S.counters[C_DK_TOTAL]) - (single ? 1 : 0); // every earlier record is final
     bool invalid = false;
-    const bool is_new = decide_new(S, r, k, m1, srel, u.a, invalid);
+    const bool is_new = decide_new_l(S, lnew, k, m1, srel, u.a, invalid);
     if (invalid) dev_fail(S, EXB200_ERR_WEIGHTS, r);
     s_piece = -1; s_tail = 0; s_target = is_new ? S.N + r : -1;
     if (!is_new) {
@@ -2348,7 +2381,6 @@ __device__ void wide_commit_block(const DevState& S, int r, unsigned long long b
   }
   __syncthreads();
   if (s_piece >= 0 && threadIdx.x < 32) {
-    const int lane = threadIdx.x;
     long long lo, hi;
     wide_piece(len, n_pieces, s_piece, lo, hi);
     const double tt = s_tt;
@@ -2356,28 +2388,25 @@ __device__ void wide_commit_block(const DevState& S, int r, unsigned long long b
     double c = s_c;
     int target = -1, lastpos = -1;
     for (long long i0 = lo; i0 < hi && target < 0; i0 += 256) {
-      int id[8], sz[8];
-      double l[8];
+      WideTile t;
+      wide_load_tile(ids, ll, i0, hi, t);
+      int sz[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const long long i = i0 + j * 32 + lane;
-        id[j] = i < hi ? ids[i] : -1;
-        l[j] = i < hi ? ll[i] : 0.0;
-      }
+      for (int j = 0; j < 8; j++) sz[j] = t.id[j] >= 0 ? live_size_cg(S, t.id[j], own, single) : 0;
+      double wj[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) sz[j] = id[j] >= 0 ? live_size(S, id[j], own, single) : 0;
+      for (int j = 0; j < 8; j++) wj[j] = sz[j] > 0 ? exp(cand_lw<DP>(S, r, t.id[j], sz[j], t.l[j]) - m1) : 0.0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         if (target >= 0 || i0 + j * 32 >= hi) break; // warp-uniform
-        double w = 0.0;
-        if (sz[j] > 0) w = exp(cand_lw<DP>(S, r, id[j], sz[j], l[j]) - m1);
+        const double w = wj[j];
         double x = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(FULL, x, o); if (lane >= o) x = x + y; }
         const unsigned pos = __ballot_sync(FULL, w > 0.0);
-        if (pos) lastpos = __shfl_sync(FULL, id[j], 31 - __clz(pos));
+        if (pos) lastpos = __shfl_sync(FULL, t.id[j], 31 - __clz(pos));
         const unsigned hit = __ballot_sync(FULL, !tail && w > 0.0 && tt < c + x);
-        if (hit) target = __shfl_sync(FULL, id[j], __ffs(hit) - 1);
+        if (hit) target = __shfl_sync(FULL, t.id[j], __ffs(hit) - 1);
         c += __shfl_sync(FULL, x, 31);
       }
     }
@@ -2392,7 +2421,8 @@ __device__ void wide_commit_block(const DevState& S, int r, unsigned long long b
 }
 template <bool DP>
 __global__ void __launch_bounds__(TPB) k_wide_commit(DevState S, int r, unsigned long long base, int len, int n_blocks, int src) {
-  wide_commit_block<DP>(S, r, base, len, n_blocks, src);
+  const int own = S.lambda[r];
+  wide_commit_block<DP>(S, r, base, len, n_blocks, src, own, S.ent_size[own] == 1, uniforms(S.seed, r, S.iter, PH_LINK_DECIDE, 0, 0), S.Lnew[r]);
 }
 
 // The turns of many wide records, one after the other, in ONE persistent kernel: same pieces, same
@@ -2421,13 +2451,27 @@ __global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* 
     const int n_blocks = max(1, min(WIDE_BLOCKS, (w.len + 2047) / 2048));
     const int taking_part = min(n_blocks, (int)gridDim.x);
     if ((int)blockIdx.x >= taking_part) continue;
+    // what does not depend on the turns before this one: the record's own entity (its link moves at
+    // its own turn only), the first tile of this warp's piece, and - block 0 - the record's draws
+    const int own = S.lambda[w.r];
+    WideTile first;
+    {
+      long long lo, hi;
+      wide_piece_of(w.len, n_blocks, (int)blockIdx.x, lo, hi);
+      wide_load_tile((w.src ? S.wlb_id : S.wl_id) + w.base, (w.src ? S.wlb_ll : S.wl_ll) + w.base, lo, hi, first);
+    }
+    U2 u = {0.0, 0.0};
+    double lnew = 0.0;
+    if (blockIdx.x == 0) { u = uniforms(S.seed, w.r, S.iter, PH_LINK_DECIDE, 0, 0); lnew = S.Lnew[w.r]; }
     if (t > 0 && waited < t - 1) { // sizes and member lists as the previous turn left them
       if (threadIdx.x == 0) while (ld_acquire_u32(&committed[t - 1]) == 0u) {}
       __syncthreads();
       waited = t - 1;
     }
+    const bool single = __ldcg(&S.ent_size[own]) == 1;
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t] = global_ns();
-    for (int vb = blockIdx.x; vb < n_blocks; vb += gridDim.x) wide_reduce_block<DP>(S, w.r, w.base, w.len, w.src, vb, n_blocks);
+    for (int vb = blockIdx.x; vb < n_blocks; vb += gridDim.x)
+      wide_reduce_block<DP>(S, w.r, w.base, w.len, w.src, vb, n_blocks, own, single, vb == (int)blockIdx.x ? &first : nullptr);
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 1] = global_ns();
     if (taking_part > 1) {
       __syncthreads();
@@ -2439,7 +2483,7 @@ __global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* 
       }
       __syncthreads();
       if (dbg && threadIdx.x == 0) dbg[4 * t + 2] = global_ns();
-      wide_commit_block<DP>(S, w.r, w.base, w.len, n_blocks, w.src);
+      wide_commit_block<DP>(S, w.r, w.base, w.len, n_blocks, w.src, own, single, u, lnew);
       __syncthreads();
       if (threadIdx.x == 0) red_release_add_u32(&committed[t], 1u);
       if (dbg && threadIdx.x == 0) dbg[4 * t + 3] = global_ns();
