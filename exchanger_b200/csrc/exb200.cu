@@ -1222,6 +1222,7 @@ int update_links(exb200_handle* h) {
     h->d_select_tmp = tmp;
     rc = dalloc(h, &h->tail.n, 8); if (rc) return rc;
     rc = dalloc(h, &h->tail.long_pos, (size_t)N); if (rc) return rc;
+    rc = dalloc(h, &h->tail.bar, 1); if (rc) return rc;
   }
   if (use_tail && h->trace && !h->tail.dbg) {
     int rc = dalloc(h, &h->tail.dbg, 257); if (rc) return rc;
@@ -1258,6 +1259,7 @@ int update_links(exb200_handle* h) {
         rc = scan_exclusive<int8_t>(h, S.dhi, S.phi_, N); if (rc) return rc;
       }
       CK(cudaMemsetAsync(h->tail.n, 0, sizeof(int) * 8, st));
+      CK(cudaMemsetAsync(h->tail.bar, 0, sizeof(unsigned long long), st));
       CK(cub::DeviceSelect::If(h->d_select_tmp, h->select_tmp_bytes, thrust::counting_iterator<int>(0), h->tail.list[0],
                                h->tail.n, N, NotFinal{S.fin}, st));
       h->n_launches += 2;

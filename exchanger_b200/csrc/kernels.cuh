@@ -1768,7 +1768,22 @@ struct TailState {
   int* blk_tot;     // [grid][3] per chunk of positions: records that stay, sum of d dlo, sum of d dhi
   int* long_pos;    // [n] positions holding a record with a long list (this round)
   unsigned long long* dbg; // trace: [round][4] = (records, ns after A, after B, after C) of the first 64 rounds (may be null)
+  unsigned long long* bar; // arrivals at the kernel's own barrier (zero at launch)
 };
+// Barrier over the first `n_blocks` blocks of the grid (the others have left the kernel): every block
+// adds one to a counter that only grows and waits until it holds all the arrivals so far.  A round
+// over a few thousand records is run by a few blocks, and their barrier costs a fraction of one
+// over the whole grid.
+__device__ __forceinline__ void tail_barrier(unsigned long long* counter, unsigned long long& expected, int n_blocks) {
+  __syncthreads();
+  expected += (unsigned long long)n_blocks;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ull) : "memory");
+    unsigned long long v;
+    do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory"); } while (v < expected);
+  }
+  __syncthreads();
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1783,19 +1798,24 @@ constexpr int TAIL_TPB = 512;
 // taken by whole blocks, again handed out one at a time, while other blocks still work on tiles -
 // turns of one round touch disjoint items, so the order does not matter.
 template <bool DP>
-__global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState T, uint32_t round0, int max_rounds) {
+__global__ void __launch_bounds__(TAIL_TPB, 2) k_rounds_tail(DevState S, TailState T, uint32_t round0, int max_rounds) {
   extern __shared__ double s_w[]; // [long_cap] weights of a long record
   __shared__ CommitLongShared sh;
   __shared__ int s_red[3][TAIL_TPB / 32];
   __shared__ int s_carry[3];
   __shared__ int s_next;
-  cg::grid_group grid = cg::this_grid();
-  const int nb = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int gw = b * (TAIL_TPB / 32) + wp, n_warps = nb * (TAIL_TPB / 32);
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   int cur = 0, rounds = 0;
   int n = T.n[0];
+  int n_long_prev = gridDim.x; // long records of the previous round (they take a block each)
+  unsigned long long expected = 0; // arrivals at the barrier so far
   if (T.dbg && b == 0 && threadIdx.x == 0) T.dbg[256] = global_ns();
   while (n > 0 && rounds < max_rounds) {
+    // The blocks that run this round: about one record per thread plus a block per long record.  The
+    // list only shrinks, so a block that is not needed now never is again and leaves.
+    const int nb = (int)min((long long)gridDim.x, (long long)(n + TAIL_TPB - 1) / TAIL_TPB + (long long)n_long_prev);
+    if (b >= nb) break;
+    const int gw = b * (TAIL_TPB / 32) + wp, n_warps = nb * (TAIL_TPB / 32);
     const uint32_t round = round0 + (uint32_t)rounds;
     const int* in = T.list[cur];
     int* out = T.list[cur ^ 1];
@@ -1831,7 +1851,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
         }
       }
     }
-    grid.sync();
+    tail_barrier(T.bar, expected, nb);
     if (T.dbg && b == 0 && threadIdx.x == 0 && rounds < 64) { T.dbg[4 * rounds] = (unsigned long long)n; T.dbg[4 * rounds + 1] = global_ns(); }
     // ---- B: turns.  Short lists: warps take tiles from the cursor ...
     for (;;) {
@@ -1862,6 +1882,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
     __syncthreads();
     // ... long lists: blocks take them one at a time
     const int n_long = T.n[5];
+    n_long_prev = n_long;
     for (;;) {
       if (threadIdx.x == 0) s_next = atomicAdd(&T.n[6], 1);
       __syncthreads();
@@ -1879,7 +1900,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
         if (dh) atomicAdd(&tot[2], dh);
       }
     }
-    grid.sync();
+    tail_barrier(T.bar, expected, nb);
     if (T.dbg && b == 0 && threadIdx.x == 0 && rounds < 64) T.dbg[4 * rounds + 2] = global_ns();
     // ---- C: prefix over the chunks before this block's, then a scan of the chunk's own positions
     {
@@ -1943,7 +1964,7 @@ __global__ void __launch_bounds__(TAIL_TPB) k_rounds_tail(DevState S, TailState 
       } else n = n_next;
       cur ^= 1;
     }
-    grid.sync();
+    tail_barrier(T.bar, expected, nb);
   }
   if (b == 0 && threadIdx.x == 0) { T.n[1] = rounds; T.n[3] = n; }
 }
