@@ -238,7 +238,7 @@ def run_ours(opt, n_records, kind, desc):
     model, t_build = shared_model(n_records, kind, opt.distort_prior, rank, world, local, barrier)
     gpu = Sampler(model, seed=1000 + rank, device=local)
     phase_keys = ("ms_clust", "ms_prep", "ms_index", "ms_index_count", "ms_index_fill", "ms_cand", "ms_cand_fast", "ms_cand_long",
-                  "ms_wide", "ms_rounds", "ms_canon", "ms_entities", "ms_distort", "ms_total")
+                  "ms_wide", "ms_rounds", "ms_tail", "ms_canon", "ms_entities", "ms_entities_single", "ms_distort", "ms_total")
 
     def timed(n, acc=None):
         """n sweeps one by one: (device ms, launches), per-phase sums into acc"""
@@ -251,7 +251,7 @@ def run_ours(opt, n_records, kind, desc):
                 st = gpu.stats()
                 for k in phase_keys:
                     acc[k] += st[k]
-                for k in ("n_candidates", "n_rounds", "n_wide", "n_tables", "n_slow", "n_probe", "n_long"):
+                for k in ("n_candidates", "n_rounds", "n_wide", "n_tables", "n_slow", "n_probe", "n_long", "n_listed", "n_scanned"):
                     acc[k] = acc.get(k, 0) + st[k]
         return ms_sum, nl_sum
 
@@ -320,17 +320,24 @@ def run_ours(opt, n_records, kind, desc):
         n, cbar, rho = n_records, acc["n_candidates"] / opt.steps / n_records, k_ent / n_records
         tbar = acc["n_tables"] / opt.steps  # blocking tables built per sweep
         fast = acc["ms_cand_fast"] > 0
-        # single kernels only (the index build, the rounds and the serial path are multi-kernel phases)
+        # Single kernels with a CUDA-event time of their own (one launch per sweep each; the index build,
+        # the serial path and the rest of the entity update are multi-kernel phases).  Algorithmic bytes:
+        # DESIGN.md section 5 - the links figure of SURVEY 8d, 5A + 8 + c(4A + 8), is split between the
+        # candidate kernel (x, z, candidate tuples) and the rounds (lambda, candidate sizes).
         kernels = {
-            ("k_cand_fast (links: candidate generation)" if fast else "k_cand (links: candidate generation)"):
+            "k_rounds_tail (links: dependency rounds, persistent)": (acc["ms_tail"], n * (4 + 4 * cbar)),
+            ("k_cand_fast (links: candidate generation, first pass)" if fast else "k_cand (links: candidate generation)"):
                 (acc["ms_cand_fast"] if fast else acc["ms_cand"], n * (5 * A + 4 + cbar * (4 * A + 4))),
-            "k_entities (entity attributes)": (acc["ms_entities"], n * (4 + 4 * A + 4 * A * rho)),
             "k_distort (distortion indicators)": (acc["ms_distort"], n * (9 * A + 4)),
             "k_prep (links: new-entity attributes)": (acc["ms_prep"], n * (5 * A + 4 + 4 * A + 8)),
         }
-        name, (ms_k, bytes_k) = max(kernels.items(), key=lambda kv: kv[1][0])
+        kernels = {k: v for k, v in kernels.items() if v[0] > 0}
+        name, (ms_k, bytes_k) = max(kernels.items(), key=lambda kv: kv[1][0])  # the dominant one: largest share of the step
         peak, peak_src = peaks()
         achieved = bytes_k / (ms_k / opt.steps * 1e-3) / 1e9
+        per_kernel = {k.split(" ")[0]: {"ms": v[0] / opt.steps, "algorithmic_bytes": v[1],
+                                        "achieved": v[1] / (v[0] / opt.steps * 1e-3) / 1e9,
+                                        "frac": v[1] / (v[0] / opt.steps * 1e-3) / 1e9 / peak} for k, v in kernels.items()}
         sweep_bytes = n * ((5 * A + 8 + cbar * (4 * A + 8)) + (4 + 4 * A + 4 * A * rho) + (9 * A + 4))
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -363,6 +370,7 @@ def run_ours(opt, n_records, kind, desc):
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_k, "kernel_ms": ms_k / opt.steps,
+                         "kernels": per_kernel,
                          "sweep": {"algorithmic_bytes": sweep_bytes, "ms": acc["ms_total"] / opt.steps,
                                    "achieved": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9,
                                    "frac": sweep_bytes / (acc["ms_total"] / opt.steps * 1e-3) / 1e9 / peak}},
@@ -372,6 +380,8 @@ def run_ours(opt, n_records, kind, desc):
             "sweep_stats": {"candidates_per_record": cbar, "entities_per_record": rho,
                             "rounds_per_sweep": acc["n_rounds"] / opt.steps, "wide_records_per_sweep": acc["n_wide"] / opt.steps,
                             "tables_per_sweep": tbar, "records_left_to_bucket_kernels": acc["n_slow"] / opt.steps,
+                            "records_listed_through_tables_per_sweep": acc["n_listed"] / opt.steps,
+                            "records_scanned_against_all_items_per_sweep": acc["n_scanned"] / opt.steps,
                             "launches_per_sweep": launches / opt.steps},
         }
         print(json.dumps(line), flush=True)

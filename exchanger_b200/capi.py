@@ -94,6 +94,7 @@ class CStats(C.Structure):
         ("ms_cand_long", C.c_float), ("ms_wide", C.c_float), ("ms_index_count", C.c_float),
         ("ms_index_fill", C.c_float), ("n_probe", C.c_int32), ("n_huge", C.c_int32),
         ("ms_cand_fast", C.c_float), ("n_slow", C.c_int32), ("n_listed", C.c_int32), ("n_scanned", C.c_int32),
+        ("ms_tail", C.c_float), ("ms_entities_single", C.c_float),
     ]
 
 

@@ -132,6 +132,7 @@ struct exb200_handle {
   int n_tab = 0; // 2^n_key
   exb200_stats stats{};
   cudaEvent_t ev[20]{};
+  bool tail_ran = false, ent_single_ran = false;
   std::string err;
   bool poisoned = false;
   bool has_index_events = false;
@@ -808,6 +809,7 @@ int update_links(exb200_handle* h) {
   const int N = h->N, NT = h->n_tab;
   cudaStream_t st = h->stream;
   S.K0 = h->K;
+  h->tail_ran = false; h->ent_single_ran = false;
   CK(cudaMemsetAsync(S.tab_usage, 0, sizeof(int) * 2 * N_TABLES, st));
   CK(cudaMemsetAsync(S.tab_est, 0, sizeof(float) * N_TABLES, st));
   CK(cudaMemsetAsync(S.counters, 0, sizeof(int) * C_NSLOTS, st));
@@ -1275,8 +1277,11 @@ int update_links(exb200_handle* h) {
       uint32_t round0 = h->round_ctr;
       int max_rounds = (int)std::min<long long>(4LL * N + 16, 0x30000000LL);
       void* args[] = {(void*)&S, (void*)&h->tail, (void*)&round0, (void*)&max_rounds};
+      CK(cudaEventRecord(h->ev[15], st));
       CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_rounds_tail<true> : (const void*)k_rounds_tail<false>,
                                      dim3((unsigned)h->tail_grid), dim3(TAIL_TPB), args, smem, st));
+      CK(cudaEventRecord(h->ev[16], st));
+      h->tail_ran = true;
       h->n_launches++;
       int tn[4];
       CK(cudaMemcpyAsync(tn, h->tail.n, sizeof tn, cudaMemcpyDeviceToHost, st));
@@ -1410,7 +1415,10 @@ int sweep_entities(exb200_handle* h, int lo, int hi) {
   const long long gen_cap = (long long)h->N * h->A;
   if (hi > lo) { // ents_.update_attributes(...)
     int* multi = S.act_in; // [N] (free outside the links update)
+    CK(cudaEventRecord(h->ev[17], h->stream));
     KLAUNCH(h, k_entities, nblk(hi - lo, 64), 64, 0, S, h->d_gen_list, h->d_gen_count, gen_cap, lo, hi, multi);
+    CK(cudaEventRecord(h->ev[18], h->stream));
+    h->ent_single_ran = true;
     KLAUNCH(h, k_entities_slow, h->n_sm * 8, TPB, 0, S, h->d_gen_list, h->d_gen_count, gen_cap);
     KLAUNCH(h, k_entities_multi, h->n_sm * 16, 128, 0, S, (const int*)multi, h->d_gen_list, h->d_gen_count);
   }
@@ -1461,6 +1469,8 @@ int sweep_finish(exb200_handle* h) {
   h->stats.ms_index_fill = h->has_index_events ? ms(14, 3) : 0.f;   // chain tables
   h->stats.ms_cand = ms(3, 10); h->stats.ms_cand_long = ms(10, 4); h->stats.ms_wide = ms(4, 11); h->stats.ms_rounds = ms(11, 5); h->stats.ms_canon = ms(5, 6);
   h->stats.ms_cand_fast = h->fast_ran ? ms(3, 13) : 0.f;
+  h->stats.ms_tail = h->tail_ran ? ms(15, 16) : 0.f;
+  h->stats.ms_entities_single = h->ent_single_ran ? ms(17, 18) : 0.f;
   h->stats.ms_entities = ms(6, 7); h->stats.ms_distort = ms(7, 8); h->stats.ms_total = ms(0, 9);
   if (h->opt_check) { rc = check_state(h); if (rc) return rc; }
   return EXB200_OK;

@@ -38,7 +38,7 @@ extern "C" {
 /* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
    estimates (exb200_pe_*) added
    3: exb200_pe_overflowed; exb200_stats grew (ms_cand_fast, n_slow)
-   4: exb200_stats grew (n_listed, n_scanned) */
+   4: exb200_stats grew (n_listed, n_scanned, ms_tail, ms_entities_single) */
 #define EXB200_ABI_VERSION 4
 
 enum {
@@ -179,6 +179,8 @@ typedef struct exb200_stats {
   int32_t n_listed;       /* records no table served directly whose possible links were listed through
                              the cheapest table built this sweep (k_wide_emit)                    */
   int32_t n_scanned;      /* records whose possible links were listed by the scan over all items  */
+  float ms_tail;          /* the persistent kernel of the dependency rounds alone (part of ms_rounds; 0: not run) */
+  float ms_entities_single; /* the first entity kernel alone: singletons (part of ms_entities)     */
 } exb200_stats;
 
 typedef struct exb200_handle exb200_handle;
