@@ -271,6 +271,9 @@ def run_ours(opt, n_records, kind, desc):
         dist.all_reduce(secs, op=dist.ReduceOp.MAX)
     t_max = float(secs.item())
     value = world * opt.steps / t_max
+    # the end-to-end runs below start from the chain as it is NOW (the state after the timed steps), so
+    # that they time the same sweeps of the chain as `value` does and not the later, slower ones
+    host_model = model_with_state(model, gpu.state())
 
     # ---- the rest of the chain, device-timed on rank 0's clock: the whole window of SURVEY.md 8d
     # (sweeps 21-120) and a late figure (sweeps 201-220: the sweep gets slower as more records carry
@@ -287,7 +290,6 @@ def run_ours(opt, n_records, kind, desc):
 
     # ---- end to end through the public API with host buffers (create -> run -> state -> destroy);
     # three repetitions, the median is reported (host-side page faults and frees make single shots noisy)
-    host_model = model_with_state(model, gpu.state())
     gpu.close()
     import gc
     e2e_runs = []
