@@ -119,6 +119,8 @@ struct DevState {
                                 //           of their pair bucket (what falling back to the pair would cost)
   const uint16_t *tab_remap;    // [2][2^n_key] wanted full mask / pair mask -> mask of a built table (0: none)
   int pk_ok;                    // the attribute domains fit a 64-bit packed tuple (fast candidate path)
+  const unsigned long long *pk; // [2N] packed tuples of the indexed items of this sweep (k_chain_pack; null: not made)
+  const uint8_t *pkfl;          // [2N] bit 0: indexed, bit 1: twin
   uint8_t pk_shift[MAX_ATTRS], pk_bits[MAX_ATTRS]; // field of attribute a in the packed tuple
   int hop_cap;                  // chain items a thread walks for one record before the record is left to the CSR path
   int *slow_list;               // [N] records the fast candidate kernel leaves to the bucket-scanning kernels

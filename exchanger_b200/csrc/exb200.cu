@@ -933,16 +933,21 @@ int update_links(exb200_handle* h) {
   }
   CK(cudaEventRecord(h->ev[12], st));
   h->has_index_events = !active.empty();
-  { int rc = build_csr_tables(h, csr_tabs); if (rc) return rc; }
-  CK(cudaEventRecord(h->ev[14], st));
-  if (!chain_tabs.empty()) {
-    for (int t : chain_tabs) CK(cudaMemsetAsync(h->tables[t].d.head, 0xFF, sizeof(int) * (size_t)h->tables[t].d.cells, st));
-    CK(cudaMemsetAsync(S.tab_over, 0, sizeof(int) * N_TABLES, st));
+  // packed tuples of the indexed items: what the chain tables store, and what every index builder reads
+  S.pk = nullptr; S.pkfl = nullptr;
+  if (S.pk_ok && S.ES == 8 && !active.empty()) {
     if (!h->d_pk) {
       int rc = dalloc(h, &h->d_pk, (size_t)2 * N); if (rc) return rc;
       rc = dalloc(h, &h->d_pkfl, (size_t)2 * N); if (rc) return rc;
     }
     KLAUNCH(h, k_chain_pack, nblk(2LL * N), TPB, 0, S, h->d_pk, h->d_pkfl);
+    S.pk = h->d_pk; S.pkfl = h->d_pkfl;
+  }
+  { int rc = build_csr_tables(h, csr_tabs); if (rc) return rc; }
+  CK(cudaEventRecord(h->ev[14], st));
+  if (!chain_tabs.empty()) {
+    for (int t : chain_tabs) CK(cudaMemsetAsync(h->tables[t].d.head, 0xFF, sizeof(int) * (size_t)h->tables[t].d.cells, st));
+    CK(cudaMemsetAsync(S.tab_over, 0, sizeof(int) * N_TABLES, st));
     for (int t : chain_tabs) KLAUNCH(h, k_chain_build, nblk(2LL * N), TPB, 0, S, t, h->d_pk, h->d_pkfl);
   }
   CK(cudaEventRecord(h->ev[3], st));
