@@ -2537,7 +2537,7 @@ __global__ void __launch_bounds__(TPB) k_wide_turns(DevState S, const WideTurn* 
 // leaves every record's list contiguous and in ascending item order (k_wide_split cuts it up).
 // WE_BLOCKS blocks per record share its tiles of bucket items (or its probes).
 // ------------------------------------------------------------------------------------------
-constexpr int WE_BLOCKS = 8;
+constexpr int WE_BLOCKS = 16;
 constexpr int WE_TILE = 2048;
 // A record that its own table does not serve (cand_cnt = -3: no table for its key mask, or too many
 // probe combinations for the candidate kernels) is listed through the cheapest of the tables built
