@@ -65,7 +65,7 @@ __device__ __forceinline__ ProbeValues probe_values(const DevState& S, int ea, c
 // their possible values (n_un = 3: more than two, or too many combinations - the table cannot
 // serve the record and its possible links are listed by the batched scan over all the items).
 constexpr int MAX_PROBES = 16384;
-constexpr int FAST_PROBES = 128; // probes one thread of the fast candidate kernel makes for a record
+constexpr int FAST_PROBES = 32;  // probes one thread of the fast candidate kernel makes for a record
 constexpr int PROBE_NOT_SERVED = 4; // Probe::n_un: more than three unpinned key attributes, or too many combinations
 struct Pv { int v1, v2, v3; };      // the probed values of the (up to three) unpinned key attributes
 struct Probe {
