@@ -1259,23 +1259,58 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
       if (pos < cap) { ids[pos] = item; lls[pos] = ll; }
       if (tw && pos + 1 < cap) { ids[pos + 1] = S.N + item; lls[pos + 1] = ll; }
     };
-    if (pr.n_un > 0) {
-      // one thread per probe: the buckets are short, the probes independent
-      for (int j = threadIdx.x; j < pr.count; j += blockDim.x) {
-        const Pv v = pr.values(j);
-        if (t.chain) { // chain form: the node holds the item's packed tuple
-          for (int item = t.head[chain_cell_probe(S, t, x, pr, v)]; item >= 0 && s_cnt <= cap;) {
+    if (pr.n_un > 0 && t.chain) {
+      // chain form, one thread per probe, four probes of a thread in flight: most cells of a probed
+      // value combination are empty, so the time goes into the reads of the cell heads
+      for (int j0 = threadIdx.x; j0 < pr.count; j0 += 4 * blockDim.x) {
+        Pv v[4];
+        int head[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = j0 + u * (int)blockDim.x;
+          head[u] = -1;
+          if (j < pr.count) { v[u] = pr.values(j); head[u] = t.head[chain_cell_probe(S, t, x, pr, v[u])]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          for (int item = head[u]; item >= 0 && s_cnt <= cap;) { // the node holds the item's packed tuple
             const ChainNode nd = load_node(&t.node[item]);
             int yv[8];
             for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
-            visit(item, v, yv);
+            visit(item, v[u], yv);
             item = nd.next;
           }
-          continue;
-        }
+      }
+    } else if (pr.n_un > 0) {
+      // one thread per probe: the buckets are short, the probes independent
+      for (int j = threadIdx.x; j < pr.count; j += blockDim.x) {
+        const Pv v = pr.values(j);
         const uint32_t b = pr.bucket(S, t, x, v);
         const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
         for (int q = lo; q < hi && s_cnt <= cap; q++) visit(t.ids[q], v, nullptr);
+      }
+    } else if (S.pk) {
+      // the bucket against the packed tuples: four items per thread in flight, one masked compare per
+      // item (the attribute row of an item is only unpacked for the few that agree)
+      const uint32_t b = S.rec_bkt[r];
+      const int lo = b ? t.ptr[b - 1] : 0, hi = t.ptr[b];
+      unsigned long long M, V;
+      record_fields(S, x, zm, M, V);
+      for (int q0 = lo; q0 < hi; q0 += 4 * blockDim.x) {
+        if (s_cnt > cap) break; // already too many: wide (benign race: any exit is a valid exit)
+        int it[4];
+        unsigned long long P[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int q = q0 + u * (int)blockDim.x + (int)threadIdx.x; it[u] = q < hi ? t.ids[q] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) P[u] = it[u] >= 0 ? S.pk[it[u]] : ~V;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (it[u] >= 0 && ((P[u] ^ V) & M) == 0) {
+            int yv[8];
+            for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, P[u], a);
+            visit(it[u], Pv{0, 0, 0}, yv);
+          }
       }
     } else {
       const uint32_t b = S.rec_bkt[r];
