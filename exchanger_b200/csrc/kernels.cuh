@@ -905,11 +905,19 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
       const bool chain = t.chain != 0;
       int j_next = gl, q = 0, q_end = 0, visited = 0, c_item = -1;
       Pv v_cur = {0, 0, 0};
+      // chain form: a node is compared as a packed word (fields Mc / values Vc of the pinned and the
+      // probed attributes) and only unpacked when it agrees
+      unsigned long long M0 = 0, V0 = 0, Mc = 0, Vc = 0;
+      if (chain) record_fields(S, x, zm, M0, V0);
       for (;;) {
         while ((chain ? c_item < 0 : q >= q_end) && j_next < pr.count) {
           v_cur = pr.values(j_next);
-          if (chain) c_item = t.head[chain_cell_probe(S, t, x, pr, v_cur)];
-          else {
+          if (chain) {
+            Mc = M0 | pk_field(S, pr.a1); Vc = V0 | ((unsigned long long)(uint32_t)v_cur.v1 << S.pk_shift[pr.a1]);
+            if (pr.n_un >= 2) { Mc |= pk_field(S, pr.a2); Vc |= (unsigned long long)(uint32_t)v_cur.v2 << S.pk_shift[pr.a2]; }
+            if (pr.n_un >= 3) { Mc |= pk_field(S, pr.a3); Vc |= (unsigned long long)(uint32_t)v_cur.v3 << S.pk_shift[pr.a3]; }
+            c_item = t.head[chain_cell(t, Vc)];
+          } else {
             const uint32_t b = pr.bucket(S, t, x, v_cur);
             q = b ? t.ptr[b - 1] : 0;
             q_end = t.ptr[b];
@@ -924,17 +932,19 @@ __global__ void __launch_bounds__(BT) k_cand(DevState S, const int* __restrict__
         if (active) {
           int yv[8];
           const int* y = yv;
+          bool agrees = true;
           if (chain) {
             item = c_item;
             const ChainNode nd = load_node(&t.node[item]);
             c_item = nd.next;
-            for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
+            agrees = ((nd.P ^ Vc) & Mc) == 0;
+            if (agrees) for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
           } else {
             item = t.ids[q++];
             y = S.ent_y + (size_t)item * S.ES;
           }
           visited++;
-          if (item != S.N + r) {
+          if (item != S.N + r && agrees) {
             // hashed buckets: an item counts in the probe of its own value only
             ok = pr.own_probe(y, v_cur) && item_compatible(S, x, zm, y);
             if (ok) {
@@ -1262,23 +1272,40 @@ __global__ void __launch_bounds__(TPB) k_cand_long(DevState S, int n_todo, int c
     if (pr.n_un > 0 && t.chain) {
       // chain form, one thread per probe, four probes of a thread in flight: most cells of a probed
       // value combination are empty, so the time goes into the reads of the cell heads
+      // (half of the probed cells hold an item of some other key: the first node of every chain is read
+      // with the others in flight too, and a node is compared as a packed word - fields M / values V of
+      // the pinned and the probed attributes - before anything is unpacked)
+      unsigned long long M, V;
+      record_fields(S, x, zm, M, V);
       for (int j0 = threadIdx.x; j0 < pr.count; j0 += 4 * blockDim.x) {
         Pv v[4];
         int head[4];
+        unsigned long long Mp[4], Vp[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int j = j0 + u * (int)blockDim.x;
           head[u] = -1;
-          if (j < pr.count) { v[u] = pr.values(j); head[u] = t.head[chain_cell_probe(S, t, x, pr, v[u])]; }
+          if (j < pr.count) {
+            v[u] = pr.values(j);
+            Mp[u] = M | pk_field(S, pr.a1); Vp[u] = V | ((unsigned long long)(uint32_t)v[u].v1 << S.pk_shift[pr.a1]);
+            if (pr.n_un >= 2) { Mp[u] |= pk_field(S, pr.a2); Vp[u] |= (unsigned long long)(uint32_t)v[u].v2 << S.pk_shift[pr.a2]; }
+            if (pr.n_un >= 3) { Mp[u] |= pk_field(S, pr.a3); Vp[u] |= (unsigned long long)(uint32_t)v[u].v3 << S.pk_shift[pr.a3]; }
+            head[u] = t.head[chain_cell(t, Vp[u])];
+          }
         }
+        ChainNode nd[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (head[u] >= 0) nd[u] = load_node(&t.node[head[u]]);
 #pragma unroll
         for (int u = 0; u < 4; u++)
-          for (int item = head[u]; item >= 0 && s_cnt <= cap;) { // the node holds the item's packed tuple
-            const ChainNode nd = load_node(&t.node[item]);
-            int yv[8];
-            for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd.P, a);
-            visit(item, v[u], yv);
-            item = nd.next;
+          for (int item = head[u]; item >= 0 && s_cnt <= cap;) {
+            if (item != head[u]) nd[u] = load_node(&t.node[item]);
+            if (((nd[u].P ^ Vp[u]) & Mp[u]) == 0) {
+              int yv[8];
+              for (int a = 0; a < S.A; a++) yv[a] = unpack_attr(S, nd[u].P, a);
+              visit(item, v[u], yv);
+            }
+            item = nd[u].next;
           }
       }
     } else if (pr.n_un > 0) {
