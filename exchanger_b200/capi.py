@@ -220,6 +220,8 @@ def load_library(path: str | None = None):
     lib = C.CDLL(p)
     H = C.c_void_p
     lib.exb200_abi_version.restype = C.c_int
+    lib.exb200_trim.restype = None
+    lib.exb200_trim.argtypes = []
     lib.exb200_device_count.restype = C.c_int
     lib.exb200_create.argtypes = [C.POINTER(CModel), C.c_int, C.POINTER(H)]
     lib.exb200_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.POINTER(CHistory),
@@ -262,6 +264,12 @@ def load_library(path: str | None = None):
     return lib
 
 
+def trim() -> None:
+    """Give the device slabs and pinned rows that destroyed samplers left in the library's cache back to
+    the driver (``exb200_trim``)."""
+    load_library().exb200_trim()
+
+
 def levenshtein_neighbours(domain, threshold: int, include_self: bool = False, device: int = 0):
     """Thresholded-Levenshtein neighbourhoods of a domain of (ASCII) strings on the GPU: the
     ``close_values`` / ``max_exp_factor`` slots that ``compute_close_values`` builds
@@ -295,7 +303,7 @@ def levenshtein_neighbours(domain, threshold: int, include_self: bool = False, d
 
 
 EXPORTED_SYMBOLS = [
-    "exb200_abi_version", "exb200_device_count", "exb200_create", "exb200_run", "exb200_sweeps", "exb200_sweeps_timed",
+    "exb200_abi_version", "exb200_trim", "exb200_device_count", "exb200_create", "exb200_run", "exb200_sweeps", "exb200_sweeps_timed",
     "exb200_get_state", "exb200_get_stats", "exb200_link_conditional", "exb200_set_option",
     "exb200_destroy", "exb200_last_error", "exb200_neighbours_create", "exb200_neighbours_nnz",
     "exb200_neighbours_get", "exb200_neighbours_destroy",

@@ -179,6 +179,60 @@ template <class F> void host_parallel(size_t work, F fn) {
   for (auto& x : th) x.join();
 }
 
+// Slabs (and the pinned staging rows of the history) of destroyed handles are kept for the next handle
+// of the process on the same device: cudaMalloc / cudaFree of a chain's ten gigabytes cost 0.05-0.5 s
+// per handle, which is what a caller that runs one chain after the other (run_inference in a loop)
+// would pay every time.  exb200_trim() gives everything back to the driver.
+struct MemPool {
+  struct Dev { int device; char* base; size_t size; };
+  struct Pin { void* p; size_t size; };
+  std::mutex mu;
+  std::vector<Dev> dev;
+  std::vector<Pin> pin;
+  size_t dev_bytes = 0;
+  static constexpr size_t MAX_DEV_BYTES = (size_t)64 << 30;
+  char* take_dev(int device, size_t want, size_t at_least, size_t* size) { // smallest slab >= want, else >= at_least
+    std::lock_guard<std::mutex> lk(mu);
+    int best = -1;
+    for (int pass = 0; pass < 2 && best < 0; pass++)
+      for (int i = 0; i < (int)dev.size(); i++)
+        if (dev[i].device == device && dev[i].size >= (pass ? at_least : want) && (best < 0 || dev[i].size < dev[best].size)) best = i;
+    if (best < 0) return nullptr;
+    char* q = dev[best].base;
+    *size = dev[best].size;
+    dev_bytes -= dev[best].size;
+    dev.erase(dev.begin() + best);
+    return q;
+  }
+  bool give_dev(int device, char* base, size_t size) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev_bytes + size > MAX_DEV_BYTES) return false;
+    dev.push_back({device, base, size});
+    dev_bytes += size;
+    return true;
+  }
+  void* take_pin(size_t size) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t i = 0; i < pin.size(); i++)
+      if (pin[i].size >= size && pin[i].size <= 2 * size) { void* q = pin[i].p; pin.erase(pin.begin() + (long)i); return q; }
+    return nullptr;
+  }
+  void give_pin(void* p, size_t size) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (pin.size() < 8) pin.push_back({p, size}); else cudaFreeHost(p);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& d : dev) { cudaSetDevice(d.device); cudaFree(d.base); }
+    for (auto& q : pin) cudaFreeHost(q.p);
+    cudaSetDevice(cur);
+    dev.clear(); pin.clear(); dev_bytes = 0;
+  }
+};
+MemPool g_pool;
+
 template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
   const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
   std::lock_guard<std::mutex> lk(h->alloc_mu);
@@ -186,10 +240,27 @@ template <class T> int dalloc(exb200_handle* h, T** p, size_t n) {
     // slabs double from 64 MiB to 2 GiB; a larger request gets a slab of its own size
     size_t want = h->slabs.empty() ? ((size_t)64 << 20) : std::min<size_t>(h->slabs.back().size * 2, (size_t)2 << 30);
     want = std::max(want, bytes);
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, want);
-    if (e != cudaSuccess && want > bytes) { want = bytes; e = cudaMalloc(&q, want); }
-    if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    size_t got = 0;
+    void* q = g_pool.take_dev(h->device, want, bytes, &got);
+    if (q) {
+      // (a slab that comes back from an earlier handle starts out zero like a fresh one usually does)
+      // (on the handle's own stream - it does not synchronise with the default stream - so that the
+      // clearing is ordered before everything the handle does with the slab)
+      cudaError_t e = cudaMemsetAsync(q, 0, got, h->stream);
+      if (e == cudaSuccess && !h->stream) e = cudaStreamSynchronize(0);
+      if (e != cudaSuccess) { cudaGetLastError(); cudaFree(q); q = nullptr; }
+      else want = got;
+    }
+    if (!q) {
+      cudaError_t e = cudaMalloc(&q, want);
+      if (e != cudaSuccess && want > bytes) { want = bytes; e = cudaMalloc(&q, want); }
+      if (e != cudaSuccess) { // the pool may be holding what is missing
+        cudaGetLastError();
+        g_pool.trim();
+        e = cudaMalloc(&q, want);
+      }
+      if (e != cudaSuccess) return fail(h, EXB200_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
     h->slabs.push_back({(char*)q, want, 0});
   }
   exb200_handle::Slab& sl = h->slabs.back();
@@ -1494,15 +1565,18 @@ int exb200_device_count(void) {
   return n;
 }
 
+void exb200_trim(void) { g_pool.trim(); }
+
 const char* exb200_last_error(const exb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 void exb200_destroy(exb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& sl : h->slabs) cudaFree(sl.base);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  for (auto& sl : h->slabs) if (!g_pool.give_dev(h->device, sl.base, sl.size)) cudaFree(sl.base); // (kept for the next handle)
   for (int b = 0; b < 2; b++) {
-    if (h->pin_snap[b]) cudaFreeHost(h->pin_snap[b]);
+    if (h->pin_snap[b]) g_pool.give_pin(h->pin_snap[b], sizeof(int) * (size_t)h->N);
     if (h->ev_snap[b]) cudaEventDestroy(h->ev_snap[b]);
     if (h->ev_d2h[b]) cudaEventDestroy(h->ev_d2h[b]);
   }
@@ -1965,6 +2039,7 @@ int ensure_sample_pipeline(exb200_handle* h) {
   if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int b = 0; b < 2; b++) {
     if (!h->d_snap[b]) { int rc = dalloc(h, &h->d_snap[b], (size_t)h->N); if (rc) return rc; }
+    if (!h->pin_snap[b]) h->pin_snap[b] = (int*)g_pool.take_pin(sizeof(int) * (size_t)h->N);
     if (!h->pin_snap[b] && cudaMallocHost((void**)&h->pin_snap[b], sizeof(int) * (size_t)h->N) != cudaSuccess) {
       h->pin_snap[b] = nullptr;
       cudaGetLastError();

@@ -38,7 +38,7 @@ extern "C" {
 /* 2: exb200_stats grew (n_probe, n_huge); slice calls (exb200_shard_*), device buffers, point
    estimates (exb200_pe_*) added
    3: exb200_pe_overflowed; exb200_stats grew (ms_cand_fast, n_slow)
-   4: exb200_stats grew (n_listed, n_scanned, ms_tail, ms_entities_single) */
+   4: exb200_stats grew (n_listed, n_scanned, ms_tail, ms_entities_single); exb200_trim */
 #define EXB200_ABI_VERSION 4
 
 enum {
@@ -187,6 +187,11 @@ typedef struct exb200_handle exb200_handle;
 
 /* returns EXB200_ABI_VERSION */
 int exb200_abi_version(void);
+
+/* Device slabs and pinned staging rows of destroyed handles are kept for the next handle of the process
+   (cudaMalloc / cudaFree of a chain's memory cost 0.05-0.5 s per handle); this gives them back to the
+   driver.  Safe to call at any time; handles that exist are not affected. */
+void exb200_trim(void);
 
 /* number of visible CUDA devices (0 without a driver/GPU) */
 int exb200_device_count(void);
