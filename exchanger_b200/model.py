@@ -153,12 +153,22 @@ def transform_dist_fn(dist_fn: Callable, threshold: float, scaling_factor: float
         raise ValueError("scaling_factor must be non-negative")
     if threshold < 0:
         raise ValueError("threshold must be non-negative")
+    return TransformedDistFn(dist_fn, threshold, scaling_factor)
 
-    def tdist(y, domain_codes, domain_lens):
-        d = scaling_factor * dist_fn(y, domain_codes, domain_lens)
-        return np.where(d <= threshold, d, np.inf)
 
-    return tdist
+@dataclass
+class TransformedDistFn:
+    """What ``transform_dist_fn`` returns: a callable object rather than a closure, so that a model that
+    holds it can be pickled (``bench.py`` hands the model built by rank 0 to the other ranks of the
+    node through /dev/shm)."""
+
+    dist_fn: Callable
+    threshold: float
+    scaling_factor: float = 1.0
+
+    def __call__(self, y, domain_codes, domain_lens):
+        d = self.scaling_factor * self.dist_fn(y, domain_codes, domain_lens)
+        return np.where(d <= self.threshold, d, np.inf)
 
 
 # ------------------------------------------------------------ attribute specs

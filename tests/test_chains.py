@@ -158,3 +158,21 @@ def test_sharded_sweep_equals_the_unsharded_one_two_ranks_gloo():
         y, z, theta = out[rank]
         assert np.array_equal(y, whole.ent_y[:23].numpy()) and np.array_equal(z, whole.rec_z.numpy())
         assert theta == whole.theta
+
+
+def test_benchmark_model_survives_pickling():
+    """bench.py builds the synthetic model once per node (rank 0) and hands it to the other ranks as a
+    pickle in /dev/shm: everything a model holds must be picklable (a closure in an attribute's
+    distance function once was not, and every multi-GPU run of the benchmark died on rank 0)."""
+    import pickle
+    import bench
+    from checkers import cpu_neighbours
+    from exchanger_b200.capi import FlatModel
+    from exchanger_b200.synthetic import synth_model
+    m, _ = synth_model(3000, bench.clust_prior("gen_coupon", 3000), seed=bench.DATA_SEED, neighbour_fn=cpu_neighbours)
+    m2 = pickle.loads(pickle.dumps(m, protocol=pickle.HIGHEST_PROTOCOL))
+    a, b = FlatModel(m, 1), FlatModel(m2, 1)
+    assert a.nbytes() == b.nbytes()
+    assert np.array_equal(m.rec_attrs, m2.rec_attrs) and np.array_equal(m.links, m2.links)
+    d = m2.attr_params[3].dist_fn  # the transformed Levenshtein distance still works
+    assert callable(d)
