@@ -439,6 +439,8 @@ def run_sharded(opt, n_records, kind, desc):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own lines (its version banner, NCCL_DEBUG output) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

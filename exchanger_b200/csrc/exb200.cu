@@ -100,6 +100,7 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
+  int emit_chunk = 65536; // records listed by one k_wide_emit pass at most (halved when their lists do not fit the scratch)
   int opt_round0 = 1; // records that found an entity whatever happens are final before round 1 (k_bounds_init)
   double emit_cost_cap = 262144.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
   int opt_tiny_always = 0;     // build every wanted table with few buckets, however few records want it (measured: slower)
@@ -1126,21 +1127,39 @@ int update_links(exb200_handle* h) {
   // Their possible links are listed from the blocking tables (k_wide_emit): the wide records from the
   // bucket they were found in, the others through the cheapest table built this sweep - instead of a
   // scan over all the items, which is left to the records no table can serve.
-  std::vector<int> listed(known.size() + unk.size()); // both kinds, ascending
-  std::merge(known.begin(), known.end(), unk.begin(), unk.end(), listed.begin());
+  std::vector<int> all_listed(known.size() + unk.size()); // both kinds, ascending
+  std::merge(known.begin(), known.end(), unk.begin(), unk.end(), all_listed.begin());
   auto is_unk = [&](int r) { return std::binary_search(unk.begin(), unk.end(), r); };
+  std::vector<int> wide; // the records that took their turn first
+  int dk_wide = 0;
+  h->stats.n_listed = 0; h->stats.n_scanned = 0;
+  // The listed records are taken in ascending id, in chunks whose lists fit the scratch together (all of
+  // them at once unless the chain has drifted into a state with tens of thousands of such records): a
+  // chunk is listed, the records that keep their list are stored, the turns of the others are taken,
+  // then the next chunk follows - the order of the serial turns is the ascending id as before.
+  size_t chunk = std::max<size_t>(1, std::min<size_t>((size_t)h->emit_chunk, (size_t)WIDE_BUCKET_MAX));
+  for (size_t c0 = 0; c0 < all_listed.size();) {
+  const size_t c1 = h->opt_wide_buckets ? std::min(all_listed.size(), c0 + chunk) : all_listed.size();
+  const std::vector<int> listed(all_listed.begin() + (long)c0, all_listed.begin() + (long)c1);
+  int n_known = 0;
+  for (int r : listed) n_known += !is_unk(r);
   std::vector<int> kb_base, kb_len, kb_served;
   bool from_buckets = false;
-  if (!listed.empty() && h->opt_wide_buckets) {
+  if (h->opt_wide_buckets) {
     const auto t_a = std::chrono::steady_clock::now();
     int rc = wide_bucket_lists(h, listed, kb_base, kb_len, kb_served, &from_buckets); if (rc) return rc;
+    if (!from_buckets && listed.size() > 1) { // the lists of this chunk do not fit the scratch together: a smaller chunk
+      chunk = std::max<size_t>(1, listed.size() / 2);
+      if (h->trace) std::fprintf(stderr, "[exb200] the lists of %d records do not fit the scratch: chunks of %d\n", (int)listed.size(), (int)chunk);
+      continue;
+    }
     if (h->trace) {
       long long sum = 0;
       int n_served = 0;
       for (size_t i = 0; i < kb_len.size(); i++) { sum += kb_len[i]; n_served += kb_served[i]; }
       std::fprintf(stderr, "[exb200] %d wide records and %d without a serving table listed from the tables: %.2f ms, %lld possible links, %d left to the scan%s\n",
-                   (int)known.size(), (int)unk.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum,
-                   from_buckets ? (int)listed.size() - n_served : (int)unk.size(), from_buckets ? "" : " (did not fit: batched scan)");
+                   n_known, (int)listed.size() - n_known, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count(), sum,
+                   from_buckets ? (int)listed.size() - n_served : (int)listed.size() - n_known, from_buckets ? "" : " (did not fit: batched scan)");
     }
   }
   std::vector<int> serial; // (record << 1) | no count of its possible links yet (listed by the batched scan, then classified)
@@ -1156,7 +1175,6 @@ int update_links(exb200_handle* h) {
       else if (kb_len[i] > h->long_cap) { listed_wide_unk[i] = 1; serial.push_back(r << 1); }
       else keep.push_back((int)i);
     }
-    h->stats.n_listed = 0; h->stats.n_scanned = 0;
     for (size_t i = 0; i < listed.size(); i++) {
       const bool u = is_unk(listed[i]);
       if (from_buckets && u && kb_served[i]) h->stats.n_listed++;
@@ -1169,8 +1187,6 @@ int update_links(exb200_handle* h) {
       CK(cudaStreamSynchronize(st)); // `keep` is on the stack
     }
   }
-  std::vector<int> wide; // the records that took their turn first
-  int dk_wide = 0;
   // The serial list is taken in ascending id, in stretches that hold at most WIDE_NB records whose
   // possible links have to be listed by the batched scan over all items; the turns of a stretch are
   // then taken in order, whichever way a record's list was made (lists are static, sizes are not).
@@ -1251,7 +1267,9 @@ int update_links(exb200_handle* h) {
     }
     g = g_end;
   }
-  if (!listed.empty()) {
+  c0 = c1;
+  } // chunks of the listed records
+  if (!all_listed.empty()) {
     CK(cudaMemcpyAsync(hc, S.counters, sizeof hc, cudaMemcpyDeviceToHost, st)); // C_NACTL_INIT, C_NFENCE moved (k_wide_store, k_wide_store_b)
     CK(cudaStreamSynchronize(st));
   }
@@ -1920,6 +1938,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "wide_buckets") h->opt_wide_buckets = value != 0;
   else if (n == "round0") h->opt_round0 = value != 0;
   else if (n == "emit_cost_cap") h->emit_cost_cap = (double)value;
+  else if (n == "emit_chunk") h->emit_chunk = (int)std::max<int64_t>(1, value);
   else if (n == "tiny_tables_always") h->opt_tiny_always = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);

@@ -1,9 +1,16 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel.
-usage: summarize_launches.py launches.csv [last_n_launches]"""
+usage: summarize_launches.py launches.csv [last_n_launches | sweeps:FIRST:COUNT]
+(sweeps:FIRST:COUNT = the launches of COUNT sweeps starting with the FIRST-th sweep (0-based) of the
+process: a sweep starts with k_clust_counts when the cluster prior has hyper-parameters, else with k_prep)"""
 import collections, csv, re, sys
 lines = [l for l in open(sys.argv[1]) if l.startswith('"')]
 rows = list(csv.DictReader(lines))
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2].startswith("sweeps:"):
+    first, count = (int(v) for v in sys.argv[2].split(":")[1:3])
+    marker = "k_clust_counts" if any("k_clust_counts" in r['Kernel Name'] for r in rows) else "k_prep"
+    starts = [i for i, r in enumerate(rows) if marker in r['Kernel Name']]
+    rows = rows[starts[first]:starts[first + count]]
+elif len(sys.argv) > 2:
     rows = rows[-int(sys.argv[2]):]
 agg = collections.OrderedDict()
 for row in rows:

@@ -63,7 +63,7 @@ def test_wide_records_take_their_turn_first(threshold, wide_buckets):
     push many records of RLdata500 through that path - their lists made from the bucket the candidate
     scan found too long and sorted (wide_buckets=1), or by one more scan over all items."""
     m, _ = readme_model("rldata500", n=250)
-    stats = lockstep(m, 8, wide_threshold=threshold, wide_buckets=wide_buckets)
+    stats = lockstep(m, 8, wide_threshold=threshold, wide_buckets=wide_buckets, emit_chunk=65536 if threshold else 16)
     assert sum(s["n_wide"] for s in stats) > (50 if threshold == 0 else 0)
 
 
@@ -160,7 +160,8 @@ def test_results_do_not_depend_on_batching_thresholds():
                  dict(table_cost_permille=1000000), dict(table_cost_permille=0, est_threshold=0),
                  dict(rounds_tail=0), dict(rounds_tail=0, long_min=2), dict(rounds_tail=1, long_min=0),
                  dict(fast_path=0), dict(hop_cap=1), dict(wide_buckets=0), dict(wide_buckets=0, fast_path=0, rounds_tail=0), dict(hop_cap=0, long_min=0), dict(hop_cap=3, cand_cap=4, bucket_cap=0),
-                 dict(round0=0), dict(round0=0, rounds_tail=0), dict(table_min_usage=150), dict(table_min_usage=150, emit_cost_cap=0), dict(table_min_usage=150, emit_cost_cap=64)):
+                 dict(round0=0), dict(round0=0, rounds_tail=0), dict(table_min_usage=150), dict(table_min_usage=150, emit_cost_cap=0), dict(table_min_usage=150, emit_cost_cap=64),
+                 dict(table_min_usage=150, emit_chunk=5), dict(emit_chunk=1)):
         with Sampler(m, seed=3) as g:
             for k, v in opts.items():
                 g.set_option(k, v)
@@ -198,6 +199,8 @@ def test_records_no_table_serves_are_listed_through_the_cheapest_table():
     stats = lockstep(m, 6, table_min_usage=150)
     assert sum(s["n_listed"] for s in stats) > 100, [(s["n_listed"], s["n_scanned"], s["n_tables"]) for s in stats]
     stats = lockstep(m, 4, table_min_usage=150, wide_threshold=20)  # ... some of them wide after all
+    assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
+    stats = lockstep(m, 4, table_min_usage=150, wide_threshold=20, emit_chunk=7)  # ... chunk by chunk
     assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
     stats = lockstep(m, 4, table_min_usage=150, emit_cost_cap=0)
     assert sum(s["n_scanned"] for s in stats) > 100 and sum(s["n_listed"] for s in stats) == 0
