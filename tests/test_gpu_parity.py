@@ -569,3 +569,26 @@ def test_r_glue_end_to_end_on_the_gpu():
     assert np.array_equal(np.array(st["ent_attrs"]["values"]).reshape(K, A).T, fit.state.ent_attrs + 1)
     assert np.array_equal(np.array(st["rec_distortions"]["values"]).reshape(N, A).T, fit.state.rec_distortions)
     assert out["increments"] == 12
+
+
+def test_handles_reuse_the_memory_of_destroyed_ones():
+    """Device slabs and pinned history rows of a destroyed handle are kept for the next one
+    (``exb200_trim`` gives them back): chains run one after the other - and after a trim - are the chain
+    a fresh process would run, history rows included."""
+    from exchanger_b200 import capi
+    m, _ = readme_model("rldata10000", n=3000)
+    runs = []
+    for k in range(4):
+        if k == 3:
+            capi.trim()
+        with Sampler(m, seed=5) as g:
+            hist = g.run(4, 2, 3)
+            runs.append((g.state(), hist["links"].copy()))
+    for st, links in runs[1:]:
+        assert_same_state(runs[0][0], st)
+        assert np.array_equal(runs[0][1], links)
+    big, _ = readme_model("rldata10000")          # a larger model after smaller ones: slabs of another size
+    with Sampler(big, seed=5) as g:
+        g.set_option("check", 1)
+        g.sweeps(3)
+    capi.trim()
