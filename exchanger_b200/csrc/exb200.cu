@@ -100,6 +100,7 @@ struct exb200_handle {
   unsigned long long* we_cursor = nullptr; unsigned long long we_cap = 0;
   int* we_recs = nullptr; int* we_seg = nullptr; void* we_tmp = nullptr; size_t we_tmp_bytes = 0;
   int opt_wide_buckets = 1;
+  long long emit_scratch = 0; // entries of the listing scratch (0: sized by the record count); set before the first sweep
   int emit_chunk = 65536; // records listed by one k_wide_emit pass at most (halved when their lists do not fit the scratch)
   int opt_round0 = 1; // records that found an entity whatever happens are final before round 1 (k_bounds_init)
   double emit_cost_cap = 262144.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
@@ -828,6 +829,7 @@ int wide_bucket_lists(exb200_handle* h, const std::vector<int>& recs, std::vecto
   const auto t_0 = std::chrono::steady_clock::now();
   if (!h->we_keys[0]) {
     h->we_cap = std::min<unsigned long long>(2ull * h->N + (1ull << 20), 48ull << 20); // (10.4 M entries at 10 M records, sweep 200)
+    if (h->emit_scratch > 0) h->we_cap = (unsigned long long)h->emit_scratch; // (tests: lists that do not fit)
     int rc = 0;
     for (int k = 0; k < 2 && !rc; k++) { rc = dalloc(h, &h->we_keys[k], (size_t)h->we_cap); if (!rc) rc = dalloc(h, &h->we_vals[k], (size_t)h->we_cap); }
     if (!rc) rc = dalloc(h, &S.wlb_id, (size_t)h->we_cap);
@@ -1939,6 +1941,7 @@ int exb200_set_option(exb200_handle* h, const char* name, int64_t value) {
   else if (n == "round0") h->opt_round0 = value != 0;
   else if (n == "emit_cost_cap") h->emit_cost_cap = (double)value;
   else if (n == "emit_chunk") h->emit_chunk = (int)std::max<int64_t>(1, value);
+  else if (n == "emit_scratch") h->emit_scratch = (long long)std::max<int64_t>(0, value);
   else if (n == "tiny_tables_always") h->opt_tiny_always = value != 0;
   else if (n == "hop_cap") h->hop_cap = (int)std::max<int64_t>(0, value);
   else if (n == "table_min_usage") h->table_min_usage = (int)std::max<int64_t>(0, value);

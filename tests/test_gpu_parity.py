@@ -202,6 +202,10 @@ def test_records_no_table_serves_are_listed_through_the_cheapest_table():
     assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
     stats = lockstep(m, 4, table_min_usage=150, wide_threshold=20, emit_chunk=7)  # ... chunk by chunk
     assert sum(s["n_listed"] for s in stats) > 100 and sum(s["n_wide"] for s in stats) > 10
+    # a scratch too small for the lists of all the records together: chunks are halved until they fit, and a
+    # record whose own list does not fit is left to the scan over all items
+    stats = lockstep(m, 4, table_min_usage=150, wide_threshold=20, emit_scratch=300)
+    assert sum(s["n_listed"] for s in stats) > 50 and sum(s["n_scanned"] for s in stats) > 0
     stats = lockstep(m, 4, table_min_usage=150, emit_cost_cap=0)
     assert sum(s["n_scanned"] for s in stats) > 100 and sum(s["n_listed"] for s in stats) == 0
 
