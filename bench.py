@@ -178,7 +178,7 @@ def run_reference(opt, n_records, kind, desc):
                          "sample": sample_text(procs, opt.steps, n_sample)},
         "e2e": {"value": v, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------- this repo's arm
@@ -389,7 +389,7 @@ def run_ours(opt, n_records, kind, desc):
                             "records_scanned_against_all_items_per_sweep": acc["n_scanned"] / opt.steps,
                             "launches_per_sweep": launches / opt.steps},
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -424,7 +424,7 @@ def run_sharded(opt, n_records, kind, desc):
     clk = clocks.stop()
     if rank == 0:
         t = float(secs.item())
-        print(json.dumps({
+        emit_line({
             "metric": "gibbs_sweeps_per_s", "value": opt.steps / t, "unit": "sweeps/s",
             "link_updates_per_s": opt.steps * n_records / t, "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
             "ms_per_step": 1e3 * t / opt.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -434,13 +434,29 @@ def run_sharded(opt, n_records, kind, desc):
                                       "distortion indicators on slices, all-gather + all-reduce per sweep",
                        "burnin_sweeps": opt.burnin},
             "clocks": clk, "timing": "wall clock around the timed sweeps, max over ranks (collectives included)",
-        }), flush=True)
+        })
     dist.destroy_process_group()
 
 
+_JSON_FD = None  # the process's real stdout, kept for the one JSON line
+
+
+def emit_line(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
-    # stdout carries exactly one JSON line: NCCL's own lines (its version banner, NCCL_DEBUG output) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner and
+    # its NCCL_DEBUG output to stdout from C), so file descriptor 1 is pointed at stderr for the run and
+    # the JSON line goes to the descriptor that was stdout.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
