@@ -281,7 +281,7 @@ def run_ours(opt, n_records, kind, desc):
     # 200 more sweeps that handle holds a dozen more tables, and creating / destroying handles next to its
     # release measured three to five times slower (0.86 s against 0.17 s for exb200_create)
     import gc
-    e2e_runs = []
+    e2e_runs, e2e_all_stages = [], []
     for _ in range(3):
         gc.collect()
         barrier()
@@ -295,8 +295,9 @@ def run_ours(opt, n_records, kind, desc):
             t_state = time.perf_counter() - te - t_create - t_run
         barrier()
         te = time.perf_counter() - te
-        e2e_stages = {"create": round(t_create, 3), "run": round(t_run, 3), "get_state": round(t_state, 3),
-                      "destroy": round(te - t_create - t_run - t_state, 3)}
+        e2e_stages = {"create": round(t_create, 3), "flatten": round(getattr(g2, "t_flat", 0.0), 3), "run": round(t_run, 3),
+                      "get_state": round(t_state, 3), "destroy": round(te - t_create - t_run - t_state, 3)}
+        e2e_all_stages.append(e2e_stages)
         d2h = sum(v.nbytes for v in hist.values() if hasattr(v, "nbytes")) + \
             sum(v.nbytes for v in fin.values() if hasattr(v, "nbytes"))
         del hist, fin
@@ -370,7 +371,7 @@ def run_ours(opt, n_records, kind, desc):
                        "l2": f"inputs larger than L2: resident state {n_records * 150 / 1e6:.0f} MB streamed every sweep"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d / opt.steps),
-                    "d2h_bytes_per_step": int(d2h / opt.steps), "runs": e2e_runs, "stages_s_last_run": e2e_stages,
+                    "d2h_bytes_per_step": int(d2h / opt.steps), "runs": e2e_runs, "stages_s_last_run": e2e_stages, "stages_s": e2e_all_stages,
                     "what": "exb200_create + exb200_run(steps saved sweeps) + exb200_get_state + exb200_destroy, host buffers; median of 3"},
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

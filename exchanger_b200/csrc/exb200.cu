@@ -172,7 +172,15 @@ int fail(exb200_handle* h, int code, const std::string& msg) {
 
 // fn(t, T) on T host threads (table construction at create time)
 template <class F> void host_parallel(size_t work, F fn) {
-  int T = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+  // (a share of the cores: with one process per GPU every rank builds its tables at the same time)
+  static const int T_max = [] {
+    if (const char* e = std::getenv("EXB200_HOST_THREADS")) return std::max(1, std::atoi(e));
+    int n_dev = 1;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess) { cudaGetLastError(); n_dev = 1; }
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    return std::max(2, std::min(16, hw / std::max(1, n_dev)));
+  }();
+  int T = T_max;
   if (work < (1u << 16)) T = 1;
   if (T == 1) { fn(0, 1); return; }
   std::vector<std::thread> th;
