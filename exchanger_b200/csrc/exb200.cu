@@ -106,6 +106,7 @@ struct exb200_handle {
   double emit_cost_cap = 262144.0; // cell / item reads k_wide_emit may spend on a record no table serves (else: scan over all items)
   int opt_tiny_always = 0;     // build every wanted table with few buckets, however few records want it (measured: slower)
   WideTurn* d_turns = nullptr; size_t turns_cap = 0; int turns_grid = 0;
+  unsigned long long* d_turn_dbg = nullptr; size_t turn_dbg_cap = 0; // (trace)
   unsigned* d_turn_sync = nullptr; // [2 * turns_cap] arrivals / commit flags of k_wide_turns
   unsigned long long* d_pk = nullptr; uint8_t* d_pkfl = nullptr; // packed tuples / flags of the items (chain build)
   int opt_fast = 1;            // thread-per-record candidate kernel over chain tables (needs packed tuples)
@@ -800,7 +801,13 @@ int wide_turns(exb200_handle* h, const std::vector<WideTurn>& turns) {
   const int grid = std::min(h->turns_grid, want);
   CK(cudaMemsetAsync(h->d_turn_sync, 0, sizeof(unsigned) * 2 * (size_t)n, st));
   unsigned long long* dbg = nullptr;
-  if (h->trace) { int rc = dalloc(h, &dbg, 4 * (size_t)n); if (rc) return rc; } // (trace only: not freed before destroy)
+  if (h->trace) { // per-turn timers of block 0 (trace only)
+    if (h->turn_dbg_cap < (size_t)n) {
+      int rc = dalloc(h, &h->d_turn_dbg, 4 * h->turns_cap); if (rc) return rc;
+      h->turn_dbg_cap = h->turns_cap;
+    }
+    dbg = h->d_turn_dbg;
+  }
   void* args[] = {(void*)&S, (void*)&h->d_turns, (void*)&n, (void*)&h->d_turn_sync, (void*)&dbg};
   CK(cudaLaunchCooperativeKernel(S.has_dp ? (const void*)k_wide_turns<true> : (const void*)k_wide_turns<false>,
                                  dim3((unsigned)grid), dim3(TPB), args, 0, st));
