@@ -732,9 +732,9 @@ int build_csr_tables(exb200_handle* h, const std::vector<int>& tabs) {
   }
   CK(cudaMemcpyAsync(h->d_active, atomic_tabs.data(), sizeof(int) * atomic_tabs.size(), cudaMemcpyHostToDevice, st));
   if (!atomic_tabs.empty()) KLAUNCH(h, k_index_count, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * g.off[g.n], S, g, 0);
+  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, h->n_sm * 8, TPB, sizeof(int) * g.off[g.n], S, g, 0);
   if (!large.empty()) {
-    KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
+    KLAUNCH(h, k_part_a, h->n_sm * 8, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 0);
     KLAUNCH(h, k_part_scan, (int)large.size(), TPB, 0, h->pb);
   }
   for (int t : small) {
@@ -742,9 +742,9 @@ int build_csr_tables(exb200_handle* h, const std::vector<int>& tabs) {
     if (rc) return rc;
   }
   if (!atomic_tabs.empty()) KLAUNCH(h, k_index_fill, nblk(2LL * N), TPB, 0, S, h->d_active, (int)atomic_tabs.size());
-  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, PA_BLOCKS, TPB, sizeof(int) * g.off[g.n], S, g, 1);
+  for (const SmallTabs& g : tiny_groups) KLAUNCH(h, k_index_small, h->n_sm * 8, TPB, sizeof(int) * g.off[g.n], S, g, 1);
   if (!large.empty()) {
-    KLAUNCH(h, k_part_a, PA_BLOCKS, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
+    KLAUNCH(h, k_part_a, h->n_sm * 8, TPB, sizeof(int) * large.size() * MAX_PARTS, S, h->pb, 1);
     k_part_b<<<dim3(MAX_PARTS, (unsigned)large.size()), TPB, sizeof(int) * PART_SIZE, st>>>(S, h->pb);
     h->n_launches++;
   }

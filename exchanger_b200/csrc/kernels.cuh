@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(TPB) k_index_small(DevState S, SmallTabs T, in
 constexpr int PART_BITS = 14;
 constexpr int PART_SIZE = 1 << PART_BITS;
 constexpr int MAX_PARTS = 1024;          // partitions per table (bucket arrays up to 2^24)
-constexpr int PA_BLOCKS = 148 * 8;       // blocks of pass A
+// (pass A and the tiny-table builder run on eight blocks per multiprocessor: the same grid in both phases)
 constexpr int PA_MAX_TABS = 24;          // tables per pass-A launch (shared memory: 8 KB each)
 
 struct PartBuild {
